@@ -1,0 +1,151 @@
+/* libctmb -- C ABI of the B200-native CTMRG move engine.
+ *
+ * Drop-in boundary for the hot path of jurajHasik/peps-torch.  The
+ * reference has no FFI: its "plugin interface" is the pair of Python modules
+ * ctm/generic/ctmrg.py and ctm/one_site_c4v/ctmrg_c4v.py.  Every entry point below replaces the
+ * reference function cited next to it; the Python host code (peps_torch_b200/) binds them with
+ * ctypes and passes torch tensors as containers only (tensor.data_ptr(), current CUDA stream).
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers to contiguous row-major tensors of dtype
+ *     CTMB_F64 (double) or CTMB_C128 (interleaved re,im doubles);
+ *   - all outputs and the workspace are allocated by the caller; query the workspace size with
+ *     the matching *_workspace function (same arguments, data pointers may be NULL);
+ *   - `stream` is a cudaStream_t (0 = legacy default stream); calls are asynchronous w.r.t. the host
+ *     except for the first call with a new shape, which builds and uploads contraction plans;
+ *   - every function returns 0 on success; on failure a negative code, and ctmb_last_error() gives
+ *     the message (no exception ever crosses the boundary);
+ *   - index conventions are the reference's (ctm/generic/env.py:57-77): on-site a[s,u,l,d,r];
+ *     C(-1,-1)[down,right] C(1,-1)[left,down] C(1,1)[up,left] C(-1,1)[up,right];
+ *     T(0,-1)[chi,d,chi] T(-1,0)[chi,chi,d] T(0,1)[d,chi,chi] T(1,0)[chi,d,chi];
+ *     fused double-layer legs are (ket,bra), ket-major.
+ */
+#ifndef CTMB_H
+#define CTMB_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ctmb_handle_s* ctmb_handle_t;
+
+typedef enum { CTMB_F64 = 0, CTMB_C128 = 1 } ctmb_dtype;
+/* directions in the order of CTMARGS.ctm_move_sequence (config.py:392) */
+typedef enum { CTMB_UP = 0, CTMB_LEFT = 1, CTMB_DOWN = 2, CTMB_RIGHT = 3 } ctmb_direction;
+/* enlarged corners (ctm/generic/ctm_components.py:314-885) */
+typedef enum { CTMB_LU = 0, CTMB_RU = 1, CTMB_RD = 2, CTMB_LD = 3 } ctmb_corner;
+
+/* Hot-path knobs of CTMARGS (config.py:369-409) plus the parameters of the randomised
+ * range finder that replaces the full LAPACK decomposition. */
+typedef struct {
+    double svd_reltol;         /* projector_svd_reltol        (1e-8)  ctm_projectors.py:266 */
+    double eps_multiplet;      /* projector_eps_multiplet     (1e-8)  custom_svd.py:70-95; C4v: 1e-12 custom_eig.py:7-8 */
+    double multiplet_abstol;   /* projector_multiplet_abstol  (1e-14) */
+    double rsvd_rank_factor;   /* sketch width k = min(n, ceil(factor*chi)); default 2.0 */
+    int rsvd_niter;            /* power iterations q (projector_rsvd_niter); default 4 */
+    int jacobi_max_sweeps;     /* default 40 */
+    int norm_type;             /* ctm_absorb_normalization: 0 = 'inf' (only value supported) */
+    int reserved;
+    unsigned long long seed;   /* seed of the Gaussian sketch (deterministic) */
+} ctmb_options;
+
+/* One unit-cell site: on-site tensor and its eight environment tensors. */
+typedef struct {
+    const void* a;             /* a[p,Du,Dl,Dd,Dr] */
+    int dims[5];               /* p, Du, Dl, Dd, Dr */
+    int pad;
+    const void* C[4];          /* C(-1,-1), C(1,-1), C(1,1), C(-1,1)   -- all chi x chi */
+    const void* T[4];          /* T(0,-1), T(-1,0), T(0,1), T(1,0) */
+} ctmb_site;
+
+int ctmb_version(void);
+const char* ctmb_last_error(void);
+int ctmb_create(ctmb_handle_t* h, int device);
+int ctmb_destroy(ctmb_handle_t h);
+void ctmb_default_options(ctmb_options* opt);
+/* kernels launched / algorithmic real flops enqueued by this handle since the last reset */
+int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops);
+int ctmb_reset_counters(ctmb_handle_t h);
+
+/* Pairwise tensor contraction "ab,buc->auc" of contiguous tensors (tn_interface.py:3-10
+ * contract/einsum/mm).  Labels: single letters; output labels come from exactly one operand. */
+int ctmb_einsum2(ctmb_handle_t h, ctmb_dtype dt, const char* spec,
+                 const void* A, const long long* dimsA, int conjA,
+                 const void* B, const long long* dimsB, int conjB, void* C, void* stream);
+
+/* Enlarged corner c2x2_{LU,RU,RD,LD}_sl_c (ctm_components.py:372-434,532-586,683-733,832-885):
+ * out is the (chi*D^2) x (chi*D^2) matrix of SURVEY Appendix A for that corner of `site`. */
+int ctmb_c2x2(ctmb_handle_t h, ctmb_dtype dt, ctmb_corner kind, int chi, const ctmb_site* site,
+              void* out, void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_c2x2_workspace(ctmb_handle_t h, ctmb_dtype dt, ctmb_corner kind, int chi, const ctmb_site* site);
+
+/* halves_of_4x4_CTM_MOVE_{UP,LEFT,DOWN,RIGHT}_c (ctm_components.py:55-75,123-139,186-201,249-265):
+ * corners[4] are the four sites of the 2x2 patch in the order the reference lists them
+ * (UP: RU,RD,LU,LD  LEFT: LU,RU,LD,RD  DOWN: LD,LU,RD,RU  RIGHT: RD,LD,RU,LU). R, Rt: n x n. */
+int ctmb_halves(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int chi, const ctmb_site* const corners[4],
+                void* R, void* Rt, void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_halves_workspace(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int chi,
+                             const ctmb_site* const corners[4]);
+
+/* ctm_get_projectors_from_matrices (ctm_projectors.py:142-293): R, Rt are n0 x n1 row-major;
+ * P, Pt are n0 x chi row-major; S_out (may be NULL) receives the chi truncated singular values. */
+int ctmb_projectors(ctmb_handle_t h, ctmb_dtype dt, const void* R, const void* Rt, int n0, int n1, int chi,
+                    const ctmb_options* opt, void* P, void* Pt, double* S_out,
+                    void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_projectors_workspace(ctmb_handle_t h, ctmb_dtype dt, int n0, int n1, int chi, const ctmb_options* opt);
+
+/* truncated_svd_gesdd with keep_multiplets (custom_svd.py:38-101) + fix_svd_signs
+ * (svd_gesdd.py:18-26): M is m x n row-major; U (m x chi) and V (n x chi) are written
+ * COLUMN-major (each singular vector contiguous); S has chi entries. */
+int ctmb_truncated_svd(ctmb_handle_t h, ctmb_dtype dt, const void* M, int m, int n, int chi,
+                       const ctmb_options* opt, void* U, double* S, void* V,
+                       void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_truncated_svd_workspace(ctmb_handle_t h, ctmb_dtype dt, int m, int n, int chi, const ctmb_options* opt);
+
+/* truncated_eig_sym with keep_multiplets (custom_eig.py:7-67): M Hermitian n x n; D: chi
+ * eigenvalues of largest magnitude (descending |.|); U (n x chi) column-major. */
+int ctmb_truncated_eig_sym(ctmb_handle_t h, ctmb_dtype dt, const void* M, int n, int chi,
+                           const ctmb_options* opt, double* D, void* U,
+                           void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_truncated_eig_sym_workspace(ctmb_handle_t h, ctmb_dtype dt, int n, int chi, const ctmb_options* opt);
+
+/* One directional move over all sites = ctm_MOVE (ctm/generic/ctmrg.py:179-319) including
+ * projectors (4X4), absorb_truncate_CTM_MOVE_* (ctmrg.py:324-804) and move_normalize_c.
+ *   sites[nsites]        the unit cell with its current environment
+ *   corner_site[4*i+j]   index into sites[] of the j-th corner of the 2x2 patch of job i
+ *                        (order as in ctmb_halves)
+ *   nb_site[i]           index of the site whose projectors P1,Pt1 job i uses (coord+shift)
+ *   nC1/nC2/nT[i]        outputs of job i (chi x chi, chi x chi, T-shaped for `dir`); the host
+ *                        stores them at site coord-direction (ctmrg.py:313-319). */
+int ctmb_move_generic(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
+                      const ctmb_site* sites, const int* corner_site, const int* nb_site,
+                      const ctmb_options* opt, void* const* nC1, void* const* nC2, void* const* nT,
+                      void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_move_generic_workspace(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
+                                   const ctmb_site* sites, const int* corner_site, const int* nb_site,
+                                   const ctmb_options* opt);
+
+/* Restricted forms used by the multi-GPU shard (each rank owns a subset of the jobs):
+ * projectors of the listed jobs only, and absorption of the listed jobs with given projectors. */
+int ctmb_move_generic_projectors(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
+                                 const ctmb_site* sites, const int* corner_site, int njobs, const int* jobs,
+                                 const ctmb_options* opt, void* const* P, void* const* Pt,
+                                 void* ws, size_t ws_bytes, void* stream);
+int ctmb_move_generic_absorb(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
+                             const ctmb_site* sites, const int* nb_site, int njobs, const int* jobs,
+                             const void* const* P, const void* const* Pt,
+                             void* const* nC1, void* const* nC2, void* const* nT,
+                             void* ws, size_t ws_bytes, void* stream);
+
+/* One C4v move = ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463): a[p,D,D,D,D], C[chi,chi],
+ * T[chi,chi,D^2] -> C_out, T_out (same shapes); D_out (may be NULL): the chi kept eigenvalues. */
+int ctmb_move_c4v(ctmb_handle_t h, ctmb_dtype dt, const void* a, const int dims[5], const void* C,
+                  const void* T, int chi, const ctmb_options* opt, void* C_out, void* T_out, double* D_out,
+                  void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_move_c4v_workspace(ctmb_handle_t h, ctmb_dtype dt, const int dims[5], int chi, const ctmb_options* opt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTMB_H */

@@ -1,0 +1,111 @@
+// Shared declarations of libctmb (B200 / sm_100a CTMRG engine).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+#include <algorithm>
+
+namespace ctmb {
+
+void set_error(const std::string& msg);
+
+#define CTMB_CHECK(cond, msg)                                                       \
+    do {                                                                            \
+        if (!(cond)) throw std::runtime_error(std::string(msg) + " [" #cond "] at " \
+                                              __FILE__ ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+#define CTMB_CUDA(call)                                                             \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) throw std::runtime_error(std::string("CUDA error ") + \
+            cudaGetErrorString(e__) + " in " #call " at " __FILE__ ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------
+// tensor-contraction GEMM  C[m,n] = alpha * sum_k opA(A)[m,k] * opB(B)[k,n]
+// element (m,k) of A lives at A + a_m[m] + a_k[k] (element offsets), same for B and C.
+// ---------------------------------------------------------------------------------
+struct TcTables {
+    const int* a_m; const int* a_k;
+    const int* b_k; const int* b_n;
+    const int* c_m; const int* c_n;
+};
+
+struct TcBatchEntry {
+    const void* A; const void* B; void* C;
+    unsigned long long* amax;   // optional: atomicMax of |C| (bits of a non-negative double)
+    int tab;                    // which table set
+    int pad;
+};
+
+constexpr int TC_MAX_BATCH = 32;
+constexpr int TC_MAX_TABS = 8;
+
+struct TcParams {
+    int M, N, K;
+    int nbatch;
+    int flags;                  // bit0 conjA, bit1 conjB, bit2 A loader k-fast, bit3 B loader k-fast
+    double alpha;
+    TcTables tab[TC_MAX_TABS];
+    TcBatchEntry batch[TC_MAX_BATCH];
+};
+
+enum { TC_CONJ_A = 1, TC_CONJ_B = 2, TC_A_KFAST = 4, TC_B_KFAST = 8 };
+
+// launches one batched contraction; cplx=false: double, cplx=true: double2 (re,im)
+void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream);
+void tc_init_attributes();
+
+// ---------------------------------------------------------------------------------
+// dense helpers (qr.cu, jacobi.cu, misc.cu) -- all batched over `nb` problems
+// matrices are column-major with leading dimension ld unless stated otherwise
+// ---------------------------------------------------------------------------------
+struct PtrBatch { void* p[TC_MAX_BATCH]; };
+
+// in-place Householder QR of (rows x cols) column-major matrices; on exit the matrix holds
+// the explicit thin Q; if Rout.p[i] != nullptr the cols x cols upper-triangular R is
+// written there (column-major, ld = cols).
+void qr_launch(const PtrBatch& A, const PtrBatch& Rout, int nb, int rows, int cols, int ld,
+               bool cplx, cudaStream_t stream);
+
+// one-sided Jacobi SVD of k x k column-major G (ld=k): on exit G = Uhat*Sigma (columns
+// orthogonal), W accumulates the right rotations (G_in * W = G_out), sig[k] the column norms.
+void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, int nb, int k,
+                   bool cplx, int max_sweeps, int shift, cudaStream_t stream);
+size_t jacobi_smem_limit();
+
+// sort sig descending -> Ssorted[k]; Uhs = normalised sorted columns of G (first ncol),
+// Ws = sorted columns of W (first ncol); both k x ncol column-major.
+void sortcols_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, const PtrBatch& Ssorted,
+                     const PtrBatch& Uhs, const PtrBatch& Ws, int nb, int k, int ncol, bool cplx,
+                     int eig_mode, cudaStream_t stream);
+
+struct ProjFinalizeArgs {
+    int nb, rowsU, rowsV, chi, kavail;   // kavail: number of valid entries of S (>= chi+1 if truncating)
+    double reltol, eps_multiplet, abstol;
+    int truncating;                       // chi < min(m,n): multiplet rule applies
+    int conj_u;                           // write conj(U)*phase*s into Uout (projector form)
+    int apply_scale;                      // multiply by S^-1/2 (else plain sign-fixed U,V)
+};
+// U (rowsU x chi), V (rowsV x chi) column-major in place -> Uout/Vout; Sout[chi] truncated spectrum
+void proj_finalize_launch(const PtrBatch& U, const PtrBatch& V, const PtrBatch& S, const PtrBatch& Sout,
+                          const ProjFinalizeArgs& a, bool cplx, cudaStream_t stream);
+
+// x /= amax (amax given as bits); count elements each
+struct ScaleBatch { void* p[TC_MAX_BATCH]; const unsigned long long* amax[TC_MAX_BATCH]; long long count[TC_MAX_BATCH]; };
+void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
+// amax of |x|
+void absmax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
+
+void c4v_sym_launch(const void* tin, void* tout, int chi, int d, unsigned long long* amax, bool cplx,
+                    cudaStream_t stream);
+void c4v_diag_launch(const double* D, void* cout, int chi, bool cplx, cudaStream_t stream);
+
+void fill_gaussian_launch(double* out, long long count, unsigned long long seed, cudaStream_t stream);
+
+}  // namespace ctmb

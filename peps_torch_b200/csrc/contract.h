@@ -1,0 +1,94 @@
+// Host-side contraction planner: labelled tensor views -> offset tables -> batched launches.
+#pragma once
+#include "common.h"
+
+namespace ctmb {
+
+constexpr int MAX_ND = 12;
+
+// A labelled, strided view of device memory. Strides in elements of the scalar type.
+struct Tn {
+    void* ptr = nullptr;
+    int nd = 0;
+    char idx[MAX_ND + 1] = {0};
+    int64_t dim[MAX_ND] = {0};
+    int64_t str[MAX_ND] = {0};
+
+    int64_t numel() const { int64_t n = 1; for (int i = 0; i < nd; ++i) n *= dim[i]; return n; }
+    int find(char c) const { for (int i = 0; i < nd; ++i) if (idx[i] == c) return i; return -1; }
+};
+
+// contiguous row-major view with the given labels
+Tn make_tn(void* ptr, const char* idx, std::initializer_list<int64_t> dims);
+Tn make_tn(void* ptr, const std::string& idx, const std::vector<int64_t>& dims);
+// split mode `c` (extent d1*d2) into two modes c1 (slow, extent d1) and c2 (fast, extent d2)
+Tn split_mode(const Tn& t, char c, char c1, char c2, int64_t d1, int64_t d2);
+// relabel / permute (no data movement)
+Tn relabel(const Tn& t, const char* idx);
+Tn transpose_view(const Tn& t, const char* new_order);
+
+struct Plan {
+    int M = 0, N = 0, K = 0;
+    int flags = 0;
+    int* dev = nullptr;        // one allocation holding the six tables
+    TcTables tab{};
+};
+
+// Two-ended stack over one caller-provided device buffer. With base == nullptr it only
+// measures (dry run used by the *_workspace_bytes queries; no kernel is launched then).
+class Workspace {
+public:
+    void reset(void* base, size_t bytes) { base_ = (char*)base; cap_ = bytes; lo_ = hi_ = 0; peak_ = 0; }
+    void* alloc(size_t bytes, bool back = false);
+    size_t mark(bool back = false) const { return back ? hi_ : lo_; }
+    void release(size_t mark, bool back = false) { (back ? hi_ : lo_) = mark; }
+    size_t peak() const { return peak_; }
+    bool dry() const { return base_ == nullptr; }
+private:
+    char* base_ = nullptr; size_t cap_ = 0, lo_ = 0, hi_ = 0, peak_ = 0;
+};
+
+class Engine {
+public:
+    explicit Engine(int device);
+    ~Engine();
+    int device() const { return device_; }
+    bool cplx = false;             // element type of the current call
+    cudaStream_t stream = nullptr;
+    Workspace ws;
+    long long launches = 0;        // kernels launched (our own), for bench accounting
+    double flops = 0;              // algorithmic real flops enqueued
+
+    size_t esize() const { return cplx ? 16 : 8; }
+
+    // C = A * B over shared labels not in C; C's labels/strides define the output layout.
+    // Enqueued into the pending batch; flushed when incompatible or on flush().
+    void contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C,
+                  unsigned long long* amax = nullptr, double alpha = 1.0);
+    // allocate a contiguous workspace tensor with the given labels
+    Tn temp(const std::string& idx, const std::vector<int64_t>& dims, bool back = false);
+    void flush();
+
+    // Evaluate, for every job, the product of its operands left to right (pairwise; an
+    // index survives a step iff a later operand or the output carries it) into job.out.
+    // All jobs must have the same number of operands; step i of all jobs shares launches.
+    struct ChainJob {
+        std::vector<Tn> ops; std::vector<bool> conj; Tn out; unsigned long long* amax = nullptr;
+    };
+    void chain_multi(std::vector<ChainJob>& jobs, size_t temp_budget_bytes = (size_t)12 << 30);
+
+    // persistent device scratch owned by the engine (random sketch matrices, amax slots ...)
+    void* persistent(const std::string& key, size_t bytes, bool* created = nullptr);
+
+private:
+    const Plan& get_plan(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C);
+    int device_;
+    std::map<std::string, Plan> plans_;
+    std::map<std::string, std::pair<void*, size_t>> persist_;
+    // pending batch
+    TcParams pend_{};
+    std::vector<const Plan*> pend_plans_;
+    bool pend_active_ = false;
+};
+
+}  // namespace ctmb

@@ -1,0 +1,287 @@
+// Small batched helper kernels of the projector / normalisation steps.
+#include "common.h"
+#include "cx.h"
+
+namespace ctmb {
+
+// ---------------------------------------------------------------------------------------------
+// sort singular values (or eigenvalues by magnitude) descending and gather the leading columns
+// ---------------------------------------------------------------------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) sortcols_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch sigb, PtrBatch Ssb,
+                                                       PtrBatch Uhb, PtrBatch Wsb, int k, int ncol, int eig_mode) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const T* G = reinterpret_cast<const T*>(Gb.p[blockIdx.x]);
+    const T* W = reinterpret_cast<const T*>(Wb.p[blockIdx.x]);
+    const double* sig = reinterpret_cast<const double*>(sigb.p[blockIdx.x]);
+    double* Ss = reinterpret_cast<double*>(Ssb.p[blockIdx.x]);
+    T* Uh = reinterpret_cast<T*>(Uhb.p[blockIdx.x]);
+    T* Ws = reinterpret_cast<T*>(Wsb.p[blockIdx.x]);
+    extern __shared__ int perm[];   // perm[rank] = source column
+    const int tid = threadIdx.x;
+    // rank by counting: stable for ties (lower index first)
+    for (int j = tid; j < k; j += blockDim.x) {
+        const double vj = fabs(sig[j]);
+        int rank = 0;
+        for (int i = 0; i < k; ++i) {
+            const double vi = fabs(sig[i]);
+            rank += (vi > vj) || (vi == vj && i < j);
+        }
+        perm[rank] = j;
+        Ss[rank] = eig_mode ? sig[j] : vj;
+    }
+    __syncthreads();
+    for (int e = tid; e < k * ncol; e += blockDim.x) {
+        const int c = e / k, r = e % k;
+        const int src = perm[c];
+        if (Ws != nullptr) Ws[e] = W[(size_t)src * k + r];
+        if (Uh != nullptr) {
+            const double s = fabs(sig[src]);
+            Uh[e] = s > 0.0 ? S::scale(G[(size_t)src * k + r], 1.0 / s) : S::zero();
+        }
+    }
+}
+
+void sortcols_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, const PtrBatch& Ssorted,
+                     const PtrBatch& Uhs, const PtrBatch& Ws, int nb, int k, int ncol, bool cplx, int eig_mode,
+                     cudaStream_t stream) {
+    size_t smem = (size_t)k * sizeof(int);
+    if (cplx) sortcols_kernel<true><<<nb, 256, smem, stream>>>(G, W, sig, Ssorted, Uhs, Ws, k, ncol, eig_mode);
+    else sortcols_kernel<false><<<nb, 256, smem, stream>>>(G, W, sig, Ssorted, Uhs, Ws, k, ncol, eig_mode);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// projector finalisation: multiplet-aware truncation (custom_svd.py:70-95), relative cut-off and
+// S^-1/2 (ctm_projectors.py:266-270), phase fixing (svd_gesdd.py:18-26); one CTA per column.
+// ---------------------------------------------------------------------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) proj_finalize_kernel(PtrBatch Ub, PtrBatch Vb, PtrBatch Sb, PtrBatch Soutb,
+                                                            ProjFinalizeArgs a) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const int j = blockIdx.x, b = blockIdx.y;
+    T* U = reinterpret_cast<T*>(Ub.p[b]);
+    T* V = reinterpret_cast<T*>(Vb.p[b]);
+    const double* Sv = reinterpret_cast<const double*>(Sb.p[b]);
+    double* Sout = reinterpret_cast<double*>(Soutb.p[b]);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chi = a.chi;
+
+    __shared__ double sh_scale;
+    __shared__ int sh_keep;
+    __shared__ long long red_amp[8];
+    __shared__ int red_idx[8];
+    if (tid == 0) {
+        // multiplet rule on |S|
+        int chi_new = chi;
+        if (a.truncating) {
+            auto gap = [&](int i) {
+                double g = fabs(Sv[i]);
+                if (g < a.abstol) g = 0.0;
+                double v = (g - fabs(Sv[i + 1])) / (g + 1.0e-16);
+                return v > 1.0 ? 0.0 : v;
+            };
+            if (gap(chi - 1) < a.eps_multiplet) {
+                for (int i = chi - 1; i >= 0; --i)
+                    if (gap(i) > a.eps_multiplet) { chi_new = i; break; }
+            }
+        }
+        const bool kept = (j <= chi_new);     // St[chi_new+1:] = 0
+        const double sj = kept ? Sv[j] : 0.0;
+        // relative cut-off: S_sqrt[:count] = rsqrt(S[mask]) ; the mask is a prefix for sorted S
+        const double s0 = (0 <= chi_new) ? fabs(Sv[0]) : 0.0;
+        double sc = 0.0;
+        if (kept && fabs(sj) / s0 > a.reltol) sc = rsqrt(fabs(sj));
+        sh_keep = kept ? 1 : 0;
+        sh_scale = a.apply_scale ? sc : (kept ? 1.0 : 0.0);
+        if (Sout != nullptr) Sout[j] = sj;
+    }
+    // first arg-max of int64(|U|*2^40) over the column
+    T* uc = U + (size_t)j * a.rowsU;
+    long long best = -1; int bidx = 0x7fffffff;
+    for (int r = tid; r < a.rowsU; r += blockDim.x) {
+        long long amp = (long long)(S::abs(uc[r]) * 1099511627776.0);
+        if (amp > best) { best = amp; bidx = r; }     // r increases: keeps the first maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if (lane == 0) { red_amp[warp] = best; red_idx[warp] = bidx; }
+    __syncthreads();
+    best = red_amp[0]; bidx = red_idx[0];
+    for (int w = 1; w < 8; ++w)
+        if (red_amp[w] > best || (red_amp[w] == best && red_idx[w] < bidx)) { best = red_amp[w]; bidx = red_idx[w]; }
+    T ph = S::one();
+    if (bidx < a.rowsU) {
+        T x = uc[bidx];
+        double ax = S::abs(x);
+        if (ax > 0.0) ph = S::scale(x, 1.0 / ax);
+    }
+    __syncthreads();       // everyone has read uc[bidx] before the column is overwritten
+    const double sc = sh_scale;
+    const T cph = S::conj(ph);
+    for (int r = tid; r < a.rowsU; r += blockDim.x) {
+        T x = S::mul(uc[r], cph);             // sign-fixed U
+        if (a.conj_u) x = S::conj(x);
+        uc[r] = S::scale(x, sc);
+    }
+    if (V != nullptr) {
+        T* vc = V + (size_t)j * a.rowsV;
+        for (int r = tid; r < a.rowsV; r += blockDim.x) vc[r] = S::scale(S::mul(vc[r], cph), sc);
+    }
+}
+
+void proj_finalize_launch(const PtrBatch& U, const PtrBatch& V, const PtrBatch& S, const PtrBatch& Sout,
+                          const ProjFinalizeArgs& a, bool cplx, cudaStream_t stream) {
+    dim3 grid(a.chi, a.nb);
+    if (cplx) proj_finalize_kernel<true><<<grid, 256, 0, stream>>>(U, V, S, Sout, a);
+    else proj_finalize_kernel<false><<<grid, 256, 0, stream>>>(U, V, S, Sout, a);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// normalisation by the infinity norm (ctmrg.py:210-230)
+// ---------------------------------------------------------------------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) absmax_kernel(ScaleBatch b) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const T* x = reinterpret_cast<const T*>(b.p[blockIdx.y]);
+    const long long n = b.count[blockIdx.y];
+    double m = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmax(m, S::abs(x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+        atomicMax(const_cast<unsigned long long*>(b.amax[blockIdx.y]), (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) scale_kernel(ScaleBatch b) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    T* x = reinterpret_cast<T*>(b.p[blockIdx.y]);
+    const long long n = b.count[blockIdx.y];
+    const double m = __longlong_as_double((long long)*b.amax[blockIdx.y]);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        x[i] = CPLX ? S::make(S::re(x[i]) / m, S::im(x[i]) / m) : S::make(S::re(x[i]) / m, 0.0);
+}
+
+static int blocks_for(const ScaleBatch& b, int nb) {
+    long long mx = 1;
+    for (int i = 0; i < nb; ++i) mx = std::max(mx, b.count[i]);
+    long long g = (mx + 256 * 8 - 1) / (256 * 8);
+    return (int)std::max(1ll, std::min(g, 1184ll));
+}
+
+void absmax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream) {
+    dim3 grid(blocks_for(b, nb), nb);
+    if (cplx) absmax_kernel<true><<<grid, 256, 0, stream>>>(b);
+    else absmax_kernel<false><<<grid, 256, 0, stream>>>(b);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream) {
+    dim3 grid(blocks_for(b, nb), nb);
+    if (cplx) scale_kernel<true><<<grid, 256, 0, stream>>>(b);
+    else scale_kernel<false><<<grid, 256, 0, stream>>>(b);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// C4v epilogue (ctmrg_c4v.py:374,446,182-197): nT <- (nT + conj(nT)^T01)/2 with |.|max, C' = diag(D)/|D0|
+// ---------------------------------------------------------------------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) c4v_sym_kernel(const void* tin, void* tout, int chi, int d,
+                                                      unsigned long long* amax) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const T* t = reinterpret_cast<const T*>(tin);
+    T* o = reinterpret_cast<T*>(tout);
+    const long long n = (long long)chi * chi * d;
+    double m = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i % d);
+        const long long xy = i / d;
+        const int y = (int)(xy % chi), x = (int)(xy / chi);
+        T v = S::scale(S::add(t[i], S::conj(t[((long long)y * chi + x) * d + r])), 0.5);
+        o[i] = v;
+        m = fmax(m, S::abs(v));
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o2));
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+        atomicMax(amax, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+template <bool CPLX>
+__global__ void c4v_diag_kernel(const double* D, void* cout, int chi) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    T* c = reinterpret_cast<T*>(cout);
+    const double d0 = fabs(D[0]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < chi * chi; i += gridDim.x * blockDim.x) {
+        const int r = i / chi, q = i % chi;
+        c[i] = (r == q) ? S::make(D[r] / d0, 0.0) : S::zero();
+    }
+}
+
+void c4v_sym_launch(const void* tin, void* tout, int chi, int d, unsigned long long* amax, bool cplx,
+                    cudaStream_t stream) {
+    long long n = (long long)chi * chi * d;
+    int grid = (int)std::max(1ll, std::min((n + 255) / 256, 1184ll));
+    if (cplx) c4v_sym_kernel<true><<<grid, 256, 0, stream>>>(tin, tout, chi, d, amax);
+    else c4v_sym_kernel<false><<<grid, 256, 0, stream>>>(tin, tout, chi, d, amax);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+void c4v_diag_launch(const double* D, void* cout, int chi, bool cplx, cudaStream_t stream) {
+    int grid = std::max(1, std::min((chi * chi + 255) / 256, 1184));
+    if (cplx) c4v_diag_kernel<true><<<grid, 256, 0, stream>>>(D, cout, chi);
+    else c4v_diag_kernel<false><<<grid, 256, 0, stream>>>(D, cout, chi);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic standard-normal fill (counter based: splitmix64 + Box-Muller)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void gaussian_kernel(double* out, long long n, unsigned long long seed) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long a = splitmix64(seed ^ (2ull * i));
+        unsigned long long b = splitmix64(seed ^ (2ull * i + 1ull));
+        double u1 = ((a >> 11) + 1.0) * (1.0 / 9007199254740993.0);   // (0,1)
+        double u2 = (b >> 11) * (1.0 / 9007199254740992.0);           // [0,1)
+        out[i] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+}
+
+void fill_gaussian_launch(double* out, long long count, unsigned long long seed, cudaStream_t stream) {
+    int grid = (int)std::max(1ll, std::min((count + 255) / 256, 2368ll));
+    gaussian_kernel<<<grid, 256, 0, stream>>>(out, count, seed);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+}  // namespace ctmb

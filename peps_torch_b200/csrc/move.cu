@@ -1,0 +1,756 @@
+// Move driver + C ABI of libctmb: sequences the batched kernels of one CTM move on one stream.
+// Reference call stack being replaced: SURVEY.md section 3.1 / 3.2
+//   ctm_MOVE (ctm/generic/ctmrg.py:179-319) -> ctm_get_projectors_4x4 (ctm_projectors.py:14-64)
+//   -> halves_of_4x4_CTM_MOVE_* -> c2x2_*_sl_c -> ctm_get_projectors_from_matrices
+//   -> absorb_truncate_CTM_MOVE_* -> move_normalize_c ;  ctm_MOVE_sl (ctmrg_c4v.py:325-463).
+#include "contract.h"
+#include "../../include/ctmb.h"
+#include <cmath>
+#include <cstring>
+#include <cctype>
+
+namespace ctmb {
+const std::string& get_error();
+
+struct Handle {
+    Engine eng;
+    explicit Handle(int dev) : eng(dev) {}
+};
+
+// ------------------------------------------------------------------------------------------
+// tables (every string was checked against the reference's *_c functions
+// through oracle/ctm_oracle.py, which uses the same tables)
+// ------------------------------------------------------------------------------------------
+struct CornerSpec { int c, t1, t2; const char* lc; const char* l1; const char* l2; const char* la; const char* out; };
+// indices into ctmb_site::C / ::T
+static const CornerSpec CORNERS[4] = {
+    /* LU */ {0, 0, 1, "ab", "buc", "ael", "ulfg", "efcg"},
+    /* RU */ {1, 3, 0, "ab", "brc", "eua", "ulfr", "elcf"},
+    /* RD */ {2, 2, 3, "ab", "feb", "cra", "ulfr", "cuel"},
+    /* LD */ {3, 1, 2, "ab", "cal", "fbe", "ulfr", "cuer"},
+};
+struct HalfSpec { int kind[4]; bool tr[4]; };
+static const HalfSpec HALVES[4] = {
+    /* UP    */ {{CTMB_RU, CTMB_RD, CTMB_LU, CTMB_LD}, {false, false, true, false}},
+    /* LEFT  */ {{CTMB_LU, CTMB_RU, CTMB_LD, CTMB_RD}, {false, false, false, true}},
+    /* DOWN  */ {{CTMB_LD, CTMB_LU, CTMB_RD, CTMB_RU}, {true, false, true, true}},
+    /* RIGHT */ {{CTMB_RD, CTMB_LD, CTMB_RU, CTMB_LU}, {false, true, true, true}},
+};
+struct AbsorbSpec {
+    int C1, T1, T, T2, C2;
+    const char *lC1, *lT1, *lPt1, *oC1;     // nC1 = C1 . T1 . Pt1
+    const char *lC2, *lT2, *lP2, *oC2;      // nC2 = C2 . T2 . P2
+    const char *lT, *lPa, *lA, *lPb, *oT;   // nT = T . Pa . a . conj(a) . Pb
+    bool pa_is_P1;                          // Pa = P1 (and Pb = Pt2) else Pa = Pt2 (and Pb = P1)
+};
+static const AbsorbSpec ABSORB[4] = {
+    /* UP    */ {1, 3, 0, 1, 0, "ab", "brc", "arx", "xc", "ab", "ael", "blx", "ex", "auc", "alx", "uldr", "cry", "xdy", false},
+    /* LEFT  */ {0, 0, 1, 2, 3, "ab", "buc", "aux", "xc", "ab", "fbe", "afx", "xe", "acl", "aux", "uldr", "cdy", "xyr", true},
+    /* DOWN  */ {3, 1, 2, 3, 2, "ab", "cal", "blx", "cx", "ab", "cra", "brx", "cx", "fbe", "blx", "ulfr", "ery", "uxy", true},
+    /* RIGHT */ {2, 2, 3, 0, 1, "ab", "feb", "afx", "xe", "ab", "eua", "bux", "ex", "arc", "aux", "uldr", "cdy", "xly", false},
+};
+
+static void t_dims(const ctmb_site& s, int which, int chi, int64_t d[3]) {
+    const int64_t Du = s.dims[1], Dl = s.dims[2], Dd = s.dims[3], Dr = s.dims[4];
+    switch (which) {
+        case 0: d[0] = chi; d[1] = Du * Du; d[2] = chi; break;
+        case 1: d[0] = chi; d[1] = chi; d[2] = Dl * Dl; break;
+        case 2: d[0] = Dd * Dd; d[1] = chi; d[2] = chi; break;
+        default: d[0] = chi; d[1] = Dr * Dr; d[2] = chi; break;
+    }
+}
+static Tn env_T(const ctmb_site& s, int which, int chi, const char* lab) {
+    int64_t d[3]; t_dims(s, which, chi, d);
+    return make_tn(const_cast<void*>(s.T[which]), lab, {d[0], d[1], d[2]});
+}
+static Tn env_C(const ctmb_site& s, int which, int chi, const char* lab) {
+    return make_tn(const_cast<void*>(s.C[which]), lab, {chi, chi});
+}
+
+// Build the single-layer chain for a double-layer spec: every label of `la` (the aux legs
+// u,l,d,r of the on-site tensor, in that order) found on an operand is split into (ket,bra) =
+// (lower, upper case); a and conj(a) are inserted at position `apos` of the operand list.
+static Engine::ChainJob sl_job(std::vector<Tn> ops, size_t apos, const char* la, const ctmb_site& s,
+                               const char* out_lab, void* out_ptr, unsigned long long* amax) {
+    Engine::ChainJob job;
+    auto Dof = [&](char c) -> int64_t { const char* p = strchr(la, c); return p ? s.dims[1 + (p - la)] : 0; };
+    std::string lab_a = std::string("s") + la, lab_ac = lab_a;
+    for (size_t i = 1; i < lab_ac.size(); ++i) lab_ac[i] = (char)toupper(lab_ac[i]);
+    Tn a = make_tn(const_cast<void*>(s.a), lab_a, {s.dims[0], s.dims[1], s.dims[2], s.dims[3], s.dims[4]});
+    Tn ac = relabel(a, lab_ac.c_str());
+    std::map<char, int64_t> ext;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        if (i == apos) { job.ops.push_back(a); job.conj.push_back(false); job.ops.push_back(ac); job.conj.push_back(true); }
+        Tn t = ops[i];
+        for (const char* p = la; *p; ++p)
+            if (t.find(*p) >= 0) t = split_mode(t, *p, *p, (char)toupper(*p), Dof(*p), Dof(*p));
+        for (int d = 0; d < t.nd; ++d) ext[t.idx[d]] = t.dim[d];
+        job.ops.push_back(t); job.conj.push_back(false);
+    }
+    if (apos >= ops.size()) { job.ops.push_back(a); job.conj.push_back(false); job.ops.push_back(ac); job.conj.push_back(true); }
+    std::string ol; std::vector<int64_t> od;
+    for (const char* p = out_lab; *p; ++p) {
+        if (strchr(la, *p)) { ol.push_back(*p); od.push_back(Dof(*p)); ol.push_back((char)toupper(*p)); od.push_back(Dof(*p)); }
+        else { ol.push_back(*p); CTMB_CHECK(ext.count(*p), "output label not found"); od.push_back(ext[*p]); }
+    }
+    job.out = make_tn(out_ptr, ol, od);
+    job.amax = amax;
+    return job;
+}
+
+static void corner_shape(int kind, const ctmb_site& s, int chi, int64_t& rows, int64_t& cols) {
+    const CornerSpec& cs = CORNERS[kind];
+    auto D = [&](char c) -> int64_t { const char* p = strchr(cs.la, c); return s.dims[1 + (p - cs.la)]; };
+    rows = chi * D(cs.out[1]) * D(cs.out[1]);
+    cols = chi * D(cs.out[3]) * D(cs.out[3]);
+}
+
+static Engine::ChainJob corner_job(int kind, const ctmb_site& s, int chi, void* out) {
+    const CornerSpec& cs = CORNERS[kind];
+    std::vector<Tn> ops = {env_C(s, cs.c, chi, cs.lc), env_T(s, cs.t1, chi, cs.l1), env_T(s, cs.t2, chi, cs.l2)};
+    return sl_job(ops, 3, cs.la, s, cs.out, out, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// randomised truncated SVD / Hermitian EVD, batched over nb equally-shaped problems
+// ------------------------------------------------------------------------------------------
+struct Rsvd {
+    int nb = 0, m = 0, n = 0, chi = 0, k = 0;
+    std::vector<void*> U, V, S;       // U: m x chi col-major, V: n x chi col-major, S: k doubles (sorted)
+};
+
+static int sketch_width(int m, int n, int chi, const ctmb_options& o) {
+    int mn = std::min(m, n);
+    int k = (int)std::ceil(o.rsvd_rank_factor * chi);
+    k = std::max(k, chi + 1);
+    return std::min(k, mn);
+}
+
+// M[b]: m x n row-major. eig_mode: M Hermitian (m == n), S receives signed eigenvalues.
+static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int n, int chi,
+                       const ctmb_options& o, bool eig_mode) {
+    Rsvd r; r.nb = (int)M.size(); r.m = m; r.n = n; r.chi = chi;
+    const int nb = r.nb, k = sketch_width(m, n, chi, o);
+    r.k = k;
+    CTMB_CHECK(nb <= TC_MAX_BATCH, "too many problems in one batch");
+    CTMB_CHECK(chi <= std::min(m, n), "chi exceeds matrix size");
+    const size_t es = e.esize();
+    // Gaussian sketch, generated once per (n,k,dtype,seed) and kept
+    char key[128];
+    snprintf(key, sizeof key, "omega:%d:%d:%d:%llu", n, k, (int)e.cplx, o.seed);
+    void* omega = nullptr;
+    if (!e.ws.dry()) {
+        bool created = false;
+        omega = e.persistent(key, (size_t)n * k * es, &created);
+        if (created) { fill_gaussian_launch((double*)omega, (long long)n * k * (e.cplx ? 2 : 1), o.seed, e.stream); ++e.launches; }
+    }
+    std::vector<Tn> Mt(nb), Y(nb), Z(nb);
+    PtrBatch pY{}, pZ{}, pR{}, pNull{}, pW{}, pSig{}, pS{}, pUh{}, pWs{}, pU{}, pV{};
+    std::vector<void*> R2(nb), W(nb), sig(nb), Uh(nb), Ws(nb);
+    for (int b = 0; b < nb; ++b) {
+        Mt[b] = make_tn(const_cast<void*>(M[b]), "ij", {m, n});
+        Y[b] = e.temp("si", {k, m});      // column-major m x k
+        Z[b] = e.temp("sj", {k, n});      // column-major n x k
+        R2[b] = e.ws.alloc((size_t)k * k * es);
+        W[b] = e.ws.alloc((size_t)k * k * es);
+        sig[b] = e.ws.alloc((size_t)k * 8);
+        r.S.push_back(e.ws.alloc((size_t)k * 8));
+        Uh[b] = e.ws.alloc((size_t)k * chi * es);
+        Ws[b] = e.ws.alloc((size_t)k * chi * es);
+        r.U.push_back(e.ws.alloc((size_t)m * chi * es));
+        r.V.push_back(eig_mode ? nullptr : e.ws.alloc((size_t)n * chi * es));
+        pY.p[b] = Y[b].ptr; pZ.p[b] = Z[b].ptr; pR.p[b] = R2[b]; pW.p[b] = W[b]; pSig.p[b] = sig[b];
+        pS.p[b] = r.S[b]; pUh.p[b] = Uh[b]; pWs.p[b] = Ws[b]; pU.p[b] = r.U[b]; pV.p[b] = r.V[b];
+    }
+    if (e.ws.dry()) return r;
+    Tn Om = make_tn(omega, "sj", {k, n});
+    auto qr = [&](const PtrBatch& A, const PtrBatch& Rout, int rows) {
+        e.flush();
+        qr_launch(A, Rout, nb, rows, k, rows, e.cplx, e.stream); ++e.launches;
+    };
+    // Y = M * Omega
+    for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, Om, false, Y[b]);
+    qr(pY, pNull, m);
+    if (!eig_mode) {
+        for (int it = 0; it < o.rsvd_niter; ++it) {
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, relabel(Y[b], "si"), false, Z[b]);     // Z = M^H Q
+            qr(pZ, pNull, n);
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, relabel(Z[b], "sj"), false, Y[b]);    // Y = M Q'
+            qr(pY, pNull, m);
+        }
+        // Bt = M^H Q = Q2 R2   =>   M ~ Q R2^H Q2^H ;  R2 W = Uh Sigma  =>  U = Q W, V = Q2 Uh
+        for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, Y[b], false, Z[b]);
+        qr(pZ, pR, n);
+        jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, e.stream); ++e.launches;
+        sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); ++e.launches;
+        for (int b = 0; b < nb; ++b) {
+            e.contract(Y[b], false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+            e.contract(Z[b], false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
+        }
+        e.flush();
+    } else {
+        // Hermitian: subspace iteration with M itself (2q+1 applications in total), then Rayleigh-Ritz
+        for (int it = 0; it < 2 * o.rsvd_niter; ++it) {
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, relabel(Y[b], "sj"), false, relabel(Z[b], "si"));
+            qr(pZ, pNull, n);
+            std::swap(Y, Z); std::swap(pY, pZ);
+        }
+        // Z = M Q ; Tm = Q^H Z (k x k, column-major [t][s]) ; Tm W = W Lambda
+        for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, relabel(Y[b], "sj"), false, relabel(Z[b], "si"));
+        e.flush();
+        for (int b = 0; b < nb; ++b)
+            e.contract(relabel(Y[b], "si"), true, relabel(Z[b], "ti"), false, make_tn(R2[b], "ts", {k, k}));
+        e.flush();
+        jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, e.stream); ++e.launches;
+        sortcols_launch(pR, pW, pSig, pS, pNull, pWs, nb, k, chi, e.cplx, 1, e.stream); ++e.launches;
+        for (int b = 0; b < nb; ++b)
+            e.contract(relabel(Y[b], "si"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+        e.flush();
+    }
+    return r;
+}
+
+static ProjFinalizeArgs finalize_args(const Rsvd& r, const ctmb_options& o, bool conj_u, bool scale) {
+    ProjFinalizeArgs a{};
+    a.nb = r.nb; a.rowsU = r.m; a.rowsV = r.n; a.chi = r.chi; a.kavail = r.k;
+    a.reltol = o.svd_reltol; a.eps_multiplet = o.eps_multiplet; a.abstol = o.multiplet_abstol;
+    a.truncating = (r.chi < std::min(r.m, r.n)) && (r.k > r.chi);
+    a.conj_u = conj_u; a.apply_scale = scale;
+    return a;
+}
+
+// ------------------------------------------------------------------------------------------
+// projectors for a list of jobs
+// ------------------------------------------------------------------------------------------
+struct MoveCtx {
+    Engine& e; int dir, nsites, chi; const ctmb_site* sites; const ctmb_options& o;
+};
+
+// R,Rt (n0 x n1 row-major) -> P, Pt (n0 x chi row-major)
+static void projectors_from_matrices(Engine& e, const std::vector<const void*>& R, const std::vector<const void*>& Rt,
+                                     int n0, int n1, int chi, const ctmb_options& o,
+                                     const std::vector<void*>& P, const std::vector<void*>& Pt,
+                                     const std::vector<double*>& Sout) {
+    const int nb = (int)R.size();
+    const size_t mark = e.ws.mark();
+    std::vector<const void*> Mp(nb);
+    std::vector<Tn> Rtn(nb), Rttn(nb);
+    for (int b = 0; b < nb; ++b) {
+        Rtn[b] = make_tn(const_cast<void*>(R[b]), "ki", {n0, n1});
+        Rttn[b] = make_tn(const_cast<void*>(Rt[b]), "kj", {n0, n1});
+        Tn M = e.temp("ij", {n1, n1});
+        Mp[b] = M.ptr;
+        e.contract(Rtn[b], false, Rttn[b], false, M);           // M = R^T Rt  (plain transpose)
+    }
+    e.flush();
+    Rsvd r = rsvd_batch(e, Mp, n1, n1, chi, o, false);
+    if (!e.ws.dry()) {
+        PtrBatch pU{}, pV{}, pS{}, pSo{};
+        for (int b = 0; b < nb; ++b) { pU.p[b] = r.U[b]; pV.p[b] = r.V[b]; pS.p[b] = r.S[b]; pSo.p[b] = Sout.empty() ? nullptr : Sout[b]; }
+        proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, true, true), e.cplx, e.stream); ++e.launches;
+        for (int b = 0; b < nb; ++b) {
+            e.contract(relabel(Rtn[b], "xi"), false, make_tn(r.U[b], "ci", {chi, n1}), false, make_tn(P[b], "xc", {n0, chi}));
+            e.contract(relabel(Rttn[b], "xi"), false, make_tn(r.V[b], "ci", {chi, n1}), false, make_tn(Pt[b], "xc", {n0, chi}));
+        }
+        e.flush();
+    }
+    e.ws.release(mark);
+}
+
+static void halves_jobs(Engine& e, int dir, int chi, const std::vector<const ctmb_site*>& corners /*4 per job*/,
+                        const std::vector<void*>& R, const std::vector<void*>& Rt, int64_t& n0, int64_t& n1) {
+    const int nj = (int)R.size();
+    const HalfSpec& hs = HALVES[dir];
+    const size_t mark = e.ws.mark();
+    std::vector<Engine::ChainJob> cj;
+    std::vector<void*> cm(4 * nj);
+    std::vector<int64_t> rows(4 * nj), cols(4 * nj);
+    for (int j = 0; j < nj; ++j)
+        for (int q = 0; q < 4; ++q) {
+            const ctmb_site& s = *corners[4 * j + q];
+            corner_shape(hs.kind[q], s, chi, rows[4 * j + q], cols[4 * j + q]);
+            cm[4 * j + q] = e.ws.alloc((size_t)rows[4 * j + q] * cols[4 * j + q] * e.esize());
+            cj.push_back(corner_job(hs.kind[q], s, chi, cm[4 * j + q]));
+        }
+    e.chain_multi(cj);
+    for (int j = 0; j < nj; ++j) {
+        for (int h = 0; h < 2; ++h) {
+            const int q0 = 4 * j + 2 * h, q1 = q0 + 1;
+            Tn X = make_tn(cm[q0], hs.tr[2 * h] ? "ki" : "ik", {rows[q0], cols[q0]});
+            Tn Yt = make_tn(cm[q1], hs.tr[2 * h + 1] ? "jk" : "kj", {rows[q1], cols[q1]});
+            const int64_t r0 = hs.tr[2 * h] ? cols[q0] : rows[q0];
+            const int64_t c1 = hs.tr[2 * h + 1] ? rows[q1] : cols[q1];
+            if (j == 0 && h == 0) { n0 = r0; n1 = c1; }
+            CTMB_CHECK(r0 == n0 && c1 == n1, "non-uniform bond dimensions across the unit cell are not supported");
+            e.contract(X, false, Yt, false, make_tn(h == 0 ? R[j] : Rt[j], "ij", {r0, c1}));
+        }
+    }
+    e.flush();
+    e.ws.release(mark);
+    // NOTE: R/Rt were allocated by the caller *before* this function took its mark.
+}
+
+static void half_shape(int dir, int chi, const ctmb_site* const* c4, int64_t& n0, int64_t& n1) {
+    const HalfSpec& hs = HALVES[dir];
+    int64_t r, c;
+    corner_shape(hs.kind[0], *c4[0], chi, r, c); n0 = hs.tr[0] ? c : r;
+    corner_shape(hs.kind[1], *c4[1], chi, r, c); n1 = hs.tr[1] ? r : c;
+}
+
+static void move_projectors(MoveCtx& mc, const int* corner_site, const std::vector<int>& jobs,
+                            const std::vector<void*>& P, const std::vector<void*>& Pt) {
+    Engine& e = mc.e;
+    const int nj = (int)jobs.size();
+    if (nj == 0) return;
+    const size_t mark = e.ws.mark();
+    std::vector<const ctmb_site*> corners(4 * nj);
+    for (int j = 0; j < nj; ++j)
+        for (int q = 0; q < 4; ++q) {
+            int si = corner_site[4 * jobs[j] + q];
+            CTMB_CHECK(si >= 0 && si < mc.nsites, "corner_site index out of range");
+            corners[4 * j + q] = &mc.sites[si];
+        }
+    int64_t n0 = 0, n1 = 0;
+    half_shape(mc.dir, mc.chi, &corners[0], n0, n1);
+    std::vector<void*> R(nj), Rt(nj);
+    for (int j = 0; j < nj; ++j) { R[j] = e.ws.alloc((size_t)n0 * n1 * e.esize()); Rt[j] = e.ws.alloc((size_t)n0 * n1 * e.esize()); }
+    halves_jobs(e, mc.dir, mc.chi, corners, R, Rt, n0, n1);
+    std::vector<const void*> Rc(R.begin(), R.end()), Rtc(Rt.begin(), Rt.end());
+    projectors_from_matrices(e, Rc, Rtc, (int)n0, (int)n1, mc.chi, mc.o, P, Pt, {});
+    e.ws.release(mark);
+}
+
+static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>& jobs,
+                        const std::vector<const void*>& Pall, const std::vector<const void*>& Ptall,
+                        void* const* nC1, void* const* nC2, void* const* nT) {
+    Engine& e = mc.e;
+    const int nj = (int)jobs.size();
+    if (nj == 0) return;
+    CTMB_CHECK(mc.o.norm_type == 0, "only ctm_absorb_normalization='inf' is implemented");
+    const AbsorbSpec& as = ABSORB[mc.dir];
+    const int chi = mc.chi;
+    unsigned long long* amax = nullptr;
+    if (!e.ws.dry()) {
+        amax = (unsigned long long*)e.persistent("amax", 3 * TC_MAX_BATCH * sizeof(unsigned long long));
+        CTMB_CUDA(cudaMemsetAsync(amax, 0, 3 * TC_MAX_BATCH * sizeof(unsigned long long), e.stream));
+    }
+    CTMB_CHECK(3 * nj <= TC_MAX_BATCH, "too many sites for one absorb batch");
+    std::vector<Engine::ChainJob> j1, j2, j3;
+    ScaleBatch sb{};
+    for (int j = 0; j < nj; ++j) {
+        const int si = jobs[j], sn = nb_site[si];
+        CTMB_CHECK(sn >= 0 && sn < mc.nsites, "nb_site index out of range");
+        const ctmb_site& s = mc.sites[si];
+        auto dimd = [&](int which) { int64_t d[3]; t_dims(s, which, chi, d); return which == 1 ? d[2] : which == 2 ? d[0] : d[1]; };
+        const int64_t d1 = dimd(as.T1), d2 = dimd(as.T2);
+        Tn Pt1 = make_tn(const_cast<void*>(Ptall[sn]), as.lPt1, {chi, d1, chi});
+        Tn P2 = make_tn(const_cast<void*>(Pall[si]), as.lP2, {chi, d2, chi});
+        // nC1
+        Engine::ChainJob a1;
+        a1.ops = {env_C(s, as.C1, chi, as.lC1), env_T(s, as.T1, chi, as.lT1), Pt1};
+        a1.conj = {false, false, false};
+        a1.out = make_tn(nC1[j], as.oC1, {chi, chi});
+        a1.amax = amax ? amax + 3 * j : nullptr;
+        j1.push_back(a1);
+        Engine::ChainJob a2;
+        a2.ops = {env_C(s, as.C2, chi, as.lC2), env_T(s, as.T2, chi, as.lT2), P2};
+        a2.conj = {false, false, false};
+        a2.out = make_tn(nC2[j], as.oC2, {chi, chi});
+        a2.amax = amax ? amax + 3 * j + 1 : nullptr;
+        j2.push_back(a2);
+        // nT: the projector on the T1 side is P1 / Pt1 of the neighbour, on the T2 side P2 / Pt2 of this site
+        const void* pa = as.pa_is_P1 ? Pall[sn] : Ptall[si];
+        const void* pb = as.pa_is_P1 ? Ptall[si] : Pall[sn];
+        const int64_t da = as.pa_is_P1 ? d1 : d2, db = as.pa_is_P1 ? d2 : d1;
+        std::vector<Tn> ops = {env_T(s, as.T, chi, as.lT), make_tn(const_cast<void*>(pa), as.lPa, {chi, da, chi}),
+                               make_tn(const_cast<void*>(pb), as.lPb, {chi, db, chi})};
+        j3.push_back(sl_job(ops, 2, as.lA, s, as.oT, nT[j], amax ? amax + 3 * j + 2 : nullptr));
+        int64_t td[3]; t_dims(s, as.T, chi, td);
+        if (!amax) continue;
+        sb.p[3 * j] = nC1[j]; sb.count[3 * j] = (long long)chi * chi; sb.amax[3 * j] = amax + 3 * j;
+        sb.p[3 * j + 1] = nC2[j]; sb.count[3 * j + 1] = (long long)chi * chi; sb.amax[3 * j + 1] = amax + 3 * j + 1;
+        sb.p[3 * j + 2] = nT[j]; sb.count[3 * j + 2] = td[0] * td[1] * td[2]; sb.amax[3 * j + 2] = amax + 3 * j + 2;
+    }
+    // nC1 and nC2 chains have identical GEMM shapes: run them as one batch
+    std::vector<Engine::ChainJob> j12 = j1;
+    j12.insert(j12.end(), j2.begin(), j2.end());
+    e.chain_multi(j12);
+    e.chain_multi(j3);
+    if (!e.ws.dry()) { scale_by_amax_launch(sb, 3 * nj, e.cplx, e.stream); ++e.launches; }
+}
+
+static ctmb_options opts_or_default(const ctmb_options* o) {
+    ctmb_options d; ctmb_default_options(&d);
+    return o ? *o : d;
+}
+
+}  // namespace ctmb
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace ctmb;
+
+struct ctmb_handle_s { Handle h; explicit ctmb_handle_s(int dev) : h(dev) {} };
+
+#define CTMB_TRY try {
+#define CTMB_CATCH(ret)                                                   \
+    } catch (const std::exception& ex) { set_error(ex.what()); return ret; } \
+      catch (...) { set_error("unknown error"); return ret; }
+
+static void begin_call(ctmb_handle_t h, ctmb_dtype dt, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_CHECK(h != nullptr, "null handle");
+    CTMB_CHECK(dt == CTMB_F64 || dt == CTMB_C128, "unsupported dtype");
+    Engine& e = h->h.eng;
+    CTMB_CUDA(cudaSetDevice(e.device()));
+    e.cplx = (dt == CTMB_C128);
+    e.stream = (cudaStream_t)stream;
+    e.ws.reset(ws, ws_bytes);
+}
+// dry run: measure the workspace the same call would use
+static void begin_dry(ctmb_handle_t h, ctmb_dtype dt) {
+    CTMB_CHECK(h != nullptr, "null handle");
+    Engine& e = h->h.eng;
+    e.cplx = (dt == CTMB_C128);
+    e.ws.reset(nullptr, 0);
+}
+
+extern "C" {
+
+int ctmb_version(void) { return 100; }
+const char* ctmb_last_error(void) { return get_error().c_str(); }
+
+int ctmb_create(ctmb_handle_t* h, int device) {
+    CTMB_TRY
+    CTMB_CHECK(h != nullptr, "null out pointer");
+    int ndev = 0;
+    CTMB_CUDA(cudaGetDeviceCount(&ndev));
+    CTMB_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+    cudaDeviceProp prop;
+    CTMB_CUDA(cudaGetDeviceProperties(&prop, device));
+    CTMB_CHECK(prop.major >= 10, "libctmb is built for sm_100a (Blackwell) only");
+    *h = new ctmb_handle_s(device);
+    return 0;
+    CTMB_CATCH(-1)
+}
+
+int ctmb_destroy(ctmb_handle_t h) {
+    CTMB_TRY
+    delete h;
+    return 0;
+    CTMB_CATCH(-1)
+}
+
+void ctmb_default_options(ctmb_options* o) {
+    if (!o) return;
+    o->svd_reltol = 1.0e-8; o->eps_multiplet = 1.0e-8; o->multiplet_abstol = 1.0e-14;
+    o->rsvd_rank_factor = 2.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->reserved = 0;
+    o->seed = 0x5eed5eedull;
+}
+
+int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops) {
+    CTMB_TRY
+    CTMB_CHECK(h != nullptr, "null handle");
+    if (launches) *launches = h->h.eng.launches;
+    if (flops) *flops = h->h.eng.flops;
+    return 0;
+    CTMB_CATCH(-1)
+}
+int ctmb_reset_counters(ctmb_handle_t h) {
+    CTMB_TRY
+    CTMB_CHECK(h != nullptr, "null handle");
+    h->h.eng.launches = 0; h->h.eng.flops = 0;
+    return 0;
+    CTMB_CATCH(-1)
+}
+
+int ctmb_einsum2(ctmb_handle_t h, ctmb_dtype dt, const char* spec, const void* A, const long long* dimsA, int conjA,
+                 const void* B, const long long* dimsB, int conjB, void* C, void* stream) {
+    CTMB_TRY
+    static char dummy[256];
+    begin_call(h, dt, dummy, 0, stream);
+    Engine& e = h->h.eng;
+    std::string s(spec);
+    size_t c1 = s.find(','), ar = s.find("->");
+    CTMB_CHECK(c1 != std::string::npos && ar != std::string::npos && c1 < ar, "spec must look like 'ab,bc->ac'");
+    std::string la = s.substr(0, c1), lb = s.substr(c1 + 1, ar - c1 - 1), lc = s.substr(ar + 2);
+    std::vector<int64_t> da(dimsA, dimsA + la.size()), db(dimsB, dimsB + lb.size()), dc;
+    for (char ch : lc) {
+        size_t p = la.find(ch);
+        if (p != std::string::npos) dc.push_back(da[p]);
+        else { p = lb.find(ch); CTMB_CHECK(p != std::string::npos, "output label not in inputs"); dc.push_back(db[p]); }
+    }
+    e.contract(make_tn(const_cast<void*>(A), la, da), conjA != 0, make_tn(const_cast<void*>(B), lb, db), conjB != 0,
+               make_tn(C, lc, dc));
+    e.flush();
+    return 0;
+    CTMB_CATCH(-1)
+}
+
+static void c2x2_impl(ctmb_handle_t h, ctmb_corner kind, int chi, const ctmb_site* site, void* out) {
+    CTMB_CHECK(kind >= 0 && kind < 4 && site != nullptr && chi > 0, "bad arguments");
+    std::vector<Engine::ChainJob> jobs = {corner_job(kind, *site, chi, out)};
+    h->h.eng.chain_multi(jobs);
+}
+int ctmb_c2x2(ctmb_handle_t h, ctmb_dtype dt, ctmb_corner kind, int chi, const ctmb_site* site, void* out,
+              void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    c2x2_impl(h, kind, chi, site, out);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_c2x2_workspace(ctmb_handle_t h, ctmb_dtype dt, ctmb_corner kind, int chi, const ctmb_site* site) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    c2x2_impl(h, kind, chi, site, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+static void halves_impl(ctmb_handle_t h, ctmb_direction dir, int chi, const ctmb_site* const corners[4], void* R, void* Rt) {
+    CTMB_CHECK(dir >= 0 && dir < 4 && chi > 0, "bad arguments");
+    std::vector<const ctmb_site*> c(corners, corners + 4);
+    int64_t n0 = 0, n1 = 0;
+    half_shape(dir, chi, corners, n0, n1);
+    halves_jobs(h->h.eng, dir, chi, c, {R}, {Rt}, n0, n1);
+}
+int ctmb_halves(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int chi, const ctmb_site* const corners[4],
+                void* R, void* Rt, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    halves_impl(h, dir, chi, corners, R, Rt);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_halves_workspace(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int chi,
+                             const ctmb_site* const corners[4]) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    halves_impl(h, dir, chi, corners, nullptr, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+int ctmb_projectors(ctmb_handle_t h, ctmb_dtype dt, const void* R, const void* Rt, int n0, int n1, int chi,
+                    const ctmb_options* opt, void* P, void* Pt, double* S_out, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    ctmb_options o = opts_or_default(opt);
+    std::vector<double*> so; if (S_out) so.push_back(S_out);
+    projectors_from_matrices(h->h.eng, {R}, {Rt}, n0, n1, chi, o, {P}, {Pt}, so);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_projectors_workspace(ctmb_handle_t h, ctmb_dtype dt, int n0, int n1, int chi, const ctmb_options* opt) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    ctmb_options o = opts_or_default(opt);
+    projectors_from_matrices(h->h.eng, {nullptr}, {nullptr}, n0, n1, chi, o, {nullptr}, {nullptr}, {});
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+static void svd_impl(ctmb_handle_t h, const void* M, int m, int n, int chi, const ctmb_options& o, void* U, double* S, void* V) {
+    Engine& e = h->h.eng;
+    Rsvd r = rsvd_batch(e, {M}, m, n, chi, o, false);
+    if (e.ws.dry()) return;
+    PtrBatch pU{}, pV{}, pS{}, pSo{};
+    pU.p[0] = r.U[0]; pV.p[0] = r.V[0]; pS.p[0] = r.S[0]; pSo.p[0] = S;
+    proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); ++e.launches;
+    CTMB_CUDA(cudaMemcpyAsync(U, r.U[0], (size_t)m * chi * e.esize(), cudaMemcpyDeviceToDevice, e.stream));
+    CTMB_CUDA(cudaMemcpyAsync(V, r.V[0], (size_t)n * chi * e.esize(), cudaMemcpyDeviceToDevice, e.stream));
+}
+int ctmb_truncated_svd(ctmb_handle_t h, ctmb_dtype dt, const void* M, int m, int n, int chi, const ctmb_options* opt,
+                       void* U, double* S, void* V, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    svd_impl(h, M, m, n, chi, opts_or_default(opt), U, S, V);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_truncated_svd_workspace(ctmb_handle_t h, ctmb_dtype dt, int m, int n, int chi, const ctmb_options* opt) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    svd_impl(h, nullptr, m, n, chi, opts_or_default(opt), nullptr, nullptr, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+static Rsvd eig_impl(ctmb_handle_t h, const void* M, int n, int chi, const ctmb_options& o, double* D, void* U) {
+    Engine& e = h->h.eng;
+    Rsvd r = rsvd_batch(e, {M}, n, n, chi, o, true);
+    if (e.ws.dry()) return r;
+    PtrBatch pU{}, pV{}, pS{}, pSo{};
+    pU.p[0] = r.U[0]; pV.p[0] = nullptr; pS.p[0] = r.S[0]; pSo.p[0] = D;
+    proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); ++e.launches;
+    if (U) CTMB_CUDA(cudaMemcpyAsync(U, r.U[0], (size_t)n * chi * e.esize(), cudaMemcpyDeviceToDevice, e.stream));
+    return r;
+}
+int ctmb_truncated_eig_sym(ctmb_handle_t h, ctmb_dtype dt, const void* M, int n, int chi, const ctmb_options* opt,
+                           double* D, void* U, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    eig_impl(h, M, n, chi, opts_or_default(opt), D, U);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_truncated_eig_sym_workspace(ctmb_handle_t h, ctmb_dtype dt, int n, int chi, const ctmb_options* opt) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    eig_impl(h, nullptr, n, chi, opts_or_default(opt), nullptr, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+static void move_generic_impl(ctmb_handle_t h, ctmb_direction dir, int nsites, int chi, const ctmb_site* sites,
+                              const int* corner_site, const int* nb_site, const ctmb_options& o,
+                              void* const* nC1, void* const* nC2, void* const* nT) {
+    CTMB_CHECK(dir >= 0 && dir < 4 && nsites > 0 && chi > 0 && sites && corner_site && nb_site, "bad arguments");
+    Engine& e = h->h.eng;
+    MoveCtx mc{e, (int)dir, nsites, chi, sites, o};
+    std::vector<int> jobs(nsites);
+    for (int i = 0; i < nsites; ++i) jobs[i] = i;
+    // projector storage: n0 x chi per site, n0 from the first job's patch
+    const ctmb_site* c4[4];
+    for (int q = 0; q < 4; ++q) c4[q] = &sites[corner_site[q]];
+    int64_t n0, n1; half_shape(dir, chi, c4, n0, n1);
+    std::vector<void*> P(nsites), Pt(nsites);
+    for (int i = 0; i < nsites; ++i) { P[i] = e.ws.alloc((size_t)n0 * chi * e.esize()); Pt[i] = e.ws.alloc((size_t)n0 * chi * e.esize()); }
+    // process the projector jobs in groups that fit the batch limits
+    const int group = std::max(1, TC_MAX_BATCH / 4);
+    for (int j0 = 0; j0 < nsites; j0 += group) {
+        std::vector<int> g(jobs.begin() + j0, jobs.begin() + std::min(nsites, j0 + group));
+        std::vector<void*> Pg(P.begin() + j0, P.begin() + j0 + g.size()), Ptg(Pt.begin() + j0, Pt.begin() + j0 + g.size());
+        move_projectors(mc, corner_site, g, Pg, Ptg);
+    }
+    std::vector<const void*> Pc(P.begin(), P.end()), Ptc(Pt.begin(), Pt.end());
+    const int agroup = TC_MAX_BATCH / 3;
+    for (int j0 = 0; j0 < nsites; j0 += agroup) {
+        std::vector<int> g(jobs.begin() + j0, jobs.begin() + std::min(nsites, j0 + agroup));
+        move_absorb(mc, nb_site, g, Pc, Ptc, nC1 ? nC1 + j0 : nullptr, nC2 ? nC2 + j0 : nullptr, nT ? nT + j0 : nullptr);
+    }
+}
+
+int ctmb_move_generic(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi, const ctmb_site* sites,
+                      const int* corner_site, const int* nb_site, const ctmb_options* opt, void* const* nC1,
+                      void* const* nC2, void* const* nT, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    move_generic_impl(h, dir, nsites, chi, sites, corner_site, nb_site, opts_or_default(opt), nC1, nC2, nT);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_move_generic_workspace(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
+                                   const ctmb_site* sites, const int* corner_site, const int* nb_site,
+                                   const ctmb_options* opt) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    std::vector<void*> dummy(nsites, nullptr);
+    move_generic_impl(h, dir, nsites, chi, sites, corner_site, nb_site, opts_or_default(opt), dummy.data(), dummy.data(), dummy.data());
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+int ctmb_move_generic_projectors(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
+                                 const ctmb_site* sites, const int* corner_site, int njobs, const int* jobs,
+                                 const ctmb_options* opt, void* const* P, void* const* Pt, void* ws, size_t ws_bytes,
+                                 void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    ctmb_options o = opts_or_default(opt);
+    MoveCtx mc{h->h.eng, (int)dir, nsites, chi, sites, o};
+    const int group = std::max(1, TC_MAX_BATCH / 4);
+    for (int j0 = 0; j0 < njobs; j0 += group) {
+        int j1 = std::min(njobs, j0 + group);
+        std::vector<int> g(jobs + j0, jobs + j1);
+        std::vector<void*> Pg(P + j0, P + j1), Ptg(Pt + j0, Pt + j1);
+        move_projectors(mc, corner_site, g, Pg, Ptg);
+    }
+    return 0;
+    CTMB_CATCH(-1)
+}
+
+int ctmb_move_generic_absorb(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
+                             const ctmb_site* sites, const int* nb_site, int njobs, const int* jobs,
+                             const void* const* P, const void* const* Pt, void* const* nC1, void* const* nC2,
+                             void* const* nT, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    ctmb_options o = opts_or_default(nullptr);
+    MoveCtx mc{h->h.eng, (int)dir, nsites, chi, sites, o};
+    std::vector<const void*> Pc(P, P + nsites), Ptc(Pt, Pt + nsites);
+    const int agroup = TC_MAX_BATCH / 3;
+    for (int j0 = 0; j0 < njobs; j0 += agroup) {
+        int j1 = std::min(njobs, j0 + agroup);
+        std::vector<int> g(jobs + j0, jobs + j1);
+        move_absorb(mc, nb_site, g, Pc, Ptc, nC1 + j0, nC2 + j0, nT + j0);
+    }
+    return 0;
+    CTMB_CATCH(-1)
+}
+
+static void move_c4v_impl(ctmb_handle_t h, const void* a, const int dims[5], const void* C, const void* T, int chi,
+                          const ctmb_options& o, void* C_out, void* T_out, double* D_out) {
+    Engine& e = h->h.eng;
+    CTMB_CHECK(dims[1] == dims[2] && dims[2] == dims[3] && dims[3] == dims[4], "C4v needs equal bond dimensions");
+    const int64_t D = dims[1], d = D * D, n = (int64_t)chi * d;
+    ctmb_site s{};
+    s.a = a; for (int i = 0; i < 5; ++i) s.dims[i] = dims[i];
+    // enlarged corner 'ab,xbu,ael,@uldr->edxr'  (ctm_components_c4v.py:52-130)
+    Tn Ct = make_tn(const_cast<void*>(C), "ab", {chi, chi});
+    void* c2 = e.ws.alloc((size_t)n * n * e.esize());
+    {
+        std::vector<Tn> ops = {Ct, make_tn(const_cast<void*>(T), "xbu", {chi, chi, d}), make_tn(const_cast<void*>(T), "ael", {chi, chi, d})};
+        std::vector<Engine::ChainJob> jobs = {sl_job(ops, 3, "uldr", s, "edxr", c2, nullptr)};
+        e.chain_multi(jobs);
+    }
+    Rsvd r = rsvd_batch(e, {c2}, (int)n, (int)n, chi, o, true);
+    double* Dv = (double*)e.ws.alloc((size_t)chi * 8);
+    void* nTraw = e.ws.alloc((size_t)chi * chi * d * e.esize());
+    if (!e.ws.dry()) {
+        PtrBatch pU{}, pV{}, pS{}, pSo{};
+        pU.p[0] = r.U[0]; pS.p[0] = r.S[0]; pSo.p[0] = Dv;
+        proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); ++e.launches;
+    }
+    // nT = 'acl,aux,@uldr,cdy->xyr' with (T, P, a, conj a, conj P), P = U viewed (chi, d, chi')
+    {
+        Tn P = make_tn(r.U[0], "xau", {chi, chi, d});        // column-major U: [x][(a,u)]
+        Tn Pc = relabel(P, "ycd");
+        std::vector<Tn> ops = {make_tn(const_cast<void*>(T), "acl", {chi, chi, d}), P, Pc};
+        Engine::ChainJob job = sl_job(ops, 2, "uldr", s, "xyr", nTraw, nullptr);
+        job.conj.back() = true;                               // conj(P) closes the chain
+        std::vector<Engine::ChainJob> jobs = {job};
+        e.chain_multi(jobs);
+    }
+    if (!e.ws.dry()) {
+        unsigned long long* amax = (unsigned long long*)e.persistent("amax", 3 * TC_MAX_BATCH * sizeof(unsigned long long));
+        CTMB_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned long long), e.stream));
+        c4v_sym_launch(nTraw, T_out, chi, (int)d, amax, e.cplx, e.stream); ++e.launches;
+        ScaleBatch sb{}; sb.p[0] = T_out; sb.count[0] = (long long)chi * chi * d; sb.amax[0] = amax;
+        scale_by_amax_launch(sb, 1, e.cplx, e.stream); ++e.launches;
+        c4v_diag_launch(Dv, C_out, chi, e.cplx, e.stream); ++e.launches;
+        if (D_out) CTMB_CUDA(cudaMemcpyAsync(D_out, Dv, (size_t)chi * 8, cudaMemcpyDeviceToDevice, e.stream));
+    }
+}
+
+int ctmb_move_c4v(ctmb_handle_t h, ctmb_dtype dt, const void* a, const int dims[5], const void* C, const void* T,
+                  int chi, const ctmb_options* opt, void* C_out, void* T_out, double* D_out, void* ws, size_t ws_bytes,
+                  void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    ctmb_options o = opts_or_default(opt);
+    if (!opt) o.eps_multiplet = 1.0e-12;   // truncated_eig_sym default (custom_eig.py:7-8)
+    move_c4v_impl(h, a, dims, C, T, chi, o, C_out, T_out, D_out);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_move_c4v_workspace(ctmb_handle_t h, ctmb_dtype dt, const int dims[5], int chi, const ctmb_options* opt) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    move_c4v_impl(h, nullptr, dims, nullptr, nullptr, chi, opts_or_default(opt), nullptr, nullptr, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+"""Host-side driver of libctmb: turns (state, env) objects into pointer tables and calls the
+C ABI.  torch is used for device memory and streams only."""
+import ctypes as C
+import torch
+from . import _lib
+from ._lib import lib, check
+
+DIRECTIONS = {(0, -1): _lib.UP, (-1, 0): _lib.LEFT, (0, 1): _lib.DOWN, (1, 0): _lib.RIGHT}
+C_KEYS = [(-1, -1), (1, -1), (1, 1), (-1, 1)]          # order of ctmb_site.C
+T_KEYS = [(0, -1), (-1, 0), (0, 1), (1, 0)]            # order of ctmb_site.T
+# coordinates of the four enlarged corners of the 2x2 patch of a projector job, in the order
+# the reference lists them (ctm/generic/ctm_components.py:37-38,105-106,168-169,231-232)
+PATCH = {
+    (0, -1): [(0, 0), (0, 1), (-1, 0), (-1, 1)],
+    (-1, 0): [(0, 0), (1, 0), (0, 1), (1, 1)],
+    (0, 1): [(0, 0), (0, -1), (1, 0), (1, -1)],
+    (1, 0): [(0, 0), (-1, 0), (0, -1), (-1, -1)],
+}
+# neighbour whose projectors P1,Pt1 the absorption uses (ctm/generic/ctmrg.py:326-334,442-450,568-576,684-692)
+SHIFT = {(0, -1): (1, 0), (-1, 0): (0, -1), (0, 1): (-1, 0), (1, 0): (0, 1)}
+# env tensors written by a move: (nC1 key, nC2 key, nT key)  (ctmrg.py:296-307)
+OUT_KEYS = {
+    (0, -1): ((1, -1), (-1, -1), (0, -1)),
+    (-1, 0): ((-1, -1), (-1, 1), (-1, 0)),
+    (0, 1): ((-1, 1), (1, 1), (0, 1)),
+    (1, 0): ((1, 1), (1, -1), (1, 0)),
+}
+
+
+def _dt(t):
+    if t.dtype == torch.float64:
+        return _lib.F64
+    if t.dtype == torch.complex128:
+        return _lib.C128
+    raise TypeError(f"libctmb computes in float64/complex128 (as the reference CLI, config.py:113-118); got {t.dtype}")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class CtmEngine:
+    """One engine (= one libctmb handle, one workspace) per process / GPU."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("peps_torch_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self._h = C.c_void_p()
+        check(lib.ctmb_create(C.byref(self._h), self.device.index))
+        self._ws = None
+        self._tables = {}
+        self.options = _lib.default_options()
+
+    def close(self):
+        if self._h:
+            lib.ctmb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ----------------------------------------------------------------------------------
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def counters(self):
+        n, f = C.c_longlong(), C.c_double()
+        check(lib.ctmb_get_counters(self._h, C.byref(n), C.byref(f)))
+        return n.value, f.value
+
+    def reset_counters(self):
+        check(lib.ctmb_reset_counters(self._h))
+
+    def _opts(self, **kw):
+        o = _lib.Options()
+        C.memmove(C.byref(o), C.byref(self.options), C.sizeof(o))
+        for k, v in kw.items():
+            if v is not None:
+                setattr(o, k, v)
+        return o
+
+    @staticmethod
+    def _prep(t, device):
+        if t.device != device:
+            raise ValueError(f"tensor on {t.device}, engine on {device}")
+        return t if t.is_contiguous() else t.contiguous()
+
+    def _site(self, a, Cs, Ts, keep):
+        s = _lib.Site()
+        a = self._prep(a, self.device); keep.append(a)
+        s.a = a.data_ptr()
+        for i in range(5):
+            s.dims[i] = a.shape[i]
+        for i, t in enumerate(Cs):
+            if t is not None:
+                t = self._prep(t, self.device); keep.append(t); s.C[i] = t.data_ptr()
+        for i, t in enumerate(Ts):
+            if t is not None:
+                t = self._prep(t, self.device); keep.append(t); s.T[i] = t.data_ptr()
+        return s
+
+    # ----------------------------------------------------------------------------------
+    # piecewise entry points (parity tests mirror the reference's *_c functions)
+    # ----------------------------------------------------------------------------------
+    def einsum2(self, spec, A, B, conjA=False, conjB=False):
+        lhs, out = spec.split('->')
+        la, lb = lhs.split(',')
+        A, B = self._prep(A, self.device), self._prep(B, self.device)
+        ext = dict(zip(la, A.shape)); ext.update(zip(lb, B.shape))
+        Cc = torch.empty([ext[c] for c in out], dtype=A.dtype, device=self.device)
+        da = (C.c_longlong * len(la))(*A.shape)
+        db = (C.c_longlong * len(lb))(*B.shape)
+        check(lib.ctmb_einsum2(self._h, _dt(A), spec.encode(), _ptr(A), da, int(conjA), _ptr(B), db, int(conjB),
+                               _ptr(Cc), self._stream()))
+        return Cc
+
+    def c2x2(self, kind, C_, T1, T2, a, chi):
+        """kind: 'LU','RU','RD','LD'; C_,T1,T2 as in SURVEY Appendix A for that corner."""
+        k = dict(LU=0, RU=1, RD=2, LD=3)[kind]
+        cslot, t1slot, t2slot = [(0, 0, 1), (1, 3, 0), (2, 2, 3), (3, 1, 2)][k]
+        Cs, Ts = [None] * 4, [None] * 4
+        Cs[cslot], Ts[t1slot], Ts[t2slot] = C_, T1, T2
+        keep = []
+        s = self._site(a, Cs, Ts, keep)
+        D = a.shape[1:]
+        rows = chi * [D[2], D[1], D[0], D[0]][k] ** 2
+        cols = chi * [D[3], D[2], D[1], D[3]][k] ** 2
+        out = torch.empty((rows, cols), dtype=a.dtype, device=self.device)
+        nb = lib.ctmb_c2x2_workspace(self._h, _dt(a), k, chi, C.byref(s))
+        ws = self._workspace(nb)
+        check(lib.ctmb_c2x2(self._h, _dt(a), k, chi, C.byref(s), _ptr(out), _ptr(ws), ws.numel(), self._stream()))
+        return out
+
+    def projectors(self, R, Rt, chi, **opt):
+        R, Rt = self._prep(R, self.device), self._prep(Rt, self.device)
+        n0, n1 = R.shape
+        o = self._opts(**opt)
+        P = torch.empty((n0, chi), dtype=R.dtype, device=self.device)
+        Pt = torch.empty_like(P)
+        S = torch.empty(chi, dtype=torch.float64, device=self.device)
+        nb = lib.ctmb_projectors_workspace(self._h, _dt(R), n0, n1, chi, C.byref(o))
+        ws = self._workspace(nb)
+        check(lib.ctmb_projectors(self._h, _dt(R), _ptr(R), _ptr(Rt), n0, n1, chi, C.byref(o), _ptr(P), _ptr(Pt),
+                                  _ptr(S), _ptr(ws), ws.numel(), self._stream()))
+        return P, Pt, S
+
+    def truncated_svd(self, M, chi, **opt):
+        """Returns U (m x chi), S (chi), V (n x chi) with M ~ U S V^H (sign-fixed, multiplet-aware)."""
+        M = self._prep(M, self.device)
+        m, n = M.shape
+        o = self._opts(**opt)
+        U = torch.empty((chi, m), dtype=M.dtype, device=self.device)
+        V = torch.empty((chi, n), dtype=M.dtype, device=self.device)
+        S = torch.empty(chi, dtype=torch.float64, device=self.device)
+        nb = lib.ctmb_truncated_svd_workspace(self._h, _dt(M), m, n, chi, C.byref(o))
+        ws = self._workspace(nb)
+        check(lib.ctmb_truncated_svd(self._h, _dt(M), _ptr(M), m, n, chi, C.byref(o), _ptr(U), _ptr(S), _ptr(V),
+                                     _ptr(ws), ws.numel(), self._stream()))
+        return U.t(), S, V.t()
+
+    def truncated_eig_sym(self, M, chi, **opt):
+        M = self._prep(M, self.device)
+        n = M.shape[0]
+        opt.setdefault('eps_multiplet', 1.0e-12)
+        o = self._opts(**opt)
+        U = torch.empty((chi, n), dtype=M.dtype, device=self.device)
+        D = torch.empty(chi, dtype=torch.float64, device=self.device)
+        nb = lib.ctmb_truncated_eig_sym_workspace(self._h, _dt(M), n, chi, C.byref(o))
+        ws = self._workspace(nb)
+        check(lib.ctmb_truncated_eig_sym(self._h, _dt(M), _ptr(M), n, chi, C.byref(o), _ptr(D), _ptr(U),
+                                         _ptr(ws), ws.numel(), self._stream()))
+        return D, U.t()
+
+    # ----------------------------------------------------------------------------------
+    # the moves
+    # ----------------------------------------------------------------------------------
+    def _move_tables(self, state, direction):
+        coords = tuple(state.sites.keys())
+        key = (id(state.vertexToSite), coords, direction)
+        tab = self._tables.get(key)
+        if tab is None:
+            index = {c: i for i, c in enumerate(coords)}
+            v2s = state.vertexToSite
+            corner = []
+            for c in coords:
+                for dx, dy in PATCH[direction]:
+                    corner.append(index[v2s((c[0] + dx, c[1] + dy))])
+            sh = SHIFT[direction]
+            nb = [index[v2s((c[0] + sh[0], c[1] + sh[1]))] for c in coords]
+            dest = [v2s((c[0] - direction[0], c[1] - direction[1])) for c in coords]
+            tab = ((C.c_int * len(corner))(*corner), (C.c_int * len(nb))(*nb), dest, state.vertexToSite)
+            self._tables[key] = tab
+        return tab
+
+    def _nT_shape(self, direction, a, chi):
+        D = a.shape[1:]
+        if direction == (0, -1):
+            return (chi, D[2] ** 2, chi)
+        if direction == (-1, 0):
+            return (chi, chi, D[3] ** 2)
+        if direction == (0, 1):
+            return (D[0] ** 2, chi, chi)
+        return (chi, D[1] ** 2, chi)
+
+    def move_generic(self, direction, state, env, **opt):
+        """One ctm_MOVE (ctm/generic/ctmrg.py:179-319): replaces the entries of env.C / env.T
+        at coord-direction by freshly allocated tensors; inputs are never modified."""
+        if direction not in DIRECTIONS:
+            raise ValueError("Invalid direction: " + str(direction))
+        coords = list(state.sites.keys())
+        n = len(coords)
+        chi = env.chi
+        corner, nb, dest, _ = self._move_tables(state, direction)
+        keep = []
+        sites = (_lib.Site * n)()
+        a0 = None
+        for i, c in enumerate(coords):
+            a = state.sites[c]
+            if a.dim() != 5:
+                raise ValueError("libctmb contracts single-layer on-site tensors a[s,u,l,d,r] (ctm_force_dl is not supported)")
+            a0 = a if a0 is None else a0
+            sites[i] = self._site(a, [env.C[(c, k)] for k in C_KEYS], [env.T[(c, k)] for k in T_KEYS], keep)
+        dt = _dt(a0)
+        nC1 = [torch.empty((chi, chi), dtype=a0.dtype, device=self.device) for _ in range(n)]
+        nC2 = [torch.empty((chi, chi), dtype=a0.dtype, device=self.device) for _ in range(n)]
+        nT = [torch.empty(self._nT_shape(direction, state.sites[c], chi), dtype=a0.dtype, device=self.device)
+              for c in coords]
+        p1 = (C.c_void_p * n)(*[t.data_ptr() for t in nC1])
+        p2 = (C.c_void_p * n)(*[t.data_ptr() for t in nC2])
+        p3 = (C.c_void_p * n)(*[t.data_ptr() for t in nT])
+        o = self._opts(**opt)
+        d = DIRECTIONS[direction]
+        wkey = ('ws', dt, d, n, chi, tuple(tuple(state.sites[c].shape) for c in coords), o.rsvd_rank_factor)
+        nbytes = self._tables.get(wkey)
+        if nbytes is None:
+            nbytes = lib.ctmb_move_generic_workspace(self._h, dt, d, n, chi, sites, corner, nb, C.byref(o))
+            if nbytes == 0:
+                raise _lib.CtmbError(lib.ctmb_last_error().decode())
+            self._tables[wkey] = nbytes
+        ws = self._workspace(nbytes)
+        check(lib.ctmb_move_generic(self._h, dt, d, n, chi, sites, corner, nb, C.byref(o), p1, p2, p3,
+                                    _ptr(ws), ws.numel(), self._stream()))
+        kC1, kC2, kT = OUT_KEYS[direction]
+        for i in range(n):
+            env.C[(dest[i], kC1)] = nC1[i]
+            env.C[(dest[i], kC2)] = nC2[i]
+            env.T[(dest[i], kT)] = nT[i]
+
+    def move_c4v(self, a, C_, T, chi, **opt):
+        """One ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463) -> (C', T', D)."""
+        a, C_, T = self._prep(a, self.device), self._prep(C_, self.device), self._prep(T, self.device)
+        dt = _dt(a)
+        opt.setdefault('eps_multiplet', 1.0e-12)      # truncated_eig_sym default (custom_eig.py:7-8)
+        o = self._opts(**opt)
+        dims = (C.c_int * 5)(*a.shape)
+        Co = torch.empty_like(C_)
+        To = torch.empty_like(T)
+        Dv = torch.empty(chi, dtype=torch.float64, device=self.device)
+        wkey = ('wsc4v', dt, tuple(a.shape), chi, o.rsvd_rank_factor)
+        nbytes = self._tables.get(wkey)
+        if nbytes is None:
+            nbytes = lib.ctmb_move_c4v_workspace(self._h, dt, dims, chi, C.byref(o))
+            if nbytes == 0:
+                raise _lib.CtmbError(lib.ctmb_last_error().decode())
+            self._tables[wkey] = nbytes
+        ws = self._workspace(nbytes)
+        check(lib.ctmb_move_c4v(self._h, dt, _ptr(a), dims, _ptr(C_), _ptr(T), chi, C.byref(o), _ptr(Co), _ptr(To),
+                                _ptr(Dv), _ptr(ws), ws.numel(), self._stream()))
+        return Co, To, Dv
+
+
+_default = None
+
+
+def default_engine():
+    """Process-wide engine on the current CUDA device (created on first use)."""
+    global _default
+    if _default is None:
+        _default = CtmEngine()
+    return _default

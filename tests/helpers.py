@@ -1,0 +1,89 @@
+"""Shared helpers of the test-suite: golden fixtures, containers, gauge-invariant comparisons."""
+import os
+import json
+from collections import OrderedDict
+import numpy as np
+import torch
+import ctm_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+C_KEYS = [(-1, -1), (1, -1), (1, 1), (-1, 1)]
+T_KEYS = [(0, -1), (-1, 0), (0, 1), (1, 0)]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    meta = json.loads(str(z['meta'])) if 'meta' in z.files else {}
+    return z, meta
+
+
+def golden_sites(z):
+    sites = OrderedDict()
+    for k in z.files:
+        if k.startswith('site_'):
+            sites[(int(k[5]), int(k[6]))] = torch.from_numpy(z[k])
+    # np.savez keeps insertion order, which is the reference's dict order
+    return sites
+
+
+def golden_env(z, prefix):
+    C, T = {}, {}
+    for k in z.files:
+        if k.startswith(prefix + 'C_') or k.startswith(prefix + 'T_'):
+            body = k[len(prefix) + 2:]
+            c, vx, vy = body.split('_')
+            key = ((int(c[0]), int(c[1])), (int(vx), int(vy)))
+            (C if k[len(prefix)] == 'C' else T)[key] = torch.from_numpy(z[k])
+    return C, T
+
+
+def v2s_for(sites):
+    n = len(sites)
+    if n == 4:
+        return orc.v2s_4site, 2, 2
+    if n == 2:
+        return orc.v2s_2site, 2, 1
+    return orc.v2s_1site, 1, 1
+
+
+class State:
+    """Minimal stand-in with the attributes the move reads from the reference's IPEPS
+    (ipeps/ipeps.py:89-250): sites, vertexToSite, lX, lY, site()."""
+
+    def __init__(self, sites, vertexToSite, lX, lY):
+        self.sites, self.vertexToSite, self.lX, self.lY = sites, vertexToSite, lX, lY
+        t = next(iter(sites.values()))
+        self.dtype, self.device = t.dtype, t.device
+
+    def site(self, coord):
+        return self.sites[self.vertexToSite(coord)]
+
+
+class Env:
+    """Stand-in for ctm.generic.env.ENV (env.py:14-109): chi, C, T dicts."""
+
+    def __init__(self, chi, C, T):
+        self.chi, self.C, self.T = chi, C, T
+
+
+def to_dev(d, device):
+    return type(d)((k, v.to(device)) for k, v in d.items())
+
+
+def maxrel(a, b):
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-300))
+
+
+def env_abs_diff(C1, T1, C2, T2):
+    w = 0.
+    for k in C2:
+        w = max(w, maxrel(C1[k].abs().cpu(), C2[k].abs().cpu()))
+    for k in T2:
+        w = max(w, maxrel(T1[k].abs().cpu(), T2[k].abs().cpu()))
+    return w
+
+
+def spectra_diff(C1, C2):
+    s1 = orc.corner_spectra({k: v.cpu() for k, v in C1.items()})
+    s2 = orc.corner_spectra({k: v.cpu() for k, v in C2.items()})
+    return max(float((s1[k] - s2[k]).abs().max()) for k in s2)
