@@ -1,0 +1,42 @@
+"""Mirror of the hot-path part of the reference's config singletons (config.py:369-409,
+507-511).  When the reference's own `config` module is importable (drop-in use through
+peps_torch_b200.run), its singletons are used instead, so that --CTMARGS_* flags keep working."""
+import torch
+
+
+class CTMARGS:
+    def __init__(self):
+        self.ctm_max_iter = 50
+        self.ctm_warmup_iter = -1
+        self.ctm_conv_tol = 1.0e-8
+        self.ctm_env_init_type = 'CTMRG'
+        self.ctm_absorb_normalization = 'inf'
+        self.projector_method = '4X4'
+        self.projector_svd_method = 'DEFAULT'
+        self.projector_svd_reltol = 1.0e-8
+        self.projector_eps_multiplet = 1.0e-8
+        self.projector_multiplet_abstol = 1.0e-14
+        self.projector_rsvd_niter = 2
+        self.ctm_move_sequence = [(0, -1), (-1, 0), (0, 1), (1, 0)]
+        self.ctm_force_dl = False
+        self.verbosity_ctm_convergence = 0
+        self.fpcm_init_iter = 1
+        self.fpcm_freq = -1
+        # engine-specific (no counterpart in the reference)
+        self.b200_rsvd_niter = 4
+        self.b200_rsvd_rank_factor = 2.0
+
+
+class GLOBALARGS:
+    def __init__(self):
+        self.dtype = 'float64'
+        self.torch_dtype = torch.float64
+        self.device = 'cuda:0'
+        self.offload_to_gpu = 'None'
+
+
+try:                                    # the reference is on sys.path: share its singletons
+    import config as _ref_cfg
+    ctm_args, global_args = _ref_cfg.ctm_args, _ref_cfg.global_args
+except Exception:                       # stand-alone use (tests, bench on the GPU box)
+    ctm_args, global_args = CTMARGS(), GLOBALARGS()

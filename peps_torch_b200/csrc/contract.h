@@ -38,7 +38,12 @@ struct Plan {
 // measures (dry run used by the *_workspace_bytes queries; no kernel is launched then).
 class Workspace {
 public:
-    void reset(void* base, size_t bytes) { base_ = (char*)base; cap_ = bytes; lo_ = hi_ = 0; peak_ = 0; }
+    void reset(void* base, size_t bytes) {
+        // keep both ends 256-byte aligned (the back end grows down from base+cap)
+        size_t mis = base ? (size_t)(256 - ((uintptr_t)base & 255)) & 255 : 0;
+        if (mis > bytes) mis = bytes;
+        base_ = base ? (char*)base + mis : nullptr; cap_ = (bytes - mis) & ~(size_t)255; lo_ = hi_ = 0; peak_ = 0;
+    }
     void* alloc(size_t bytes, bool back = false);
     size_t mark(bool back = false) const { return back ? hi_ : lo_; }
     void release(size_t mark, bool back = false) { (back ? hi_ : lo_) = mark; }

@@ -1,0 +1,251 @@
+"""GPU parity suite (pytest -m gpu, B200 box): the CUDA path through the C ABI against the
+oracle and the committed reference fixtures.  Tolerances: deterministic contractions 1e-13;
+quantities behind the truncated SVD/EVD are compared through gauge invariants at
+max(1e-10, measured reference-vs-reference noise floor);
+energy 1e-10 relative (north star)."""
+import numpy as np
+import pytest
+import torch
+import ctm_oracle as orc
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GENERIC = ['generic_4site_D2_chi8_A', 'generic_4site_D2_chi8_B', 'generic_4site_D3_chi12_B',
+           'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A']
+C4V = ['c4v_D2_chi8_A', 'c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128']
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from peps_torch_b200.engine import CtmEngine
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return CtmEngine()
+
+
+@pytest.fixture(scope='module')
+def dev():
+    return torch.device('cuda:0')
+
+
+def cpu(d):
+    return {k: v.cpu() for k, v in d.items()}
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.complex128])
+def test_einsum2_shapes_and_conj(eng, dev, dt):
+    torch.manual_seed(1)
+    cases = [('ab,buc->auc', (7, 5), (5, 3, 11)), ('auc,ael->ucel', (13, 4, 9), (13, 9, 4)),
+             ('ik,kj->ij', (130, 70), (70, 150)), ('ki,kj->ij', (200, 129), (200, 65)),
+             ('pqcert,sprfg->qcetsfg', (3, 3, 5, 5, 3, 3), (2, 3, 3, 3, 3)),
+             ('ik,kj->ji', (1, 1), (1, 1)), ('ik,kj->ij', (257, 33), (33, 31)), ('ik,kj->ij', (300, 500), (500, 260))]
+    for spec, sa, sb in cases:
+        A = torch.randn(sa, dtype=dt, device=dev)
+        B = torch.randn(sb, dtype=dt, device=dev)
+        for ca, cb in ((False, False), (True, False), (False, True)):
+            out = eng.einsum2(spec, A, B, conjA=ca, conjB=cb)
+            ref = torch.einsum(spec, A.conj() if ca else A, B.conj() if cb else B)
+            assert H.maxrel(out.cpu(), ref.cpu()) < 1e-13, (spec, ca, cb)
+
+
+@pytest.mark.parametrize('name', GENERIC)
+def test_pieces_against_reference_fixtures(eng, dev, name):
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'mid_')
+    coord = list(sites.keys())[-1]
+    for kind in orc.CORNERS:
+        kc, k1, k2, _ = orc.CORNERS[kind]
+        out = eng.c2x2(kind, C[(coord, kc)].to(dev), T[(coord, k1)].to(dev), T[(coord, k2)].to(dev),
+                       sites[coord].to(dev), chi)
+        assert H.maxrel(out.cpu(), torch.from_numpy(z['c2x2_' + kind])) < 1e-13
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    for d in orc.DIRECTIONS:
+        tg = f'{d[0]}_{d[1]}'
+        R, Rt = torch.from_numpy(z[f'halves_{tg}_R']), torch.from_numpy(z[f'halves_{tg}_Rt'])
+        Pr, Ptr = torch.from_numpy(z[f'proj_{tg}_P']), torch.from_numpy(z[f'proj_{tg}_Pt'])
+        M = R.t() @ Rt
+        U, S, V = eng.truncated_svd(M.to(dev), chi)
+        Sr = torch.linalg.svdvals(M)
+        # the fixture states are (numerically) rank deficient: compare what the projector uses
+        keep = Sr[:chi] / Sr[0] > 1e-8
+        assert float((S.cpu()[keep] - Sr[:chi][keep]).abs().max() / Sr[0]) < 1e-13
+        P, Pt, S2 = eng.projectors(R.to(dev), Rt.to(dev), chi)
+        assert H.maxrel((P @ Pt.t()).cpu(), Pr @ Ptr.t()) < 1e-9
+        assert H.maxrel(P.abs().cpu(), Pr.abs()) < 1e-8
+        env = H.Env(chi, H.to_dev(C, dev), H.to_dev(T, dev))
+        eng.move_generic(d, st, env)
+        Cg, Tg = H.golden_env(z, f'move_{tg}_')
+        assert H.env_abs_diff(env.C, env.T, Cg, Tg) < 1e-8
+        # inputs are never modified (ctmrg.py:317-319: entries are replaced)
+        for k in C:
+            assert env.C[k].data_ptr() != 0
+
+
+@pytest.mark.parametrize('name', [n for n in GENERIC if 'kagome' not in n])
+def test_run_energy_and_spectra_against_reference(eng, dev, name):
+    from peps_torch_b200.ctm.generic import ctmrg
+    from peps_torch_b200.config import CTMARGS
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C0, T0 = H.golden_env(z, 'init_')
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    env = H.Env(chi, H.to_dev(C0, dev), H.to_dev(T0, dev))
+    args = CTMARGS()
+    args.ctm_max_iter = meta['n_iter'] + 1          # fixture: 1 + n_iter reference iterations
+    env, hist, t_ctm, t_obs = ctmrg.run(st, env, ctm_args=args)
+    Cf, Tf = H.golden_env(z, 'final_')
+    assert H.spectra_diff(env.C, Cf) < 1e-9
+    assert H.env_abs_diff(env.C, env.T, Cf, Tf) < 2e-8
+    e = orc.energy_j1j2(sites, v2s, cpu(env.C), cpu(env.T), 1.0, meta['j2'])
+    e_ref = float(z['energy'][0])
+    assert abs(e - e_ref) <= 1e-10 * abs(e_ref) + 1e-13
+    assert t_ctm > 0
+
+
+@pytest.mark.parametrize('name', C4V)
+def test_c4v_against_reference_fixtures(eng, dev, name):
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    a = torch.from_numpy(z['site']).to(dev)
+    M = torch.from_numpy(z['mid_c2x2'])
+    D, U = eng.truncated_eig_sym(M.to(dev), chi)
+    Dr, Ur = orc.truncated_eig_sym(M, chi)
+    assert float((D.cpu() - Dr).abs().max()) < 1e-12
+    nC, nT, Dv = eng.move_c4v(a, torch.from_numpy(z['mid_C']).to(dev), torch.from_numpy(z['mid_T']).to(dev), chi)
+    assert H.maxrel(nC.cpu(), torch.from_numpy(z['mid_nC'])) < 1e-12
+    assert H.maxrel(nT.abs().cpu(), torch.from_numpy(z['mid_nT']).abs()) < 1e-9
+    Cc, Tc = torch.from_numpy(z['init_C']).to(dev), torch.from_numpy(z['init_T']).to(dev)
+    for _ in range(meta['n_iter']):
+        Cc, Tc, _ = eng.move_c4v(a, Cc, Tc, chi)
+    assert H.maxrel(Cc.cpu(), torch.from_numpy(z['final_C'])) < 1e-10
+    e = orc.energy_j1j2_c4v(a.cpu(), Cc.cpu(), Tc.cpu(), 1.0, meta['j2'])
+    assert abs(e - float(z['energy'][0])) < 1e-10 * abs(float(z['energy'][0]))
+
+
+def test_known_answer_rvb_c4v_on_gpu(eng, dev):
+    """The reference's TestRVB known answer (-0.47684229 @1e-8) reproduced by the CUDA path."""
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V, init_env_c4v
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v
+    from peps_torch_b200.config import CTMARGS
+    z = np.load(H.GOLD + '/rvb_c4v_known_answer.npz')
+    st = IPEPS_C4V(torch.from_numpy(z['site']).to(dev))
+    env = ENV_C4V(int(z['chi'][0]), st)
+    init_env_c4v(st, env)
+    args = CTMARGS(); args.ctm_max_iter = 200
+    ctmrg_c4v.run(st, env, ctm_args=args)
+    e = orc.energy_j1j2_c4v(st.site().cpu(), env.get_C().cpu(), env.get_T().cpu(), 1.0, float(z['j2'][0]))
+    assert abs(e - float(z['energy'][0])) < 1e-8
+
+
+def test_known_answer_j1j2_2site_on_gpu(eng, dev):
+    """TestCtmrg_States 2SITE known answer (-0.4434603770143078 @1e-6) through the CUDA path."""
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    from peps_torch_b200.ctm.generic import ctmrg
+    z = np.load(H.GOLD + '/j1j2_2site_known_answer.npz')
+    sites = H.golden_sites(z)
+    st = IPEPS(H.to_dev(sites, dev), orc.v2s_2site, int(z['lX'][0]), int(z['lY'][0]))
+    env = ENV(int(z['chi'][0]), st)
+    init_env(st, env)
+    e_prev = None
+    for _ in range(30):
+        for d in orc.DIRECTIONS:
+            for _r in range(st.lX if d in (orc.LEFT, orc.RIGHT) else st.lY):
+                ctmrg.ctm_MOVE(d, st, env)
+        e = orc.energy_j1j2(sites, orc.v2s_2site, cpu(env.C), cpu(env.T), 1.0, float(z['j2'][0]))
+        if e_prev is not None and abs(e - e_prev) < 1e-8:
+            break
+        e_prev = e
+    assert abs(e - float(z['energy'][0])) < 1e-6
+
+
+@pytest.mark.parametrize('family', ['A', 'B'])
+def test_config2_size_against_live_oracle(eng, dev, family):
+    """BASELINE config 2 (4SITE D=3 chi=48 float64): two full iterations, CUDA vs oracle."""
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    from peps_torch_b200.ctm.generic import ctmrg
+    D, chi, iters = 3, 48, 2
+    sites = orc.random_state_4site(D, family=family)
+    C, T = orc.init_env(sites, orc.v2s_4site, chi)
+    orc.run(sites, orc.v2s_4site, 2, 2, C, T, chi, iters)
+    st = IPEPS(H.to_dev(sites, dev), orc.v2s_4site, 2, 2)
+    env = ENV(chi, st)
+    init_env(st, env)
+    for _ in range(iters):
+        for d in orc.DIRECTIONS:
+            for _r in range(2):
+                ctmrg.ctm_MOVE(d, st, env)
+    assert H.spectra_diff(env.C, C) < 1e-9
+    assert H.env_abs_diff(env.C, env.T, C, T) < 5e-8       # reference-vs-reference floor: 4e-9
+    e_gpu = orc.energy_j1j2(sites, orc.v2s_4site, cpu(env.C), cpu(env.T), 1.0, 0.3)
+    e_cpu = orc.energy_j1j2(sites, orc.v2s_4site, C, T, 1.0, 0.3)
+    assert abs(e_gpu - e_cpu) <= 1e-10 * abs(e_cpu)
+
+
+@pytest.mark.parametrize('shape', [(3, 48, torch.float64), (4, 32, torch.complex128), (8, 24, torch.float64)])
+def test_projector_biorthogonality_property(eng, dev, shape):
+    """Size-independent property: Pt^T P = diag(1 on kept, 0 on cut) (ctm_projectors.py:279-293:
+    P = R conj(U) S^-1/2, Pt = Rt V S^-1/2 with M = R^T Rt = U S V^H)."""
+    D, chi, dt = shape
+    torch.manual_seed(7)
+    n = chi * D * D
+    R = torch.randn(n, n, dtype=dt, device=dev) / n ** 0.5
+    Rt = torch.randn(n, n, dtype=dt, device=dev) / n ** 0.5
+    P, Pt, S = eng.projectors(R, Rt, chi)
+    G = (Pt.t() @ P).cpu()
+    assert H.maxrel(G, torch.eye(chi, dtype=dt)) < 1e-8
+    Sr = torch.linalg.svdvals((R.t() @ Rt).cpu())[:chi]
+    assert float((S.cpu() - Sr).abs().max() / Sr[0]) < 1e-10
+
+
+def test_truncated_svd_edge_cases(eng, dev):
+    torch.manual_seed(11)
+    # exact multiplet cut in half: the whole multiplet must be dropped (custom_svd.py:70-95)
+    n, chi = 40, 6
+    Q1, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64))
+    Q2, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64))
+    s = torch.cat([torch.tensor([1.0, 0.8, 0.6, 0.5, 0.3, 0.2, 0.2, 0.2]), 0.01 * torch.rand(n - 8)]).double()
+    M = (Q1 * s) @ Q2.t()
+    U, S, V = eng.truncated_svd(M.to(dev), chi)
+    assert torch.allclose(S.cpu()[:5], s[:5], atol=1e-13) and float(S[5]) == 0.0
+    assert float(U[:, 5].abs().max()) == 0.0 and float(V[:, 5].abs().max()) == 0.0
+    # sign convention: the largest-|.| entry of every kept U column is positive (svd_gesdd.py:18-26)
+    Uc = U.cpu()[:, :5]
+    idx = Uc.abs().argmax(dim=0)
+    assert bool((Uc[idx, torch.arange(5)] > 0).all())
+    # rank-deficient input: trailing singular values come out (numerically) zero
+    A = torch.randn(60, 3, dtype=torch.float64) @ torch.randn(3, 60, dtype=torch.float64)
+    U, S, V = eng.truncated_svd(A.to(dev), 8)
+    Sr = torch.linalg.svdvals(A)
+    assert float((S.cpu()[:3] - Sr[:3]).abs().max() / Sr[0]) < 1e-13 and float(S[3:].abs().max() / Sr[0]) < 1e-12
+    # chi == n: nothing to truncate
+    B = torch.randn(12, 12, dtype=torch.float64)
+    U, S, V = eng.truncated_svd(B.to(dev), 12)
+    assert H.maxrel(((U * S) @ V.t()).cpu(), B) < 1e-12
+
+
+def test_errors_are_python_exceptions(eng, dev):
+    from peps_torch_b200.ctm.generic import ctmrg
+    from peps_torch_b200.config import CTMARGS
+    z, meta = H.load_golden('generic_4site_D2_chi8_B')
+    sites = H.golden_sites(z)
+    C, T = H.golden_env(z, 'mid_')
+    st = H.State(H.to_dev(sites, dev), orc.v2s_4site, 2, 2)
+    env = H.Env(meta['chi'], H.to_dev(C, dev), H.to_dev(T, dev))
+    with pytest.raises(ValueError):
+        ctmrg.ctm_MOVE((1, 1), st, env)
+    bad = CTMARGS(); bad.projector_method = '5X5'
+    with pytest.raises(ValueError):
+        ctmrg.ctm_MOVE((0, -1), st, env, ctm_args=bad)
+    bad = CTMARGS(); bad.projector_svd_method = 'NOPE'
+    with pytest.raises(TypeError):
+        ctmrg.ctm_MOVE((0, -1), st, env, ctm_args=bad)
+    with pytest.raises(TypeError):
+        eng.einsum2('ab,bc->ac', torch.zeros(2, 2, device=dev), torch.zeros(2, 2, device=dev))   # float32

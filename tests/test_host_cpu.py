@@ -1,0 +1,76 @@
+"""CPU suite, host side: the C-ABI library loads and exports every symbol include/ctmb.h
+declares; error reporting works without a GPU; site tables agree with the oracle's."""
+import os
+import re
+import ctypes
+import pytest
+import torch
+import ctm_oracle as orc
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from peps_torch_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'ctmb.h')).read()
+    declared = set(re.findall(r'\b(ctmb_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(_lib.lib, name), f'{name} declared in ctmb.h but not exported'
+    assert declared == set(_lib.SIGNATURES), 'ctypes signatures out of sync with ctmb.h'
+    assert _lib.lib.ctmb_version() >= 100
+
+
+def test_struct_layout_matches_header():
+    from peps_torch_b200 import _lib
+    assert ctypes.sizeof(_lib.Options) == 56
+    assert ctypes.sizeof(_lib.Site) == 8 + 24 + 32 + 32
+    o = _lib.default_options()
+    assert (o.svd_reltol, o.eps_multiplet, o.multiplet_abstol) == (1e-8, 1e-8, 1e-14)
+    assert o.rsvd_niter >= 2 and o.rsvd_rank_factor >= 1.5
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU error path')
+def test_no_cpu_fallback():
+    from peps_torch_b200 import _lib
+    from peps_torch_b200.engine import CtmEngine
+    h = ctypes.c_void_p()
+    assert _lib.lib.ctmb_create(ctypes.byref(h), 0) != 0
+    assert b'CUDA' in _lib.lib.ctmb_last_error()
+    with pytest.raises(RuntimeError):
+        CtmEngine()
+    from peps_torch_b200.ctm.generic import ctmrg
+    with pytest.raises(RuntimeError):
+        ctmrg.ctm_MOVE((0, -1), None, None)
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v
+    with pytest.raises(RuntimeError):
+        ctmrg_c4v.ctm_MOVE_sl(None, None)
+
+
+def test_move_tables_agree_with_oracle():
+    from peps_torch_b200 import engine as E
+    for d in orc.DIRECTIONS:
+        flat = [(k, dx, dy, tr) for pair in orc.HALVES[d] for (k, dx, dy, tr) in pair]
+        assert [(dx, dy) for (_, dx, dy, _) in flat] == E.PATCH[d]
+        assert orc.ABSORB[d]['shift'] == E.SHIFT[d]
+        assert orc.ABSORB[d]['out'] == E.OUT_KEYS[d]
+    assert [orc.CORNERS[k][0] for k in ('LU', 'RU', 'RD', 'LD')] == E.C_KEYS
+
+
+def test_host_env_init_matches_oracle_and_reference_fixture():
+    from peps_torch_b200.ipeps import IPEPS, IPEPS_C4V
+    from peps_torch_b200.env import ENV, init_env, ENV_C4V, init_env_c4v
+    z, meta = H.load_golden('generic_4site_D2_chi8_B')
+    sites = H.golden_sites(z)
+    st = IPEPS(sites, orc.v2s_4site, 2, 2)
+    env = ENV(meta['chi'], st)
+    init_env(st, env)
+    Cg, Tg = H.golden_env(z, 'init_')
+    assert all(torch.equal(env.C[k], Cg[k]) for k in Cg) and all(torch.equal(env.T[k], Tg[k]) for k in Tg)
+    z, meta = H.load_golden('c4v_D2_chi8_B')
+    st = IPEPS_C4V(torch.from_numpy(z['site']))
+    env = ENV_C4V(meta['chi'], st)
+    init_env_c4v(st, env)
+    assert H.maxrel(env.get_C(), torch.from_numpy(z['init_C'])) < 1e-14
+    assert H.maxrel(env.get_T().abs(), torch.from_numpy(z['init_T']).abs()) < 1e-12
