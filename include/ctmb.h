@@ -67,6 +67,13 @@ void ctmb_default_options(ctmb_options* opt);
 /* kernels launched / algorithmic real flops enqueued by this handle since the last reset */
 int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops);
 int ctmb_reset_counters(ctmb_handle_t h);
+/* Per-kernel-class device timing with CUDA events on the launching stream (used by bench.py for
+ * the roofline entry).  Classes: 0 tensor-contraction GEMM, 1 Householder QR, 2 Jacobi, 3 misc.
+ * ctmb_profile_get synchronises the recorded events and fills four-element arrays with the
+ * totals since the last ctmb_reset_counters: milliseconds, algorithmic flops, algorithmic bytes,
+ * launches. */
+int ctmb_profile_enable(ctmb_handle_t h, int on);
+int ctmb_profile_get(ctmb_handle_t h, double* ms, double* flops, double* bytes, long long* launches);
 
 /* Pairwise tensor contraction "ab,buc->auc" of contiguous tensors (tn_interface.py:3-10
  * contract/einsum/mm).  Labels: single letters; output labels come from exactly one operand. */

@@ -41,6 +41,9 @@ SIGNATURES = {
     'ctmb_default_options': (None, [_PO]),
     'ctmb_get_counters': (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     'ctmb_reset_counters': (C.c_int, [_vp]),
+    'ctmb_profile_enable': (C.c_int, [_vp, _i]),
+    'ctmb_profile_get': (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_longlong)]),
     'ctmb_einsum2': (C.c_int, [_vp, _i, C.c_char_p, _vp, C.POINTER(C.c_longlong), _i, _vp,
                                C.POINTER(C.c_longlong), _i, _vp, _vp]),
     'ctmb_c2x2': (C.c_int, [_vp, _i, _i, _i, _PS, _vp, _vp, _sz, _vp]),

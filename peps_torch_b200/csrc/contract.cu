@@ -75,6 +75,8 @@ Engine::Engine(int device) : device_(device) {
 Engine::~Engine() {
     for (auto& kv : plans_) if (kv.second.dev) cudaFree(kv.second.dev);
     for (auto& kv : persist_) if (kv.second.first) cudaFree(kv.second.first);
+    prof_reset();
+    for (auto e : ev_pool_) cudaEventDestroy(e);
 }
 
 void* Engine::persistent(const std::string& key, size_t bytes, bool* created) {
@@ -180,11 +182,43 @@ const Plan& Engine::get_plan(const Tn& A, bool conjA, const Tn& B, bool conjB, c
     return res.first->second;
 }
 
+cudaEvent_t Engine::get_event() {
+    if (!ev_pool_.empty()) { cudaEvent_t e = ev_pool_.back(); ev_pool_.pop_back(); return e; }
+    cudaEvent_t e; CTMB_CUDA(cudaEventCreate(&e)); return e;
+}
+void Engine::prof_begin(int) {
+    prof_open_ = get_event();
+    CTMB_CUDA(cudaEventRecord(prof_open_, stream));
+}
+void Engine::prof_end(int cat, double fl, double by) {
+    cudaEvent_t b = get_event();
+    CTMB_CUDA(cudaEventRecord(b, stream));
+    prof_.push_back({cat, prof_open_, b, fl, by});
+    prof_open_ = nullptr;
+}
+void Engine::prof_collect(ProfTotals out[CAT_COUNT]) {
+    for (int i = 0; i < CAT_COUNT; ++i) out[i] = ProfTotals{};
+    for (auto& r : prof_) {
+        CTMB_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0; CTMB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        out[r.cat].ms += ms; out[r.cat].flops += r.flops; out[r.cat].bytes += r.bytes; out[r.cat].launches += 1;
+    }
+}
+void Engine::prof_reset() {
+    for (auto& r : prof_) { ev_pool_.push_back(r.a); ev_pool_.push_back(r.b); }
+    prof_.clear();
+}
+
 void Engine::flush() {
     if (!pend_active_) return;
     pend_active_ = false;
-    tc_launch(pend_, cplx, stream);
-    ++launches;
+    {
+        const double es = cplx ? 16.0 : 8.0;
+        const double fl = 2.0 * pend_.M * (double)pend_.N * pend_.K * (cplx ? 4.0 : 1.0) * pend_.nbatch;
+        const double by = es * pend_.nbatch * ((double)pend_.M * pend_.K + (double)pend_.K * pend_.N + (double)pend_.M * pend_.N);
+        ProfScope ps(*this, CAT_GEMM, fl, by);
+        tc_launch(pend_, cplx, stream);
+    }
     pend_plans_.clear();
 }
 

@@ -64,6 +64,15 @@ public:
     long long launches = 0;        // kernels launched (our own), for bench accounting
     double flops = 0;              // algorithmic real flops enqueued
 
+    // optional per-kernel-class timing with CUDA events on the launching stream
+    enum Cat { CAT_GEMM = 0, CAT_QR = 1, CAT_JACOBI = 2, CAT_MISC = 3, CAT_COUNT = 4 };
+    bool profiling = false;
+    void prof_begin(int cat);
+    void prof_end(int cat, double flops, double bytes);
+    struct ProfTotals { double ms = 0, flops = 0, bytes = 0; long long launches = 0; };
+    void prof_collect(ProfTotals out[CAT_COUNT]);     // synchronises the recorded events
+    void prof_reset();
+
     size_t esize() const { return cplx ? 16 : 8; }
 
     // C = A * B over shared labels not in C; C's labels/strides define the output layout.
@@ -94,6 +103,18 @@ private:
     TcParams pend_{};
     std::vector<const Plan*> pend_plans_;
     bool pend_active_ = false;
+    struct ProfRec { int cat; cudaEvent_t a, b; double flops, bytes; };
+    std::vector<ProfRec> prof_;
+    std::vector<cudaEvent_t> ev_pool_;
+    cudaEvent_t prof_open_ = nullptr;
+    cudaEvent_t get_event();
+};
+
+// RAII helper: times one launch of class `cat` when profiling is on
+struct ProfScope {
+    Engine& e; int cat; double flops, bytes;
+    ProfScope(Engine& eng, int c, double f = 0, double b = 0) : e(eng), cat(c), flops(f), bytes(b) { ++e.launches; if (e.profiling) e.prof_begin(c); }
+    ~ProfScope() { if (e.profiling) e.prof_end(cat, flops, bytes); }
 };
 
 }  // namespace ctmb

@@ -142,7 +142,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     if (!e.ws.dry()) {
         bool created = false;
         omega = e.persistent(key, (size_t)n * k * es, &created);
-        if (created) { fill_gaussian_launch((double*)omega, (long long)n * k * (e.cplx ? 2 : 1), o.seed, e.stream); ++e.launches; }
+        if (created) { ProfScope ps(e, Engine::CAT_MISC); fill_gaussian_launch((double*)omega, (long long)n * k * (e.cplx ? 2 : 1), o.seed, e.stream); }
     }
     std::vector<Tn> Mt(nb), Y(nb), Z(nb);
     PtrBatch pY{}, pZ{}, pR{}, pNull{}, pW{}, pSig{}, pS{}, pUh{}, pWs{}, pU{}, pV{};
@@ -166,7 +166,10 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     Tn Om = make_tn(omega, "sj", {k, n});
     auto qr = [&](const PtrBatch& A, const PtrBatch& Rout, int rows) {
         e.flush();
-        qr_launch(A, Rout, nb, rows, k, rows, e.cplx, e.stream); ++e.launches;
+        const double cf = e.cplx ? 4.0 : 1.0;
+        ProfScope ps(e, Engine::CAT_QR, cf * nb * 4.0 * ((double)rows * k * k - (double)k * k * k / 3.0),
+                     2.0 * e.esize() * nb * (double)rows * k);
+        qr_launch(A, Rout, nb, rows, k, rows, e.cplx, e.stream);
     };
     // Y = M * Omega
     for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, Om, false, Y[b]);
@@ -181,16 +184,16 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         // Bt = M^H Q = Q2 R2   =>   M ~ Q R2^H Q2^H ;  R2 W = Uh Sigma  =>  U = Q W, V = Q2 Uh
         for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, Y[b], false, Z[b]);
         qr(pZ, pR, n);
-        jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, e.stream); ++e.launches;
-        sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); ++e.launches;
+        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); }
         for (int b = 0; b < nb; ++b) {
             e.contract(Y[b], false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
             e.contract(Z[b], false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
         }
         e.flush();
     } else {
-        // Hermitian: subspace iteration with M itself (2q+1 applications in total), then Rayleigh-Ritz
-        for (int it = 0; it < 2 * o.rsvd_niter; ++it) {
+        // Hermitian: subspace iteration with M itself (4q+1 applications: the spectrum of the corner itself decays half as fast as that of M = R^T Rt), then Rayleigh-Ritz
+        for (int it = 0; it < 4 * o.rsvd_niter; ++it) {
             for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, relabel(Y[b], "sj"), false, relabel(Z[b], "si"));
             qr(pZ, pNull, n);
             std::swap(Y, Z); std::swap(pY, pZ);
@@ -201,8 +204,8 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         for (int b = 0; b < nb; ++b)
             e.contract(relabel(Y[b], "si"), true, relabel(Z[b], "ti"), false, make_tn(R2[b], "ts", {k, k}));
         e.flush();
-        jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, e.stream); ++e.launches;
-        sortcols_launch(pR, pW, pSig, pS, pNull, pWs, nb, k, chi, e.cplx, 1, e.stream); ++e.launches;
+        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pNull, pWs, nb, k, chi, e.cplx, 1, e.stream); }
         for (int b = 0; b < nb; ++b)
             e.contract(relabel(Y[b], "si"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
         e.flush();
@@ -247,7 +250,7 @@ static void projectors_from_matrices(Engine& e, const std::vector<const void*>& 
     if (!e.ws.dry()) {
         PtrBatch pU{}, pV{}, pS{}, pSo{};
         for (int b = 0; b < nb; ++b) { pU.p[b] = r.U[b]; pV.p[b] = r.V[b]; pS.p[b] = r.S[b]; pSo.p[b] = Sout.empty() ? nullptr : Sout[b]; }
-        proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, true, true), e.cplx, e.stream); ++e.launches;
+        { ProfScope ps(e, Engine::CAT_MISC); proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, true, true), e.cplx, e.stream); }
         for (int b = 0; b < nb; ++b) {
             e.contract(relabel(Rtn[b], "xi"), false, make_tn(r.U[b], "ci", {chi, n1}), false, make_tn(P[b], "xc", {n0, chi}));
             e.contract(relabel(Rttn[b], "xi"), false, make_tn(r.V[b], "ci", {chi, n1}), false, make_tn(Pt[b], "xc", {n0, chi}));
@@ -376,7 +379,7 @@ static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>&
     j12.insert(j12.end(), j2.begin(), j2.end());
     e.chain_multi(j12);
     e.chain_multi(j3);
-    if (!e.ws.dry()) { scale_by_amax_launch(sb, 3 * nj, e.cplx, e.stream); ++e.launches; }
+    if (!e.ws.dry()) { { ProfScope ps(e, Engine::CAT_MISC); scale_by_amax_launch(sb, 3 * nj, e.cplx, e.stream); } }
 }
 
 static ctmb_options opts_or_default(const ctmb_options* o) {
@@ -460,6 +463,28 @@ int ctmb_reset_counters(ctmb_handle_t h) {
     CTMB_TRY
     CTMB_CHECK(h != nullptr, "null handle");
     h->h.eng.launches = 0; h->h.eng.flops = 0;
+    h->h.eng.prof_reset();
+    return 0;
+    CTMB_CATCH(-1)
+}
+int ctmb_profile_enable(ctmb_handle_t h, int on) {
+    CTMB_TRY
+    CTMB_CHECK(h != nullptr, "null handle");
+    h->h.eng.profiling = on != 0;
+    return 0;
+    CTMB_CATCH(-1)
+}
+int ctmb_profile_get(ctmb_handle_t h, double* ms, double* flops, double* bytes, long long* launches) {
+    CTMB_TRY
+    CTMB_CHECK(h != nullptr, "null handle");
+    Engine::ProfTotals t[Engine::CAT_COUNT];
+    h->h.eng.prof_collect(t);
+    for (int i = 0; i < Engine::CAT_COUNT; ++i) {
+        if (ms) ms[i] = t[i].ms;
+        if (flops) flops[i] = t[i].flops;
+        if (bytes) bytes[i] = t[i].bytes;
+        if (launches) launches[i] = t[i].launches;
+    }
     return 0;
     CTMB_CATCH(-1)
 }
@@ -557,7 +582,7 @@ static void svd_impl(ctmb_handle_t h, const void* M, int m, int n, int chi, cons
     if (e.ws.dry()) return;
     PtrBatch pU{}, pV{}, pS{}, pSo{};
     pU.p[0] = r.U[0]; pV.p[0] = r.V[0]; pS.p[0] = r.S[0]; pSo.p[0] = S;
-    proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); ++e.launches;
+    { ProfScope ps(e, Engine::CAT_MISC); proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); }
     CTMB_CUDA(cudaMemcpyAsync(U, r.U[0], (size_t)m * chi * e.esize(), cudaMemcpyDeviceToDevice, e.stream));
     CTMB_CUDA(cudaMemcpyAsync(V, r.V[0], (size_t)n * chi * e.esize(), cudaMemcpyDeviceToDevice, e.stream));
 }
@@ -583,7 +608,7 @@ static Rsvd eig_impl(ctmb_handle_t h, const void* M, int n, int chi, const ctmb_
     if (e.ws.dry()) return r;
     PtrBatch pU{}, pV{}, pS{}, pSo{};
     pU.p[0] = r.U[0]; pV.p[0] = nullptr; pS.p[0] = r.S[0]; pSo.p[0] = D;
-    proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); ++e.launches;
+    { ProfScope ps(e, Engine::CAT_MISC); proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); }
     if (U) CTMB_CUDA(cudaMemcpyAsync(U, r.U[0], (size_t)n * chi * e.esize(), cudaMemcpyDeviceToDevice, e.stream));
     return r;
 }
@@ -711,7 +736,7 @@ static void move_c4v_impl(ctmb_handle_t h, const void* a, const int dims[5], con
     if (!e.ws.dry()) {
         PtrBatch pU{}, pV{}, pS{}, pSo{};
         pU.p[0] = r.U[0]; pS.p[0] = r.S[0]; pSo.p[0] = Dv;
-        proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); ++e.launches;
+        { ProfScope ps(e, Engine::CAT_MISC); proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, false, false), e.cplx, e.stream); }
     }
     // nT = 'acl,aux,@uldr,cdy->xyr' with (T, P, a, conj a, conj P), P = U viewed (chi, d, chi')
     {
@@ -726,10 +751,10 @@ static void move_c4v_impl(ctmb_handle_t h, const void* a, const int dims[5], con
     if (!e.ws.dry()) {
         unsigned long long* amax = (unsigned long long*)e.persistent("amax", 3 * TC_MAX_BATCH * sizeof(unsigned long long));
         CTMB_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned long long), e.stream));
-        c4v_sym_launch(nTraw, T_out, chi, (int)d, amax, e.cplx, e.stream); ++e.launches;
+        { ProfScope ps(e, Engine::CAT_MISC); c4v_sym_launch(nTraw, T_out, chi, (int)d, amax, e.cplx, e.stream); }
         ScaleBatch sb{}; sb.p[0] = T_out; sb.count[0] = (long long)chi * chi * d; sb.amax[0] = amax;
-        scale_by_amax_launch(sb, 1, e.cplx, e.stream); ++e.launches;
-        c4v_diag_launch(Dv, C_out, chi, e.cplx, e.stream); ++e.launches;
+        { ProfScope ps(e, Engine::CAT_MISC); scale_by_amax_launch(sb, 1, e.cplx, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); c4v_diag_launch(Dv, C_out, chi, e.cplx, e.stream); }
         if (D_out) CTMB_CUDA(cudaMemcpyAsync(D_out, Dv, (size_t)chi * 8, cudaMemcpyDeviceToDevice, e.stream));
     }
 }

@@ -81,6 +81,18 @@ class CtmEngine:
     def reset_counters(self):
         check(lib.ctmb_reset_counters(self._h))
 
+    PROFILE_CLASSES = ('tc_gemm', 'qr', 'jacobi', 'misc')
+
+    def profile(self, on):
+        """Per-kernel-class CUDA-event timing inside libctmb (bench.py's roofline entry)."""
+        check(lib.ctmb_profile_enable(self._h, int(bool(on))))
+
+    def profile_totals(self):
+        ms, fl, by = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_double * 4)()
+        n = (C.c_longlong * 4)()
+        check(lib.ctmb_profile_get(self._h, ms, fl, by, n))
+        return {k: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=n[i]) for i, k in enumerate(self.PROFILE_CLASSES)}
+
     def _opts(self, **kw):
         o = _lib.Options()
         C.memmove(C.byref(o), C.byref(self.options), C.sizeof(o))
