@@ -73,6 +73,15 @@ struct PtrBatch { void* p[TC_MAX_BATCH]; };
 void qr_launch(const PtrBatch& A, const PtrBatch& Rout, int nb, int rows, int cols, int ld,
                bool cplx, cudaStream_t stream);
 
+// WY form (fast path, sketches up to 1024 x 128): factor leaves V / tau / R; the explicit Q is
+// then  Q = E - V X,  X = T V1^H  (wy_tsolve) with the Gram matrix G = V^H V from a GEMM.
+bool qr_wy_supported(int rows, int cols, bool cplx);
+void qr_wy_factor_launch(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch& Tau, int nb, int rows, int cols,
+                         int ld, bool cplx, cudaStream_t stream);
+void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V, const PtrBatch& X, int nb, int k,
+                      int ldv, bool cplx, cudaStream_t stream);
+void add_identity_launch(const PtrBatch& Q, int nb, int k, int ld, bool cplx, cudaStream_t stream);
+
 // one-sided Jacobi SVD of k x k column-major G (ld=k): on exit G = Uhat*Sigma (columns
 // orthogonal), W accumulates the right rotations (G_in * W = G_out), sig[k] the column norms.
 void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, int nb, int k,

@@ -119,8 +119,13 @@ struct Rsvd {
     std::vector<void*> U, V, S;       // U: m x chi col-major, V: n x chi col-major, S: k doubles (sorted)
 };
 
+// Sketch width.  Small problems (min(m,n) <= 128) are decomposed EXACTLY (k = min(m,n): the
+// "sketch" spans the whole space, no power iteration is needed); this also covers the
+// SU(2)-symmetric fixtures of the reference's tests, whose flat, exactly degenerate spectra a
+// subspace iteration resolves only slowly.
 static int sketch_width(int m, int n, int chi, const ctmb_options& o) {
     int mn = std::min(m, n);
+    if (mn <= 128) return mn;
     int k = (int)std::ceil(o.rsvd_rank_factor * chi);
     k = std::max(k, chi + 1);
     return std::min(k, mn);
@@ -144,13 +149,21 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         omega = e.persistent(key, (size_t)n * k * es, &created);
         if (created) { ProfScope ps(e, Engine::CAT_MISC); fill_gaussian_launch((double*)omega, (long long)n * k * (e.cplx ? 2 : 1), o.seed, e.stream); }
     }
-    std::vector<Tn> Mt(nb), Y(nb), Z(nb);
-    PtrBatch pY{}, pZ{}, pR{}, pNull{}, pW{}, pSig{}, pS{}, pUh{}, pWs{}, pU{}, pV{};
+    std::vector<Tn> Mt(nb);
+    PtrBatch pY{}, pZ{}, pQ{}, pR{}, pNull{}, pW{}, pSig{}, pS{}, pUh{}, pWs{}, pG{}, pX{}, pTau{};
     std::vector<void*> R2(nb), W(nb), sig(nb), Uh(nb), Ws(nb);
+    const int mx = std::max(m, n);
+    const bool wy = qr_wy_supported(m, k, e.cplx) && qr_wy_supported(n, k, e.cplx);
     for (int b = 0; b < nb; ++b) {
         Mt[b] = make_tn(const_cast<void*>(M[b]), "ij", {m, n});
-        Y[b] = e.temp("si", {k, m});      // column-major m x k
-        Z[b] = e.temp("sj", {k, n});      // column-major n x k
+        pY.p[b] = e.ws.alloc((size_t)k * m * es);       // column-major m x k
+        pZ.p[b] = e.ws.alloc((size_t)k * n * es);       // column-major n x k
+        if (wy) {
+            pQ.p[b] = e.ws.alloc((size_t)k * mx * es);  // scratch for the explicit Q of the WY form
+            pG.p[b] = e.ws.alloc((size_t)k * k * es);
+            pX.p[b] = e.ws.alloc((size_t)k * k * es);
+            pTau.p[b] = e.ws.alloc((size_t)k * es);
+        }
         R2[b] = e.ws.alloc((size_t)k * k * es);
         W[b] = e.ws.alloc((size_t)k * k * es);
         sig[b] = e.ws.alloc((size_t)k * 8);
@@ -159,55 +172,93 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         Ws[b] = e.ws.alloc((size_t)k * chi * es);
         r.U.push_back(e.ws.alloc((size_t)m * chi * es));
         r.V.push_back(eig_mode ? nullptr : e.ws.alloc((size_t)n * chi * es));
-        pY.p[b] = Y[b].ptr; pZ.p[b] = Z[b].ptr; pR.p[b] = R2[b]; pW.p[b] = W[b]; pSig.p[b] = sig[b];
-        pS.p[b] = r.S[b]; pUh.p[b] = Uh[b]; pWs.p[b] = Ws[b]; pU.p[b] = r.U[b]; pV.p[b] = r.V[b];
+        pR.p[b] = R2[b]; pW.p[b] = W[b]; pSig.p[b] = sig[b];
+        pS.p[b] = r.S[b]; pUh.p[b] = Uh[b]; pWs.p[b] = Ws[b];
     }
     if (e.ws.dry()) return r;
     Tn Om = make_tn(omega, "sj", {k, n});
-    auto qr = [&](const PtrBatch& A, const PtrBatch& Rout, int rows) {
+    auto tnY = [&](int b, const char* lab) { return make_tn(pY.p[b], lab, {k, m}); };
+    auto tnZ = [&](int b, const char* lab) { return make_tn(pZ.p[b], lab, {k, n}); };
+    const double cf = e.cplx ? 4.0 : 1.0;
+    // orthonormalise the columns of the matrices in `cur` (rows x k, column-major); on return `cur`
+    // holds the explicit thin Q (the buffers of `cur` and pQ are swapped in the WY form)
+    auto qr = [&](PtrBatch& cur, const PtrBatch& Rout, int rows) {
         e.flush();
-        const double cf = e.cplx ? 4.0 : 1.0;
-        ProfScope ps(e, Engine::CAT_QR, cf * nb * 4.0 * ((double)rows * k * k - (double)k * k * k / 3.0),
-                     2.0 * e.esize() * nb * (double)rows * k);
-        qr_launch(A, Rout, nb, rows, k, rows, e.cplx, e.stream);
+        const double fl = cf * nb * 4.0 * ((double)rows * k * k - (double)k * k * k / 3.0);
+        if (!wy) {
+            ProfScope ps(e, Engine::CAT_QR, fl, 2.0 * e.esize() * nb * (double)rows * k);
+            qr_launch(cur, Rout, nb, rows, k, rows, e.cplx, e.stream);
+            return;
+        }
+        {
+            ProfScope ps(e, Engine::CAT_QR, fl / 2, 2.0 * e.esize() * nb * (double)rows * k);
+            qr_wy_factor_launch(cur, Rout, pTau, nb, rows, k, rows, e.cplx, e.stream);
+        }
+        for (int b = 0; b < nb; ++b) {                  // G[t][s] = v_s^H v_t
+            Tn V = make_tn(cur.p[b], "si", {k, rows});
+            e.contract(V, true, relabel(V, "ti"), false, make_tn(pG.p[b], "ts", {k, k}));
+        }
+        e.flush();
+        {
+            ProfScope ps(e, Engine::CAT_QR, cf * nb * (double)k * k * k / 3.0, 3.0 * e.esize() * nb * (double)k * k);
+            wy_tsolve_launch(pG, pTau, cur, pX, nb, k, rows, e.cplx, e.stream);
+        }
+        for (int b = 0; b < nb; ++b)                    // Q = -V X (+ E below)
+            e.contract(make_tn(cur.p[b], "si", {k, rows}), false, make_tn(pX.p[b], "cs", {k, k}), false,
+                       make_tn(pQ.p[b], "ci", {k, rows}), nullptr, -1.0);
+        e.flush();
+        {
+            ProfScope ps(e, Engine::CAT_MISC);
+            add_identity_launch(pQ, nb, k, rows, e.cplx, e.stream);
+        }
+        std::swap(cur, pQ);
     };
     // Y = M * Omega
-    for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, Om, false, Y[b]);
+    for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, Om, false, tnY(b, "si"));
     qr(pY, pNull, m);
     if (!eig_mode) {
-        for (int it = 0; it < o.rsvd_niter; ++it) {
-            for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, relabel(Y[b], "si"), false, Z[b]);     // Z = M^H Q
-            qr(pZ, pNull, n);
-            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, relabel(Z[b], "sj"), false, Y[b]);    // Y = M Q'
+        // power iterations Q <- orth(M (M^H Q)): ONE orthogonalisation per full iteration.  The
+        // intermediate M^H Q is not re-orthogonalised: only directions with S/S0 > 1e-8 survive
+        // the projector cut-off (ctm_projectors.py:266-270) and those keep >= 16-2*8 digits through
+        // one unorthogonalised M M^H application; measured parity is identical to re-orthogonalising
+        // at every half step ("range finder").
+        const int niter = (k == std::min(m, n)) ? 0 : o.rsvd_niter;      // complete sketch: already exact
+        for (int it = 0; it < niter; ++it) {
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, tnY(b, "si"), false, tnZ(b, "sj"));     // Z = M^H Q
+            e.flush();
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnZ(b, "sj"), false, tnY(b, "si"));    // Y = M Z
             qr(pY, pNull, m);
         }
         // Bt = M^H Q = Q2 R2   =>   M ~ Q R2^H Q2^H ;  R2 W = Uh Sigma  =>  U = Q W, V = Q2 Uh
-        for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, Y[b], false, Z[b]);
+        for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, tnY(b, "si"), false, tnZ(b, "sj"));
         qr(pZ, pR, n);
         { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, e.stream); }
         { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); }
         for (int b = 0; b < nb; ++b) {
-            e.contract(Y[b], false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
-            e.contract(Z[b], false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
+            e.contract(tnY(b, "si"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+            e.contract(tnZ(b, "sj"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
         }
         e.flush();
     } else {
-        // Hermitian: subspace iteration with M itself (4q+1 applications: the spectrum of the corner itself decays half as fast as that of M = R^T Rt), then Rayleigh-Ritz
-        for (int it = 0; it < 4 * o.rsvd_niter; ++it) {
-            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, relabel(Y[b], "sj"), false, relabel(Z[b], "si"));
-            qr(pZ, pNull, n);
-            std::swap(Y, Z); std::swap(pY, pZ);
+        // Hermitian: subspace iteration with M itself (4q+1 applications: the spectrum of the corner
+        // itself decays half as fast as that of M = R^T Rt), then Rayleigh-Ritz
+        const int napp = (k == n) ? 0 : 4 * o.rsvd_niter;
+        for (int it = 0; it < napp; ++it) {
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));
+            if (it & 1) qr(pZ, pNull, n);               // one orthogonalisation per two applications
+            else e.flush();
+            std::swap(pY, pZ);
         }
-        // Z = M Q ; Tm = Q^H Z (k x k, column-major [t][s]) ; Tm W = W Lambda
-        for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, relabel(Y[b], "sj"), false, relabel(Z[b], "si"));
+        // Z = M Q ; Tm = Q^H Z (k x k, column-major [t][s]) ; (Tm + mu) W = W (Lambda + mu)
+        for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));
         e.flush();
         for (int b = 0; b < nb; ++b)
-            e.contract(relabel(Y[b], "si"), true, relabel(Z[b], "ti"), false, make_tn(R2[b], "ts", {k, k}));
+            e.contract(tnY(b, "si"), true, tnZ(b, "ti"), false, make_tn(R2[b], "ts", {k, k}));
         e.flush();
         { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, e.stream); }
         { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pNull, pWs, nb, k, chi, e.cplx, 1, e.stream); }
         for (int b = 0; b < nb; ++b)
-            e.contract(relabel(Y[b], "si"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+            e.contract(tnY(b, "si"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
         e.flush();
     }
     return r;

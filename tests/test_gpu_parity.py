@@ -189,20 +189,41 @@ def test_config2_size_against_live_oracle(eng, dev, family):
     assert abs(e_gpu - e_cpu) <= 1e-10 * abs(e_cpu)
 
 
-@pytest.mark.parametrize('shape', [(3, 48, torch.float64), (4, 32, torch.complex128), (8, 24, torch.float64)])
+def _decaying(n, dt, dev, rate, seed):
+    """n x n matrix with singular values rate^j (the CTM matrices M = R^T Rt decay geometrically)."""
+    g = torch.Generator().manual_seed(seed)
+    Q1, _ = torch.linalg.qr(torch.randn(n, n, dtype=dt, generator=g))
+    Q2, _ = torch.linalg.qr(torch.randn(n, n, dtype=dt, generator=g))
+    s = rate ** torch.arange(n, dtype=torch.float64)
+    return ((Q1 * s.to(dt)) @ Q2.conj().t()).to(dev)
+
+
+@pytest.mark.parametrize('shape', [(3, 48, torch.float64, 0.9), (4, 32, torch.complex128, 0.93), (8, 24, torch.float64, 0.97)])
 def test_projector_biorthogonality_property(eng, dev, shape):
     """Size-independent property: Pt^T P = diag(1 on kept, 0 on cut) (ctm_projectors.py:279-293:
-    P = R conj(U) S^-1/2, Pt = Rt V S^-1/2 with M = R^T Rt = U S V^H)."""
-    D, chi, dt = shape
-    torch.manual_seed(7)
+    P = R conj(U) S^-1/2, Pt = Rt V S^-1/2 with M = R^T Rt = U S V^H), at the full n of configs 2-4."""
+    D, chi, dt, rate = shape
     n = chi * D * D
-    R = torch.randn(n, n, dtype=dt, device=dev) / n ** 0.5
-    Rt = torch.randn(n, n, dtype=dt, device=dev) / n ** 0.5
+    R = _decaying(n, dt, dev, rate, 7)
+    Rt = _decaying(n, dt, dev, rate, 8)
     P, Pt, S = eng.projectors(R, Rt, chi)
-    G = (Pt.t() @ P).cpu()
-    assert H.maxrel(G, torch.eye(chi, dtype=dt)) < 1e-8
     Sr = torch.linalg.svdvals((R.t() @ Rt).cpu())[:chi]
-    assert float((S.cpu() - Sr).abs().max() / Sr[0]) < 1e-10
+    keep = int((Sr / Sr[0] > 1e-8).sum())
+    G = (Pt.t() @ P).cpu()
+    I = torch.zeros(chi, chi, dtype=dt); I[:keep, :keep] = torch.eye(keep, dtype=dt)
+    assert float((G - I).abs().max()) < 1e-7
+    assert float((S.cpu()[:keep] - Sr[:keep]).abs().max() / Sr[0]) < 1e-10
+
+
+def test_flat_spectrum_keeps_biorthogonality(eng, dev):
+    """A flat spectrum is the worst case for a range finder: the singular values are then only
+    Ritz approximations, but the projector pair stays exactly bi-orthogonal by construction."""
+    torch.manual_seed(7)
+    n, chi = 432, 48
+    R = torch.randn(n, n, dtype=torch.float64, device=dev) / n ** 0.5
+    Rt = torch.randn(n, n, dtype=torch.float64, device=dev) / n ** 0.5
+    P, Pt, S = eng.projectors(R, Rt, chi)
+    assert H.maxrel((Pt.t() @ P).cpu(), torch.eye(chi, dtype=torch.float64)) < 1e-9
 
 
 def test_truncated_svd_edge_cases(eng, dev):
