@@ -85,7 +85,7 @@ void add_identity_launch(const PtrBatch& Q, int nb, int k, int ld, bool cplx, cu
 // one-sided Jacobi SVD of k x k column-major G (ld=k): on exit G = Uhat*Sigma (columns
 // orthogonal), W accumulates the right rotations (G_in * W = G_out), sig[k] the column norms.
 void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, int nb, int k,
-                   bool cplx, int max_sweeps, int shift, cudaStream_t stream);
+                   bool cplx, int max_sweeps, int shift, int transpose_in, cudaStream_t stream);
 size_t jacobi_smem_limit();
 
 // sort sig descending -> Ssorted[k]; Uhs = normalised sorted columns of G (first ncol),
@@ -100,6 +100,7 @@ struct ProjFinalizeArgs {
     int truncating;                       // chi < min(m,n): multiplet rule applies
     int conj_u;                           // write conj(U)*phase*s into Uout (projector form)
     int apply_scale;                      // multiply by S^-1/2 (else plain sign-fixed U,V)
+    int v_div_sigma;                      // V holds M^H U: divide column j by S_j first (0 if S_j is below the cut)
 };
 // U (rowsU x chi), V (rowsV x chi) column-major in place -> Uout/Vout; Sout[chi] truncated spectrum
 void proj_finalize_launch(const PtrBatch& U, const PtrBatch& V, const PtrBatch& S, const PtrBatch& Sout,

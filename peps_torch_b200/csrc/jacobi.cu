@@ -20,25 +20,35 @@ constexpr int JAC_THREADS = 1024;
 
 template <bool CPLX>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch Sb, int k,
-                                                              int gs, int use_smem, int max_sweeps, int shift) {
+                                                              int gs, int use_smem, int max_sweeps, int shift,
+                                                              int transpose_in) {
     using S = Sc<CPLX>;
     using T = typename S::T;
     extern __shared__ __align__(16) unsigned char jac_smem[];
     T* Gg = reinterpret_cast<T*>(Gb.p[blockIdx.x]);
-    T* Wg = reinterpret_cast<T*>(Wb.p[blockIdx.x]);
+    T* Wg = reinterpret_cast<T*>(Wb.p[blockIdx.x]);      // nullptr: right rotations are not accumulated
     double* sig = reinterpret_cast<double*>(Sb.p[blockIdx.x]);
     const int tid = threadIdx.x;
+    const bool accw = Wg != nullptr;
     T* G = Gg;
     T* W = Wg;
     if (use_smem) {
         G = reinterpret_cast<T*>(jac_smem);
         W = G + (size_t)k * k;
-        for (int e = tid; e < k * k; e += JAC_THREADS) G[e] = Gg[e];
+        if (transpose_in) for (int e = tid; e < k * k; e += JAC_THREADS) G[e] = S::conj(Gg[(size_t)(e % k) * k + e / k]);
+        else for (int e = tid; e < k * k; e += JAC_THREADS) G[e] = Gg[e];
+    } else if (transpose_in) {
+        // in-place conjugate transpose in global memory
+        for (int e = tid; e < k * k; e += JAC_THREADS) {
+            const int c = e / k, r = e % k;
+            if (r > c) { T x = Gg[e], y = Gg[(size_t)r * k + c]; Gg[e] = S::conj(y); Gg[(size_t)r * k + c] = S::conj(x); }
+            else if (r == c) Gg[e] = S::conj(Gg[e]);
+        }
     }
-    for (int e = tid; e < k * k; e += JAC_THREADS) W[e] = (e / k == e % k) ? S::one() : S::zero();
+    if (accw) for (int e = tid; e < k * k; e += JAC_THREADS) W[e] = (e / k == e % k) ? S::one() : S::zero();
     __shared__ int rotated;
-    __shared__ unsigned long long maxcos;     // bits of the largest |cos(angle)| rotated in this sweep
-    if (tid == 0) { rotated = 0; maxcos = 0ull; }
+    __shared__ int notsmall;                  // a rotation with |cos(angle)| > 1e-8 happened in this sweep
+    if (tid == 0) { rotated = 0; notsmall = 0; }
     __syncthreads();
 
     const int kk = (k + 1) & ~1;          // even number of players (kk-1 >= k means a bye)
@@ -48,9 +58,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBat
     // lanes of one group shuffle among themselves only (groups of a warp may diverge)
     const unsigned gmask = (gs == 32) ? 0xffffffffu : (((1u << gs) - 1u) << ((tid & 31) & ~(gs - 1)));
     const double tol = 2.2e-16 * sqrt((double)k);   // as LAPACK xGESVJ: sqrt(m)*eps
+    const double tol2 = tol * tol;
     // optional spectral shift (eigen mode): G <- G + mu*I with mu = ||G||_F >= ||G||_2 makes a
     // Hermitian G positive semi-definite, so that its SVD is its eigen-decomposition
-    // (lambda_j = sigma_j - mu, eigenvectors = W) without the +-lambda ambiguity.
+    // (lambda_j = sigma_j - mu, eigenvectors = normalised columns) without the +-lambda ambiguity.
     double mu = 0.0;
     if (shift) {
         __shared__ double redm[JAC_THREADS / 32];
@@ -66,6 +77,8 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBat
         for (int e = tid; e < k; e += JAC_THREADS) G[(size_t)e * k + e] = S::add(G[(size_t)e * k + e], S::make(mu, 0.0));
         __syncthreads();
     }
+    constexpr int NR = 8;                 // register-cached rows per lane (k <= NR*gs)
+    const bool cached = k <= NR * gs;
 
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         for (int round = 0; round < kk - 1; ++round) {
@@ -79,59 +92,95 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBat
                 T* gq = G + (size_t)q * k;
                 double a = 0.0, b = 0.0;
                 T g = S::zero();
-                for (int r = gl; r < k; r += gs) {
-                    T x = gp[r], y = gq[r];
-                    a += S::abs2(x); b += S::abs2(y);
-                    g = S::fma(S::conj(x), y, g);
+                T xc[NR], yc[NR];
+                if (cached) {
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int r = gl + i * gs;
+                        xc[i] = r < k ? gp[r] : S::zero();
+                        yc[i] = r < k ? gq[r] : S::zero();
+                        a += S::abs2(xc[i]); b += S::abs2(yc[i]);
+                        g = S::fma(S::conj(xc[i]), yc[i], g);
+                    }
+                } else {
+                    for (int r = gl; r < k; r += gs) {
+                        T x = gp[r], y = gq[r];
+                        a += S::abs2(x); b += S::abs2(y);
+                        g = S::fma(S::conj(x), y, g);
+                    }
                 }
                 for (int o = gs >> 1; o > 0; o >>= 1) {
                     a += __shfl_xor_sync(gmask, a, o);
                     b += __shfl_xor_sync(gmask, b, o);
                     g = S::add(g, S::shfl_xor_m(gmask, g, o));
                 }
-                const double ag = S::abs(g);
-                const double lim = tol * sqrt(a) * sqrt(b);
-                if (ag > lim && ag > 0.0) {
-                    if (gl == 0) { rotated = 1; atomicMax(&maxcos, (unsigned long long)__double_as_longlong(ag / (sqrt(a) * sqrt(b)))); }
-                    const double zeta = (b - a) / (2.0 * ag);
-                    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + t * t);
-                    const double s = c * t;
-                    // y2 = y * conj(phase), phase = g/|g|  (so that x^H y2 = |g| is real)
-                    const T cph = S::scale(S::conj(g), 1.0 / ag);
-                    T* wp = W + (size_t)p * k;
-                    T* wq = W + (size_t)q * k;
-                    for (int r = gl; r < k; r += gs) {
-                        T x = gp[r], y = S::mul(gq[r], cph);
-                        gp[r] = S::sub(S::scale(x, c), S::scale(y, s));
-                        gq[r] = S::add(S::scale(x, s), S::scale(y, c));
-                        T u = wp[r], v = S::mul(wq[r], cph);
-                        wp[r] = S::sub(S::scale(u, c), S::scale(v, s));
-                        wq[r] = S::add(S::scale(u, s), S::scale(v, c));
+                const double ag2 = S::abs2(g);
+                if (ag2 > tol2 * a * b && ag2 > 0.0) {
+                    if (gl == 0) { rotated = 1; if (ag2 > 1.0e-16 * a * b) notsmall = 1; }
+                    // Rotation [x y] <- [x y] [[c, conj(al)], [-al, c]] that makes the columns orthogonal:
+                    //   tan(2 theta) = 2|g| / |b-a|,  c = cos(theta) >= 1/sqrt(2),  al = sign(b-a) conj(g) sin(theta)/|g|.
+                    // Written with two reciprocal square roots and no division / square root:
+                    //   r = 1/sqrt(d^2 + 4|g|^2), cos(2 theta) = |d| r, c^2 = (1 + cos(2 theta))/2, rc = 1/sqrt(c^2),
+                    //   c = c^2 rc,  sin(theta)/|g| = r rc.
+                    const double d = b - a;
+                    const double r = rsqrt(d * d + 4.0 * ag2);
+                    const double c2 = 0.5 + 0.5 * fabs(d) * r;
+                    const double rc = rsqrt(c2);
+                    const double c = c2 * rc;
+                    const T al = S::scale(S::conj(g), copysign(r * rc, d));
+                    const T cal = S::conj(al);
+                    if (cached) {
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int r = gl + i * gs;
+                            if (r < k) {
+                                const T x = xc[i], y = yc[i];
+                                gp[r] = S::sub(S::scale(x, c), S::mul(al, y));
+                                gq[r] = S::add(S::mul(cal, x), S::scale(y, c));
+                            }
+                        }
+                    } else {
+                        for (int r = gl; r < k; r += gs) {
+                            T x = gp[r], y = gq[r];
+                            gp[r] = S::sub(S::scale(x, c), S::mul(al, y));
+                            gq[r] = S::add(S::mul(cal, x), S::scale(y, c));
+                        }
+                    }
+                    if (accw) {
+                        T* wp = W + (size_t)p * k;
+                        T* wq = W + (size_t)q * k;
+                        for (int r = gl; r < k; r += gs) {
+                            T u = wp[r], v = wq[r];
+                            wp[r] = S::sub(S::scale(u, c), S::mul(al, v));
+                            wq[r] = S::add(S::mul(cal, u), S::scale(v, c));
+                        }
                     }
                 }
             }
             __syncthreads();
         }
         const int any = rotated;
-        const double mc = __longlong_as_double((long long)maxcos);
+        const int big = notsmall;
         __syncthreads();
-        if (tid == 0) { rotated = 0; maxcos = 0ull; }
+        if (tid == 0) { rotated = 0; notsmall = 0; }
         __syncthreads();
         // cyclic Jacobi converges quadratically: if the largest cosine met in this sweep was below
         // 1e-8 the columns are now orthogonal to ~1e-16 and the verification sweep can be skipped
-        if (!any || mc < 1.0e-8) break;
+        if (!any || !big) break;
     }
-    // column norms, write back
+    // column norms; the columns are written back NORMALISED (left singular vectors / eigenvectors)
     for (int c = grp; c < k; c += ngroups) {
         double a = 0.0;
         for (int r = gl; r < k; r += gs) a += S::abs2(G[(size_t)c * k + r]);
         for (int o = gs >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(gmask, a, o);
-        if (gl == 0) sig[c] = sqrt(a) - mu;
+        const double nrm = sqrt(a);
+        if (gl == 0) sig[c] = nrm - mu;
+        const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        for (int r = gl; r < k; r += gs) G[(size_t)c * k + r] = S::scale(G[(size_t)c * k + r], inv);
     }
     if (use_smem) {
         __syncthreads();
-        for (int e = tid; e < k * k; e += JAC_THREADS) { Gg[e] = G[e]; Wg[e] = W[e]; }
+        for (int e = tid; e < k * k; e += JAC_THREADS) { Gg[e] = G[e]; if (accw) Wg[e] = W[e]; }
     }
 }
 
@@ -147,9 +196,10 @@ size_t jacobi_smem_limit() {
 }
 
 void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, int nb, int k, bool cplx,
-                   int max_sweeps, int shift, cudaStream_t stream) {
+                   int max_sweeps, int shift, int transpose_in, cudaStream_t stream) {
     CTMB_CHECK(nb >= 1 && nb <= TC_MAX_BATCH, "bad batch");
-    const size_t need = 2 * (size_t)k * k * (cplx ? 16 : 8);
+    const bool accw = W.p[0] != nullptr;
+    const size_t need = (accw ? 2 : 1) * (size_t)k * k * (cplx ? 16 : 8);
     const int use_smem = need <= jacobi_smem_limit();
     const size_t smem = use_smem ? need : 0;
     const int npairs = (k + 1) / 2;
@@ -159,12 +209,12 @@ void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, in
         auto kern = jacobi_kernel<true>;
         static size_t set = 0;
         if (smem > set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jacobi_smem_limit())); set = jacobi_smem_limit(); }
-        kern<<<nb, JAC_THREADS, smem, stream>>>(G, W, sig, k, gs, use_smem, max_sweeps, shift);
+        kern<<<nb, JAC_THREADS, smem, stream>>>(G, W, sig, k, gs, use_smem, max_sweeps, shift, transpose_in);
     } else {
         auto kern = jacobi_kernel<false>;
         static size_t set = 0;
         if (smem > set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jacobi_smem_limit())); set = jacobi_smem_limit(); }
-        kern<<<nb, JAC_THREADS, smem, stream>>>(G, W, sig, k, gs, use_smem, max_sweeps, shift);
+        kern<<<nb, JAC_THREADS, smem, stream>>>(G, W, sig, k, gs, use_smem, max_sweeps, shift, transpose_in);
     }
     CTMB_CUDA(cudaGetLastError());
 }

@@ -36,10 +36,7 @@ __global__ void __launch_bounds__(256) sortcols_kernel(PtrBatch Gb, PtrBatch Wb,
         const int c = e / k, r = e % k;
         const int src = perm[c];
         if (Ws != nullptr) Ws[e] = W[(size_t)src * k + r];
-        if (Uh != nullptr) {
-            const double s = fabs(sig[src]);
-            Uh[e] = s > 0.0 ? S::scale(G[(size_t)src * k + r], 1.0 / s) : S::zero();
-        }
+        if (Uh != nullptr) Uh[e] = G[(size_t)src * k + r];      // columns arrive normalised from the Jacobi kernel
     }
 }
 
@@ -70,6 +67,7 @@ __global__ void __launch_bounds__(256) proj_finalize_kernel(PtrBatch Ub, PtrBatc
     const int chi = a.chi;
 
     __shared__ double sh_scale;
+    __shared__ double sh_vscale;
     __shared__ int sh_keep;
     __shared__ long long red_amp[8];
     __shared__ int red_idx[8];
@@ -96,6 +94,8 @@ __global__ void __launch_bounds__(256) proj_finalize_kernel(PtrBatch Ub, PtrBatc
         if (kept && fabs(sj) / s0 > a.reltol) sc = rsqrt(fabs(sj));
         sh_keep = kept ? 1 : 0;
         sh_scale = a.apply_scale ? sc : (kept ? 1.0 : 0.0);
+        // V = M^H U / S is formed only where the projector uses it (S/S0 above 1e-2 x the cut-off)
+        sh_vscale = !a.v_div_sigma ? 1.0 : ((kept && fabs(sj) > 1.0e-2 * a.reltol * s0 && fabs(sj) > 0.0) ? 1.0 / fabs(sj) : 0.0);
         if (Sout != nullptr) Sout[j] = sj;
     }
     // first arg-max of int64(|U|*2^40) over the column
@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(256) proj_finalize_kernel(PtrBatch Ub, PtrBatc
     }
     if (V != nullptr) {
         T* vc = V + (size_t)j * a.rowsV;
-        for (int r = tid; r < a.rowsV; r += blockDim.x) vc[r] = S::scale(S::mul(vc[r], cph), sc);
+        const double vs = sc * sh_vscale;
+        for (int r = tid; r < a.rowsV; r += blockDim.x) vc[r] = S::scale(S::mul(vc[r], cph), vs);
     }
 }
 

@@ -229,14 +229,16 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnZ(b, "sj"), false, tnY(b, "si"));    // Y = M Z
             qr(pY, pNull, m);
         }
-        // Bt = M^H Q = Q2 R2   =>   M ~ Q R2^H Q2^H ;  R2 W = Uh Sigma  =>  U = Q W, V = Q2 Uh
+        // Bt = M^H Q = Q2 R2  =>  M ~ Q R2^H Q2^H.  One-sided Jacobi on G = R2^H:  G W = Uh Sigma, so
+        // U = Q Uh (normalised columns of the rotated G) and V = Q2 W (accumulated rotations); both come
+        // out of the small problem with high relative accuracy down to the projector cut-off.
         for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, tnY(b, "si"), false, tnZ(b, "sj"));
         qr(pZ, pR, n);
-        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, e.stream); }
+        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, 1, e.stream); }
         { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); }
         for (int b = 0; b < nb; ++b) {
-            e.contract(tnY(b, "si"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
-            e.contract(tnZ(b, "sj"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
+            e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+            e.contract(tnZ(b, "sj"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
         }
         e.flush();
     } else {
@@ -255,10 +257,10 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         for (int b = 0; b < nb; ++b)
             e.contract(tnY(b, "si"), true, tnZ(b, "ti"), false, make_tn(R2[b], "ts", {k, k}));
         e.flush();
-        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, e.stream); }
-        { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pNull, pWs, nb, k, chi, e.cplx, 1, e.stream); }
+        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, chi, e.cplx, 1, e.stream); }
         for (int b = 0; b < nb; ++b)
-            e.contract(tnY(b, "si"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+            e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
         e.flush();
     }
     return r;
@@ -270,6 +272,7 @@ static ProjFinalizeArgs finalize_args(const Rsvd& r, const ctmb_options& o, bool
     a.reltol = o.svd_reltol; a.eps_multiplet = o.eps_multiplet; a.abstol = o.multiplet_abstol;
     a.truncating = (r.chi < std::min(r.m, r.n)) && (r.k > r.chi);
     a.conj_u = conj_u; a.apply_scale = scale;
+    a.v_div_sigma = 0;
     return a;
 }
 

@@ -267,14 +267,20 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_cluster_kernel(PtrBatch Ab, Pt
         // reflector parameters (computed redundantly by every thread from local shared memory)
         T tj = S::zero(), sc = S::zero(); double beta = 0.0;
         if (lane == 0) {
+            // ||x||^2 = |alpha|^2 + tail; one rsqrt and one reciprocal:
+            //   beta = -sign(Re alpha)||x||, 1/beta = -sign/||x||, tau = (beta-alpha)/beta, s = 1/(alpha-beta)
             const double tail = S::re(tot[j]);
             const T alpha = tot[cols + j];
             if (tail == 0.0 && S::im(alpha) == 0.0) { beta = S::re(alpha); }
             else {
-                beta = -copysign(sqrt(S::abs2(alpha) + tail), S::re(alpha));
-                const double ib = 1.0 / beta;
+                const double nsq = S::abs2(alpha) + tail;
+                const double rn = rsqrt(nsq);
+                const double sg = copysign(1.0, S::re(alpha));
+                beta = -sg * (nsq * rn);
+                const double ib = -sg * rn;
                 tj = S::make((beta - S::re(alpha)) * ib, -S::im(alpha) * ib);
-                sc = S::div(S::one(), S::sub(alpha, S::make(beta, 0.0)));
+                const T amb = S::sub(alpha, S::make(beta, 0.0));
+                sc = S::scale(S::conj(amb), 1.0 / S::abs2(amb));
             }
         }
         tj = S::make(__shfl_sync(0xffffffffu, S::re(tj), 0), __shfl_sync(0xffffffffu, S::im(tj), 0));
@@ -525,14 +531,20 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         QRP(4)
         T tj = S::zero(), sc = S::zero(); double beta = 0.0;
         if (lane == 0) {
+            // ||x||^2 = |alpha|^2 + tail; one rsqrt and one reciprocal:
+            //   beta = -sign(Re alpha)||x||, 1/beta = -sign/||x||, tau = (beta-alpha)/beta, s = 1/(alpha-beta)
             const double tail = S::re(tot[j]);
             const T alpha = tot[cols + j];
             if (tail == 0.0 && S::im(alpha) == 0.0) { beta = S::re(alpha); }
             else {
-                beta = -copysign(sqrt(S::abs2(alpha) + tail), S::re(alpha));
-                const double ib = 1.0 / beta;
+                const double nsq = S::abs2(alpha) + tail;
+                const double rn = rsqrt(nsq);
+                const double sg = copysign(1.0, S::re(alpha));
+                beta = -sg * (nsq * rn);
+                const double ib = -sg * rn;
                 tj = S::make((beta - S::re(alpha)) * ib, -S::im(alpha) * ib);
-                sc = S::div(S::one(), S::sub(alpha, S::make(beta, 0.0)));
+                const T amb = S::sub(alpha, S::make(beta, 0.0));
+                sc = S::scale(S::conj(amb), 1.0 / S::abs2(amb));
             }
         }
         tj = S::make(__shfl_sync(0xffffffffu, S::re(tj), 0), __shfl_sync(0xffffffffu, S::im(tj), 0));
@@ -730,7 +742,7 @@ void qr_wy_factor_launch(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch
 // the top k x k block of V:  T^-1 = striu(G) + diag(1/tau)  =>  back substitution
 //   X[s,c] = tau_s ( V1^H[s,c] - sum_{t>s} G[s,t] X[t,c] ),   s = k-1 .. 0.
 template <bool CPLX>
-__global__ void __launch_bounds__(128) wy_tsolve_kernel(PtrBatch Gb, PtrBatch Taub, PtrBatch Vb, PtrBatch Xb, int k, int ldv,
+__global__ void __launch_bounds__(512) wy_tsolve_kernel(PtrBatch Gb, PtrBatch Taub, PtrBatch Vb, PtrBatch Xb, int k, int ldv,
                                                         int g_in_smem) {
     using S = Sc<CPLX>;
     using T = typename S::T;
@@ -739,44 +751,45 @@ __global__ void __launch_bounds__(128) wy_tsolve_kernel(PtrBatch Gb, PtrBatch Ta
     const T* __restrict__ V = reinterpret_cast<const T*>(Vb.p[blockIdx.x]);
     T* __restrict__ X = reinterpret_cast<T*>(Xb.p[blockIdx.x]);
     extern __shared__ __align__(16) unsigned char wy_smem[];
-    T* Xs = reinterpret_cast<T*>(wy_smem);                // [t][c]: column c is private to thread c
+    T* Xs = reinterpret_cast<T*>(wy_smem);                // [t][c]: column c belongs to one group of 4 lanes
     T* Gs = Xs + (size_t)k * k;                           // [s][t] (optional)
-    const int c = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int c = tid >> 2, part = tid & 3;
+    const int cc = c < k ? c : k - 1;
     if (g_in_smem) {
-        for (int e = c; e < k * k; e += 128) { const int t = e / k, s2 = e % k; Gs[s2 * k + t] = G[e]; }
+        for (int e = tid; e < k * k; e += 512) { const int t = e / k, s2 = e % k; Gs[s2 * k + t] = G[e]; }
         __syncthreads();
     }
-    // every column of X = T V1^H is an independent back substitution: one thread per column, no
-    // synchronisation; G(s,t) is the same address for all threads of a warp (broadcast)
-    if (c < k) {
-        for (int s = k - 1; s >= 0; --s) {
-            T a0 = S::zero(), a1 = S::zero(), a2 = S::zero(), a3 = S::zero();
-            int t = s + 1;
-            if (g_in_smem) {
-                const T* gr = Gs + (size_t)s * k;
-                for (; t + 3 < k; t += 4) {
-                    a0 = S::fma(gr[t], Xs[t * k + c], a0);
-                    a1 = S::fma(gr[t + 1], Xs[(t + 1) * k + c], a1);
-                    a2 = S::fma(gr[t + 2], Xs[(t + 2) * k + c], a2);
-                    a3 = S::fma(gr[t + 3], Xs[(t + 3) * k + c], a3);
-                }
-                for (; t < k; ++t) a0 = S::fma(gr[t], Xs[t * k + c], a0);
-            } else {
-                for (; t + 3 < k; t += 4) {
-                    a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + c], a0);
-                    a1 = S::fma(G[(size_t)(t + 1) * k + s], Xs[(t + 1) * k + c], a1);
-                    a2 = S::fma(G[(size_t)(t + 2) * k + s], Xs[(t + 2) * k + c], a2);
-                    a3 = S::fma(G[(size_t)(t + 3) * k + s], Xs[(t + 3) * k + c], a3);
-                }
-                for (; t < k; ++t) a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + c], a0);
+    // every column of X = T V1^H is an independent back substitution: four lanes per column split
+    // the inner sum, no block-level synchronisation; G(s,t) is read at the same address by all groups
+    for (int s = k - 1; s >= 0; --s) {
+        T a0 = S::zero(), a1 = S::zero();
+        int t = s + 1 + part;
+        if (g_in_smem) {
+            const T* gr = Gs + (size_t)s * k;
+            for (; t + 4 < k; t += 8) {
+                a0 = S::fma(gr[t], Xs[t * k + cc], a0);
+                a1 = S::fma(gr[t + 4], Xs[(t + 4) * k + cc], a1);
             }
-            const T acc = S::add(S::add(a0, a1), S::add(a2, a3));
+            if (t < k) a0 = S::fma(gr[t], Xs[t * k + cc], a0);
+        } else {
+            for (; t + 4 < k; t += 8) {
+                a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + cc], a0);
+                a1 = S::fma(G[(size_t)(t + 4) * k + s], Xs[(t + 4) * k + cc], a1);
+            }
+            if (t < k) a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + cc], a0);
+        }
+        T acc = S::add(a0, a1);
+        acc = S::add(acc, S::shfl_xor(acc, 1));
+        acc = S::add(acc, S::shfl_xor(acc, 2));
+        if (part == 0 && c < k) {
             const T v1 = c > s ? S::conj(V[(size_t)s * ldv + c]) : (c == s ? S::one() : S::zero());
             Xs[s * k + c] = S::mul(tau[s], S::sub(v1, acc));
         }
+        __syncwarp();
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < k * k; e += 128) { const int cc = e / k, s2 = e % k; X[e] = Xs[s2 * k + cc]; }
+    for (int e = tid; e < k * k; e += 512) { const int c2 = e / k, s2 = e % k; X[e] = Xs[s2 * k + c2]; }
 }
 
 void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V, const PtrBatch& X, int nb, int k,
@@ -789,12 +802,12 @@ void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V,
         auto kern = wy_tsolve_kernel<true>;
         static bool set = false;
         if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
-        kern<<<nb, 128, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
+        kern<<<nb, 512, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
     } else {
         auto kern = wy_tsolve_kernel<false>;
         static bool set = false;
         if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
-        kern<<<nb, 128, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
+        kern<<<nb, 512, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
     }
     CTMB_CUDA(cudaGetLastError());
 }

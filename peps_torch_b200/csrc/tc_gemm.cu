@@ -227,14 +227,18 @@ static void tc_run(const TcParams& p, cudaStream_t stream) {
 void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream) {
     CTMB_CHECK(p.nbatch >= 1 && p.nbatch <= TC_MAX_BATCH, "bad batch count");
     if (p.M == 0 || p.N == 0) return;
-    const long long tiles128 = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * p.nbatch;
+    auto ntiles = [&](int bm, int bn) { return (long long)((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * p.nbatch; };
+    // One SM retires only ~64 FP64 FMA per clock, so the serial K loop of a CTA is the latency of
+    // a small contraction: prefer the tile that spreads the work over at least ~2 waves of CTAs.
     if (!cplx) {
-        if (p.N <= 32) tc_run<128, 32, 16, 32, 16, 3, false>(p, stream);
-        else if (tiles128 >= 120 && p.M > 64 && p.N > 64) tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
-        else tc_run<64, 64, 16, 32, 16, 4, false>(p, stream);
+        if (p.N <= 16) tc_run<128, 32, 16, 32, 16, 3, false>(p, stream);
+        else if (ntiles(128, 128) >= 240 && p.M > 64 && p.N > 64) tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
+        else if (ntiles(64, 64) >= 296) tc_run<64, 64, 16, 32, 16, 4, false>(p, stream);
+        else tc_run<32, 32, 16, 16, 8, 4, false>(p, stream);
     } else {
-        if (p.N <= 32) tc_run<128, 32, 16, 32, 16, 3, true>(p, stream);
-        else tc_run<64, 64, 16, 32, 16, 3, true>(p, stream);
+        if (p.N <= 16) tc_run<128, 32, 16, 32, 16, 3, true>(p, stream);
+        else if (ntiles(64, 64) >= 296) tc_run<64, 64, 16, 32, 16, 3, true>(p, stream);
+        else tc_run<32, 32, 16, 16, 8, 4, true>(p, stream);
     }
 }
 
