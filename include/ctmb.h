@@ -46,8 +46,11 @@ typedef struct {
     int rsvd_niter;            /* power iterations q (projector_rsvd_niter); default 4 */
     int jacobi_max_sweeps;     /* default 40 */
     int norm_type;             /* ctm_absorb_normalization: 0 = 'inf' (only value supported) */
-    int reserved;
+    int rsvd_max_rounds;       /* adaptive mode: at most this many doublings of the iteration count (default 3) */
     unsigned long long seed;   /* seed of the Gaussian sketch (deterministic) */
+    double rsvd_tol;           /* > 0: after the power iterations check max_j ||M v_j - s_j u_j|| / s_0 <= rsvd_tol on the
+                                  kept triplets (one host synchronisation) and iterate further if needed; 0 = fixed count.
+                                  Default: 0 for the generic SVD path, 1e-11 for the C4v eigen path. */
 } ctmb_options;
 
 /* One unit-cell site: on-site tensor and its eight environment tensors. */

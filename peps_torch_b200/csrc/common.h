@@ -112,6 +112,8 @@ void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t s
 // amax of |x|
 void absmax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
 
+void resid_launch(const PtrBatch& MX, const PtrBatch& Y, const PtrBatch& S, int nb, int rows, int chi, double reltol,
+                  unsigned long long* out, bool cplx, cudaStream_t stream);
 void c4v_sym_launch(const void* tin, void* tout, int chi, int d, unsigned long long* amax, bool cplx,
                     cudaStream_t stream);
 void c4v_diag_launch(const double* D, void* cout, int chi, bool cplx, cudaStream_t stream);

@@ -146,6 +146,41 @@ void proj_finalize_launch(const PtrBatch& U, const PtrBatch& V, const PtrBatch& 
 }
 
 // ---------------------------------------------------------------------------------------------
+// convergence check of the range finder: max_j || (M X)_j - s_j Y_j || / |s_0| over the columns with
+// |s_j| / |s_0| > reltol  (eigen mode: X = Y = U, s = lambda; SVD mode: X = V, Y = U, s = sigma)
+// ---------------------------------------------------------------------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) resid_kernel(PtrBatch MXb, PtrBatch Yb, PtrBatch Sb, int rows, double reltol,
+                                                    unsigned long long* out) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const int j = blockIdx.x, b = blockIdx.y;
+    const T* mx = reinterpret_cast<const T*>(MXb.p[b]) + (size_t)j * rows;
+    const T* y = reinterpret_cast<const T*>(Yb.p[b]) + (size_t)j * rows;
+    const double* Sv = reinterpret_cast<const double*>(Sb.p[b]);
+    const double s0 = fabs(Sv[0]), sj = Sv[j];
+    if (!(fabs(sj) > reltol * s0) || s0 == 0.0) return;
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) acc += S::abs2(S::sub(mx[r], S::scale(y[r], sj)));
+    acc = warp_sum(acc);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) acc += red[w];
+        atomicMax(out, (unsigned long long)__double_as_longlong(sqrt(acc) / s0));
+    }
+}
+
+void resid_launch(const PtrBatch& MX, const PtrBatch& Y, const PtrBatch& S, int nb, int rows, int chi, double reltol,
+                  unsigned long long* out, bool cplx, cudaStream_t stream) {
+    dim3 grid(chi, nb);
+    if (cplx) resid_kernel<true><<<grid, 256, 0, stream>>>(MX, Y, S, rows, reltol, out);
+    else resid_kernel<false><<<grid, 256, 0, stream>>>(MX, Y, S, rows, reltol, out);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
 // normalisation by the infinity norm (ctmrg.py:210-230)
 // ---------------------------------------------------------------------------------------------
 template <bool CPLX>

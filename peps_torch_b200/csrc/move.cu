@@ -125,7 +125,7 @@ struct Rsvd {
 // subspace iteration resolves only slowly.
 static int sketch_width(int m, int n, int chi, const ctmb_options& o) {
     int mn = std::min(m, n);
-    if (mn <= 128) return mn;
+    if (mn <= 160) return mn;
     int k = (int)std::ceil(o.rsvd_rank_factor * chi);
     k = std::max(k, chi + 1);
     return std::min(k, mn);
@@ -216,52 +216,80 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     // Y = M * Omega
     for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, Om, false, tnY(b, "si"));
     qr(pY, pNull, m);
-    if (!eig_mode) {
-        // power iterations Q <- orth(M (M^H Q)): ONE orthogonalisation per full iteration.  The
-        // intermediate M^H Q is not re-orthogonalised: only directions with S/S0 > 1e-8 survive
-        // the projector cut-off (ctm_projectors.py:266-270) and those keep >= 16-2*8 digits through
-        // one unorthogonalised M M^H application; measured parity is identical to re-orthogonalising
-        // at every half step ("range finder").
-        const int niter = (k == std::min(m, n)) ? 0 : o.rsvd_niter;      // complete sketch: already exact
-        for (int it = 0; it < niter; ++it) {
-            for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, tnY(b, "si"), false, tnZ(b, "sj"));     // Z = M^H Q
+    const bool complete = (k == std::min(m, n));          // the sketch spans everything: exact, no iteration
+    const bool adaptive = o.rsvd_tol > 0.0 && !complete;
+    unsigned long long* dres = nullptr;
+    unsigned long long* hres = nullptr;
+    if (adaptive) {
+        dres = (unsigned long long*)e.persistent("resid", sizeof(unsigned long long));
+        static unsigned long long* pinned = nullptr;
+        if (!pinned) CTMB_CUDA(cudaMallocHost(&pinned, sizeof(unsigned long long)));
+        hres = pinned;
+    }
+    int todo = complete ? 0 : o.rsvd_niter;               // full power iterations still to run
+    for (int round = 0;; ++round) {
+        if (!eig_mode) {
+            // power iterations Q <- orth(M (M^H Q)): ONE orthogonalisation per full iteration.  The
+            // intermediate M^H Q is not re-orthogonalised: only directions with S/S0 > 1e-8 survive
+            // the projector cut-off (ctm_projectors.py:266-270) and those keep >= 16-2*8 digits through
+            // one unorthogonalised M M^H application; measured parity is identical to re-orthogonalising
+            // at every half step ("range finder").
+            for (int it = 0; it < todo; ++it) {
+                for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, tnY(b, "si"), false, tnZ(b, "sj"));     // Z = M^H Q
+                e.flush();
+                for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnZ(b, "sj"), false, tnY(b, "si"));    // Y = M Z
+                qr(pY, pNull, m);
+            }
+            // Bt = M^H Q = Q2 R2  =>  M ~ Q R2^H Q2^H.  One-sided Jacobi on G = R2^H:  G W = Uh Sigma, so
+            // U = Q Uh (normalised columns of the rotated G) and V = Q2 W (accumulated rotations); both come
+            // out of the small problem with high relative accuracy down to the projector cut-off.
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, tnY(b, "si"), false, tnZ(b, "sj"));
+            qr(pZ, pR, n);
+            { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, 1, e.stream); }
+            { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); }
+            for (int b = 0; b < nb; ++b) {
+                e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+                e.contract(tnZ(b, "sj"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
+            }
             e.flush();
-            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnZ(b, "sj"), false, tnY(b, "si"));    // Y = M Z
-            qr(pY, pNull, m);
+        } else {
+            // Hermitian: subspace iteration with M itself (4 applications per "iteration": the spectrum of
+            // the corner decays half as fast as that of M = R^T Rt), one QR per two applications, then
+            // Rayleigh-Ritz; the eigenvectors are the normalised columns of the rotated (T + mu).
+            for (int it = 0; it < 4 * todo; ++it) {
+                for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));
+                if (it & 1) qr(pZ, pNull, n);
+                else e.flush();
+                std::swap(pY, pZ);
+            }
+            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));   // Z = M Q
+            e.flush();
+            for (int b = 0; b < nb; ++b)
+                e.contract(tnY(b, "si"), true, tnZ(b, "ti"), false, make_tn(R2[b], "ts", {k, k}));       // Tm = Q^H Z
+            e.flush();
+            { ProfScope ps(e, Engine::CAT_JACOBI, 0, 2.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
+            { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, chi, e.cplx, 1, e.stream); }
+            for (int b = 0; b < nb; ++b)
+                e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+            e.flush();
         }
-        // Bt = M^H Q = Q2 R2  =>  M ~ Q R2^H Q2^H.  One-sided Jacobi on G = R2^H:  G W = Uh Sigma, so
-        // U = Q Uh (normalised columns of the rotated G) and V = Q2 W (accumulated rotations); both come
-        // out of the small problem with high relative accuracy down to the projector cut-off.
-        for (int b = 0; b < nb; ++b) e.contract(Mt[b], true, tnY(b, "si"), false, tnZ(b, "sj"));
-        qr(pZ, pR, n);
-        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, 1, e.stream); }
-        { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); }
+        if (!adaptive || round + 1 >= std::max(1, o.rsvd_max_rounds)) break;
+        // residual of the kept triplets; pZ is free at this point and serves as scratch for M X
+        PtrBatch pMX{}, pYv{};
         for (int b = 0; b < nb; ++b) {
-            e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
-            e.contract(tnZ(b, "sj"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
+            pMX.p[b] = pZ.p[b];
+            const void* X = eig_mode ? r.U[b] : r.V[b];
+            e.contract(Mt[b], false, make_tn(const_cast<void*>(X), "cj", {chi, n}), false, make_tn(pMX.p[b], "ci", {chi, m}));
+            pYv.p[b] = r.U[b];
         }
         e.flush();
-    } else {
-        // Hermitian: subspace iteration with M itself (4q+1 applications: the spectrum of the corner
-        // itself decays half as fast as that of M = R^T Rt), then Rayleigh-Ritz
-        const int napp = (k == n) ? 0 : 4 * o.rsvd_niter;
-        for (int it = 0; it < napp; ++it) {
-            for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));
-            if (it & 1) qr(pZ, pNull, n);               // one orthogonalisation per two applications
-            else e.flush();
-            std::swap(pY, pZ);
-        }
-        // Z = M Q ; Tm = Q^H Z (k x k, column-major [t][s]) ; (Tm + mu) W = W (Lambda + mu)
-        for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));
-        e.flush();
-        for (int b = 0; b < nb; ++b)
-            e.contract(tnY(b, "si"), true, tnZ(b, "ti"), false, make_tn(R2[b], "ts", {k, k}));
-        e.flush();
-        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
-        { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, chi, e.cplx, 1, e.stream); }
-        for (int b = 0; b < nb; ++b)
-            e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
-        e.flush();
+        CTMB_CUDA(cudaMemsetAsync(dres, 0, sizeof(unsigned long long), e.stream));
+        { ProfScope ps(e, Engine::CAT_MISC); resid_launch(pMX, pYv, pS, nb, m, chi, o.svd_reltol, dres, e.cplx, e.stream); }
+        CTMB_CUDA(cudaMemcpyAsync(hres, dres, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
+        CTMB_CUDA(cudaStreamSynchronize(e.stream));
+        double res; memcpy(&res, hres, sizeof res);
+        if (res <= o.rsvd_tol) break;
+        todo = o.rsvd_niter << round;                     // q, 2q, 4q ... additional iterations
     }
     return r;
 }
@@ -501,8 +529,8 @@ int ctmb_destroy(ctmb_handle_t h) {
 void ctmb_default_options(ctmb_options* o) {
     if (!o) return;
     o->svd_reltol = 1.0e-8; o->eps_multiplet = 1.0e-8; o->multiplet_abstol = 1.0e-14;
-    o->rsvd_rank_factor = 2.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->reserved = 0;
-    o->seed = 0x5eed5eedull;
+    o->rsvd_rank_factor = 2.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->rsvd_max_rounds = 3;
+    o->seed = 0x5eed5eedull; o->rsvd_tol = 0.0;
 }
 
 int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops) {
@@ -819,7 +847,7 @@ int ctmb_move_c4v(ctmb_handle_t h, ctmb_dtype dt, const void* a, const int dims[
     CTMB_TRY
     begin_call(h, dt, ws, ws_bytes, stream);
     ctmb_options o = opts_or_default(opt);
-    if (!opt) o.eps_multiplet = 1.0e-12;   // truncated_eig_sym default (custom_eig.py:7-8)
+    if (!opt) { o.eps_multiplet = 1.0e-12; o.rsvd_tol = 1.0e-11; }   // truncated_eig_sym defaults (custom_eig.py:7-8)
     move_c4v_impl(h, a, dims, C, T, chi, o, C_out, T_out, D_out);
     return 0;
     CTMB_CATCH(-1)

@@ -26,7 +26,8 @@ def _options(ctm_args):
                 eps_multiplet=ctm_args.projector_eps_multiplet,
                 multiplet_abstol=ctm_args.projector_multiplet_abstol,
                 rsvd_niter=getattr(ctm_args, 'b200_rsvd_niter', None),
-                rsvd_rank_factor=getattr(ctm_args, 'b200_rsvd_rank_factor', None))
+                rsvd_rank_factor=getattr(ctm_args, 'b200_rsvd_rank_factor', None),
+                rsvd_tol=getattr(ctm_args, 'b200_rsvd_tol', None))
 
 
 def ctm_MOVE(direction, state, env, ctm_args=cfg.ctm_args, global_args=cfg.global_args,

@@ -24,7 +24,8 @@ def ctm_MOVE_sl(a, env, f_c2x2_decomp=None, ctm_args=cfg.ctm_args, global_args=c
         raise ValueError("libctmb implements ctm_absorb_normalization='inf' only")
     nC, nT, _ = eng.move_c4v(a, env.C[env.keyC], env.T[env.keyT], env.chi,
                              rsvd_niter=getattr(ctm_args, 'b200_rsvd_niter', None),
-                             rsvd_rank_factor=getattr(ctm_args, 'b200_rsvd_rank_factor', None))
+                             rsvd_rank_factor=getattr(ctm_args, 'b200_rsvd_rank_factor', None),
+                             rsvd_tol=getattr(ctm_args, 'b200_rsvd_tol_c4v', None))
     env.C[env.keyC] = nC
     env.T[env.keyT] = nT
 

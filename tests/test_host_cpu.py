@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from peps_torch_b200 import _lib
-    assert ctypes.sizeof(_lib.Options) == 56
+    assert ctypes.sizeof(_lib.Options) == 64
     assert ctypes.sizeof(_lib.Site) == 8 + 24 + 32 + 32
     o = _lib.default_options()
     assert (o.svd_reltol, o.eps_multiplet, o.multiplet_abstol) == (1e-8, 1e-8, 1e-14)
