@@ -198,12 +198,23 @@ def run_ours(args):
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if os.environ.get('CTMB_BENCH_SINGLE_DEVICE'):     # functional dry-run of the N>1 control flow on one GPU
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        backend = os.environ.get('CTMB_BENCH_BACKEND', 'nccl')
+        if backend == 'nccl':
+            dist.init_process_group('nccl', device_id=dev)
+        else:
+            dist.init_process_group(backend)
     eng = default_engine()
     kind, D, chi, dt, fam, desc = CONFIGS[args.config]
+    shard = world > 1 and args.parallel == 'shard' and kind != 'c4v'
+    sharded = None
+    if shard:
+        from peps_torch_b200.dist import ShardedCtm
+        sharded = ShardedCtm(eng)
     kind, sites_cpu, v2s, lX, lY, chi = make_state(args.config)
     cplx = dt == 'complex128'
     ctm_args = pcfg.CTMARGS()
@@ -228,7 +239,10 @@ def run_ours(args):
         p_phys = next(iter(sites_cpu.values())).shape[0]
 
         def one_step(state, e):
-            ctmrg.run(state, e, ctm_args=ctm_args)
+            if shard:
+                sharded.iteration(state, e, ctm_args.ctm_move_sequence)
+            else:
+                ctmrg.run(state, e, ctm_args=ctm_args)
         moves_per_step = 2 * (lX + lY)
     # a few iterations so that the timed environment is not the zero-padded initial one
     for _ in range(max(args.warmup, 3)):
@@ -259,6 +273,8 @@ def run_ours(args):
     def resident_step():
         if kind == 'c4v':
             ctmrg_c4v.ctm_MOVE_sl(st.site(), env, ctm_args=ctm_args)
+        elif shard:
+            sharded.iteration(st, env, ctm_args.ctm_move_sequence)
         else:
             for direction in ctm_args.ctm_move_sequence:
                 for _ in range(lX if direction in [(-1, 0), (1, 0)] else lY):
@@ -277,8 +293,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    # every rank runs its own replica of the workload (multi-GPU): aggregate
-    value = world * moves_per_step * args.steps / (ms * 1e-3)
+    # shard: ONE CTM run spread over the ranks; replicas: every rank runs its own CTM run
+    mult = 1 if (shard or world == 1) else world
+    value = mult * moves_per_step * args.steps / (ms * 1e-3)
 
     # ------------------------------------------------------------------ e2e (host buffers)
     if kind == 'c4v':
@@ -313,19 +330,20 @@ def run_ours(args):
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * moves_per_step * args.steps / (float(t.item()) * 1e-3)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    e2e_value = mult * moves_per_step * args.steps / (float(t.item()) * 1e-3)
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
+    # (all ranks take part: in shard mode a step contains collectives)
     eng.profile(True)
     eng.reset_counters()
     timed_region(resident_step, args.steps)
     prof = eng.profile_totals()
     eng.profile(False)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     fp64_peak = measure_fp64_peak(dev)
     peaks = {}
     try:
@@ -358,18 +376,18 @@ def run_ours(args):
     base = cpu_baseline(args.config) if world == 1 or True else None
     line = {'metric': 'CTM moves/sec', 'value': value, 'unit': 'ctm_MOVE/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c128' if cplx else 'f64', 'data': 'synthetic',
+            'scaling': 'strong' if shard else 'weak', 'vs_baseline': None, 'dtype': 'c128' if cplx else 'f64', 'data': 'synthetic',
             'config': {'workload': desc + f' ({"1 ctm_MOVE_sl" if kind == "c4v" else str(moves_per_step) + " ctm_MOVE"} per step)',
                        'family': fam, 'seed': 123, 'moves_per_step': moves_per_step, 'l2': 'flushed between timed steps (256 MiB write)',
-                       'parallelism': 'single GPU' if world == 1 else f'{world} independent replicas (one CTM run per GPU)',
+                       'parallelism': 'single GPU' if world == 1 else (f'per-site shard over {world} GPUs, NCCL all-gather of P/Pt and of the new C/T per move' if shard else f'{world} independent replicas (one CTM run per GPU)'),
                        'rsvd': {'rank_factor': eng.options.rsvd_rank_factor, 'niter': eng.options.rsvd_niter}},
             'e2e': {'value': e2e_value, 'unit': 'ctm_MOVE/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': base,
             'flops': {'reference_algorithm_per_move': F_move, 'executed_per_move': flops_exec / (moves_per_step * args.steps),
                       'move_level_frac_of_fp64_peak': F_move * value / world / (fp64_peak * 1e12)}}
-    print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        line['cpu_baseline']['note'] = 'measured on rank 0 host cores while the other ranks idle'
+    print(json.dumps(line))
 
 
 def main():
@@ -379,6 +397,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--parallel', default='shard', choices=['shard', 'replicas'],
+                    help='N>1: per-site shard of ONE CTM run with NCCL all-gathers (strong scaling, default) or one independent CTM run per GPU (weak scaling)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -1,0 +1,95 @@
+"""Per-site sharding of one CTM move over the GPUs of a node (one process per GPU).
+
+Inside ctm_MOVE all N projector pairs are computed from the same environment snapshot, then
+all N absorptions from that snapshot plus the projectors, and results are written only
+afterwards (ctm/generic/ctmrg.py:246-275,313-319).  Rank r therefore owns the site jobs
+r, r+W, r+2W, ...; the move has exactly two exchange steps:
+
+  1. all-gather of (P, Pt) of every job   -- the absorption at `coord` needs the projectors of
+     the neighbouring site coord+shift (ctmrg.py:326-334), which another rank may own;
+  2. all-gather of the new (nC1, nC2, nT) -- every rank keeps a full replica of the (small)
+     environment, as the next move reads all of it.
+
+Collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).
+The compute backend is anything with the two methods of CtmEngine used below, so the same
+code is exercised on CPU with the oracle as backend (tests/test_dist_cpu.py).
+"""
+import torch
+import torch.distributed as dist
+from .engine import OUT_KEYS, DIRECTIONS
+
+
+def partition_jobs(nsites, world):
+    """Job (site index) lists per rank: round-robin, ranks beyond nsites stay idle."""
+    return [list(range(r, nsites, world)) for r in range(world)]
+
+
+class ShardedCtm:
+    def __init__(self, backend, group=None):
+        self.backend = backend
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def _all_gather(self, flat, counts):
+        """all-gather of ragged per-rank 1-D tensors (padded to the maximum count)."""
+        m = max(counts)
+        buf = flat.new_zeros(m)
+        buf[:flat.numel()] = flat
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(out, buf, group=self.group)
+        return [o[:c] for o, c in zip(out, counts)]
+
+    def ctm_MOVE(self, direction, state, env, **opt):
+        """Same contract as ctm.generic.ctmrg.ctm_MOVE; every rank ends with the same env."""
+        if direction not in DIRECTIONS:
+            raise ValueError("Invalid direction: " + str(direction))
+        coords = list(state.sites.keys())
+        n = len(coords)
+        parts = partition_jobs(n, self.world)
+        mine = parts[self.rank]
+        n0, chi = self.backend.projector_shape(direction, state, env)
+        a0 = state.sites[coords[0]]
+        # 1) projectors of my jobs, then all-gather
+        if mine:
+            P, Pt = self.backend.move_generic_projectors(direction, state, env, mine, **opt)
+            flat = torch.cat([t.reshape(-1) for pair in zip(P, Pt) for t in pair])
+        else:
+            flat = a0.new_zeros(0)
+        per_job = 2 * n0 * chi
+        gathered = self._all_gather(flat, [len(p) * per_job for p in parts])
+        P_all, Pt_all = [None] * n, [None] * n
+        for r, jobs in enumerate(parts):
+            for i, j in enumerate(jobs):
+                blk = gathered[r][i * per_job:(i + 1) * per_job]
+                P_all[j] = blk[:n0 * chi].view(n0, chi)
+                Pt_all[j] = blk[n0 * chi:].view(n0, chi)
+        # 2) absorption of my jobs, then all-gather of the new tensors
+        res = self.backend.move_generic_absorb(direction, state, env, mine, P_all, Pt_all) if mine else []
+        flat = torch.cat([t.reshape(-1) for (_, c1, c2, t3) in res for t in (c1, c2, t3)]) if res else a0.new_zeros(0)
+        shapes = {j: self.backend._nT_shape(direction, state.sites[coords[j]], chi) for j in range(n)}
+        def job_len(j):
+            s = shapes[j]
+            return 2 * chi * chi + s[0] * s[1] * s[2]
+        gathered = self._all_gather(flat, [sum(job_len(j) for j in p) for p in parts])
+        kC1, kC2, kT = OUT_KEYS[direction]
+        v2s = state.vertexToSite
+        for r, jobs in enumerate(parts):
+            off = 0
+            for j in jobs:
+                c = coords[j]
+                dest = v2s((c[0] - direction[0], c[1] - direction[1]))
+                blk = gathered[r]
+                env.C[(dest, kC1)] = blk[off:off + chi * chi].view(chi, chi).clone(); off += chi * chi
+                env.C[(dest, kC2)] = blk[off:off + chi * chi].view(chi, chi).clone(); off += chi * chi
+                s = shapes[j]
+                ln = s[0] * s[1] * s[2]
+                env.T[(dest, kT)] = blk[off:off + ln].view(*s).clone(); off += ln
+
+    def iteration(self, state, env, move_sequence=((0, -1), (-1, 0), (0, 1), (1, 0)), **opt):
+        n = 0
+        for direction in move_sequence:
+            for _ in range(state.lX if direction in [(-1, 0), (1, 0)] else state.lY):
+                self.ctm_MOVE(direction, state, env, **opt)
+                n += 1
+        return n

@@ -269,6 +269,72 @@ class CtmEngine:
             env.C[(dest[i], kC2)] = nC2[i]
             env.T[(dest[i], kT)] = nT[i]
 
+    # ----------------------------------------------------------------------------------
+    # the two halves of a move, restricted to a subset of the site jobs (multi-GPU shard)
+    # ----------------------------------------------------------------------------------
+    def _sites_array(self, state, env, keep):
+        coords = list(state.sites.keys())
+        sites = (_lib.Site * len(coords))()
+        for i, c in enumerate(coords):
+            sites[i] = self._site(state.sites[c], [env.C[(c, k)] for k in C_KEYS], [env.T[(c, k)] for k in T_KEYS], keep)
+        return coords, sites
+
+    def projector_shape(self, direction, state, env):
+        """(n0, chi) of the projectors of `direction` (uniform bond dimensions)."""
+        a = next(iter(state.sites.values()))
+        D = a.shape[1:]
+        leg = {(0, -1): D[1], (-1, 0): D[0], (0, 1): D[3], (1, 0): D[2]}[direction]   # bond being truncated
+        return env.chi * leg * leg, env.chi
+
+    def move_generic_projectors(self, direction, state, env, jobs, **opt):
+        """Projector pairs (P, Pt), each n0 x chi, of the listed site jobs (ctm_get_projectors_4x4)."""
+        keep = []
+        coords, sites = self._sites_array(state, env, keep)
+        n, chi = len(coords), env.chi
+        corner, nb, dest, _ = self._move_tables(state, direction)
+        a0 = state.sites[coords[0]]
+        dt = _dt(a0)
+        n0, _ = self.projector_shape(direction, state, env)
+        P = [torch.empty((n0, chi), dtype=a0.dtype, device=self.device) for _ in jobs]
+        Pt = [torch.empty((n0, chi), dtype=a0.dtype, device=self.device) for _ in jobs]
+        o = self._opts(**opt)
+        d = DIRECTIONS[direction]
+        nbytes = lib.ctmb_move_generic_workspace(self._h, dt, d, n, chi, sites, corner, nb, C.byref(o))
+        ws = self._workspace(nbytes)
+        jl = (C.c_int * len(jobs))(*jobs)
+        pp = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in P])
+        ppt = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in Pt])
+        check(lib.ctmb_move_generic_projectors(self._h, dt, d, n, chi, sites, corner, len(jobs), jl, C.byref(o), pp, ppt,
+                                               _ptr(ws), ws.numel(), self._stream()))
+        return P, Pt
+
+    def move_generic_absorb(self, direction, state, env, jobs, P_all, Pt_all):
+        """Absorb + truncate + normalise the listed jobs given the projectors of ALL sites;
+        returns [(dest_coord, nC1, nC2, nT)] without touching env."""
+        keep = []
+        coords, sites = self._sites_array(state, env, keep)
+        n, chi = len(coords), env.chi
+        corner, nb, dest, _ = self._move_tables(state, direction)
+        a0 = state.sites[coords[0]]
+        dt = _dt(a0)
+        nC1 = [torch.empty((chi, chi), dtype=a0.dtype, device=self.device) for _ in jobs]
+        nC2 = [torch.empty((chi, chi), dtype=a0.dtype, device=self.device) for _ in jobs]
+        nT = [torch.empty(self._nT_shape(direction, state.sites[coords[j]], chi), dtype=a0.dtype, device=self.device)
+              for j in jobs]
+        d = DIRECTIONS[direction]
+        o = self._opts()
+        nbytes = lib.ctmb_move_generic_workspace(self._h, dt, d, n, chi, sites, corner, nb, C.byref(o))
+        ws = self._workspace(nbytes)
+        jl = (C.c_int * len(jobs))(*jobs)
+        pa = (C.c_void_p * n)(*[t.data_ptr() for t in P_all])
+        pta = (C.c_void_p * n)(*[t.data_ptr() for t in Pt_all])
+        p1 = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in nC1])
+        p2 = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in nC2])
+        p3 = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in nT])
+        check(lib.ctmb_move_generic_absorb(self._h, dt, d, n, chi, sites, nb, len(jobs), jl, pa, pta, p1, p2, p3,
+                                           _ptr(ws), ws.numel(), self._stream()))
+        return [(dest[j], nC1[i], nC2[i], nT[i]) for i, j in enumerate(jobs)]
+
     def move_c4v(self, a, C_, T, chi, **opt):
         """One ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463) -> (C', T', D)."""
         a, C_, T = self._prep(a, self.device), self._prep(C_, self.device), self._prep(T, self.device)

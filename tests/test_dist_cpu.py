@@ -1,0 +1,89 @@
+"""CPU, world_size 2, gloo: the per-site sharding logic of peps_torch_b200.dist (job partition,
+the two all-gathers, environment bookkeeping) with the oracle as compute backend."""
+import os
+import sys
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import ctm_oracle as orc
+import helpers as H
+
+
+class OracleBackend:
+    """CPU stand-in for CtmEngine exposing the three methods ShardedCtm uses."""
+
+    def projector_shape(self, direction, state, env):
+        a = next(iter(state.sites.values()))
+        D = a.shape[1:]
+        leg = {(0, -1): D[1], (-1, 0): D[0], (0, 1): D[3], (1, 0): D[2]}[direction]
+        return env.chi * leg * leg, env.chi
+
+    def _nT_shape(self, direction, a, chi):
+        D = a.shape[1:]
+        return {(0, -1): (chi, D[2] ** 2, chi), (-1, 0): (chi, chi, D[3] ** 2),
+                (0, 1): (D[0] ** 2, chi, chi), (1, 0): (chi, D[1] ** 2, chi)}[direction]
+
+    def move_generic_projectors(self, direction, state, env, jobs, **opt):
+        coords = list(state.sites.keys())
+        P, Pt = [], []
+        for j in jobs:
+            R, Rt = orc.halves(direction, coords[j], state.sites, state.vertexToSite, env.C, env.T)
+            p, pt = orc.projectors_from_matrices(R, Rt, env.chi, orc.OracleArgs())
+            P.append(p.contiguous()); Pt.append(pt.contiguous())
+        return P, Pt
+
+    def move_generic_absorb(self, direction, state, env, jobs, P_all, Pt_all):
+        coords = list(state.sites.keys())
+        P = {coords[i]: p for i, p in enumerate(P_all)}
+        Pt = {coords[i]: p for i, p in enumerate(Pt_all)}
+        out = []
+        for j in jobs:
+            c = coords[j]
+            nC1, nC2, nT = orc.absorb(direction, c, state.sites, state.vertexToSite, env.C, env.T, P, Pt, orc.OracleArgs())
+            dest = state.vertexToSite((c[0] - direction[0], c[1] - direction[1]))
+            out.append((dest, nC1.contiguous(), nC2.contiguous(), nT.contiguous()))
+        return out
+
+
+def _worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from peps_torch_b200.dist import ShardedCtm
+        torch.set_num_threads(2)
+        z, meta = H.load_golden('generic_4site_D2_chi8_B')
+        sites = H.golden_sites(z)
+        C, T = H.golden_env(z, 'mid_')
+        st = H.State(sites, orc.v2s_4site, 2, 2)
+        env = H.Env(meta['chi'], C, T)
+        sh = ShardedCtm(OracleBackend())
+        moves = sh.iteration(st, env)
+        # single-process oracle on the same snapshot
+        C2, T2 = H.golden_env(z, 'mid_')
+        orc.ctm_iteration(sites, orc.v2s_4site, 2, 2, C2, T2, meta['chi'])
+        worst = max([float((env.C[k] - C2[k]).abs().max()) for k in C2] + [float((env.T[k] - T2[k]).abs().max()) for k in T2])
+        # every rank must hold the same replica bit for bit
+        flat = torch.cat([env.C[k].reshape(-1) for k in sorted(env.C)] + [env.T[k].reshape(-1) for k in sorted(env.T)])
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        same = all(torch.equal(other[0], o) for o in other)
+        ret[rank] = (moves, worst, same)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_move_world2_gloo():
+    from peps_torch_b200.dist import partition_jobs
+    assert partition_jobs(4, 2) == [[0, 2], [1, 3]]
+    assert partition_jobs(4, 8)[5] == [] and partition_jobs(1, 2) == [[0], []]
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        moves, worst, same = ret[r]
+        assert moves == 8
+        assert worst < 1e-12, worst          # same arithmetic as the single-process oracle, job order aside
+        assert same
