@@ -40,7 +40,7 @@ struct TcBatchEntry {
     const void* A; const void* B; void* C;
     unsigned long long* amax;   // optional: atomicMax of |C| (bits of a non-negative double)
     int tab;                    // which table set
-    int pad;
+    int flags;                  // bit0 conjA, bit1 conjB, bit2 A loader k-fast, bit3 B loader k-fast
 };
 
 constexpr int TC_MAX_BATCH = 32;
@@ -49,7 +49,7 @@ constexpr int TC_MAX_TABS = 8;
 struct TcParams {
     int M, N, K;
     int nbatch;
-    int flags;                  // bit0 conjA, bit1 conjB, bit2 A loader k-fast, bit3 B loader k-fast
+    int pad;
     double alpha;
     TcTables tab[TC_MAX_TABS];
     TcBatchEntry batch[TC_MAX_BATCH];

@@ -228,7 +228,7 @@ void Engine::contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn
     const Plan& pl = get_plan(A, conjA && cplx, B, conjB && cplx, C);
     flops += 2.0 * pl.M * (double)pl.N * pl.K * (cplx ? 4.0 : 1.0);
     if (pend_active_) {
-        bool ok = pend_.M == pl.M && pend_.N == pl.N && pend_.K == pl.K && pend_.flags == pl.flags &&
+        bool ok = pend_.M == pl.M && pend_.N == pl.N && pend_.K == pl.K &&
                   pend_.alpha == alpha && pend_.nbatch < TC_MAX_BATCH;
         if (ok) {
             bool have = std::find(pend_plans_.begin(), pend_plans_.end(), &pl) != pend_plans_.end();
@@ -238,7 +238,7 @@ void Engine::contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn
     }
     if (!pend_active_) {
         pend_ = TcParams{};
-        pend_.M = pl.M; pend_.N = pl.N; pend_.K = pl.K; pend_.flags = pl.flags; pend_.alpha = alpha;
+        pend_.M = pl.M; pend_.N = pl.N; pend_.K = pl.K; pend_.alpha = alpha;
         pend_.nbatch = 0;
         pend_plans_.clear();
         pend_active_ = true;
@@ -247,7 +247,7 @@ void Engine::contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn
     for (size_t i = 0; i < pend_plans_.size(); ++i) if (pend_plans_[i] == &pl) ti = (int)i;
     if (ti < 0) { ti = (int)pend_plans_.size(); pend_plans_.push_back(&pl); pend_.tab[ti] = pl.tab; }
     TcBatchEntry& e = pend_.batch[pend_.nbatch++];
-    e.A = A.ptr; e.B = B.ptr; e.C = C.ptr; e.amax = amax; e.tab = ti; e.pad = 0;
+    e.A = A.ptr; e.B = B.ptr; e.C = C.ptr; e.amax = amax; e.tab = ti; e.flags = pl.flags;
 }
 
 void Engine::chain_multi(std::vector<ChainJob>& jobs, size_t temp_budget) {

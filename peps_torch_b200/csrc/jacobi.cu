@@ -17,6 +17,8 @@
 namespace ctmb {
 
 constexpr int JAC_THREADS = 1024;
+// diagnostics: total sweeps executed / matrices processed since the last read (tools/ only)
+__device__ unsigned long long g_jac_stats[2];
 
 template <bool CPLX>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch Sb, int k,
@@ -166,8 +168,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBat
         __syncthreads();
         // cyclic Jacobi converges quadratically: if the largest cosine met in this sweep was below
         // 1e-8 the columns are now orthogonal to ~1e-16 and the verification sweep can be skipped
-        if (!any || !big) break;
+        if (!any || !big) { if (tid == 0) atomicAdd(&g_jac_stats[0], (unsigned long long)(sweep + 1)); break; }
+        if (sweep + 1 == max_sweeps && tid == 0) atomicAdd(&g_jac_stats[0], (unsigned long long)max_sweeps);
     }
+    if (tid == 0) atomicAdd(&g_jac_stats[1], 1ull);
     // column norms; the columns are written back NORMALISED (left singular vectors / eigenvectors)
     for (int c = grp; c < k; c += ngroups) {
         double a = 0.0;
@@ -182,6 +186,12 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBat
         __syncthreads();
         for (int e = tid; e < k * k; e += JAC_THREADS) { Gg[e] = G[e]; if (accw) Wg[e] = W[e]; }
     }
+}
+
+void jacobi_stats(unsigned long long out[2]) {
+    cudaMemcpyFromSymbol(out, g_jac_stats, sizeof(unsigned long long) * 2);
+    unsigned long long z[2] = {0, 0};
+    cudaMemcpyToSymbol(g_jac_stats, z, sizeof z);
 }
 
 static size_t g_jac_smem_limit = 0;

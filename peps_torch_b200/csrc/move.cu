@@ -11,6 +11,7 @@
 
 namespace ctmb {
 const std::string& get_error();
+void jacobi_stats(unsigned long long out[2]);
 
 struct Handle {
     Engine eng;
@@ -503,6 +504,8 @@ static void begin_dry(ctmb_handle_t h, ctmb_dtype dt) {
 extern "C" {
 
 int ctmb_version(void) { return 100; }
+// diagnostics for tools/ (not part of include/ctmb.h): Jacobi sweeps and matrices since the last call
+void ctmb_debug_jacobi_stats(unsigned long long* out) { ctmb::jacobi_stats(out); }
 const char* ctmb_last_error(void) { return get_error().c_str(); }
 
 int ctmb_create(ctmb_handle_t* h, int device) {

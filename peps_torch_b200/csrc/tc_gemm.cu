@@ -55,11 +55,15 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TcBatchEntry be = p.batch[blockIdx.z];
     const TcTables tb = p.tab[be.tab];
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // tiles are linearised on grid.x (n-tiles fastest): grid.y is limited to 65535, the row count of a
+    // corner intermediate at D=8, chi=256 (4.2M) is not
+    const int ntn = (p.N + BN - 1) / BN;
+    const int m0 = (blockIdx.x / ntn) * BM, n0 = (blockIdx.x % ntn) * BN;
     const T* __restrict__ A = reinterpret_cast<const T*>(be.A);
     const T* __restrict__ B = reinterpret_cast<const T*>(be.B);
     const int M = p.M, N = p.N, K = p.K;
-    const bool a_kfast = (p.flags & TC_A_KFAST) != 0, b_kfast = (p.flags & TC_B_KFAST) != 0;
+    const int flags = be.flags;
+    const bool a_kfast = (flags & TC_A_KFAST) != 0, b_kfast = (flags & TC_B_KFAST) != 0;
 
     // loader maps: element e = tid + i*256 of a BMxBK (BNxBK) tile
     int a_row[A_PER], a_col[A_PER], a_off[A_PER];
@@ -120,8 +124,8 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
         if (s < ktiles) load_tile(s, s);
         cp_async_commit();
     }
-    const double sa = (p.flags & TC_CONJ_A) ? -1.0 : 1.0;
-    const double sb = (p.flags & TC_CONJ_B) ? -1.0 : 1.0;
+    const double sa = (flags & TC_CONJ_A) ? -1.0 : 1.0;
+    const double sb = (flags & TC_CONJ_B) ? -1.0 : 1.0;
 
     for (int kt = 0; kt < ktiles; ++kt) {
         cp_async_wait<STAGES - 2>();
@@ -219,7 +223,9 @@ static void tc_run(const TcParams& p, cudaStream_t stream) {
         CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.nbatch);
+    const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
+    CTMB_CHECK(tiles < (1ll << 31), "too many tiles for one launch");
+    dim3 grid((unsigned)tiles, 1, p.nbatch);
     kern<<<grid, 256, smem, stream>>>(p);
     CTMB_CUDA(cudaGetLastError());
 }

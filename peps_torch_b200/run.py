@@ -1,0 +1,89 @@
+"""Launcher that runs an UNMODIFIED peps-torch script with the CTM move replaced by libctmb:
+
+    python -m peps_torch_b200.run <peps-torch>/examples/j1j2/ctmrg_j1j2.py --tiling 4SITE --bond_dim 3 --chi 48 \
+           --GLOBALARGS_device cuda:0
+
+The reference's move modules look ``ctm_MOVE`` up as a module global at call time
+(ctm/generic/ctmrg.py:68, ctm/one_site_c4v/ctmrg_c4v.py:89) and the scripts hold the module object
+(``from ctm.generic import ctmrg``), so rebinding the attribute is seen everywhere.
+Everything else of the reference (states, models, RDMs, config, argparse) is used as it is.
+"""
+import importlib
+import os
+import runpy
+import sys
+
+
+def find_reference_root(script):
+    """The scripts' own ``context.py`` prepends <script dir>/../.. (examples/j1j2/context.py:1-3)."""
+    root = os.environ.get('PEPS_TORCH_ROOT')
+    if root:
+        return os.path.abspath(root)
+    return os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(script)), '..', '..'))
+
+
+def enable(engine_factory=None):
+    """Rebind the hot-path functions of the (already importable) reference to libctmb.
+    ``engine_factory`` is for host-logic tests only; the default is the CUDA engine (no fallback)."""
+    from . import ctm as _pkg                                   # noqa: F401  (package import check)
+    from .ctm.generic import ctmrg as ours
+    from .ctm.one_site_c4v import ctmrg_c4v as ours_c4v
+    if engine_factory is not None:
+        ours._engine = engine_factory
+        ours_c4v._engine = engine_factory
+    ref = importlib.import_module('ctm.generic.ctmrg')
+    ref_c4v = importlib.import_module('ctm.one_site_c4v.ctmrg_c4v')
+
+    def ctm_MOVE(direction, state, env, ctm_args=ref.cfg.ctm_args, global_args=ref.cfg.global_args,
+                 verbosity=0, diagnostics=None):
+        return ours.ctm_MOVE(direction, state, env, ctm_args=ctm_args, global_args=global_args,
+                             verbosity=verbosity, diagnostics=diagnostics)
+
+    def ctm_MOVE_sl(a, env, f_c2x2_decomp=None, ctm_args=ref_c4v.cfg.ctm_args, global_args=ref_c4v.cfg.global_args,
+                    past_steps_data=None):
+        return ours_c4v.ctm_MOVE_sl(a, env, f_c2x2_decomp, ctm_args=ctm_args, global_args=global_args,
+                                    past_steps_data=past_steps_data)
+
+    ref.ctm_MOVE = ctm_MOVE
+    ref_c4v.ctm_MOVE_sl = ctm_MOVE_sl
+    # Without opt_einsum the reference's generic rdm2x2 dispatch is broken (ctm/generic/rdm.py:1354-1362
+    # passes force_cpu= to rdm2x2_legacy, which does not take it) and the 'sl' one/two-site RDMs need oe:
+    # route them to the reference's own pure-torch implementations.
+    try:
+        import opt_einsum                                       # noqa: F401
+    except ImportError:
+        rdm = importlib.import_module('ctm.generic.rdm')
+
+        def rdm2x2(coord, state, env, sym_pos_def=False, **kw):
+            return rdm.rdm2x2_legacy(coord, state, env, sym_pos_def=sym_pos_def,
+                                     **{k: v for k, v in kw.items() if k in ('verbosity',)})
+        rdm.rdm2x2 = rdm2x2
+        def _dl(f):
+            def wrapped(*a, mode='sl', unroll=False, checkpoint_unrolled=False, checkpoint_on_device=False, **kw):
+                return f(*a, **kw)
+            return wrapped
+        for name in ('rdm1x1', 'rdm2x1', 'rdm1x2'):
+            if hasattr(rdm, name + '_dl'):
+                setattr(rdm, name, _dl(getattr(rdm, name + '_dl')))
+    return ref, ref_c4v
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        print(__doc__)
+        return 2
+    script = argv[0]
+    root = find_reference_root(script)
+    for p in (os.path.dirname(os.path.abspath(script)), root):
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
+    enable()
+    sys.argv = [script] + argv[1:]
+    runpy.run_path(script, run_name='__main__')
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
