@@ -55,7 +55,7 @@ struct TcParams {
     TcBatchEntry batch[TC_MAX_BATCH];
 };
 
-enum { TC_CONJ_A = 1, TC_CONJ_B = 2, TC_A_KFAST = 4, TC_B_KFAST = 8 };
+enum { TC_CONJ_A = 1, TC_CONJ_B = 2, TC_A_KFAST = 4, TC_B_KFAST = 8, TC_ACCUM = 16 /* C += alpha A B */ };
 
 // launches one batched contraction; cplx=false: double, cplx=true: double2 (re,im)
 void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream);
@@ -81,6 +81,15 @@ void qr_wy_factor_launch(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch
 void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V, const PtrBatch& X, int nb, int k,
                       int ldv, bool cplx, cudaStream_t stream);
 void add_identity_launch(const PtrBatch& Q, int nb, int k, int ld, bool cplx, cudaStream_t stream);
+// blocked factorisation of sketches too large for one cluster (see qr.cu): panel width, panel factorisation in
+// WY form, extraction of the rows of R belonging to a panel, Q <- E.  wy_tsolve_launch with ldv <= 0 returns T
+// itself (X = T, stored [c][s]) instead of T V1^H.
+int qr_panel_width(int rows, int cols, bool cplx);
+void qr_panel_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& Tau, int nb, int rows, int b, int ld,
+                     bool cplx, cudaStream_t stream);
+void qr_copy_r_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& R, int nb, int k, int j0, int b, int ld,
+                      bool cplx, cudaStream_t stream);
+void set_identity_launch(const PtrBatch& Q, int nb, int rows, int k, bool cplx, cudaStream_t stream);
 
 // one-sided Jacobi SVD of k x k column-major G (ld=k): on exit G = Uhat*Sigma (columns
 // orthogonal), W accumulates the right rotations (G_in * W = G_out), sig[k] the column norms.
@@ -119,5 +128,18 @@ void c4v_sym_launch(const void* tin, void* tout, int chi, int d, unsigned long l
 void c4v_diag_launch(const double* D, void* cout, int chi, bool cplx, cudaStream_t stream);
 
 void fill_gaussian_launch(double* out, long long count, unsigned long long seed, cudaStream_t stream);
+
+// fused double-layer absorption of the enlarged corner (dl_fused.cu)
+struct DlParams {
+    const double* X;            // [npairs][(K1,K2)][(k1,k2)]: C.T1.T2 per pair of environment indices, bra-major
+    const double* a;            // on-site tensor a[s,u,l,d,r]
+    double* out;                // corner matrix
+    int npairs, n2;             // pair = i1 * n2 + i2
+    long long st1, st2;         // element strides of the two environment indices in `out`
+    int as_s, as_k1, as_k2, as_o1, as_o2;   // element strides of a for (s, contracted legs, open legs)
+    int ro[64], co[64];         // offsets of the ket (o1,o2) and bra (O1,O2) open pairs in `out`
+};
+bool dl_corner_supported(int dk1, int dk2, int do1, int do2, int pdim, bool cplx);
+void dl_corner_launch(const DlParams& p, int dk, int dopen, int pdim, cudaStream_t stream);
 
 }  // namespace ctmb

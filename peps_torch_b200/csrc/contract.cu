@@ -22,6 +22,14 @@ Tn make_tn(void* ptr, const char* idx, std::initializer_list<int64_t> dims) {
     return make_tn(ptr, std::string(idx), std::vector<int64_t>(dims));
 }
 
+Tn make_strided(void* ptr, const char* idx, std::initializer_list<int64_t> dims, std::initializer_list<int64_t> strides) {
+    Tn t = make_tn(ptr, std::string(idx), std::vector<int64_t>(dims));
+    CTMB_CHECK(strides.size() == dims.size(), "bad strides");
+    int i = 0;
+    for (auto s : strides) t.str[i++] = s;
+    return t;
+}
+
 Tn split_mode(const Tn& t, char c, char c1, char c2, int64_t d1, int64_t d2) {
     int p = t.find(c);
     CTMB_CHECK(p >= 0, "split_mode: label not found");
@@ -223,7 +231,7 @@ void Engine::flush() {
 }
 
 void Engine::contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C,
-                      unsigned long long* amax, double alpha) {
+                      unsigned long long* amax, double alpha, bool accumulate) {
     if (ws.dry()) return;
     const Plan& pl = get_plan(A, conjA && cplx, B, conjB && cplx, C);
     flops += 2.0 * pl.M * (double)pl.N * pl.K * (cplx ? 4.0 : 1.0);
@@ -247,7 +255,7 @@ void Engine::contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn
     for (size_t i = 0; i < pend_plans_.size(); ++i) if (pend_plans_[i] == &pl) ti = (int)i;
     if (ti < 0) { ti = (int)pend_plans_.size(); pend_plans_.push_back(&pl); pend_.tab[ti] = pl.tab; }
     TcBatchEntry& e = pend_.batch[pend_.nbatch++];
-    e.A = A.ptr; e.B = B.ptr; e.C = C.ptr; e.amax = amax; e.tab = ti; e.flags = pl.flags;
+    e.A = A.ptr; e.B = B.ptr; e.C = C.ptr; e.amax = amax; e.tab = ti; e.flags = pl.flags | (accumulate ? TC_ACCUM : 0);
 }
 
 void Engine::chain_multi(std::vector<ChainJob>& jobs, size_t temp_budget) {

@@ -21,6 +21,8 @@ struct Tn {
 // contiguous row-major view with the given labels
 Tn make_tn(void* ptr, const char* idx, std::initializer_list<int64_t> dims);
 Tn make_tn(void* ptr, const std::string& idx, const std::vector<int64_t>& dims);
+// view with explicit element strides
+Tn make_strided(void* ptr, const char* idx, std::initializer_list<int64_t> dims, std::initializer_list<int64_t> strides);
 // split mode `c` (extent d1*d2) into two modes c1 (slow, extent d1) and c2 (fast, extent d2)
 Tn split_mode(const Tn& t, char c, char c1, char c2, int64_t d1, int64_t d2);
 // relabel / permute (no data movement)
@@ -78,7 +80,7 @@ public:
     // C = A * B over shared labels not in C; C's labels/strides define the output layout.
     // Enqueued into the pending batch; flushed when incompatible or on flush().
     void contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C,
-                  unsigned long long* amax = nullptr, double alpha = 1.0);
+                  unsigned long long* amax = nullptr, double alpha = 1.0, bool accumulate = false);
     // allocate a contiguous workspace tensor with the given labels
     Tn temp(const std::string& idx, const std::vector<int64_t>& dims, bool back = false);
     void flush();

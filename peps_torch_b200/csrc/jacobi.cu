@@ -20,23 +20,28 @@ constexpr int JAC_THREADS = 1024;
 // diagnostics: total sweeps executed / matrices processed since the last read (tools/ only)
 __device__ unsigned long long g_jac_stats[2];
 
-template <bool CPLX>
-__global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch Sb, int k,
-                                                              int gs, int use_smem, int max_sweeps, int shift,
-                                                              int transpose_in) {
+// Template parameters: SMEM = matrix (and W) resident in shared memory (compile-time, so that the column
+// accesses are LDS/STS and not generic loads); GS = lanes per pair; THREADS = block size.  The first version
+// ran 1024 threads (64 registers per thread): the register-cached columns spilled to local memory and 40 % of
+// the stall samples sat on STL (profiles/r1_c2_qr_jacobi.md).  Now: real 512 threads x GS 8 (16 rows per lane,
+// four pairs share the scalar rotation arithmetic of one warp instruction), complex 512 x GS 16.
+template <bool CPLX, bool SMEM, int GS, int THREADS>
+__global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch Sb, int k,
+                                                          int max_sweeps, int shift, int transpose_in) {
     using S = Sc<CPLX>;
     using T = typename S::T;
+    constexpr int JAC_THREADS = THREADS;
+    constexpr int gs = GS;
+    constexpr bool use_smem = SMEM;
     extern __shared__ __align__(16) unsigned char jac_smem[];
     T* Gg = reinterpret_cast<T*>(Gb.p[blockIdx.x]);
     T* Wg = reinterpret_cast<T*>(Wb.p[blockIdx.x]);      // nullptr: right rotations are not accumulated
     double* sig = reinterpret_cast<double*>(Sb.p[blockIdx.x]);
     const int tid = threadIdx.x;
     const bool accw = Wg != nullptr;
-    T* G = Gg;
-    T* W = Wg;
+    T* G = use_smem ? reinterpret_cast<T*>(jac_smem) : Gg;
+    T* W = use_smem ? reinterpret_cast<T*>(jac_smem) + (size_t)k * k : Wg;
     if (use_smem) {
-        G = reinterpret_cast<T*>(jac_smem);
-        W = G + (size_t)k * k;
         if (transpose_in) for (int e = tid; e < k * k; e += JAC_THREADS) G[e] = S::conj(Gg[(size_t)(e % k) * k + e / k]);
         else for (int e = tid; e < k * k; e += JAC_THREADS) G[e] = Gg[e];
     } else if (transpose_in) {
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBat
         for (int e = tid; e < k; e += JAC_THREADS) G[(size_t)e * k + e] = S::add(G[(size_t)e * k + e], S::make(mu, 0.0));
         __syncthreads();
     }
-    constexpr int NR = 8;                 // register-cached rows per lane (k <= NR*gs)
+    constexpr int NR = 128 / GS;          // register-cached rows per lane (k <= NR*gs = 128)
     const bool cached = k <= NR * gs;
 
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
@@ -188,6 +193,160 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_kernel(PtrBatch Gb, PtrBat
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Multi-CTA variant for matrices that do not fit the shared memory of one SM (k = 192 complex at
+// D=4 chi=96, k = 512 at D=8 chi=256): G and W stay in global memory (L2-resident), the pairs of a
+// round are dealt to the warps of `cpm` CTAs per matrix, and the rounds are separated by a
+// per-matrix barrier in global memory (all CTAs are co-resident: cooperative launch).  Loads
+// bypass L1 (ld.global.cg): the columns are rewritten by other SMs between rounds.
+// ---------------------------------------------------------------------------------------------
+constexpr int JC_THREADS = 256;
+__device__ unsigned int g_jc_bar[TC_MAX_BATCH];
+__device__ int g_jc_flag[TC_MAX_BATCH][3][2];
+__device__ double g_jc_mu[TC_MAX_BATCH];
+
+__device__ __forceinline__ double ldcg_t(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ double2 ldcg_t(const double2* p) { return __ldcg(p); }
+
+// prologue (one CTA per matrix): optional in-place conjugate transpose, optional spectral shift, W <- I,
+// barrier / flag reset
+template <bool CPLX>
+__global__ void __launch_bounds__(1024) jacobi_prep_kernel(PtrBatch Gb, PtrBatch Wb, int k, int shift, int transpose_in) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    T* G = reinterpret_cast<T*>(Gb.p[blockIdx.x]);
+    T* W = reinterpret_cast<T*>(Wb.p[blockIdx.x]);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) {
+        g_jc_bar[blockIdx.x] = 0u;
+        for (int i = 0; i < 3; ++i) g_jc_flag[blockIdx.x][i][0] = g_jc_flag[blockIdx.x][i][1] = 0;
+        g_jc_mu[blockIdx.x] = 0.0;
+    }
+    if (transpose_in) {
+        for (int e = tid; e < k * k; e += nt) {
+            const int c = e / k, r = e % k;
+            if (r > c) { T x = G[e], y = G[(size_t)r * k + c]; G[e] = S::conj(y); G[(size_t)r * k + c] = S::conj(x); }
+            else if (r == c) G[e] = S::conj(G[e]);
+        }
+        __syncthreads();
+    }
+    if (W != nullptr) for (int e = tid; e < k * k; e += nt) W[e] = (e / k == e % k) ? S::one() : S::zero();
+    if (shift) {
+        __shared__ double redm[32];
+        double a = 0.0;
+        for (int e = tid; e < k * k; e += nt) a += S::abs2(G[e]);
+        a = warp_sum(a);
+        if ((tid & 31) == 0) redm[tid >> 5] = a;
+        __syncthreads();
+        a = 0.0;
+        for (int w = 0; w < nt / 32; ++w) a += redm[w];
+        const double mu = sqrt(a);
+        for (int e = tid; e < k; e += nt) G[(size_t)e * k + e] = S::add(G[(size_t)e * k + e], S::make(mu, 0.0));
+        if (tid == 0) g_jc_mu[blockIdx.x] = mu;
+    }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch Sb, int k, int cpm,
+                                                                   int max_sweeps) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const int mat = blockIdx.x / cpm, cta = blockIdx.x % cpm;
+    T* G = reinterpret_cast<T*>(Gb.p[mat]);
+    T* W = reinterpret_cast<T*>(Wb.p[mat]);
+    double* sig = reinterpret_cast<double*>(Sb.p[mat]);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = JC_THREADS / 32;
+    const int gw = cta * NWARP + warp, nw = cpm * NWARP;       // this warp among the warps of the matrix
+    const bool accw = W != nullptr;
+    const int kk = (k + 1) & ~1, npairs = kk / 2;
+    const double tol = 2.2e-16 * sqrt((double)k);
+    const double tol2 = tol * tol;
+    unsigned int epoch = 0;
+    volatile unsigned int* bar = &g_jc_bar[mat];
+    auto mat_barrier = [&]() {
+        __syncthreads();
+        ++epoch;
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(const_cast<unsigned int*>(bar), 1u);
+            const unsigned int target = epoch * (unsigned int)cpm;
+            while (*bar < target) { }
+            __threadfence();
+        }
+        __syncthreads();
+    };
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        int* flag = g_jc_flag[mat][sweep % 3];
+        if (cta == 0 && tid == 0) { int* nxt = g_jc_flag[mat][(sweep + 1) % 3]; nxt[0] = 0; nxt[1] = 0; }
+        int rot = 0, big = 0;
+        for (int round = 0; round < kk - 1; ++round) {
+            for (int pi = gw; pi < npairs; pi += nw) {
+                int p, q;
+                if (pi == 0) { p = kk - 1; q = round; }
+                else { p = (round + pi) % (kk - 1); q = (round - pi + (kk - 1)) % (kk - 1); }
+                if (p >= k || q >= k) continue;
+                if (p > q) { int t = p; p = q; q = t; }
+                T* gp = G + (size_t)p * k;
+                T* gq = G + (size_t)q * k;
+                double a = 0.0, b = 0.0;
+                T g = S::zero();
+                for (int r = lane; r < k; r += 32) {
+                    const T x = ldcg_t(gp + r), y = ldcg_t(gq + r);
+                    a += S::abs2(x); b += S::abs2(y);
+                    g = S::fma(S::conj(x), y, g);
+                }
+                a = warp_sum(a); b = warp_sum(b); g = warp_sum_t<CPLX>(g);
+                const double ag2 = S::abs2(g);
+                if (ag2 > tol2 * a * b && ag2 > 0.0) {
+                    rot = 1; if (ag2 > 1.0e-16 * a * b) big = 1;
+                    const double d = b - a;
+                    const double r = rsqrt(d * d + 4.0 * ag2);
+                    const double c2 = 0.5 + 0.5 * fabs(d) * r;
+                    const double rc = rsqrt(c2);
+                    const double c = c2 * rc;
+                    const T al = S::scale(S::conj(g), copysign(r * rc, d));
+                    const T cal = S::conj(al);
+                    for (int rr = lane; rr < k; rr += 32) {
+                        const T x = ldcg_t(gp + rr), y = ldcg_t(gq + rr);
+                        gp[rr] = S::sub(S::scale(x, c), S::mul(al, y));
+                        gq[rr] = S::add(S::mul(cal, x), S::scale(y, c));
+                    }
+                    if (accw) {
+                        T* wp = W + (size_t)p * k;
+                        T* wq = W + (size_t)q * k;
+                        for (int rr = lane; rr < k; rr += 32) {
+                            const T u = ldcg_t(wp + rr), v = ldcg_t(wq + rr);
+                            wp[rr] = S::sub(S::scale(u, c), S::mul(al, v));
+                            wq[rr] = S::add(S::mul(cal, u), S::scale(v, c));
+                        }
+                    }
+                }
+            }
+            mat_barrier();
+        }
+        if (lane == 0 && rot) { atomicOr(&flag[0], 1); if (big) atomicOr(&flag[1], 1); }
+        mat_barrier();
+        const int any = *(volatile int*)&flag[0], anybig = *(volatile int*)&flag[1];
+        if (!any || !anybig || sweep + 1 == max_sweeps) {
+            if (cta == 0 && tid == 0) { atomicAdd(&g_jac_stats[0], (unsigned long long)(sweep + 1)); atomicAdd(&g_jac_stats[1], 1ull); }
+            break;
+        }
+    }
+    // column norms; the columns are written back NORMALISED
+    const double mu = g_jc_mu[mat];
+    for (int c = gw; c < k; c += nw) {
+        double a = 0.0;
+        for (int r = lane; r < k; r += 32) a += S::abs2(ldcg_t(G + (size_t)c * k + r));
+        a = warp_sum(a);
+        const double nrm = sqrt(a);
+        if (lane == 0) sig[c] = nrm - mu;
+        const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        for (int r = lane; r < k; r += 32) G[(size_t)c * k + r] = S::scale(ldcg_t(G + (size_t)c * k + r), inv);
+    }
+}
+
 void jacobi_stats(unsigned long long out[2]) {
     cudaMemcpyFromSymbol(out, g_jac_stats, sizeof(unsigned long long) * 2);
     unsigned long long z[2] = {0, 0};
@@ -212,19 +371,37 @@ void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, in
     const size_t need = (accw ? 2 : 1) * (size_t)k * k * (cplx ? 16 : 8);
     const int use_smem = need <= jacobi_smem_limit();
     const size_t smem = use_smem ? need : 0;
-    const int npairs = (k + 1) / 2;
-    int gs = 32;
-    while (gs > 8 && npairs * gs > JAC_THREADS) gs >>= 1;
-    if (cplx) {
-        auto kern = jacobi_kernel<true>;
-        static size_t set = 0;
-        if (smem > set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jacobi_smem_limit())); set = jacobi_smem_limit(); }
-        kern<<<nb, JAC_THREADS, smem, stream>>>(G, W, sig, k, gs, use_smem, max_sweeps, shift, transpose_in);
+    static int coop_mode = -1;
+    if (coop_mode < 0) { const char* ev = getenv("CTMB_JACOBI_COOP"); coop_mode = ev ? atoi(ev) : 1; }
+    if (!use_smem && coop_mode) {
+        int dev = 0, nsm = 0;
+        CTMB_CUDA(cudaGetDevice(&dev));
+        CTMB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        int cpm = std::max(1, std::min(nsm / nb, ((k + 1) / 2 + JC_THREADS / 32 - 1) / (JC_THREADS / 32)));
+        int mxs = max_sweeps, kk_ = k;
+        if (cplx) jacobi_prep_kernel<true><<<nb, 1024, 0, stream>>>(G, W, k, shift, transpose_in);
+        else jacobi_prep_kernel<false><<<nb, 1024, 0, stream>>>(G, W, k, shift, transpose_in);
+        CTMB_CUDA(cudaGetLastError());
+        PtrBatch g = G, w = W, sg = sig;
+        void* args[] = {&g, &w, &sg, &kk_, &cpm, &mxs};
+        const void* kern = cplx ? (const void*)jacobi_coop_kernel<true> : (const void*)jacobi_coop_kernel<false>;
+        CTMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * cpm), dim3(JC_THREADS), args, 0, stream));
+        return;
+    }
+    auto launch = [&](auto kern, int threads) {
+        static thread_local const void* set_for = nullptr;
+        if (smem > 0 && set_for != (const void*)kern) {
+            CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jacobi_smem_limit()));
+            set_for = (const void*)kern;
+        }
+        kern<<<nb, threads, smem, stream>>>(G, W, sig, k, max_sweeps, shift, transpose_in);
+    };
+    if (use_smem) {
+        if (cplx) launch(jacobi_kernel<true, true, 16, 512>, 512);
+        else launch(jacobi_kernel<false, true, 8, 512>, 512);
     } else {
-        auto kern = jacobi_kernel<false>;
-        static size_t set = 0;
-        if (smem > set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jacobi_smem_limit())); set = jacobi_smem_limit(); }
-        kern<<<nb, JAC_THREADS, smem, stream>>>(G, W, sig, k, gs, use_smem, max_sweeps, shift, transpose_in);
+        if (cplx) launch(jacobi_kernel<true, false, 32, 1024>, 1024);
+        else launch(jacobi_kernel<false, false, 32, 1024>, 1024);
     }
     CTMB_CUDA(cudaGetLastError());
 }

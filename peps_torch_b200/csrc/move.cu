@@ -112,6 +112,95 @@ static Engine::ChainJob corner_job(int kind, const ctmb_site& s, int chi, void* 
     return sl_job(ops, 3, cs.la, s, cs.out, out, nullptr);
 }
 
+struct CornerReq { int kind; const ctmb_site* site; void* out; };
+
+// label roles of a corner: k1/k2 = auxiliary legs of a contracted with T1/T2, x1/x2 = the free
+// environment legs of T1/T2, o1/o2 = the open auxiliary legs in output order
+struct CornerRoles { char k1, k2, x1, x2, o1, o2; };
+static CornerRoles corner_roles(const CornerSpec& cs) {
+    CornerRoles r{};
+    for (const char* p = cs.l1; *p; ++p) { if (strchr(cs.la, *p)) r.k1 = *p; else if (!strchr(cs.lc, *p)) r.x1 = *p; }
+    for (const char* p = cs.l2; *p; ++p) { if (strchr(cs.la, *p)) r.k2 = *p; else if (!strchr(cs.lc, *p)) r.x2 = *p; }
+    for (const char* p = cs.out; *p; ++p) if (strchr(cs.la, *p)) { if (!r.o1) r.o1 = *p; else r.o2 = *p; }
+    return r;
+}
+
+static bool corner_fusable(const Engine& e, int kind, const ctmb_site& s) {
+    const CornerSpec& cs = CORNERS[kind];
+    const CornerRoles r = corner_roles(cs);
+    auto D = [&](char c) { return s.dims[1 + (strchr(cs.la, c) - cs.la)]; };
+    return dl_corner_supported(D(r.k1), D(r.k2), D(r.o1), D(r.o2), s.dims[0], e.cplx);
+}
+
+// Enlarged corners of a list of requests.  Large real corners (D = 8) go through the fused
+// double-layer kernel: chain C.T1.T2 -> X (laid out per environment-index pair), then dl_corner_kernel;
+// everything else is the four-step contraction chain.
+static void corners_run(Engine& e, int chi, const std::vector<CornerReq>& reqs) {
+    std::vector<Engine::ChainJob> plain;
+    std::vector<size_t> fused;
+    for (size_t i = 0; i < reqs.size(); ++i) {
+        if (corner_fusable(e, reqs[i].kind, *reqs[i].site)) fused.push_back(i);
+        else plain.push_back(corner_job(reqs[i].kind, *reqs[i].site, chi, reqs[i].out));
+    }
+    if (!plain.empty()) e.chain_multi(plain);
+    const size_t group = 4;                              // X buffers alive at a time (2.1 GB each at D=8, chi=256)
+    for (size_t g0 = 0; g0 < fused.size(); g0 += group) {
+        const size_t g1 = std::min(fused.size(), g0 + group);
+        const size_t mark = e.ws.mark();
+        std::vector<Engine::ChainJob> jobs;
+        std::vector<DlParams> dl;
+        for (size_t g = g0; g < g1; ++g) {
+            const CornerReq& rq = reqs[fused[g]];
+            const ctmb_site& s = *rq.site;
+            const CornerSpec& cs = CORNERS[rq.kind];
+            const CornerRoles r = corner_roles(cs);
+            auto pos = [&](char c) { return (int)(strchr(cs.la, c) - cs.la); };
+            auto D = [&](char c) -> int64_t { return s.dims[1 + pos(c)]; };
+            const int64_t dk1 = D(r.k1), dk2 = D(r.k2);
+            const char K1 = (char)toupper(r.k1), K2 = (char)toupper(r.k2);
+            Engine::ChainJob job;
+            job.ops = {env_C(s, cs.c, chi, cs.lc),
+                       split_mode(env_T(s, cs.t1, chi, cs.l1), r.k1, r.k1, K1, dk1, dk1),
+                       split_mode(env_T(s, cs.t2, chi, cs.l2), r.k2, r.k2, K2, dk2, dk2)};
+            job.conj = {false, false, false};
+            void* X = e.ws.alloc((size_t)chi * chi * dk1 * dk1 * dk2 * dk2 * e.esize());
+            const char xl[7] = {r.x1, r.x2, K1, K2, r.k1, r.k2, 0};
+            job.out = make_tn(X, std::string(xl), {chi, chi, dk1, dk2, dk1, dk2});
+            jobs.push_back(job);
+            // the output view and the strides of a, from the same label machinery the chain uses
+            const Tn out = corner_job(rq.kind, s, chi, rq.out).out;
+            DlParams p{};
+            p.X = (const double*)X; p.a = (const double*)s.a; p.out = (double*)rq.out;
+            p.npairs = chi * chi; p.n2 = chi;
+            p.st1 = out.str[out.find(r.x1)]; p.st2 = out.str[out.find(r.x2)];
+            int64_t astr[5]; astr[4] = 1;
+            for (int q = 3; q >= 0; --q) astr[q] = astr[q + 1] * s.dims[q + 1];
+            p.as_s = (int)astr[0];
+            p.as_k1 = (int)astr[1 + pos(r.k1)]; p.as_k2 = (int)astr[1 + pos(r.k2)];
+            p.as_o1 = (int)astr[1 + pos(r.o1)]; p.as_o2 = (int)astr[1 + pos(r.o2)];
+            const int do1 = (int)D(r.o1), do2 = (int)D(r.o2);
+            const char O1 = (char)toupper(r.o1), O2 = (char)toupper(r.o2);
+            for (int i1 = 0; i1 < do1; ++i1)
+                for (int i2 = 0; i2 < do2; ++i2) {
+                    p.ro[i1 * do2 + i2] = (int)(i1 * out.str[out.find(r.o1)] + i2 * out.str[out.find(r.o2)]);
+                    p.co[i1 * do2 + i2] = (int)(i1 * out.str[out.find(O1)] + i2 * out.str[out.find(O2)]);
+                }
+            dl.push_back(p);
+        }
+        e.chain_multi(jobs);
+        if (!e.ws.dry())
+            for (size_t g = 0; g < dl.size(); ++g) {
+                const ctmb_site& s = *reqs[fused[g0 + g]].site;
+                const double d2 = 64.0, n3 = 128.0;
+                ProfScope ps(e, Engine::CAT_GEMM, 2.0 * dl[g].npairs * (d2 * d2 * n3 + d2 * d2 * n3),
+                             8.0 * dl[g].npairs * 2.0 * d2 * d2);
+                e.flops += 2.0 * dl[g].npairs * 2.0 * d2 * d2 * n3;
+                dl_corner_launch(dl[g], 8, 8, s.dims[0], e.stream);
+            }
+        e.ws.release(mark);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // randomised truncated SVD / Hermitian EVD, batched over nb equally-shaped problems
 // ------------------------------------------------------------------------------------------
@@ -130,6 +219,93 @@ static int sketch_width(int m, int n, int chi, const ctmb_options& o) {
     int k = (int)std::ceil(o.rsvd_rank_factor * chi);
     k = std::max(k, chi + 1);
     return std::min(k, mn);
+}
+
+// Blocked Householder QR (explicit thin Q) for sketches that fit neither the registers nor the shared
+// memory of one cluster: panels of width w.b are factored in WY form by qr_panel_launch, the trailing
+// matrix is updated with three GEMMs per panel  A2 -= V (T^H (V^H A2)),  and Q = H_1 .. H_P E is
+// accumulated backwards into a second buffer the same way.  All GEMMs are batched over the nb matrices.
+struct QrBlockedWs { PtrBatch Q{}, Tau{}, Rpp{}, G{}, T{}, W{}, W2{}; int b = 0; };
+
+static void qr_blocked_alloc(Engine& e, QrBlockedWs& w, int bidx, int rows_max, int k, int b) {
+    const size_t es = e.esize();
+    const int np = (k + b - 1) / b;
+    w.b = b;
+    w.Q.p[bidx] = e.ws.alloc((size_t)rows_max * k * es);
+    w.Tau.p[bidx] = e.ws.alloc((size_t)k * es);
+    w.Rpp.p[bidx] = e.ws.alloc((size_t)b * b * es);
+    w.G.p[bidx] = e.ws.alloc((size_t)b * b * es);
+    w.T.p[bidx] = e.ws.alloc((size_t)np * b * b * es);
+    w.W.p[bidx] = e.ws.alloc((size_t)b * k * es);
+    w.W2.p[bidx] = e.ws.alloc((size_t)b * k * es);
+}
+
+static void qr_blocked(Engine& e, PtrBatch& cur, const PtrBatch& Rout, int nb, int rows, int k, QrBlockedWs& w) {
+    const size_t es = e.esize();
+    const int b = w.b;
+    auto off = [&](const PtrBatch& P, int i, size_t elems) { return (void*)((char*)P.p[i] + elems * es); };
+    e.flush();
+    for (int j0 = 0; j0 < k; j0 += b) {
+        const int bw = std::min(b, k - j0), prow = rows - j0, nt = k - j0 - bw, pi = j0 / b;
+        PtrBatch Ap{}, TauP{}, Tp{};
+        for (int i = 0; i < nb; ++i) {
+            Ap.p[i] = off(cur, i, (size_t)j0 * rows + j0);
+            TauP.p[i] = off(w.Tau, i, j0);
+            Tp.p[i] = off(w.T, i, (size_t)pi * b * b);
+        }
+        { ProfScope ps(e, Engine::CAT_QR, (e.cplx ? 4.0 : 1.0) * nb * 2.0 * prow * bw * bw, 2.0 * es * nb * (double)prow * bw);
+          qr_panel_launch(Ap, w.Rpp, TauP, nb, prow, bw, rows, e.cplx, e.stream); }
+        for (int i = 0; i < nb; ++i) {                  // G[t][s] = v_s^H v_t
+            Tn V = make_strided(Ap.p[i], "si", {bw, prow}, {rows, 1});
+            e.contract(V, true, relabel(V, "ti"), false, make_tn(w.G.p[i], "ts", {bw, bw}));
+        }
+        e.flush();
+        { ProfScope ps(e, Engine::CAT_QR, 0, 3.0 * es * nb * (double)bw * bw);
+          wy_tsolve_launch(w.G, TauP, Ap, Tp, nb, bw, 0, e.cplx, e.stream); }          // Tp[c][s] = T[s,c]
+        if (nt > 0) {
+            for (int i = 0; i < nb; ++i) {
+                Tn V = make_strided(Ap.p[i], "si", {bw, prow}, {rows, 1});
+                Tn A2 = make_strided(off(cur, i, (size_t)(j0 + bw) * rows + j0), "ci", {nt, prow}, {rows, 1});
+                e.contract(V, true, A2, false, make_tn(w.W.p[i], "cs", {nt, bw}));
+            }
+            e.flush();
+            for (int i = 0; i < nb; ++i)                // W2[c][t] = sum_s conj(T[s,t]) W[c][s]
+                e.contract(make_tn(Tp.p[i], "ts", {bw, bw}), true, make_tn(w.W.p[i], "cs", {nt, bw}), false,
+                           make_tn(w.W2.p[i], "ct", {nt, bw}));
+            e.flush();
+            for (int i = 0; i < nb; ++i) {
+                Tn V = make_strided(Ap.p[i], "ti", {bw, prow}, {rows, 1});
+                Tn A2 = make_strided(off(cur, i, (size_t)(j0 + bw) * rows + j0), "ci", {nt, prow}, {rows, 1});
+                e.contract(V, false, make_tn(w.W2.p[i], "ct", {nt, bw}), false, A2, nullptr, -1.0, true);
+            }
+            e.flush();
+        }
+        if (Rout.p[0] != nullptr) {
+            ProfScope ps(e, Engine::CAT_MISC);
+            qr_copy_r_launch(cur, w.Rpp, Rout, nb, k, j0, bw, rows, e.cplx, e.stream);
+        }
+    }
+    { ProfScope ps(e, Engine::CAT_MISC); set_identity_launch(w.Q, nb, rows, k, e.cplx, e.stream); }
+    for (int j0 = ((k - 1) / b) * b; j0 >= 0; j0 -= b) {
+        const int bw = std::min(b, k - j0), prow = rows - j0, nq = k - j0, pi = j0 / b;
+        for (int i = 0; i < nb; ++i) {
+            Tn V = make_strided(off(cur, i, (size_t)j0 * rows + j0), "si", {bw, prow}, {rows, 1});
+            Tn Q2 = make_strided(off(w.Q, i, (size_t)j0 * rows + j0), "ci", {nq, prow}, {rows, 1});
+            e.contract(V, true, Q2, false, make_tn(w.W.p[i], "cs", {nq, bw}));
+        }
+        e.flush();
+        for (int i = 0; i < nb; ++i)                    // W2[c][t] = sum_s T[t,s] W[c][s]
+            e.contract(make_tn(off(w.T, i, (size_t)pi * b * b), "st", {bw, bw}), false, make_tn(w.W.p[i], "cs", {nq, bw}), false,
+                       make_tn(w.W2.p[i], "ct", {nq, bw}));
+        e.flush();
+        for (int i = 0; i < nb; ++i) {
+            Tn V = make_strided(off(cur, i, (size_t)j0 * rows + j0), "ti", {bw, prow}, {rows, 1});
+            Tn Q2 = make_strided(off(w.Q, i, (size_t)j0 * rows + j0), "ci", {nq, prow}, {rows, 1});
+            e.contract(V, false, make_tn(w.W2.p[i], "ct", {nq, bw}), false, Q2, nullptr, -1.0, true);
+        }
+        e.flush();
+    }
+    std::swap(cur, w.Q);
 }
 
 // M[b]: m x n row-major. eig_mode: M Hermitian (m == n), S receives signed eigenvalues.
@@ -155,16 +331,23 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     std::vector<void*> R2(nb), W(nb), sig(nb), Uh(nb), Ws(nb);
     const int mx = std::max(m, n);
     const bool wy = qr_wy_supported(m, k, e.cplx) && qr_wy_supported(n, k, e.cplx);
+    // neither the register / WY path nor one cluster holds the whole sketch: blocked factorisation
+    const int pw = std::min(qr_panel_width(m, k, e.cplx), qr_panel_width(n, k, e.cplx));
+    const bool blocked = !wy && pw < k;
+    CTMB_CHECK(!blocked || pw >= 4, "sketch too tall for the panel kernels");
+    QrBlockedWs qbw;
     for (int b = 0; b < nb; ++b) {
         Mt[b] = make_tn(const_cast<void*>(M[b]), "ij", {m, n});
-        pY.p[b] = e.ws.alloc((size_t)k * m * es);       // column-major m x k
-        pZ.p[b] = e.ws.alloc((size_t)k * n * es);       // column-major n x k
+        // (the QR drivers swap these with their Q scratch, so all of them are sized for the taller side)
+        pY.p[b] = e.ws.alloc((size_t)k * ((wy || blocked) ? mx : m) * es);       // column-major m x k
+        pZ.p[b] = e.ws.alloc((size_t)k * ((wy || blocked) ? mx : n) * es);       // column-major n x k
         if (wy) {
             pQ.p[b] = e.ws.alloc((size_t)k * mx * es);  // scratch for the explicit Q of the WY form
             pG.p[b] = e.ws.alloc((size_t)k * k * es);
             pX.p[b] = e.ws.alloc((size_t)k * k * es);
             pTau.p[b] = e.ws.alloc((size_t)k * es);
         }
+        if (blocked) qr_blocked_alloc(e, qbw, b, mx, k, pw);
         R2[b] = e.ws.alloc((size_t)k * k * es);
         W[b] = e.ws.alloc((size_t)k * k * es);
         sig[b] = e.ws.alloc((size_t)k * 8);
@@ -186,6 +369,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     auto qr = [&](PtrBatch& cur, const PtrBatch& Rout, int rows) {
         e.flush();
         const double fl = cf * nb * 4.0 * ((double)rows * k * k - (double)k * k * k / 3.0);
+        if (blocked) { qr_blocked(e, cur, Rout, nb, rows, k, qbw); return; }
         if (!wy) {
             ProfScope ps(e, Engine::CAT_QR, fl, 2.0 * e.esize() * nb * (double)rows * k);
             qr_launch(cur, Rout, nb, rows, k, rows, e.cplx, e.stream);
@@ -348,7 +532,7 @@ static void halves_jobs(Engine& e, int dir, int chi, const std::vector<const ctm
     const int nj = (int)R.size();
     const HalfSpec& hs = HALVES[dir];
     const size_t mark = e.ws.mark();
-    std::vector<Engine::ChainJob> cj;
+    std::vector<CornerReq> cj;
     std::vector<void*> cm(4 * nj);
     std::vector<int64_t> rows(4 * nj), cols(4 * nj);
     for (int j = 0; j < nj; ++j)
@@ -356,9 +540,9 @@ static void halves_jobs(Engine& e, int dir, int chi, const std::vector<const ctm
             const ctmb_site& s = *corners[4 * j + q];
             corner_shape(hs.kind[q], s, chi, rows[4 * j + q], cols[4 * j + q]);
             cm[4 * j + q] = e.ws.alloc((size_t)rows[4 * j + q] * cols[4 * j + q] * e.esize());
-            cj.push_back(corner_job(hs.kind[q], s, chi, cm[4 * j + q]));
+            cj.push_back(CornerReq{hs.kind[q], &s, cm[4 * j + q]});
         }
-    e.chain_multi(cj);
+    corners_run(e, chi, cj);
     for (int j = 0; j < nj; ++j) {
         for (int h = 0; h < 2; ++h) {
             const int q0 = 4 * j + 2 * h, q1 = q0 + 1;
@@ -599,8 +783,7 @@ int ctmb_einsum2(ctmb_handle_t h, ctmb_dtype dt, const char* spec, const void* A
 
 static void c2x2_impl(ctmb_handle_t h, ctmb_corner kind, int chi, const ctmb_site* site, void* out) {
     CTMB_CHECK(kind >= 0 && kind < 4 && site != nullptr && chi > 0, "bad arguments");
-    std::vector<Engine::ChainJob> jobs = {corner_job(kind, *site, chi, out)};
-    h->h.eng.chain_multi(jobs);
+    corners_run(h->h.eng, chi, {CornerReq{(int)kind, site, out}});
 }
 int ctmb_c2x2(ctmb_handle_t h, ctmb_dtype dt, ctmb_corner kind, int chi, const ctmb_site* site, void* out,
               void* ws, size_t ws_bytes, void* stream) {

@@ -195,8 +195,8 @@ __device__ __forceinline__ void slab_dots(const typename Sc<CPLX>::T* __restrict
 }
 
 template <bool CPLX>
-__global__ void __launch_bounds__(QRC_THREADS) qr_cluster_kernel(PtrBatch Ab, PtrBatch Rb, int rows, int cols,
-                                                                  int ld, int CL) {
+__global__ void __launch_bounds__(QRC_THREADS) qr_cluster_kernel(PtrBatch Ab, PtrBatch Rb, PtrBatch Taub, int rows, int cols,
+                                                                  int ld, int CL, int wy_mode) {
     using S = Sc<CPLX>;
     using T = typename S::T;
     namespace cg = cooperative_groups;
@@ -330,6 +330,18 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_cluster_kernel(PtrBatch Ab, Pt
         }
     }
     __syncthreads();
+    if (wy_mode) {
+        // WY mode (panel of the blocked factorisation): A <- V (explicit unit diagonal, zeros above), Taub <- tau
+        T* tau_out = reinterpret_cast<T*>(Taub.p[mat]);
+        if (rank == 0) for (int c = tid; c < cols; c += QRC_THREADS) tau_out[c] = c < kmax ? tau[c] : S::zero();
+        for (int e = tid; e < cols * ldl; e += QRC_THREADS) {
+            const int c = e / ldl, lr = e % ldl;
+            const int r = lr * CL + rank;
+            if (lr < nloc) A[(size_t)c * ld + r] = r > c ? slab[e] : (r == c ? S::one() : S::zero());
+        }
+        cluster.sync();
+        return;
+    }
     // ---------------- Phase B: explicit Q in place ----------------
     for (int j = cols - 1; j >= kmax; --j)
         for (int lr = tid; lr < nloc; lr += QRC_THREADS) slab[(size_t)j * ldl + lr] = S::zero();
@@ -741,9 +753,15 @@ void qr_wy_factor_launch(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch
 // X = T V1^H (k x k, stored [c][s]) from the Gram matrix G = V^H V ([t][s] = v_s^H v_t), tau and
 // the top k x k block of V:  T^-1 = striu(G) + diag(1/tau)  =>  back substitution
 //   X[s,c] = tau_s ( V1^H[s,c] - sum_{t>s} G[s,t] X[t,c] ),   s = k-1 .. 0.
+// Every column of X is an independent recurrence: ONE THREAD PER COLUMN walks it with no
+// synchronisation at all (it only reads what it wrote itself).  G(s,t) is the same address for
+// all threads (broadcast), X[t][c] is consecutive in c (conflict-free).  The first version split a
+// column over four lanes and read V / tau from global memory inside the loop: 4-way bank conflicts
+// plus an L2 round trip per step made it 122 us for k = 96 (profiles/r1_c2_qr_jacobi.md).
+constexpr int TS_THREADS = 128;
 template <bool CPLX>
-__global__ void __launch_bounds__(512) wy_tsolve_kernel(PtrBatch Gb, PtrBatch Taub, PtrBatch Vb, PtrBatch Xb, int k, int ldv,
-                                                        int g_in_smem) {
+__global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrBatch Taub, PtrBatch Vb, PtrBatch Xb, int k, int ldv,
+                                                               int g_in_smem) {
     using S = Sc<CPLX>;
     using T = typename S::T;
     const T* __restrict__ G = reinterpret_cast<const T*>(Gb.p[blockIdx.x]);
@@ -751,55 +769,48 @@ __global__ void __launch_bounds__(512) wy_tsolve_kernel(PtrBatch Gb, PtrBatch Ta
     const T* __restrict__ V = reinterpret_cast<const T*>(Vb.p[blockIdx.x]);
     T* __restrict__ X = reinterpret_cast<T*>(Xb.p[blockIdx.x]);
     extern __shared__ __align__(16) unsigned char wy_smem[];
-    T* Xs = reinterpret_cast<T*>(wy_smem);                // [t][c]: column c belongs to one group of 4 lanes
+    T* Xs = reinterpret_cast<T*>(wy_smem);                // [t][c]
     T* Gs = Xs + (size_t)k * k;                           // [s][t] (optional)
+    __shared__ T taus[TS_THREADS];
     const int tid = threadIdx.x;
-    const int c = tid >> 2, part = tid & 3;
-    const int cc = c < k ? c : k - 1;
-    // Preload everything the recurrence touches: a global load inside the serial loop would put one
-    // L2 round trip on the critical path of each of the k steps (it did: 1.4 us per step).
-    //   Xs[s][c] <- V1^H[s,c]  (unit lower trapezoidal V: conj(V[c,s]) above the diagonal, 1 on it, 0 below)
-    __shared__ T taus[128];
-    for (int e = tid; e < k * k; e += 512) {
+    // Xs[s][c] <- V1^H[s,c]  (unit lower trapezoidal V: conj(V[c,s]) above the diagonal, 1 on it, 0 below)
+    for (int e = tid; e < k * k; e += TS_THREADS) {
         const int s2 = e / k, c2 = e % k;                 // V[(size_t)s2 * ldv + c2] = V(row c2, column s2)
-        Xs[e] = c2 > s2 ? S::conj(V[(size_t)s2 * ldv + c2]) : (c2 == s2 ? S::one() : S::zero());
+        Xs[e] = (c2 > s2 && ldv > 0) ? S::conj(V[(size_t)s2 * ldv + c2]) : (c2 == s2 ? S::one() : S::zero());
     }
-    for (int e = tid; e < k; e += 512) taus[e] = tau[e];
+    for (int e = tid; e < k; e += TS_THREADS) taus[e] = tau[e];
     if (g_in_smem)
-        for (int e = tid; e < k * k; e += 512) { const int t = e / k, s2 = e % k; Gs[s2 * k + t] = G[e]; }
+        for (int e = tid; e < k * k; e += TS_THREADS) { const int t = e / k, s2 = e % k; Gs[s2 * k + t] = G[e]; }
     __syncthreads();
-    // every column of X = T V1^H is an independent back substitution: four lanes per column split
-    // the inner sum, no block-level synchronisation; G(s,t) is read at the same address by all groups
-    for (int s = k - 1; s >= 0; --s) {
-        T a0 = S::zero(), a1 = S::zero();
-        int t = s + 1 + part;
-        if (g_in_smem) {
-            const T* gr = Gs + (size_t)s * k;
-            for (; t + 4 < k; t += 8) {
-                a0 = S::fma(gr[t], Xs[t * k + cc], a0);
-                a1 = S::fma(gr[t + 4], Xs[(t + 4) * k + cc], a1);
+    const int c = tid;
+    if (c < k) {
+        // X is upper triangular (T and V1^H are): row s of column c is zero for s > c
+        for (int s = c; s >= 0; --s) {
+            T a0 = S::zero(), a1 = S::zero(), a2 = S::zero(), a3 = S::zero();
+            int t = s + 1;
+            if (g_in_smem) {
+                const T* gr = Gs + (size_t)s * k;
+                for (; t + 3 <= c; t += 4) {
+                    a0 = S::fma(gr[t], Xs[t * k + c], a0);
+                    a1 = S::fma(gr[t + 1], Xs[(t + 1) * k + c], a1);
+                    a2 = S::fma(gr[t + 2], Xs[(t + 2) * k + c], a2);
+                    a3 = S::fma(gr[t + 3], Xs[(t + 3) * k + c], a3);
+                }
+                for (; t <= c; ++t) a0 = S::fma(gr[t], Xs[t * k + c], a0);
+            } else {
+                for (; t <= c; ++t) a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + c], a0);
             }
-            if (t < k) a0 = S::fma(gr[t], Xs[t * k + cc], a0);
-        } else {
-            for (; t + 4 < k; t += 8) {
-                a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + cc], a0);
-                a1 = S::fma(G[(size_t)(t + 4) * k + s], Xs[(t + 4) * k + cc], a1);
-            }
-            if (t < k) a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + cc], a0);
+            const T acc = S::add(S::add(a0, a1), S::add(a2, a3));
+            Xs[s * k + c] = S::mul(taus[s], S::sub(Xs[s * k + c], acc));
         }
-        T acc = S::add(a0, a1);
-        acc = S::add(acc, S::shfl_xor(acc, 1));
-        acc = S::add(acc, S::shfl_xor(acc, 2));
-        if (part == 0 && c < k) Xs[s * k + c] = S::mul(taus[s], S::sub(Xs[s * k + c], acc));
-        __syncwarp();
     }
     __syncthreads();
-    for (int e = tid; e < k * k; e += 512) { const int c2 = e / k, s2 = e % k; X[e] = Xs[s2 * k + c2]; }
+    for (int e = tid; e < k * k; e += TS_THREADS) { const int c2 = e / k, s2 = e % k; X[e] = Xs[s2 * k + c2]; }
 }
 
 void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V, const PtrBatch& X, int nb, int k,
                       int ldv, bool cplx, cudaStream_t stream) {
-    CTMB_CHECK(k <= 128, "wy_tsolve: k too large");
+    CTMB_CHECK(k <= TS_THREADS, "wy_tsolve: k too large");
     const size_t es = cplx ? 16 : 8;
     const int g_in_smem = 2 * (size_t)k * k * es <= 200 * 1024;
     const size_t smem = (g_in_smem ? 2 : 1) * (size_t)k * k * es;
@@ -807,12 +818,12 @@ void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V,
         auto kern = wy_tsolve_kernel<true>;
         static bool set = false;
         if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
-        kern<<<nb, 512, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
+        kern<<<nb, TS_THREADS, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
     } else {
         auto kern = wy_tsolve_kernel<false>;
         static bool set = false;
         if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
-        kern<<<nb, 512, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
+        kern<<<nb, TS_THREADS, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
     }
     CTMB_CUDA(cudaGetLastError());
 }
@@ -851,8 +862,8 @@ static int qr_cluster_size(int rows, int cols, bool cplx, size_t& smem) {
 }
 
 template <bool CPLX>
-static void qr_cluster_run(const PtrBatch& A, const PtrBatch& Rout, int nb, int rows, int cols, int ld, int cl,
-                           size_t smem, cudaStream_t stream) {
+static void qr_cluster_run(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch& Tau, int nb, int rows, int cols, int ld, int cl,
+                           size_t smem, int wy_mode, cudaStream_t stream) {
     auto kern = qr_cluster_kernel<CPLX>;
     static size_t set = 0;
     if (smem > set) {
@@ -868,7 +879,7 @@ static void qr_cluster_run(const PtrBatch& A, const PtrBatch& Rout, int nb, int 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CTMB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, Rout, rows, cols, ld, cl));
+    CTMB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, Rout, Tau, rows, cols, ld, cl, wy_mode));
 }
 
 void qr_launch(const PtrBatch& A, const PtrBatch& Rout, int nb, int rows, int cols, int ld,
@@ -879,13 +890,82 @@ void qr_launch(const PtrBatch& A, const PtrBatch& Rout, int nb, int rows, int co
     size_t csmem = 0;
     const int cl = qr_cluster_size(rows, cols, cplx, csmem);
     if (cl > 0) {
-        if (cplx) qr_cluster_run<true>(A, Rout, nb, rows, cols, ld, cl, csmem, stream);
-        else qr_cluster_run<false>(A, Rout, nb, rows, cols, ld, cl, csmem, stream);
+        PtrBatch none{};
+        if (cplx) qr_cluster_run<true>(A, Rout, none, nb, rows, cols, ld, cl, csmem, 0, stream);
+        else qr_cluster_run<false>(A, Rout, none, nb, rows, cols, ld, cl, csmem, 0, stream);
         return;
     }
     size_t smem = (size_t)cols * (cplx ? 16 : 8);
     if (cplx) qr_kernel<true><<<nb, QR_THREADS, smem, stream>>>(A, Rout, rows, cols, ld);
     else qr_kernel<false><<<nb, QR_THREADS, smem, stream>>>(A, Rout, rows, cols, ld);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panels of the blocked factorisation (sketches that fit neither the registers nor the shared
+// memory of one cluster, e.g. 1536 x 192 complex at D=4 chi=96 or 16384 x 512 at D=8 chi=256).
+// ---------------------------------------------------------------------------------------------
+// widest panel (power of two, <= 128, <= cols) whose rows x b slab fits the registers or the shared memory of a cluster
+int qr_panel_width(int rows, int cols, bool cplx) {
+    for (int b = 128; b >= 4; b >>= 1) {
+        if (b > cols && (b >> 1) >= cols) continue;
+        const int bb = std::min(b, cols);
+        int rpl, cl; size_t smem;
+        if (qr_reg_shape(rows, bb, cplx, rpl, cl)) return bb;
+        if (qr_cluster_size(rows, bb, cplx, smem) > 0) return bb;
+    }
+    return 0;
+}
+// factor one panel in WY form: A (rows x b, leading dimension ld) <- V, Tau <- tau, Rpp (b x b column-major) <- R
+void qr_panel_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& Tau, int nb, int rows, int b, int ld,
+                     bool cplx, cudaStream_t stream) {
+    if (qr_reg_try(A, Rpp, Tau, nb, rows, b, ld, cplx, 1, stream)) return;
+    size_t csmem = 0;
+    const int cl = qr_cluster_size(rows, b, cplx, csmem);
+    CTMB_CHECK(cl > 0, "qr_panel: panel does not fit a cluster");
+    if (cplx) qr_cluster_run<true>(A, Rpp, Tau, nb, rows, b, ld, cl, csmem, 1, stream);
+    else qr_cluster_run<false>(A, Rpp, Tau, nb, rows, b, ld, cl, csmem, 1, stream);
+}
+
+// rows j0 .. j0+b-1 of the k x k factor R (column-major, ld = k): the diagonal block from Rpp, the
+// blocks to its right from the updated trailing matrix A (leading dimension ld), zeros to the left
+template <bool CPLX>
+__global__ void qr_copy_r_kernel(PtrBatch Ab, PtrBatch Rppb, PtrBatch Rb, int k, int j0, int b, int ld) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const T* A = reinterpret_cast<const T*>(Ab.p[blockIdx.y]);
+    const T* Rpp = reinterpret_cast<const T*>(Rppb.p[blockIdx.y]);
+    T* R = reinterpret_cast<T*>(Rb.p[blockIdx.y]);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < b * k; e += gridDim.x * blockDim.x) {
+        const int c = e / b, r = e % b;
+        T v = S::zero();
+        if (c >= j0 + b) v = A[(size_t)c * ld + j0 + r];
+        else if (c >= j0) v = Rpp[(size_t)(c - j0) * b + r];
+        R[(size_t)c * k + j0 + r] = v;
+    }
+}
+void qr_copy_r_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& R, int nb, int k, int j0, int b, int ld,
+                      bool cplx, cudaStream_t stream) {
+    dim3 grid((unsigned)std::min(64, (b * k + 255) / 256), nb);
+    if (cplx) qr_copy_r_kernel<true><<<grid, 256, 0, stream>>>(A, Rpp, R, k, j0, b, ld);
+    else qr_copy_r_kernel<false><<<grid, 256, 0, stream>>>(A, Rpp, R, k, j0, b, ld);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// Q <- first k columns of the identity (rows x k column-major, ld = rows)
+template <bool CPLX>
+__global__ void set_identity_kernel(PtrBatch Qb, int rows, int k) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    T* Q = reinterpret_cast<T*>(Qb.p[blockIdx.y]);
+    const long long n = (long long)rows * k;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        Q[e] = (e / rows == e % rows) ? S::one() : S::zero();
+}
+void set_identity_launch(const PtrBatch& Q, int nb, int rows, int k, bool cplx, cudaStream_t stream) {
+    dim3 grid((unsigned)std::min<long long>(1024, ((long long)rows * k + 255) / 256), nb);
+    if (cplx) set_identity_kernel<true><<<grid, 256, 0, stream>>>(Q, rows, k);
+    else set_identity_kernel<false><<<grid, 256, 0, stream>>>(Q, rows, k);
     CTMB_CUDA(cudaGetLastError());
 }
 

@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
     // epilogue: registers -> global through the C offset tables
     T* __restrict__ C = reinterpret_cast<T*>(be.C);
     const double alpha = p.alpha;
+    const bool accum = (flags & TC_ACCUM) != 0;
     double lmax = 0.0;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -184,10 +185,12 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
                 if (c >= N) continue;
                 if constexpr (!CPLX) {
                     double v = alpha * acc[i][j][h];
+                    if (accum) v += C[ro + tb.c_n[c]];
                     C[ro + tb.c_n[c]] = v;
                     lmax = fmax(lmax, fabs(v));
                 } else {
                     double2 v = make_double2(alpha * acc[i][j][h], alpha * acci[i][j][h]);
+                    if (accum) { const double2 o = C[ro + tb.c_n[c]]; v.x += o.x; v.y += o.y; }
                     C[ro + tb.c_n[c]] = v;
                     lmax = fmax(lmax, hypot(v.x, v.y));
                 }
@@ -207,6 +210,172 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
             atomicMax(be.amax, (unsigned long long)__double_as_longlong(m));
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised variant for large contractions (128 x 128 x 16 tiles, double).
+// The ncu source view of tc_kernel<128,128,..> on a 4096^3 product (profiles/r1_gemm4096.md) shows
+// the DMMA pipe 59 % busy: every warp alternates between ~300 gather/address instructions (one
+// of them waiting for the offset-table load) and its 128 DMMAs, and all eight warps meet at a
+// __syncthreads per k-tile, so the tensor pipe idles during every load phase.  Here the roles are
+// split: 4 PRODUCER warps run the table look-ups and cp.async gathers and signal "full" mbarriers
+// (cp.async.mbarrier.arrive.noinc), 8 CONSUMER warps only issue LDS + DMMA and hand stages back
+// through "empty" mbarriers.  No block-wide barrier inside the k loop.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_cp_async_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 16, WS_STAGES = 5;
+constexpr int WS_CONSUMERS = 256, WS_PRODUCERS = 128, WS_THREADS = WS_CONSUMERS + WS_PRODUCERS;
+constexpr int WS_LDS = WS_BK + 4;
+
+__global__ void __launch_bounds__(WS_THREADS, 1) tc_kernel_ws(const __grid_constant__ TcParams p) {
+    constexpr int BM = WS_BM, BN = WS_BN, BK = WS_BK, STAGES = WS_STAGES, LDS = WS_LDS;
+    constexpr int WM = 64, WN = 32, TM = WM / 8, TN = WN / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);
+    double* Bs = As + STAGES * BM * LDS;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(Bs + STAGES * BN * LDS);
+    unsigned long long* empty = full + STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TcBatchEntry be = p.batch[blockIdx.z];
+    const TcTables tb = p.tab[be.tab];
+    const int ntn = (p.N + BN - 1) / BN;
+    const int m0 = (blockIdx.x / ntn) * BM, n0 = (blockIdx.x % ntn) * BN;
+    const int M = p.M, N = p.N, K = p.K;
+    const int ktiles = (K + BK - 1) / BK;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], WS_PRODUCERS); mbar_init(&empty[s], WS_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= WS_CONSUMERS) {
+        // ------------------------------ producers ------------------------------
+        const int pt = tid - WS_CONSUMERS;
+        const double* __restrict__ A = reinterpret_cast<const double*>(be.A);
+        const double* __restrict__ B = reinterpret_cast<const double*>(be.B);
+        const bool a_kfast = (be.flags & TC_A_KFAST) != 0, b_kfast = (be.flags & TC_B_KFAST) != 0;
+        constexpr int PER = BM * BK / WS_PRODUCERS;          // 16 elements of A and of B per thread and k-tile
+        // element e = pt + i*128 of a 128 x 16 tile: k-fast operands -> (row e/16, k e%16) so that a warp
+        // reads two 128-byte rows; m-fast operands -> (row e%128, k e/128) so that a warp reads 32 consecutive rows
+        int a_row[PER], a_col[PER], a_off[PER], b_row[PER], b_col[PER], b_off[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int e = pt + i * WS_PRODUCERS;
+            a_row[i] = a_kfast ? e / BK : e % BM; a_col[i] = a_kfast ? e % BK : e / BM;
+            b_row[i] = b_kfast ? e / BK : e % BN; b_col[i] = b_kfast ? e % BK : e / BN;
+            a_off[i] = (m0 + a_row[i] < M) ? tb.a_m[m0 + a_row[i]] : -1;
+            b_off[i] = (n0 + b_row[i] < N) ? tb.b_n[n0 + b_row[i]] : -1;
+        }
+        for (int kt = 0; kt < ktiles; ++kt) {
+            const int s = kt % STAGES;
+            mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);
+            double* as = As + s * BM * LDS;
+            double* bs = Bs + s * BN * LDS;
+            const int k0 = kt * BK;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int ka = k0 + a_col[i], kb = k0 + b_col[i];
+                const bool va = (a_off[i] >= 0) && (ka < K);
+                const bool vb = (b_off[i] >= 0) && (kb < K);
+                cp_async_8(as + a_row[i] * LDS + a_col[i], va ? (A + a_off[i] + tb.a_k[ka]) : A, va);
+                cp_async_8(bs + b_row[i] * LDS + b_col[i], vb ? (B + b_off[i] + tb.b_k[kb]) : B, vb);
+            }
+            mbar_cp_async_arrive(&full[s]);
+        }
+        return;
+    }
+    // ------------------------------ consumers ------------------------------
+    constexpr int WARPS_M = BM / WM;
+    const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+    double acc[TM][TN][2];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kt = 0; kt < ktiles; ++kt) {
+        const int s = kt % STAGES;
+        mbar_wait(&full[s], (kt / STAGES) & 1);
+        const double* as = As + s * BM * LDS + (wm0 + (lane >> 2)) * LDS + (lane & 3);
+        const double* bs = Bs + s * BN * LDS + (wn0 + (lane >> 2)) * LDS + (lane & 3);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[TM], bf[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) af[i] = as[i * 8 * LDS + kk];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bf[j] = bs[j * 8 * LDS + kk];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    double* __restrict__ C = reinterpret_cast<double*>(be.C);
+    const double alpha = p.alpha;
+    const bool accum = (be.flags & TC_ACCUM) != 0;
+    double lmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int r = m0 + wm0 + i * 8 + (lane >> 2);
+        if (r >= M) continue;
+        const int ro = tb.c_m[r];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = n0 + wn0 + j * 8 + (lane & 3) * 2 + h;
+                if (c >= N) continue;
+                double v = alpha * acc[i][j][h];
+                if (accum) v += C[ro + tb.c_n[c]];
+                C[ro + tb.c_n[c]] = v;
+                lmax = fmax(lmax, fabs(v));
+            }
+        }
+    }
+    if (be.amax != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if (lane == 0) atomicMax(be.amax, (unsigned long long)__double_as_longlong(lmax));
+    }
+}
+
+static void tc_run_ws(const TcParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)WS_STAGES * (WS_BM + WS_BN) * WS_LDS * 8 + 2 * WS_STAGES * 8;
+    if (!attr_set) {
+        CTMB_CUDA(cudaFuncSetAttribute(tc_kernel_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long tiles = (long long)((p.N + WS_BN - 1) / WS_BN) * ((p.M + WS_BM - 1) / WS_BM);
+    CTMB_CHECK(tiles < (1ll << 31), "too many tiles for one launch");
+    dim3 grid((unsigned)tiles, 1, p.nbatch);
+    tc_kernel_ws<<<grid, WS_THREADS, smem, stream>>>(p);
+    CTMB_CUDA(cudaGetLastError());
 }
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool CPLX>
@@ -238,7 +407,12 @@ void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream) {
     // a small contraction: prefer the tile that spreads the work over at least ~2 waves of CTAs.
     if (!cplx) {
         if (p.N <= 16) tc_run<128, 32, 16, 32, 16, 3, false>(p, stream);
-        else if (ntiles(128, 128) >= 240 && p.M > 64 && p.N > 64) tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
+        else if (ntiles(128, 128) >= 240 && p.M > 64 && p.N > 64) {
+            static int ws_mode = -1;
+            if (ws_mode < 0) { const char* ev = getenv("CTMB_GEMM_WS"); ws_mode = ev ? atoi(ev) : 1; }
+            if (ws_mode) tc_run_ws(p, stream);
+            else tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
+        }
         else if (ntiles(64, 64) >= 296) tc_run<64, 64, 16, 32, 16, 4, false>(p, stream);
         else tc_run<32, 32, 16, 16, 8, 4, false>(p, stream);
     } else {

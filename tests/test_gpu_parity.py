@@ -270,3 +270,63 @@ def test_errors_are_python_exceptions(eng, dev):
         ctmrg.ctm_MOVE((0, -1), st, env, ctm_args=bad)
     with pytest.raises(TypeError):
         eng.einsum2('ab,bc->ac', torch.zeros(2, 2, device=dev), torch.zeros(2, 2, device=dev))   # float32
+
+
+def _graded(n, dt, decades, seed):
+    """n x n matrix with geometrically decaying singular values sigma_i = 10^(-decades*i/n)."""
+    g = torch.Generator().manual_seed(seed)
+    U, _ = torch.linalg.qr(torch.randn(n, n, dtype=dt, generator=g))
+    V, _ = torch.linalg.qr(torch.randn(n, n, dtype=dt, generator=g))
+    s = torch.logspace(0, -decades, n, dtype=torch.float64)
+    return (U * s.to(dt)) @ V.conj().t(), s
+
+
+@pytest.mark.parametrize('n,chi,dt', [(1300, 100, torch.float64), (800, 70, torch.complex128)])
+def test_large_sketch_blocked_qr_and_multi_cta_jacobi(eng, dev, n, chi, dt):
+    """Sizes beyond the register / single-cluster QR and the shared-memory Jacobi (the decomposition path of
+    configs c3 and c5): sketch k = 2 chi > 128 columns -> blocked Householder QR, k x k Jacobi over several CTAs.
+    Checked against the full LAPACK SVD: singular values to 1e-10 relative, U/V through the rank-chi projector."""
+    M, s = _graded(n, dt, 12.0, 5)
+    U, S, V = eng.truncated_svd(M.to(dev), chi, rsvd_tol=1e-12)      # residual-checked range finder
+    Ur, Sr, Vhr = torch.linalg.svd(M)
+    S, U, V = S.cpu(), U.cpu(), V.cpu()
+    assert float(((S - Sr[:chi]).abs() / Sr[:chi]).max()) < 1e-10
+    eye = torch.eye(chi, dtype=dt)
+    assert float((U.conj().t() @ U - eye).abs().max()) < 1e-12
+    assert float((V.conj().t() @ V - eye).abs().max()) < 1e-12
+    best = (Ur[:, :chi] * Sr[:chi].to(dt)) @ Vhr[:chi]
+    rec = (U * S.to(dt)) @ V.conj().t()
+    assert H.maxrel(rec, best) < 1e-10
+
+
+def test_large_hermitian_eig_multi_cta(eng, dev):
+    n, chi = 900, 80
+    g = torch.Generator().manual_seed(11)
+    Q, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.complex128, generator=g))
+    lam = torch.logspace(0, -5, n, dtype=torch.float64) * torch.where(torch.arange(n) % 3 == 0, -1.0, 1.0)
+    M = (Q * lam.to(Q.dtype)) @ Q.conj().t()
+    M = 0.5 * (M + M.conj().t())
+    D, U = eng.truncated_eig_sym(M.to(dev), chi)
+    Dr, Ur = orc.truncated_eig_sym(M, chi)
+    assert float(((D.cpu() - Dr).abs() / Dr.abs()).max()) < 1e-10
+    U = U.cpu()
+    assert float((U.conj().t() @ U - torch.eye(chi, dtype=U.dtype)).abs().max()) < 1e-12
+    assert H.maxrel((U * D.cpu().to(U.dtype)) @ U.conj().t(), (Ur * Dr.to(Ur.dtype)) @ Ur.conj().t()) < 1e-9
+
+
+@pytest.mark.parametrize('kind', ['LU', 'RU', 'RD', 'LD'])
+def test_fused_double_layer_corner_D8(eng, dev, kind):
+    """D = 8, p = 2 real corners take the fused double-layer kernel (dl_fused.cu): checked element-wise
+    against the oracle's restatement of c2x2_*_sl_c on the same random inputs (deterministic: 1e-13)."""
+    D, chi, p = 8, 12, 2
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(p, D, D, D, D, dtype=torch.float64, generator=g)
+    C = torch.randn(chi, chi, dtype=torch.float64, generator=g)
+    shapes = {(0, -1): (chi, D * D, chi), (-1, 0): (chi, chi, D * D), (0, 1): (D * D, chi, chi), (1, 0): (chi, D * D, chi)}
+    kc, k1, k2, _ = orc.CORNERS[kind]
+    T1 = torch.randn(shapes[k1], dtype=torch.float64, generator=g)
+    T2 = torch.randn(shapes[k2], dtype=torch.float64, generator=g)
+    ref = orc.c2x2(kind, C, T1, T2, a)
+    out = eng.c2x2(kind, C.to(dev), T1.to(dev), T2.to(dev), a.to(dev), chi)
+    assert out.shape == ref.shape
+    assert H.maxrel(out.cpu(), ref) < 1e-13

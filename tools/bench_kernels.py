@@ -31,6 +31,14 @@ if 'gemm1' in what:      # one large GEMM, short enough for an `ncu --set full` 
     A = torch.randn(n, n, dtype=torch.float64, device=dev); B = torch.randn(n, n, dtype=torch.float64, device=dev)
     ms = timeit(lambda: eng.einsum2('ik,kj->ij', A, B), reps=2, warm=1)
     print(json.dumps(dict(kind='gemm1', n=n, ms=ms, tflops=2.0 * n ** 3 / ms / 1e9)), flush=True)
+if 'gemmbig' in what:
+    for n in (2048, 4096, 8192):
+        A = torch.randn(n, n, dtype=torch.float64, device=dev); B = torch.randn(n, n, dtype=torch.float64, device=dev)
+        for spec in ('ik,kj->ij', 'ki,kj->ij', 'ik,jk->ij'):
+            ms = timeit(lambda: eng.einsum2(spec, A, B), reps=3, warm=1)
+            err = float((eng.einsum2(spec, A, B) - torch.einsum(spec, A, B)).abs().max())
+            r = dict(kind='gemmbig', n=n, spec=spec, ms=ms, tflops=2.0 * n ** 3 / ms / 1e9, maxerr=err)
+            out.append(r); print(json.dumps(r), flush=True)
 if 'gemm' in what:
     for dt in (torch.float64, torch.complex128):
         for n in ((432, 1536, 4096, 8192) if dt == torch.float64 else (432, 1536, 4096)):

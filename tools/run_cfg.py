@@ -43,6 +43,11 @@ def iteration():
 
 
 iteration(); torch.cuda.synchronize()
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record()
+plain_moves = sum(iteration() for _ in range(iters))
+t1.record(); torch.cuda.synchronize()
+plain_ms = t0.elapsed_time(t1) / plain_moves
 stats = (ctypes.c_ulonglong * 2)()
 _lib.lib.ctmb_debug_jacobi_stats(stats)
 eng.profile(True); eng.reset_counters()
@@ -52,7 +57,7 @@ moves = sum(iteration() for _ in range(iters))
 e1.record(); torch.cuda.synchronize()
 prof = eng.profile_totals()
 _lib.lib.ctmb_debug_jacobi_stats(stats)
-out = {'config': cfg, 'moves': moves, 'ms_per_move': e0.elapsed_time(e1) / moves, 'launches_per_move': eng.counters()[0] / moves,
+out = {'config': cfg, 'moves': moves, 'ms_per_move': plain_ms, 'ms_per_move_profiled': e0.elapsed_time(e1) / moves, 'launches_per_move': eng.counters()[0] / moves,
        'per_move_ms_by_class': {k: round(v['ms'] / moves, 4) for k, v in prof.items()},
        'launches_by_class': {k: v['launches'] / moves for k, v in prof.items()},
        'gemm_tflops': prof['tc_gemm']['flops'] / max(prof['tc_gemm']['ms'], 1e-9) / 1e9,
