@@ -185,6 +185,46 @@ def measure_fp64_peak(dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def kernel_level(eng, dev, fp64_peak):
+    """FLOP-bound evidence next to the (latency-bound) c2 step: the enlarged corner at config-5 size
+    (D=8, chi=256, float64: the north star's named kernel, F_c = 2.77e11 FLOP, 2.1 GB output) and the
+    n x n x n contraction that carries 94 % of a config-5 move, timed alone with CUDA events (best of 3,
+    warm; inputs 2-4 GB >> L2)."""
+    out = {}
+
+    def best_ms(fn, reps=3):
+        fn(); torch.cuda.synchronize(dev)
+        b = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+            b = min(b, e0.elapsed_time(e1))
+        return b
+    try:
+        D, chi, p = 8, 256, 2
+        d = D * D
+        g = torch.Generator(device='cpu').manual_seed(1)
+        a = torch.randn(p, D, D, D, D, dtype=torch.float64, generator=g).to(dev)
+        C = torch.randn(chi, chi, dtype=torch.float64, generator=g).to(dev)
+        T1 = torch.randn(chi, d, chi, dtype=torch.float64, generator=g).to(dev)
+        T2 = torch.randn(chi, chi, d, dtype=torch.float64, generator=g).to(dev)
+        Fc = 2 * chi ** 3 * d + 2 * chi ** 3 * d ** 2 + 4 * p * chi ** 2 * D ** 6
+        ms = best_ms(lambda: eng.c2x2('LU', C, T1, T2, a, chi))
+        out['enlarged_corner_D8_chi256'] = {'ms': ms, 'flops': Fc, 'tflops': Fc / ms / 1e9, 'frac_of_fp64_dgemm_peak': Fc / ms / 1e9 / fp64_peak}
+        del a, C, T1, T2
+        n = 8192
+        A = torch.randn(n, n, dtype=torch.float64, device=dev)
+        B = torch.randn(n, n, dtype=torch.float64, device=dev)
+        ms = best_ms(lambda: eng.einsum2('ki,kj->ij', A, B))
+        out['gemm_RtR_8192'] = {'ms': ms, 'flops': 2.0 * n ** 3, 'tflops': 2.0 * n ** 3 / ms / 1e9, 'frac_of_fp64_dgemm_peak': 2.0 * n ** 3 / ms / 1e9 / fp64_peak}
+        del A, B
+        eng._ws = None
+        torch.cuda.empty_cache()
+    except Exception as ex:          # never lose the bench line over the side measurement
+        out['error'] = str(ex)[:200]
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import ctm_oracle as orc
@@ -372,6 +412,7 @@ def run_ours(args):
     roof['gemm_tflops_in_step'] = g['flops'] / max(g['ms'], 1e-9) / 1e9
     roof['fp64_dgemm_peak_tflops'] = fp64_peak
 
+    roof['kernel_level'] = kernel_level(eng, dev, fp64_peak)
     F_move = algorithmic_flops_per_move(kind, D, chi, p_phys, cplx)
     base = cpu_baseline(args.config) if world == 1 or True else None
     line = {'metric': 'CTM moves/sec', 'value': value, 'unit': 'ctm_MOVE/s', 'n_gpus': world, 'steps': args.steps,

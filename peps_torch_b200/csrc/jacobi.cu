@@ -16,7 +16,6 @@
 
 namespace ctmb {
 
-constexpr int JAC_THREADS = 1024;
 // diagnostics: total sweeps executed / matrices processed since the last read (tools/ only)
 __device__ unsigned long long g_jac_stats[2];
 

@@ -715,8 +715,11 @@ static bool qr_reg_shape(int rows, int cols, bool cplx, int& rpl_out, int& cl_ou
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("CTMB_QR_REG"); mode = e ? atoi(e) : 1; }
     if (!mode) return false;
+    static int rpl_min = -1;                             // tuning knob: prefer fewer CTAs with more rows per lane
+    if (rpl_min < 0) { const char* e = getenv("CTMB_QR_RPL_MIN"); rpl_min = e ? atoi(e) : 1; }
     for (int rpl : {1, 2, 4}) {
         if (cplx && rpl == 4) break;
+        if (rpl < rpl_min && !(cplx && rpl == 2)) continue;
         for (int cl = 1; cl <= 8; cl <<= 1) {
             if ((rows + cl - 1) / cl > 32 * rpl) continue;
             rpl_out = rpl; cl_out = cl;
@@ -758,7 +761,7 @@ void qr_wy_factor_launch(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch
 // all threads (broadcast), X[t][c] is consecutive in c (conflict-free).  The first version split a
 // column over four lanes and read V / tau from global memory inside the loop: 4-way bank conflicts
 // plus an L2 round trip per step made it 122 us for k = 96 (profiles/r1_c2_qr_jacobi.md).
-constexpr int TS_THREADS = 128;
+constexpr int TS_THREADS = 512;     // all of them stage the operands; the first k walk the recurrences
 template <bool CPLX>
 __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrBatch Taub, PtrBatch Vb, PtrBatch Xb, int k, int ldv,
                                                                int g_in_smem) {
@@ -771,37 +774,82 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
     extern __shared__ __align__(16) unsigned char wy_smem[];
     T* Xs = reinterpret_cast<T*>(wy_smem);                // [t][c]
     T* Gs = Xs + (size_t)k * k;                           // [s][t] (optional)
-    __shared__ T taus[TS_THREADS];
+    __shared__ T taus[128];
     const int tid = threadIdx.x;
+    // Staging: every load is independent, so keep many in flight per thread (batches of 8): with one
+    // outstanding load per thread this kernel was nothing but 2 x 72 serial L2 round trips (~120 us).
     // Xs[s][c] <- V1^H[s,c]  (unit lower trapezoidal V: conj(V[c,s]) above the diagonal, 1 on it, 0 below)
-    for (int e = tid; e < k * k; e += TS_THREADS) {
-        const int s2 = e / k, c2 = e % k;                 // V[(size_t)s2 * ldv + c2] = V(row c2, column s2)
-        Xs[e] = (c2 > s2 && ldv > 0) ? S::conj(V[(size_t)s2 * ldv + c2]) : (c2 == s2 ? S::one() : S::zero());
+    const int kk2 = k * k;
+    for (int e0 = tid; e0 < kk2; e0 += TS_THREADS * 8) {
+        T v[8], g[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * TS_THREADS;
+            const int s2 = e / k, c2 = e % k;             // V[(size_t)s2 * ldv + c2] = V(row c2, column s2)
+            v[u] = (e < kk2 && c2 > s2 && ldv > 0) ? V[(size_t)s2 * ldv + c2] : S::zero();
+            g[u] = (e < kk2 && g_in_smem) ? G[e] : S::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * TS_THREADS;
+            if (e < kk2) {
+                const int s2 = e / k, c2 = e % k;
+                Xs[e] = c2 > s2 ? S::conj(v[u]) : (c2 == s2 ? S::one() : S::zero());
+                if (g_in_smem) Gs[c2 * k + s2] = g[u];    // G[e] = G[t = s2][s = c2]  ->  Gs[s][t]
+            }
+        }
     }
     for (int e = tid; e < k; e += TS_THREADS) taus[e] = tau[e];
-    if (g_in_smem)
-        for (int e = tid; e < k * k; e += TS_THREADS) { const int t = e / k, s2 = e % k; Gs[s2 * k + t] = G[e]; }
     __syncthreads();
-    const int c = tid;
-    if (c < k) {
-        // X is upper triangular (T and V1^H are): row s of column c is zero for s > c
-        for (int s = c; s >= 0; --s) {
-            T a0 = S::zero(), a1 = S::zero(), a2 = S::zero(), a3 = S::zero();
-            int t = s + 1;
-            if (g_in_smem) {
-                const T* gr = Gs + (size_t)s * k;
-                for (; t + 3 <= c; t += 4) {
-                    a0 = S::fma(gr[t], Xs[t * k + c], a0);
-                    a1 = S::fma(gr[t + 1], Xs[(t + 1) * k + c], a1);
-                    a2 = S::fma(gr[t + 2], Xs[(t + 2) * k + c], a2);
-                    a3 = S::fma(gr[t + 3], Xs[(t + 3) * k + c], a3);
+    if (g_in_smem) {
+        // Blocked back substitution (row blocks of NB, last block first).  Phase 1: inside the block every
+        // column is an independent short recurrence (one thread per column, no synchronisation).  Phase 2:
+        // the finished rows are eliminated from all rows above them -- s0 x (k - s0) independent 16-term
+        // dot products spread over the whole CTA (G(r,t) is a warp-wide broadcast, X(t,c) is consecutive in c).
+        // A single thread walking a whole column (4560 dependent shared-memory FMAs for k = 96) took 74 us.
+        constexpr int NB = 16;
+        for (int s1 = k; s1 > 0; s1 -= NB) {
+            const int s0 = s1 > NB ? s1 - NB : 0;
+            const int c = s0 + tid;                          // X is upper triangular: columns c >= s0 only
+            if (c < k) {
+                for (int s = min(s1 - 1, c); s >= s0; --s) {
+                    const T* gr = Gs + (size_t)s * k;
+                    T a0 = S::zero(), a1 = S::zero();
+                    int t = s + 1;
+                    const int te = min(s1 - 1, c);
+                    for (; t + 1 <= te; t += 2) {
+                        a0 = S::fma(gr[t], Xs[t * k + c], a0);
+                        a1 = S::fma(gr[t + 1], Xs[(t + 1) * k + c], a1);
+                    }
+                    if (t <= te) a0 = S::fma(gr[t], Xs[t * k + c], a0);
+                    Xs[s * k + c] = S::mul(taus[s], S::sub(Xs[s * k + c], S::add(a0, a1)));
                 }
-                for (; t <= c; ++t) a0 = S::fma(gr[t], Xs[t * k + c], a0);
-            } else {
-                for (; t <= c; ++t) a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + c], a0);
             }
-            const T acc = S::add(S::add(a0, a1), S::add(a2, a3));
-            Xs[s * k + c] = S::mul(taus[s], S::sub(Xs[s * k + c], acc));
+            __syncthreads();
+            const int wcols = k - s0;
+            for (int it = tid; it < s0 * wcols; it += TS_THREADS) {
+                const int r = it / wcols, cc = s0 + it % wcols;
+                const T* gr = Gs + (size_t)r * k;
+                T a0 = S::zero(), a1 = S::zero();
+                const int te = min(s1 - 1, cc);              // X(t,cc) = 0 for t > cc
+                int t = s0;
+                for (; t + 1 <= te; t += 2) {
+                    a0 = S::fma(gr[t], Xs[t * k + cc], a0);
+                    a1 = S::fma(gr[t + 1], Xs[(t + 1) * k + cc], a1);
+                }
+                if (t <= te) a0 = S::fma(gr[t], Xs[t * k + cc], a0);
+                Xs[r * k + cc] = S::sub(Xs[r * k + cc], S::add(a0, a1));
+            }
+            __syncthreads();
+        }
+    } else {
+        const int c = tid;
+        if (c < k) {
+            for (int s = c; s >= 0; --s) {
+                T a0 = S::zero();
+                for (int t = s + 1; t <= c; ++t) a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + c], a0);
+                Xs[s * k + c] = S::mul(taus[s], S::sub(Xs[s * k + c], a0));
+            }
         }
     }
     __syncthreads();
@@ -810,7 +858,7 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
 
 void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V, const PtrBatch& X, int nb, int k,
                       int ldv, bool cplx, cudaStream_t stream) {
-    CTMB_CHECK(k <= TS_THREADS, "wy_tsolve: k too large");
+    CTMB_CHECK(k <= 128, "wy_tsolve: k too large");
     const size_t es = cplx ? 16 : 8;
     const int g_in_smem = 2 * (size_t)k * k * es <= 200 * 1024;
     const size_t smem = (g_in_smem ? 2 : 1) * (size_t)k * k * es;
@@ -968,5 +1016,18 @@ void set_identity_launch(const PtrBatch& Q, int nb, int rows, int k, bool cplx, 
     else set_identity_kernel<false><<<grid, 256, 0, stream>>>(Q, rows, k);
     CTMB_CUDA(cudaGetLastError());
 }
+
+#ifdef QR_PROFILE
+// per-phase clock64 totals of CTA 0 (tools/micro/qr_bench.cu built with -DQR_PROFILE)
+void qr_profile_dump(int steps) {
+    long long h[16];
+    cudaMemcpyFromSymbol(h, g_qr_prof, sizeof h);
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_qr_prof, z, sizeof z);
+    printf("qr phases, cycles per column step:");
+    for (int i = 0; i < 12; ++i) printf(" [%d] %.0f", i, (double)h[i] / steps);
+    printf("\n");
+}
+#endif
 
 }  // namespace ctmb

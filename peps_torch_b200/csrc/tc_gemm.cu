@@ -247,15 +247,25 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 16, WS_STAGES = 5;
 constexpr int WS_CONSUMERS = 256, WS_PRODUCERS = 128, WS_THREADS = WS_CONSUMERS + WS_PRODUCERS;
-constexpr int WS_LDS = WS_BK + 4;
+// Two shared-memory layouts per operand tile, chosen by the operand's fast direction in global memory so
+// that the producers' cp.async writes AND the consumers' fragment reads are both bank-conflict free:
+//   k-fast operand:  tile[row][k], row stride LDK = 20  (a warp writes two rows of 16 consecutive k)
+//   m-fast operand:  tile[k][row], k stride   LDM = 132 (a warp writes 32 consecutive rows of one k)
+// Fragment read of lane l: row = l>>2, k = l&3: half-warp addresses r*20+k resp. k*132+r hit 16 distinct
+// 8-byte bank pairs (20 = 4 mod 16, 132 = 4 mod 16).  With the first version's single [row][k] layout the
+// m-fast gathers wrote with an 8-way conflict (5.8e8 conflict wavefronts in the corner's C.T1.T2 product,
+// shared-memory pipe 64 % busy, DMMA 66 %: profiles/r1_c5_corner.md).
+constexpr int WS_LDK = WS_BK + 4, WS_LDM = WS_BM + 4;
+constexpr int WS_TILE = (WS_BM * WS_LDK > WS_BK * WS_LDM) ? WS_BM * WS_LDK : WS_BK * WS_LDM;   // doubles per operand stage
 
+template <bool A_KF, bool B_KF>
 __global__ void __launch_bounds__(WS_THREADS, 1) tc_kernel_ws(const __grid_constant__ TcParams p) {
-    constexpr int BM = WS_BM, BN = WS_BN, BK = WS_BK, STAGES = WS_STAGES, LDS = WS_LDS;
+    constexpr int BM = WS_BM, BN = WS_BN, BK = WS_BK, STAGES = WS_STAGES;
     constexpr int WM = 64, WN = 32, TM = WM / 8, TN = WN / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);
-    double* Bs = As + STAGES * BM * LDS;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(Bs + STAGES * BN * LDS);
+    double* Bs = As + STAGES * WS_TILE;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(Bs + STAGES * WS_TILE);
     unsigned long long* empty = full + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -265,6 +275,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_kernel_ws(const __grid_const
     const int m0 = (blockIdx.x / ntn) * BM, n0 = (blockIdx.x % ntn) * BN;
     const int M = p.M, N = p.N, K = p.K;
     const int ktiles = (K + BK - 1) / BK;
+    constexpr bool a_kfast = A_KF, b_kfast = B_KF;          // uniform over the batch (checked by the launcher)
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], WS_PRODUCERS); mbar_init(&empty[s], WS_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -276,32 +287,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_kernel_ws(const __grid_const
         const int pt = tid - WS_CONSUMERS;
         const double* __restrict__ A = reinterpret_cast<const double*>(be.A);
         const double* __restrict__ B = reinterpret_cast<const double*>(be.B);
-        const bool a_kfast = (be.flags & TC_A_KFAST) != 0, b_kfast = (be.flags & TC_B_KFAST) != 0;
         constexpr int PER = BM * BK / WS_PRODUCERS;          // 16 elements of A and of B per thread and k-tile
-        // element e = pt + i*128 of a 128 x 16 tile: k-fast operands -> (row e/16, k e%16) so that a warp
-        // reads two 128-byte rows; m-fast operands -> (row e%128, k e/128) so that a warp reads 32 consecutive rows
-        int a_row[PER], a_col[PER], a_off[PER], b_row[PER], b_col[PER], b_off[PER];
+        // element e = pt + i*128 of a 128 x 16 tile: k-fast operands -> (row pt/16 + 8i, k pt%16), m-fast -> (row pt, k i);
+        // everything but the row offsets is an arithmetic progression in i (128 % 16 == 0)
+        const int a_c0 = a_kfast ? (pt & 15) : 0, b_c0 = b_kfast ? (pt & 15) : 0;
+        constexpr int a_cs = a_kfast ? 0 : 1, b_cs = b_kfast ? 0 : 1;
+        const int a_s0 = a_kfast ? (pt >> 4) * WS_LDK + (pt & 15) : pt, b_s0 = b_kfast ? (pt >> 4) * WS_LDK + (pt & 15) : pt;
+        constexpr int a_ss = a_kfast ? 8 * WS_LDK : WS_LDM, b_ss = b_kfast ? 8 * WS_LDK : WS_LDM;
+        int a_off[PER], b_off[PER];
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            const int e = pt + i * WS_PRODUCERS;
-            a_row[i] = a_kfast ? e / BK : e % BM; a_col[i] = a_kfast ? e % BK : e / BM;
-            b_row[i] = b_kfast ? e / BK : e % BN; b_col[i] = b_kfast ? e % BK : e / BN;
-            a_off[i] = (m0 + a_row[i] < M) ? tb.a_m[m0 + a_row[i]] : -1;
-            b_off[i] = (n0 + b_row[i] < N) ? tb.b_n[n0 + b_row[i]] : -1;
+            const int ar = a_kfast ? (pt >> 4) + 8 * i : pt, br = b_kfast ? (pt >> 4) + 8 * i : pt;
+            a_off[i] = (m0 + ar < M) ? tb.a_m[m0 + ar] : -1;
+            b_off[i] = (n0 + br < N) ? tb.b_n[n0 + br] : -1;
         }
         for (int kt = 0; kt < ktiles; ++kt) {
             const int s = kt % STAGES;
             mbar_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);
-            double* as = As + s * BM * LDS;
-            double* bs = Bs + s * BN * LDS;
+            double* as = As + s * WS_TILE + a_s0;
+            double* bs = Bs + s * WS_TILE + b_s0;
             const int k0 = kt * BK;
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
-                const int ka = k0 + a_col[i], kb = k0 + b_col[i];
+                const int ka = k0 + a_c0 + i * a_cs, kb = k0 + b_c0 + i * b_cs;
                 const bool va = (a_off[i] >= 0) && (ka < K);
                 const bool vb = (b_off[i] >= 0) && (kb < K);
-                cp_async_8(as + a_row[i] * LDS + a_col[i], va ? (A + a_off[i] + tb.a_k[ka]) : A, va);
-                cp_async_8(bs + b_row[i] * LDS + b_col[i], vb ? (B + b_off[i] + tb.b_k[kb]) : B, vb);
+                cp_async_8(as + i * a_ss, va ? (A + a_off[i] + tb.a_k[ka]) : A, va);
+                cp_async_8(bs + i * b_ss, vb ? (B + b_off[i] + tb.b_k[kb]) : B, vb);
             }
             mbar_cp_async_arrive(&full[s]);
         }
@@ -310,6 +322,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_kernel_ws(const __grid_const
     // ------------------------------ consumers ------------------------------
     constexpr int WARPS_M = BM / WM;
     const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
+    const int fr = lane >> 2, fk = lane & 3;
+    // fragment addressing: base + i * (8 rows) + kk * (k stride)
+    const int a_base = a_kfast ? (wm0 + fr) * WS_LDK + fk : fk * WS_LDM + wm0 + fr;
+    const int b_base = b_kfast ? (wn0 + fr) * WS_LDK + fk : fk * WS_LDM + wn0 + fr;
+    constexpr int a_si = a_kfast ? 8 * WS_LDK : 8, a_sk = a_kfast ? 1 : WS_LDM;
+    constexpr int b_si = b_kfast ? 8 * WS_LDK : 8, b_sk = b_kfast ? 1 : WS_LDM;
     double acc[TM][TN][2];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -318,15 +336,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_kernel_ws(const __grid_const
     for (int kt = 0; kt < ktiles; ++kt) {
         const int s = kt % STAGES;
         mbar_wait(&full[s], (kt / STAGES) & 1);
-        const double* as = As + s * BM * LDS + (wm0 + (lane >> 2)) * LDS + (lane & 3);
-        const double* bs = Bs + s * BN * LDS + (wn0 + (lane >> 2)) * LDS + (lane & 3);
+        const double* as = As + s * WS_TILE + a_base;
+        const double* bs = Bs + s * WS_TILE + b_base;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             double af[TM], bf[TN];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) af[i] = as[i * 8 * LDS + kk];
+            for (int i = 0; i < TM; ++i) af[i] = as[i * a_si + kk * a_sk];
 #pragma unroll
-            for (int j = 0; j < TN; ++j) bf[j] = bs[j * 8 * LDS + kk];
+            for (int j = 0; j < TN; ++j) bf[j] = bs[j * b_si + kk * b_sk];
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -364,18 +382,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_kernel_ws(const __grid_const
     }
 }
 
-static void tc_run_ws(const TcParams& p, cudaStream_t stream) {
+template <bool A_KF, bool B_KF>
+static void tc_run_ws_t(const TcParams& p, cudaStream_t stream) {
+    auto kern = tc_kernel_ws<A_KF, B_KF>;
     static bool attr_set = false;
-    const size_t smem = (size_t)WS_STAGES * (WS_BM + WS_BN) * WS_LDS * 8 + 2 * WS_STAGES * 8;
+    const size_t smem = (size_t)WS_STAGES * 2 * WS_TILE * 8 + 2 * WS_STAGES * 8;
     if (!attr_set) {
-        CTMB_CUDA(cudaFuncSetAttribute(tc_kernel_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const long long tiles = (long long)((p.N + WS_BN - 1) / WS_BN) * ((p.M + WS_BM - 1) / WS_BM);
     CTMB_CHECK(tiles < (1ll << 31), "too many tiles for one launch");
     dim3 grid((unsigned)tiles, 1, p.nbatch);
-    tc_kernel_ws<<<grid, WS_THREADS, smem, stream>>>(p);
+    kern<<<grid, WS_THREADS, smem, stream>>>(p);
     CTMB_CUDA(cudaGetLastError());
+}
+// false if the loader flags differ inside the batch (the caller then uses the generic kernel)
+static bool tc_run_ws(const TcParams& p, cudaStream_t stream) {
+    const int lf = p.batch[0].flags & (TC_A_KFAST | TC_B_KFAST);
+    for (int i = 1; i < p.nbatch; ++i)
+        if ((p.batch[i].flags & (TC_A_KFAST | TC_B_KFAST)) != lf) return false;
+    const bool ak = (lf & TC_A_KFAST) != 0, bk = (lf & TC_B_KFAST) != 0;
+    if (ak && bk) tc_run_ws_t<true, true>(p, stream);
+    else if (ak) tc_run_ws_t<true, false>(p, stream);
+    else if (bk) tc_run_ws_t<false, true>(p, stream);
+    else tc_run_ws_t<false, false>(p, stream);
+    return true;
 }
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool CPLX>
@@ -410,11 +442,10 @@ void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream) {
         else if (ntiles(128, 128) >= 240 && p.M > 64 && p.N > 64) {
             static int ws_mode = -1;
             if (ws_mode < 0) { const char* ev = getenv("CTMB_GEMM_WS"); ws_mode = ev ? atoi(ev) : 1; }
-            if (ws_mode) tc_run_ws(p, stream);
-            else tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
+            if (!ws_mode || !tc_run_ws(p, stream)) tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
         }
         else if (ntiles(64, 64) >= 296) tc_run<64, 64, 16, 32, 16, 4, false>(p, stream);
-        else tc_run<32, 32, 16, 16, 8, 4, false>(p, stream);
+        else tc_run<32, 32, 32, 16, 8, 3, false>(p, stream);
     } else {
         if (p.N <= 16) tc_run<128, 32, 16, 32, 16, 3, true>(p, stream);
         else if (ntiles(64, 64) >= 296) tc_run<64, 64, 16, 32, 16, 3, true>(p, stream);

@@ -3,6 +3,10 @@
 #include <vector>
 #include <cstdlib>
 using namespace ctmb;
+#ifdef QR_PROFILE
+namespace ctmb { void qr_profile_dump(int steps); }
+#endif
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 [-DQR_PROFILE] -o tools/micro/qr_bench tools/micro/qr_bench.cu peps_torch_b200/csrc/qr.cu
 int main(int argc, char** argv) {
     int rows = argc > 1 ? atoi(argv[1]) : 432, cols = argc > 2 ? atoi(argv[2]) : 96, nb = 4;
     std::vector<double> h((size_t)rows * cols);
@@ -18,7 +22,9 @@ int main(int argc, char** argv) {
     for (int it = 0; it < 3; ++it) {
         for (int b = 0; b < nb; ++b) cudaMemcpy(A.p[b], h.data(), h.size() * 8, cudaMemcpyHostToDevice);
         cudaEventRecord(e0);
+#ifndef QR_PROFILE
         qr_launch(A, R, nb, rows, cols, rows, false, 0);
+#endif
         cudaEventRecord(e1);
         for (int b = 0; b < nb; ++b) cudaMemcpyAsync(A.p[b], h.data(), h.size() * 8, cudaMemcpyHostToDevice, 0);
         cudaEventRecord(e2);
@@ -33,6 +39,9 @@ int main(int argc, char** argv) {
         }
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
+#ifdef QR_PROFILE
+        qr_profile_dump(cols);
+#endif
         printf("qr %dx%d x%d: full (explicit Q) %.1f us | WY factor %.1f us | tsolve %.1f us  (%s)\n", rows, cols, nb, ms * 1e3,
                ms_f * 1e3, ms_t * 1e3, cudaGetErrorString(cudaGetLastError()));
     }
