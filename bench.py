@@ -438,9 +438,14 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
-    ap.add_argument('--parallel', default='shard', choices=['shard', 'replicas'],
-                    help='N>1: per-site shard of ONE CTM run with NCCL all-gathers (strong scaling, default) or one independent CTM run per GPU (weak scaling)')
+    ap.add_argument('--parallel', default='auto', choices=['auto', 'shard', 'replicas'],
+                    help='N>1: "shard" = per-site shard of ONE CTM run with NCCL all-gathers of P/Pt and C/T (strong scaling; '
+                         'default for c5, whose move is FLOP-bound); "replicas" = one independent CTM run per GPU (weak scaling; '
+                         'default for c1-c4, whose move time is set by the serial column steps of the decomposition and does not '
+                         'drop when a rank holds one site instead of four)')
     args = ap.parse_args()
+    if args.parallel == 'auto':
+        args.parallel = 'shard' if args.config == 'c5' else 'replicas'
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
 
     extern __shared__ __align__(16) unsigned char qrr_smem[];
     T* xs = reinterpret_cast<T*>(qrr_smem);               // [32*RPL]   broadcast of x / v
-    T* xbuf = xs + 32 * RPL;                              // [2][2*cols]
-    T* tot = xbuf + 4 * cols;                             // [2*cols]
+    T* xbuf = xs + 32 * RPL;                              // [2 parities][CL ranks][2*cols]: partials + row j, PUSHED by every rank
+    T* tot = xbuf + 4 * CL * cols;                        // [2*cols]
     T* tau = tot + 2 * cols;                              // [cols]
 
     T a[CPW][RPL];
@@ -442,7 +442,11 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
             a[i][r] = (lr < nloc && c < cols) ? A[(size_t)c * ld + (size_t)lr * CL + rank] : S::zero();
         }
     }
-    for (int c = tid; c < 4 * cols; c += QRC_THREADS) xbuf[c] = S::zero();
+    for (int c = tid; c < 4 * CL * cols; c += QRC_THREADS) xbuf[c] = S::zero();
+    // this CTA's slot inside every peer's xbuf (remote stores are fire-and-forget; the cluster barrier that
+    // follows publishes them, so that after the barrier every reduction is a LOCAL shared-memory read --
+    // the first version pulled the partials from the eight peers after the barrier: 1400 cycles per column step)
+    T* const myslot = xbuf + (size_t)rank * 2 * cols;     // local address of the slot; mapped to each peer per store
     __syncthreads();
     cluster.sync();
 
@@ -451,24 +455,24 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
 #endif
     int par = 0;
     auto gather = [&](int cbeg, int owner, bool with_row) {
-        const int off = par * 2 * cols;
+        const int off = par * CL * 2 * cols;
         const int ncol = cols - cbeg;
         const int per = QRC_THREADS / CL;
         for (int base = 0; base < ncol; base += per) {
             const int ci = base + tid / CL, r = tid % CL;
             T v = S::zero();
-            if (ci < ncol) v = cluster.map_shared_rank(xbuf, r)[off + cbeg + ci];
+            if (ci < ncol) v = xbuf[off + r * 2 * cols + cbeg + ci];
             for (int o = 1; o < CL; o <<= 1) v = S::add(v, S::shfl_xor(v, o));
             if (ci < ncol && r == 0) tot[cbeg + ci] = v;
         }
         if (with_row) {
-            const T* rowp = cluster.map_shared_rank(xbuf, owner) + off + cols;
+            const T* rowp = xbuf + off + owner * 2 * cols + cols;
             for (int c = cbeg + tid; c < cols; c += QRC_THREADS) tot[cols + c] = rowp[c];
         }
         __syncthreads();
     };
     // folded butterfly over the 8 per-column accumulators of a warp -> out[warp + NW*idx]
-    auto fold_publish = [&](T (&acc)[CPW], T* out) {
+    auto fold_publish = [&](T (&acc)[CPW], int poff) {
         const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0, hi4 = (lane & 4) != 0;
         T b4[4], b2[2], b1;
 #pragma unroll
@@ -492,7 +496,10 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         b1 = S::add(b1, S::shfl_xor(b1, 1));
         const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
         const int c = warp + NW * idx;
-        if ((lane & 3) == 0 && c < cols) out[c] = b1;
+        if ((lane & 3) == 0 && c < cols) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (r < CL) *cluster.map_shared_rank(myslot + poff + c, r) = b1;
+        }
     };
 
     const int kmax = min(rows, cols);
@@ -502,7 +509,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         const int wj = j % NW, ij = j / NW;               // column j: warp wj, register slot ij
         const bool mine_row = (rank == owner) && (lane == (lj & 31));
         const int rj = lj >> 5;
-        T* xb = xbuf + par * 2 * cols;
+        const int poff = par * CL * 2 * cols;
         QRP(0)
         if (warp == wj) {
 #pragma unroll
@@ -518,7 +525,10 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
                 const int c = warp + NW * i;
 #pragma unroll
                 for (int r = 0; r < RPL; ++r)
-                    if (r == rj && c < cols) xb[cols + c] = a[i][r];
+                    if (r == rj && c < cols) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) if (q < CL) *cluster.map_shared_rank(myslot + poff + cols + c, q) = a[i][r];
+                    }
             }
         }
         __syncthreads();
@@ -534,7 +544,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) acc[i] = S::fma(S::conj(xr[r]), a[i][r], acc[i]);
             }
-            fold_publish(acc, xb);
+            fold_publish(acc, poff);
         }
         QRP(2)
         cluster.sync();
@@ -623,7 +633,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         const bool mine_row = (rank == owner) && (lane == (lj & 31));
         const int rj = lj >> 5;
         const T tj = tau[j];
-        T* xb = xbuf + par * 2 * cols;
+        const int poff = par * CL * 2 * cols;
         if (warp == wj) {
 #pragma unroll
             for (int i = 0; i < CPW; ++i)
@@ -647,7 +657,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
                     for (int r = 0; r < RPL; ++r) acc[i] = S::fma(S::conj(vr[r]), a[i][r], acc[i]);
                 }
             }
-            fold_publish(acc, xb);
+            fold_publish(acc, poff);
             cluster.sync();
             gather(j + 1, owner, false);
 #pragma unroll
@@ -696,7 +706,7 @@ template <bool CPLX, int RPL>
 static void qr_reg_run(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch& Tau, int nb, int rows, int cols, int ld, int cl,
                        int wy_mode, cudaStream_t stream) {
     auto kern = qr_reg_kernel<CPLX, RPL>;
-    const size_t smem = ((size_t)32 * RPL + 7 * (size_t)cols) * (CPLX ? 16 : 8);
+    const size_t smem = ((size_t)32 * RPL + (4 * (size_t)cl + 3) * (size_t)cols) * (CPLX ? 16 : 8);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nb * cl);
     cfg.blockDim = dim3(QRC_THREADS);
