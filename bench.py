@@ -397,14 +397,19 @@ def run_ours(args):
     share = {k_: round(v['ms'] / total_ms, 4) for k_, v in prof.items()}
     if dom == 'tc_gemm':
         ach = g['flops'] / (g['ms'] * 1e-3) / 1e12
-        roof = {'kernel': 'tc_kernel (DMMA tensor-contraction GEMM)', 'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak,
+        roof = {'kernel': 'tc_kernel / tc_kernel_ws (DMMA tensor-contraction GEMM)', 'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak,
                 'unit': 'TFLOP/s', 'frac': ach / fp64_peak, 'traffic': None}
     else:
         v = prof[dom]
         ach = v['bytes'] / (v['ms'] * 1e-3) / 1e9
-        roof = {'kernel': {'qr': 'qr_kernel (Householder QR, one CTA per matrix)', 'jacobi': 'jacobi_kernel (one-sided Jacobi SVD in shared memory)',
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+        # (profiles/r1_c2_qr_tsolve_metrics.csv: qr_reg_kernel reads 1.37 MB = the four 432x96 sketches, writes stay in L2)
+        traffic = {'qr': 1.370624e6 if args.config == 'c2' else None, 'jacobi': None, 'misc': None}[dom]
+        roof = {'kernel': {'qr': 'qr_reg_kernel + wy_tsolve_kernel (Householder QR of the range-finder sketches, register-resident over a cluster of 8 CTAs per matrix; latency-bound: one cluster barrier per column)',
+                           'jacobi': 'jacobi_kernel (one-sided Jacobi SVD of the k x k factor in shared memory; shared-memory-bandwidth bound)',
                            'misc': 'misc kernels'}[dom], 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': ach / hbm_peak, 'traffic': None}
+                'frac': ach / hbm_peak, 'traffic': traffic,
+                'note': 'the step is latency-bound (2.8 GFLOP per move); the FLOP-bound kernels of the path are reported under kernel_level'}
     roof['peak_source'] = ('cuBLAS DGEMM 8192^3 measured in this run' if roof['bound'] == 'tensor'
                            else ('MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'))
     roof['avg_launch_us'] = 1e3 * prof[dom]['ms'] / max(1, prof[dom]['launches'])

@@ -49,7 +49,10 @@ constexpr int TC_MAX_TABS = 8;
 struct TcParams {
     int M, N, K;
     int nbatch;
+    int ksplit;                 // > 1: split-K, slice y of the grid reduces k in [y*kchunk, (y+1)*kchunk) into `partial`
+    int kchunk;
     int pad;
+    void* partial;              // [nbatch][ksplit][M][N] dense partial products (summed by tc_splitk_reduce_launch)
     double alpha;
     TcTables tab[TC_MAX_TABS];
     TcBatchEntry batch[TC_MAX_BATCH];
@@ -59,6 +62,10 @@ enum { TC_CONJ_A = 1, TC_CONJ_B = 2, TC_A_KFAST = 4, TC_B_KFAST = 8, TC_ACCUM = 
 
 // launches one batched contraction; cplx=false: double, cplx=true: double2 (re,im)
 void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream);
+// tile shape tc_launch will use for this problem (for the split-K decision of the caller)
+void tc_tile_shape(const TcParams& p, bool cplx, int& bm, int& bn);
+// C[c_m[m] + c_n[n]] (+)= alpha * sum_s partial[z][s][m][n], optional max|.|
+void tc_splitk_reduce_launch(const TcParams& p, bool cplx, cudaStream_t stream);
 void tc_init_attributes();
 
 // ---------------------------------------------------------------------------------

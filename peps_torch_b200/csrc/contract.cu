@@ -224,8 +224,28 @@ void Engine::flush() {
         const double es = cplx ? 16.0 : 8.0;
         const double fl = 2.0 * pend_.M * (double)pend_.N * pend_.K * (cplx ? 4.0 : 1.0) * pend_.nbatch;
         const double by = es * pend_.nbatch * ((double)pend_.M * pend_.K + (double)pend_.K * pend_.N + (double)pend_.M * pend_.N);
+        // Split-K for long reductions that would otherwise run on a handful of CTAs (the V^H A products of the
+        // blocked QR at chi*D^2 = 16384: 8 x 504 outputs, K = 16384): slices write dense partials into an
+        // engine-owned buffer, a second kernel sums them in a fixed order (deterministic, no atomics).
+        pend_.ksplit = 1; pend_.kchunk = 0; pend_.partial = nullptr;
+        int bm = 32, bn = 32;
+        tc_tile_shape(pend_, cplx, bm, bn);
+        const long long tiles = (long long)((pend_.M + bm - 1) / bm) * ((pend_.N + bn - 1) / bn) * pend_.nbatch;
+        static int sk_mode = -1;
+        if (sk_mode < 0) { const char* ev = getenv("CTMB_SPLITK"); sk_mode = ev ? atoi(ev) : 1; }
+        if (sk_mode && pend_.K >= 1024 && tiles <= 64) {
+            int S = (int)std::min<long long>(std::min<long long>(148 / tiles, pend_.K / 256), 32);
+            if (S >= 2) {
+                int kchunk = ((pend_.K + S - 1) / S + 31) & ~31;
+                S = (pend_.K + kchunk - 1) / kchunk;
+                pend_.ksplit = S; pend_.kchunk = kchunk;
+                pend_.partial = persistent("splitk", (size_t)pend_.nbatch * S * pend_.M * pend_.N * (cplx ? 16 : 8));
+                tc_tile_shape(pend_, cplx, bm, bn);
+            }
+        }
         ProfScope ps(*this, CAT_GEMM, fl, by);
         tc_launch(pend_, cplx, stream);
+        if (pend_.ksplit > 1) { ++launches; tc_splitk_reduce_launch(pend_, cplx, stream); }
     }
     pend_plans_.clear();
 }

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
     }
     constexpr int NR = 128 / GS;          // register-cached rows per lane (k <= NR*gs = 128)
     const bool cached = k <= NR * gs;
+    const bool vec2 = cached && (k & 1) == 0;   // even k: columns are 16-byte aligned
 
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         for (int round = 0; round < kk - 1; ++round) {
@@ -94,6 +95,66 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
                 else { p = (round + pi) % (kk - 1); q = (round - pi + (kk - 1)) % (kk - 1); }
                 if (p >= k || q >= k) continue;      // bye (uniform within the group)
                 if (p > q) { int t = p; p = q; q = t; }
+                if constexpr (!CPLX && SMEM) {
+                    if (vec2) {
+                        // 128-bit shared-memory accesses: lane owns the row PAIRS v = gl, gl+gs, ... (rows 2v, 2v+1).
+                        // Halves the LDS/STS instruction count of a kernel whose rounds are bound by the
+                        // shared-memory pipe (mio_throttle + barrier stalls, profiles/r1_c2_qr_jacobi.md).
+                        constexpr int NV = NR / 2;
+                        double2* gp2 = reinterpret_cast<double2*>(G + (size_t)p * k);
+                        double2* gq2 = reinterpret_cast<double2*>(G + (size_t)q * k);
+                        const int kv = k >> 1;
+                        double2 xv[NV], yv[NV];
+                        double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            const int v = gl + i * gs;
+                            xv[i] = v < kv ? gp2[v] : make_double2(0.0, 0.0);
+                            yv[i] = v < kv ? gq2[v] : make_double2(0.0, 0.0);
+                            a = fma(xv[i].x, xv[i].x, fma(xv[i].y, xv[i].y, a));
+                            b = fma(yv[i].x, yv[i].x, fma(yv[i].y, yv[i].y, b));
+                            g = fma(xv[i].x, yv[i].x, fma(xv[i].y, yv[i].y, g));
+                        }
+                        for (int o = gs >> 1; o > 0; o >>= 1) {
+                            a += __shfl_xor_sync(gmask, a, o);
+                            b += __shfl_xor_sync(gmask, b, o);
+                            g += __shfl_xor_sync(gmask, g, o);
+                        }
+                        const double ag2 = g * g;
+                        if (ag2 > tol2 * a * b && ag2 > 0.0) {
+                            if (gl == 0) { rotated = 1; if (ag2 > 1.0e-16 * a * b) notsmall = 1; }
+                            const double d = b - a;
+                            const double r = rsqrt(d * d + 4.0 * ag2);
+                            const double c2 = 0.5 + 0.5 * fabs(d) * r;
+                            const double rc = rsqrt(c2);
+                            const double c = c2 * rc;
+                            const double al = g * copysign(r * rc, d);
+#pragma unroll
+                            for (int i = 0; i < NV; ++i) {
+                                const int v = gl + i * gs;
+                                if (v < kv) {
+                                    const double2 x = xv[i], y = yv[i];
+                                    gp2[v] = make_double2(x.x * c - al * y.x, x.y * c - al * y.y);
+                                    gq2[v] = make_double2(al * x.x + y.x * c, al * x.y + y.y * c);
+                                }
+                            }
+                            if (accw) {
+                                double2* wp2 = reinterpret_cast<double2*>(W + (size_t)p * k);
+                                double2* wq2 = reinterpret_cast<double2*>(W + (size_t)q * k);
+#pragma unroll
+                                for (int i = 0; i < NV; ++i) {
+                                    const int v = gl + i * gs;
+                                    if (v < kv) {
+                                        const double2 u = wp2[v], w = wq2[v];
+                                        wp2[v] = make_double2(u.x * c - al * w.x, u.y * c - al * w.y);
+                                        wq2[v] = make_double2(al * u.x + w.x * c, al * u.y + w.y * c);
+                                    }
+                                }
+                            }
+                        }
+                        continue;
+                    }
+                }
                 T* gp = G + (size_t)p * k;
                 T* gq = G + (size_t)q * k;
                 double a = 0.0, b = 0.0;
@@ -397,6 +458,7 @@ void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, in
     };
     if (use_smem) {
         if (cplx) launch(jacobi_kernel<true, true, 16, 512>, 512);
+        else if ((k + 1) / 2 <= 48) launch(jacobi_kernel<false, true, 8, 384>, 384);   // 170 registers: no spills
         else launch(jacobi_kernel<false, true, 8, 512>, 512);
     } else {
         if (cplx) launch(jacobi_kernel<true, false, 32, 1024>, 1024);

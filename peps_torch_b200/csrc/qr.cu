@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
 
     extern __shared__ __align__(16) unsigned char qrr_smem[];
     T* xs = reinterpret_cast<T*>(qrr_smem);               // [32*RPL]   broadcast of x / v
-    T* xbuf = xs + 32 * RPL;                              // [2 parities][CL ranks][2*cols]: partials + row j, PUSHED by every rank
-    T* tot = xbuf + 4 * CL * cols;                        // [2*cols]
+    T* xbuf = xs + 32 * RPL;                              // [2][2*cols]
+    T* tot = xbuf + 4 * cols;                             // [2*cols]
     T* tau = tot + 2 * cols;                              // [cols]
 
     T a[CPW][RPL];
@@ -442,11 +442,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
             a[i][r] = (lr < nloc && c < cols) ? A[(size_t)c * ld + (size_t)lr * CL + rank] : S::zero();
         }
     }
-    for (int c = tid; c < 4 * CL * cols; c += QRC_THREADS) xbuf[c] = S::zero();
-    // this CTA's slot inside every peer's xbuf (remote stores are fire-and-forget; the cluster barrier that
-    // follows publishes them, so that after the barrier every reduction is a LOCAL shared-memory read --
-    // the first version pulled the partials from the eight peers after the barrier: 1400 cycles per column step)
-    T* const myslot = xbuf + (size_t)rank * 2 * cols;     // local address of the slot; mapped to each peer per store
+    for (int c = tid; c < 4 * cols; c += QRC_THREADS) xbuf[c] = S::zero();
     __syncthreads();
     cluster.sync();
 
@@ -455,24 +451,24 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
 #endif
     int par = 0;
     auto gather = [&](int cbeg, int owner, bool with_row) {
-        const int off = par * CL * 2 * cols;
+        const int off = par * 2 * cols;
         const int ncol = cols - cbeg;
         const int per = QRC_THREADS / CL;
         for (int base = 0; base < ncol; base += per) {
             const int ci = base + tid / CL, r = tid % CL;
             T v = S::zero();
-            if (ci < ncol) v = xbuf[off + r * 2 * cols + cbeg + ci];
+            if (ci < ncol) v = cluster.map_shared_rank(xbuf, r)[off + cbeg + ci];
             for (int o = 1; o < CL; o <<= 1) v = S::add(v, S::shfl_xor(v, o));
             if (ci < ncol && r == 0) tot[cbeg + ci] = v;
         }
         if (with_row) {
-            const T* rowp = xbuf + off + owner * 2 * cols + cols;
+            const T* rowp = cluster.map_shared_rank(xbuf, owner) + off + cols;
             for (int c = cbeg + tid; c < cols; c += QRC_THREADS) tot[cols + c] = rowp[c];
         }
         __syncthreads();
     };
     // folded butterfly over the 8 per-column accumulators of a warp -> out[warp + NW*idx]
-    auto fold_publish = [&](T (&acc)[CPW], int poff) {
+    auto fold_publish = [&](T (&acc)[CPW], T* out) {
         const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0, hi4 = (lane & 4) != 0;
         T b4[4], b2[2], b1;
 #pragma unroll
@@ -496,10 +492,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         b1 = S::add(b1, S::shfl_xor(b1, 1));
         const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
         const int c = warp + NW * idx;
-        if ((lane & 3) == 0 && c < cols) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) if (r < CL) *cluster.map_shared_rank(myslot + poff + c, r) = b1;
-        }
+        if ((lane & 3) == 0 && c < cols) out[c] = b1;
     };
 
     const int kmax = min(rows, cols);
@@ -509,7 +502,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         const int wj = j % NW, ij = j / NW;               // column j: warp wj, register slot ij
         const bool mine_row = (rank == owner) && (lane == (lj & 31));
         const int rj = lj >> 5;
-        const int poff = par * CL * 2 * cols;
+        T* xb = xbuf + par * 2 * cols;
         QRP(0)
         if (warp == wj) {
 #pragma unroll
@@ -525,10 +518,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
                 const int c = warp + NW * i;
 #pragma unroll
                 for (int r = 0; r < RPL; ++r)
-                    if (r == rj && c < cols) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) if (q < CL) *cluster.map_shared_rank(myslot + poff + cols + c, q) = a[i][r];
-                    }
+                    if (r == rj && c < cols) xb[cols + c] = a[i][r];
             }
         }
         __syncthreads();
@@ -544,7 +534,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) acc[i] = S::fma(S::conj(xr[r]), a[i][r], acc[i]);
             }
-            fold_publish(acc, poff);
+            fold_publish(acc, xb);
         }
         QRP(2)
         cluster.sync();
@@ -633,7 +623,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         const bool mine_row = (rank == owner) && (lane == (lj & 31));
         const int rj = lj >> 5;
         const T tj = tau[j];
-        const int poff = par * CL * 2 * cols;
+        T* xb = xbuf + par * 2 * cols;
         if (warp == wj) {
 #pragma unroll
             for (int i = 0; i < CPW; ++i)
@@ -657,7 +647,7 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
                     for (int r = 0; r < RPL; ++r) acc[i] = S::fma(S::conj(vr[r]), a[i][r], acc[i]);
                 }
             }
-            fold_publish(acc, poff);
+            fold_publish(acc, xb);
             cluster.sync();
             gather(j + 1, owner, false);
 #pragma unroll
@@ -706,7 +696,7 @@ template <bool CPLX, int RPL>
 static void qr_reg_run(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch& Tau, int nb, int rows, int cols, int ld, int cl,
                        int wy_mode, cudaStream_t stream) {
     auto kern = qr_reg_kernel<CPLX, RPL>;
-    const size_t smem = ((size_t)32 * RPL + (4 * (size_t)cl + 3) * (size_t)cols) * (CPLX ? 16 : 8);
+    const size_t smem = ((size_t)32 * RPL + 7 * (size_t)cols) * (CPLX ? 16 : 8);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nb * cl);
     cfg.blockDim = dim3(QRC_THREADS);
@@ -818,37 +808,48 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
         // dot products spread over the whole CTA (G(r,t) is a warp-wide broadcast, X(t,c) is consecutive in c).
         // A single thread walking a whole column (4560 dependent shared-memory FMAs for k = 96) took 74 us.
         constexpr int NB = 16;
+        constexpr int RG = TS_THREADS / 128;                 // row groups of the elimination phase
         for (int s1 = k; s1 > 0; s1 -= NB) {
             const int s0 = s1 > NB ? s1 - NB : 0;
-            const int c = s0 + tid;                          // X is upper triangular: columns c >= s0 only
+            const int nbk = s1 - s0;
+            // phase 1: thread c solves the nbk x nbk triangular block for its column with the block of X in registers
+            // (rows below the diagonal of X are zero and come out as zero: no special casing)
+            const int c = s0 + tid;
             if (c < k) {
-                for (int s = min(s1 - 1, c); s >= s0; --s) {
-                    const T* gr = Gs + (size_t)s * k;
-                    T a0 = S::zero(), a1 = S::zero();
-                    int t = s + 1;
-                    const int te = min(s1 - 1, c);
-                    for (; t + 1 <= te; t += 2) {
-                        a0 = S::fma(gr[t], Xs[t * k + c], a0);
-                        a1 = S::fma(gr[t + 1], Xs[(t + 1) * k + c], a1);
+                T x[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) x[i] = i < nbk ? Xs[(s0 + i) * k + c] : S::zero();
+#pragma unroll
+                for (int i = NB - 1; i >= 0; --i) {
+                    if (i < nbk) {
+                        const T* gr = Gs + (size_t)(s0 + i) * k + s0;
+                        T acc = S::zero();
+#pragma unroll
+                        for (int t = i + 1; t < NB; ++t) if (t < nbk) acc = S::fma(gr[t], x[t], acc);
+                        x[i] = S::mul(taus[s0 + i], S::sub(x[i], acc));
                     }
-                    if (t <= te) a0 = S::fma(gr[t], Xs[t * k + c], a0);
-                    Xs[s * k + c] = S::mul(taus[s], S::sub(Xs[s * k + c], S::add(a0, a1)));
                 }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) if (i < nbk) Xs[(s0 + i) * k + c] = x[i];
             }
             __syncthreads();
-            const int wcols = k - s0;
-            for (int it = tid; it < s0 * wcols; it += TS_THREADS) {
-                const int r = it / wcols, cc = s0 + it % wcols;
-                const T* gr = Gs + (size_t)r * k;
-                T a0 = S::zero(), a1 = S::zero();
-                const int te = min(s1 - 1, cc);              // X(t,cc) = 0 for t > cc
-                int t = s0;
-                for (; t + 1 <= te; t += 2) {
-                    a0 = S::fma(gr[t], Xs[t * k + cc], a0);
-                    a1 = S::fma(gr[t + 1], Xs[(t + 1) * k + cc], a1);
+            // phase 2: eliminate the finished rows from all rows above: thread (g, cc) keeps the block of column cc
+            // in registers and walks rows g, g+RG, ...; G(r, s0..s1) is a warp-wide broadcast
+            const int cc = s0 + (tid & 127), g = tid >> 7;
+            if (cc < k && s0 > 0) {
+                T x[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) x[i] = i < nbk ? Xs[(s0 + i) * k + cc] : S::zero();
+                for (int r = g; r < s0; r += RG) {
+                    const T* gr = Gs + (size_t)r * k + s0;
+                    T a0 = S::zero(), a1 = S::zero();
+#pragma unroll
+                    for (int t = 0; t < NB; t += 2) {
+                        if (t < nbk) a0 = S::fma(gr[t], x[t], a0);
+                        if (t + 1 < nbk) a1 = S::fma(gr[t + 1], x[t + 1], a1);
+                    }
+                    Xs[r * k + cc] = S::sub(Xs[r * k + cc], S::add(a0, a1));
                 }
-                if (t <= te) a0 = S::fma(gr[t], Xs[t * k + cc], a0);
-                Xs[r * k + cc] = S::sub(Xs[r * k + cc], S::add(a0, a1));
             }
             __syncthreads();
         }

@@ -85,8 +85,12 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
         b_off[i] = (n0 + r < N) ? tb.b_n[n0 + r] : -1;
     }
 
+    // split-K: this CTA reduces k in [kbeg, kend) only and writes a dense partial tile
+    const int kbeg = p.ksplit > 1 ? blockIdx.y * p.kchunk : 0;
+    const int kend = p.ksplit > 1 ? min(K, kbeg + p.kchunk) : K;
     auto load_tile = [&](int kt, int stage) {
-        const int k0 = kt * BK;
+        const int k0 = kbeg + kt * BK;
+        const int K = kend;                    // shadows the full extent: loads beyond the slice are zero-filled
         T* as = As + stage * BM * LDS;
         T* bs = Bs + stage * BN * LDS;
 #pragma unroll
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
             if constexpr (CPLX) acci[i][j][0] = acci[i][j][1] = 0.0;
         }
 
-    const int ktiles = (K + BK - 1) / BK;
+    const int ktiles = (kend - kbeg + BK - 1) / BK;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < ktiles) load_tile(s, s);
@@ -167,6 +171,25 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
     }
     cp_async_wait<0>();
 
+    if (p.ksplit > 1) {
+        // split-K epilogue: dense partial tile, no alpha / accumulate / amax (the reduction kernel applies them)
+        T* __restrict__ P = reinterpret_cast<T*>(p.partial) + ((size_t)(blockIdx.z * p.ksplit + blockIdx.y) * M) * N;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int r = m0 + wm0 + i * 8 + (lane >> 2);
+            if (r >= M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = n0 + wn0 + j * 8 + (lane & 3) * 2 + h;
+                    if (c >= N) continue;
+                    if constexpr (!CPLX) P[(size_t)r * N + c] = acc[i][j][h];
+                    else P[(size_t)r * N + c] = make_double2(acc[i][j][h], acci[i][j][h]);
+                }
+        }
+        return;
+    }
     // epilogue: registers -> global through the C offset tables
     T* __restrict__ C = reinterpret_cast<T*>(be.C);
     const double alpha = p.alpha;
@@ -426,29 +449,89 @@ static void tc_run(const TcParams& p, cudaStream_t stream) {
     }
     const long long tiles = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM);
     CTMB_CHECK(tiles < (1ll << 31), "too many tiles for one launch");
-    dim3 grid((unsigned)tiles, 1, p.nbatch);
+    dim3 grid((unsigned)tiles, p.ksplit > 1 ? p.ksplit : 1, p.nbatch);
     kern<<<grid, 256, smem, stream>>>(p);
     CTMB_CUDA(cudaGetLastError());
+}
+
+template <bool CPLX>
+__global__ void tc_splitk_reduce_kernel(const __grid_constant__ TcParams p) {
+    using T = typename std::conditional<CPLX, double2, double>::type;
+    const TcBatchEntry be = p.batch[blockIdx.y];
+    const TcTables tb = p.tab[be.tab];
+    const long long mn = (long long)p.M * p.N;
+    const T* __restrict__ P = reinterpret_cast<const T*>(p.partial) + (size_t)blockIdx.y * p.ksplit * mn;
+    T* __restrict__ C = reinterpret_cast<T*>(be.C);
+    const bool accum = (be.flags & TC_ACCUM) != 0;
+    double lmax = 0.0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < mn; e += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(e / p.N), n = (int)(e % p.N);
+        const int off = tb.c_m[m] + tb.c_n[n];
+        if constexpr (!CPLX) {
+            double v = 0.0;
+            for (int s = 0; s < p.ksplit; ++s) v += P[(size_t)s * mn + e];
+            v *= p.alpha;
+            if (accum) v += C[off];
+            C[off] = v;
+            lmax = fmax(lmax, fabs(v));
+        } else {
+            double2 v = make_double2(0.0, 0.0);
+            for (int s = 0; s < p.ksplit; ++s) { const double2 q = P[(size_t)s * mn + e]; v.x += q.x; v.y += q.y; }
+            v.x *= p.alpha; v.y *= p.alpha;
+            if (accum) { const double2 o = C[off]; v.x += o.x; v.y += o.y; }
+            C[off] = v;
+            lmax = fmax(lmax, hypot(v.x, v.y));
+        }
+    }
+    if (be.amax != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if ((threadIdx.x & 31) == 0) atomicMax(be.amax, (unsigned long long)__double_as_longlong(lmax));
+    }
+}
+void tc_splitk_reduce_launch(const TcParams& p, bool cplx, cudaStream_t stream) {
+    const long long mn = (long long)p.M * p.N;
+    dim3 grid((unsigned)std::min<long long>(256, (mn + 255) / 256), p.nbatch);
+    if (cplx) tc_splitk_reduce_kernel<true><<<grid, 256, 0, stream>>>(p);
+    else tc_splitk_reduce_kernel<false><<<grid, 256, 0, stream>>>(p);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// 0: 128x32, 1: 128x128 (warp-specialised when possible), 2: 64x64, 3: 32x32
+static int tc_config(const TcParams& p, bool cplx) {
+    auto ntiles = [&](int bm, int bn) { return (long long)((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * p.nbatch; };
+    if (p.N <= 16) return 0;
+    if (!cplx && p.ksplit <= 1 && ntiles(128, 128) >= 240 && p.M > 64 && p.N > 64) return 1;
+    if (ntiles(64, 64) >= 296) return 2;
+    return 3;
+}
+void tc_tile_shape(const TcParams& p, bool cplx, int& bm, int& bn) {
+    switch (tc_config(p, cplx)) {
+        case 0: bm = 128; bn = 32; break;
+        case 1: bm = 128; bn = 128; break;
+        case 2: bm = 64; bn = 64; break;
+        default: bm = 32; bn = 32; break;
+    }
 }
 
 void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream) {
     CTMB_CHECK(p.nbatch >= 1 && p.nbatch <= TC_MAX_BATCH, "bad batch count");
     if (p.M == 0 || p.N == 0) return;
-    auto ntiles = [&](int bm, int bn) { return (long long)((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * p.nbatch; };
     // One SM retires only ~64 FP64 FMA per clock, so the serial K loop of a CTA is the latency of
     // a small contraction: prefer the tile that spreads the work over at least ~2 waves of CTAs.
+    const int cfg = tc_config(p, cplx);
     if (!cplx) {
-        if (p.N <= 16) tc_run<128, 32, 16, 32, 16, 3, false>(p, stream);
-        else if (ntiles(128, 128) >= 240 && p.M > 64 && p.N > 64) {
+        if (cfg == 0) tc_run<128, 32, 16, 32, 16, 3, false>(p, stream);
+        else if (cfg == 1) {
             static int ws_mode = -1;
             if (ws_mode < 0) { const char* ev = getenv("CTMB_GEMM_WS"); ws_mode = ev ? atoi(ev) : 1; }
             if (!ws_mode || !tc_run_ws(p, stream)) tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
         }
-        else if (ntiles(64, 64) >= 296) tc_run<64, 64, 16, 32, 16, 4, false>(p, stream);
+        else if (cfg == 2) tc_run<64, 64, 16, 32, 16, 4, false>(p, stream);
         else tc_run<32, 32, 32, 16, 8, 3, false>(p, stream);
     } else {
-        if (p.N <= 16) tc_run<128, 32, 16, 32, 16, 3, true>(p, stream);
-        else if (ntiles(64, 64) >= 296) tc_run<64, 64, 16, 32, 16, 3, true>(p, stream);
+        if (cfg == 0) tc_run<128, 32, 16, 32, 16, 3, true>(p, stream);
+        else if (cfg == 2) tc_run<64, 64, 16, 32, 16, 3, true>(p, stream);
         else tc_run<32, 32, 16, 16, 8, 4, true>(p, stream);
     }
 }

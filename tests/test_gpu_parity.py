@@ -38,7 +38,9 @@ def test_einsum2_shapes_and_conj(eng, dev, dt):
     cases = [('ab,buc->auc', (7, 5), (5, 3, 11)), ('auc,ael->ucel', (13, 4, 9), (13, 9, 4)),
              ('ik,kj->ij', (130, 70), (70, 150)), ('ki,kj->ij', (200, 129), (200, 65)),
              ('pqcert,sprfg->qcetsfg', (3, 3, 5, 5, 3, 3), (2, 3, 3, 3, 3)),
-             ('ik,kj->ji', (1, 1), (1, 1)), ('ik,kj->ij', (257, 33), (33, 31)), ('ik,kj->ij', (300, 500), (500, 260))]
+             ('ik,kj->ji', (1, 1), (1, 1)), ('ik,kj->ij', (257, 33), (33, 31)), ('ik,kj->ij', (300, 500), (500, 260)),
+             # long reductions on few tiles: split-K path (slices + deterministic reduction kernel)
+             ('ik,kj->ij', (40, 5000), (5000, 24)), ('ki,kj->ji', (3001, 8), (3001, 70)), ('ik,jk->ij', (130, 2048), (9, 2048))]
     for spec, sa, sb in cases:
         A = torch.randn(sa, dtype=dt, device=dev)
         B = torch.randn(sb, dtype=dt, device=dev)

@@ -20,6 +20,7 @@ for kv in sys.argv[3:]:
     opts[k] = float(v) if '.' in v or 'e' in v else int(v)
 dev = torch.device('cuda:0')
 eng = default_engine()
+onemove = bool(opts.pop('onemove', 0))      # time single ctm_MOVE calls (config c5: seconds per move)
 for k, v in opts.items():
     setattr(eng.options, k, v)
 kind, sites, v2s, lX, lY, chi = bench.make_state(cfg)
@@ -30,7 +31,13 @@ else:
 DIRS = [(0, -1), (-1, 0), (0, 1), (1, 0)]
 
 
+_dir = [0]
+
+
 def iteration():
+    if onemove and kind != 'c4v':
+        eng.move_generic(DIRS[_dir[0] % 4], st, env); _dir[0] += 1
+        return 1
     if kind == 'c4v':
         nC, nT, _ = eng.move_c4v(st.site(), env.C[env.keyC], env.T[env.keyT], chi)
         env.C[env.keyC], env.T[env.keyT] = nC, nT
