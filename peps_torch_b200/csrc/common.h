@@ -97,6 +97,8 @@ void qr_panel_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& Tau
 void qr_copy_r_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& R, int nb, int k, int j0, int b, int ld,
                       bool cplx, cudaStream_t stream);
 void set_identity_launch(const PtrBatch& Q, int nb, int rows, int k, bool cplx, cudaStream_t stream);
+void qr_copy_v_launch(const PtrBatch& A, const PtrBatch& V, int nb, int rows, int J0, int j0, int bw, bool cplx,
+                      cudaStream_t stream);
 
 // one-sided Jacobi SVD of k x k column-major G (ld=k): on exit G = Uhat*Sigma (columns
 // orthogonal), W accumulates the right rotations (G_in * W = G_out), sig[k] the column norms.

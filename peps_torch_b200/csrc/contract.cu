@@ -233,8 +233,8 @@ void Engine::flush() {
         const long long tiles = (long long)((pend_.M + bm - 1) / bm) * ((pend_.N + bn - 1) / bn) * pend_.nbatch;
         static int sk_mode = -1;
         if (sk_mode < 0) { const char* ev = getenv("CTMB_SPLITK"); sk_mode = ev ? atoi(ev) : 1; }
-        if (sk_mode && pend_.K >= 1024 && tiles <= 64) {
-            int S = (int)std::min<long long>(std::min<long long>(148 / tiles, pend_.K / 256), 32);
+        if (sk_mode && pend_.K >= 1024 && tiles <= 148) {
+            int S = (int)std::min<long long>(std::min<long long>(296 / tiles, pend_.K / 256), 32);
             if (S >= 2) {
                 int kchunk = ((pend_.K + S - 1) / S + 31) & ~31;
                 S = (pend_.K + kchunk - 1) / kchunk;

@@ -222,88 +222,99 @@ static int sketch_width(int m, int n, int chi, const ctmb_options& o) {
 }
 
 // Blocked Householder QR (explicit thin Q) for sketches that fit neither the registers nor the shared
-// memory of one cluster: panels of width w.b are factored in WY form by qr_panel_launch, the trailing
-// matrix is updated with three GEMMs per panel  A2 -= V (T^H (V^H A2)),  and Q = H_1 .. H_P E is
-// accumulated backwards into a second buffer the same way.  All GEMMs are batched over the nb matrices.
-struct QrBlockedWs { PtrBatch Q{}, Tau{}, Rpp{}, G{}, T{}, W{}, W2{}; int b = 0; };
+// memory of one cluster.  Two levels: LEAF panels of width w.b (what one cluster can hold: 8 columns at
+// 16384 rows) are factored in WY form by qr_panel_launch and applied only inside their SUPER panel of
+// width w.B <= 128; the reflectors of a super panel are then aggregated (T from the Gram matrix of its
+// V, wy_tsolve) and applied to the rest of the matrix with three GEMMs  A2 -= V (T^H (V^H A2)).
+// Q = H_1 .. H_P E is accumulated backwards per super panel the same way.  (With leaf panels only, the
+// 16384 x 512 sketch of config c5 paid 64 full-width trailing updates with K = 8 per QR: 1.4 s per move.)
+// V is kept in its own buffer (zeros above each leaf's diagonal), the factor R stays in the upper part of A.
+struct QrBlockedWs { PtrBatch Q{}, V{}, Tau{}, Rpp{}, G{}, Tl{}, T{}, W{}, W2{}; int b = 0, B = 0; };
 
 static void qr_blocked_alloc(Engine& e, QrBlockedWs& w, int bidx, int rows_max, int k, int b) {
     const size_t es = e.esize();
-    const int np = (k + b - 1) / b;
-    w.b = b;
+    const int B = std::max(b, std::min(e.cplx ? 64 : 128, k));      // wy_tsolve keeps a B x B matrix in shared memory
+    w.b = b; w.B = B;
+    const int nl = (k + b - 1) / b, ns = (k + B - 1) / B;
     w.Q.p[bidx] = e.ws.alloc((size_t)rows_max * k * es);
+    w.V.p[bidx] = e.ws.alloc((size_t)rows_max * k * es);
     w.Tau.p[bidx] = e.ws.alloc((size_t)k * es);
-    w.Rpp.p[bidx] = e.ws.alloc((size_t)b * b * es);
-    w.G.p[bidx] = e.ws.alloc((size_t)b * b * es);
-    w.T.p[bidx] = e.ws.alloc((size_t)np * b * b * es);
-    w.W.p[bidx] = e.ws.alloc((size_t)b * k * es);
-    w.W2.p[bidx] = e.ws.alloc((size_t)b * k * es);
+    w.Rpp.p[bidx] = e.ws.alloc((size_t)nl * b * b * es);
+    w.G.p[bidx] = e.ws.alloc((size_t)B * B * es);
+    w.Tl.p[bidx] = e.ws.alloc((size_t)b * b * es);
+    w.T.p[bidx] = e.ws.alloc((size_t)ns * B * B * es);
+    w.W.p[bidx] = e.ws.alloc((size_t)B * k * es);
+    w.W2.p[bidx] = e.ws.alloc((size_t)B * k * es);
 }
 
 static void qr_blocked(Engine& e, PtrBatch& cur, const PtrBatch& Rout, int nb, int rows, int k, QrBlockedWs& w) {
     const size_t es = e.esize();
-    const int b = w.b;
+    const int b = w.b, B = w.B;
     auto off = [&](const PtrBatch& P, int i, size_t elems) { return (void*)((char*)P.p[i] + elems * es); };
-    e.flush();
-    for (int j0 = 0; j0 < k; j0 += b) {
-        const int bw = std::min(b, k - j0), prow = rows - j0, nt = k - j0 - bw, pi = j0 / b;
-        PtrBatch Ap{}, TauP{}, Tp{};
+    auto sub = [&](const PtrBatch& P, size_t elems) { PtrBatch r{}; for (int i = 0; i < nb; ++i) r.p[i] = off(P, i, elems); return r; };
+    // A2[:, c0:c0+nc] (rows r0..) -= V (T^H (V^H A2)) resp. (T (V^H A2)) with V = Vbuf[r0:, v0:v0+vw], Tm stored [c][s] = T[s,c]
+    auto apply = [&](const PtrBatch& Tgt, int r0, int v0, int vw, const PtrBatch& Tm, int c0, int nc, bool adjoint) {
+        if (nc <= 0) return;
+        const int prow = rows - r0;
         for (int i = 0; i < nb; ++i) {
-            Ap.p[i] = off(cur, i, (size_t)j0 * rows + j0);
-            TauP.p[i] = off(w.Tau, i, j0);
-            Tp.p[i] = off(w.T, i, (size_t)pi * b * b);
-        }
-        { ProfScope ps(e, Engine::CAT_QR, (e.cplx ? 4.0 : 1.0) * nb * 2.0 * prow * bw * bw, 2.0 * es * nb * (double)prow * bw);
-          qr_panel_launch(Ap, w.Rpp, TauP, nb, prow, bw, rows, e.cplx, e.stream); }
-        for (int i = 0; i < nb; ++i) {                  // G[t][s] = v_s^H v_t
-            Tn V = make_strided(Ap.p[i], "si", {bw, prow}, {rows, 1});
-            e.contract(V, true, relabel(V, "ti"), false, make_tn(w.G.p[i], "ts", {bw, bw}));
+            Tn V = make_strided(off(w.V, i, (size_t)v0 * rows + r0), "si", {vw, prow}, {rows, 1});
+            Tn A2 = make_strided(off(Tgt, i, (size_t)c0 * rows + r0), "ci", {nc, prow}, {rows, 1});
+            e.contract(V, true, A2, false, make_tn(w.W.p[i], "cs", {nc, vw}));
         }
         e.flush();
-        { ProfScope ps(e, Engine::CAT_QR, 0, 3.0 * es * nb * (double)bw * bw);
-          wy_tsolve_launch(w.G, TauP, Ap, Tp, nb, bw, 0, e.cplx, e.stream); }          // Tp[c][s] = T[s,c]
-        if (nt > 0) {
-            for (int i = 0; i < nb; ++i) {
-                Tn V = make_strided(Ap.p[i], "si", {bw, prow}, {rows, 1});
-                Tn A2 = make_strided(off(cur, i, (size_t)(j0 + bw) * rows + j0), "ci", {nt, prow}, {rows, 1});
-                e.contract(V, true, A2, false, make_tn(w.W.p[i], "cs", {nt, bw}));
-            }
-            e.flush();
-            for (int i = 0; i < nb; ++i)                // W2[c][t] = sum_s conj(T[s,t]) W[c][s]
-                e.contract(make_tn(Tp.p[i], "ts", {bw, bw}), true, make_tn(w.W.p[i], "cs", {nt, bw}), false,
-                           make_tn(w.W2.p[i], "ct", {nt, bw}));
-            e.flush();
-            for (int i = 0; i < nb; ++i) {
-                Tn V = make_strided(Ap.p[i], "ti", {bw, prow}, {rows, 1});
-                Tn A2 = make_strided(off(cur, i, (size_t)(j0 + bw) * rows + j0), "ci", {nt, prow}, {rows, 1});
-                e.contract(V, false, make_tn(w.W2.p[i], "ct", {nt, bw}), false, A2, nullptr, -1.0, true);
-            }
-            e.flush();
+        for (int i = 0; i < nb; ++i) {
+            if (adjoint)    // W2[c][t] = sum_s conj(T[s,t]) W[c][s]
+                e.contract(make_tn(Tm.p[i], "ts", {vw, vw}), true, make_tn(w.W.p[i], "cs", {nc, vw}), false, make_tn(w.W2.p[i], "ct", {nc, vw}));
+            else            // W2[c][t] = sum_s T[t,s] W[c][s]
+                e.contract(make_tn(Tm.p[i], "st", {vw, vw}), false, make_tn(w.W.p[i], "cs", {nc, vw}), false, make_tn(w.W2.p[i], "ct", {nc, vw}));
         }
+        e.flush();
+        for (int i = 0; i < nb; ++i) {
+            Tn V = make_strided(off(w.V, i, (size_t)v0 * rows + r0), "ti", {vw, prow}, {rows, 1});
+            Tn A2 = make_strided(off(Tgt, i, (size_t)c0 * rows + r0), "ci", {nc, prow}, {rows, 1});
+            e.contract(V, false, make_tn(w.W2.p[i], "ct", {nc, vw}), false, A2, nullptr, -1.0, true);
+        }
+        e.flush();
+    };
+    // T (stored [c][s]) of the reflectors V[r0:, v0:v0+vw] with the scalars Tau[v0..]
+    auto make_T = [&](int r0, int v0, int vw, const PtrBatch& Tm) {
+        const int prow = rows - r0;
+        for (int i = 0; i < nb; ++i) {                  // G[t][s] = v_s^H v_t
+            Tn V = make_strided(off(w.V, i, (size_t)v0 * rows + r0), "si", {vw, prow}, {rows, 1});
+            e.contract(V, true, relabel(V, "ti"), false, make_tn(w.G.p[i], "ts", {vw, vw}));
+        }
+        e.flush();
+        ProfScope ps(e, Engine::CAT_QR, 0, 3.0 * es * nb * (double)vw * vw);
+        wy_tsolve_launch(w.G, sub(w.Tau, v0), w.G, Tm, nb, vw, 0, e.cplx, e.stream);
+    };
+    e.flush();
+    for (int J0 = 0; J0 < k; J0 += B) {
+        const int BW = std::min(B, k - J0), J1 = J0 + BW;
+        for (int j0 = J0; j0 < J1; j0 += b) {
+            const int bw = std::min(b, J1 - j0), prow = rows - j0;
+            PtrBatch Ap = sub(cur, (size_t)j0 * rows + j0), Rp = sub(w.Rpp, (size_t)(j0 / b) * b * b);
+            { ProfScope ps(e, Engine::CAT_QR, (e.cplx ? 4.0 : 1.0) * nb * 2.0 * prow * bw * bw, 2.0 * es * nb * (double)prow * bw);
+              qr_panel_launch(Ap, Rp, sub(w.Tau, j0), nb, prow, bw, rows, e.cplx, e.stream); }
+            { ProfScope ps(e, Engine::CAT_MISC);          // V buffer <- the leaf's reflectors, zeros above its diagonal (rows J0..)
+              qr_copy_v_launch(cur, w.V, nb, rows, J0, j0, bw, e.cplx, e.stream); }
+            if (b < B || J1 < k) {
+                if (b == B) make_T(j0, j0, bw, sub(w.T, (size_t)(J0 / B) * B * B));
+                else { make_T(j0, j0, bw, w.Tl); apply(cur, j0, j0, bw, w.Tl, j0 + bw, J1 - j0 - bw, true); }
+            }
+        }
+        if (b < B) make_T(J0, J0, BW, sub(w.T, (size_t)(J0 / B) * B * B));
+        else if (J1 >= k) make_T(J0, J0, BW, sub(w.T, (size_t)(J0 / B) * B * B));
+        apply(cur, J0, J0, BW, sub(w.T, (size_t)(J0 / B) * B * B), J1, k - J1, true);
         if (Rout.p[0] != nullptr) {
             ProfScope ps(e, Engine::CAT_MISC);
-            qr_copy_r_launch(cur, w.Rpp, Rout, nb, k, j0, bw, rows, e.cplx, e.stream);
+            for (int j0 = J0; j0 < J1; j0 += b)
+                qr_copy_r_launch(cur, sub(w.Rpp, (size_t)(j0 / b) * b * b), Rout, nb, k, j0, std::min(b, J1 - j0), rows, e.cplx, e.stream);
         }
     }
     { ProfScope ps(e, Engine::CAT_MISC); set_identity_launch(w.Q, nb, rows, k, e.cplx, e.stream); }
-    for (int j0 = ((k - 1) / b) * b; j0 >= 0; j0 -= b) {
-        const int bw = std::min(b, k - j0), prow = rows - j0, nq = k - j0, pi = j0 / b;
-        for (int i = 0; i < nb; ++i) {
-            Tn V = make_strided(off(cur, i, (size_t)j0 * rows + j0), "si", {bw, prow}, {rows, 1});
-            Tn Q2 = make_strided(off(w.Q, i, (size_t)j0 * rows + j0), "ci", {nq, prow}, {rows, 1});
-            e.contract(V, true, Q2, false, make_tn(w.W.p[i], "cs", {nq, bw}));
-        }
-        e.flush();
-        for (int i = 0; i < nb; ++i)                    // W2[c][t] = sum_s T[t,s] W[c][s]
-            e.contract(make_tn(off(w.T, i, (size_t)pi * b * b), "st", {bw, bw}), false, make_tn(w.W.p[i], "cs", {nq, bw}), false,
-                       make_tn(w.W2.p[i], "ct", {nq, bw}));
-        e.flush();
-        for (int i = 0; i < nb; ++i) {
-            Tn V = make_strided(off(cur, i, (size_t)j0 * rows + j0), "ti", {bw, prow}, {rows, 1});
-            Tn Q2 = make_strided(off(w.Q, i, (size_t)j0 * rows + j0), "ci", {nq, prow}, {rows, 1});
-            e.contract(V, false, make_tn(w.W2.p[i], "ct", {nq, bw}), false, Q2, nullptr, -1.0, true);
-        }
-        e.flush();
+    for (int J0 = ((k - 1) / B) * B; J0 >= 0; J0 -= B) {
+        const int BW = std::min(B, k - J0);
+        apply(w.Q, J0, J0, BW, sub(w.T, (size_t)(J0 / B) * B * B), J0, k - J0, false);
     }
     std::swap(cur, w.Q);
 }
@@ -332,7 +343,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     const int mx = std::max(m, n);
     const bool wy = qr_wy_supported(m, k, e.cplx) && qr_wy_supported(n, k, e.cplx);
     // neither the register / WY path nor one cluster holds the whole sketch: blocked factorisation
-    const int pw = std::min(qr_panel_width(m, k, e.cplx), qr_panel_width(n, k, e.cplx));
+    const int pw = std::min(std::min(qr_panel_width(m, k, e.cplx), qr_panel_width(n, k, e.cplx)), e.cplx ? 64 : 128);
     const bool blocked = !wy && pw < k;
     CTMB_CHECK(!blocked || pw >= 4, "sketch too tall for the panel kernels");
     QrBlockedWs qbw;

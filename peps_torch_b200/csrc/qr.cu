@@ -801,18 +801,24 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
     }
     for (int e = tid; e < k; e += TS_THREADS) taus[e] = tau[e];
     __syncthreads();
-    if (g_in_smem) {
+    {
         // Blocked back substitution (row blocks of NB, last block first).  Phase 1: inside the block every
-        // column is an independent short recurrence (one thread per column, no synchronisation).  Phase 2:
-        // the finished rows are eliminated from all rows above them -- s0 x (k - s0) independent 16-term
-        // dot products spread over the whole CTA (G(r,t) is a warp-wide broadcast, X(t,c) is consecutive in c).
-        // A single thread walking a whole column (4560 dependent shared-memory FMAs for k = 96) took 74 us.
+        // column is an independent short recurrence (one thread per column, the block of X in registers, no
+        // synchronisation).  Phase 2: the finished rows are eliminated from all rows above them.  G(r,t) is a
+        // warp-wide broadcast (from shared memory, or through L1 when G and X do not both fit), X(t,c) is
+        // consecutive in c.  A single thread walking a whole column (4560 dependent FMAs for k = 96) took 74 us.
         constexpr int NB = 16;
         constexpr int RG = TS_THREADS / 128;                 // row groups of the elimination phase
+        // when G and X do not both fit (k = 128 real), only the 16 columns of G the current block needs are staged
+        T* Gp = Gs;                                          // [NB][k], column t of G contiguous
         for (int s1 = k; s1 > 0; s1 -= NB) {
             const int s0 = s1 > NB ? s1 - NB : 0;
             const int nbk = s1 - s0;
-            // phase 1: thread c solves the nbk x nbk triangular block for its column with the block of X in registers
+            if (!g_in_smem) {
+                for (int e = tid; e < nbk * k; e += TS_THREADS) Gp[e] = G[(size_t)(s0 + e / k) * k + e % k];
+                __syncthreads();
+            }
+            auto Gat = [&](int row, int col) -> T { return g_in_smem ? Gs[(size_t)row * k + col] : Gp[(size_t)(col - s0) * k + row]; };
             // (rows below the diagonal of X are zero and come out as zero: no special casing)
             const int c = s0 + tid;
             if (c < k) {
@@ -822,10 +828,9 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
 #pragma unroll
                 for (int i = NB - 1; i >= 0; --i) {
                     if (i < nbk) {
-                        const T* gr = Gs + (size_t)(s0 + i) * k + s0;
                         T acc = S::zero();
 #pragma unroll
-                        for (int t = i + 1; t < NB; ++t) if (t < nbk) acc = S::fma(gr[t], x[t], acc);
+                        for (int t = i + 1; t < NB; ++t) if (t < nbk) acc = S::fma(Gat(s0 + i, s0 + t), x[t], acc);
                         x[i] = S::mul(taus[s0 + i], S::sub(x[i], acc));
                     }
                 }
@@ -833,34 +838,23 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
                 for (int i = 0; i < NB; ++i) if (i < nbk) Xs[(s0 + i) * k + c] = x[i];
             }
             __syncthreads();
-            // phase 2: eliminate the finished rows from all rows above: thread (g, cc) keeps the block of column cc
-            // in registers and walks rows g, g+RG, ...; G(r, s0..s1) is a warp-wide broadcast
+            // thread (g, cc) keeps the block of column cc in registers and walks rows g, g+RG, ...
             const int cc = s0 + (tid & 127), g = tid >> 7;
             if (cc < k && s0 > 0) {
                 T x[NB];
 #pragma unroll
                 for (int i = 0; i < NB; ++i) x[i] = i < nbk ? Xs[(s0 + i) * k + cc] : S::zero();
                 for (int r = g; r < s0; r += RG) {
-                    const T* gr = Gs + (size_t)r * k + s0;
                     T a0 = S::zero(), a1 = S::zero();
 #pragma unroll
                     for (int t = 0; t < NB; t += 2) {
-                        if (t < nbk) a0 = S::fma(gr[t], x[t], a0);
-                        if (t + 1 < nbk) a1 = S::fma(gr[t + 1], x[t + 1], a1);
+                        if (t < nbk) a0 = S::fma(Gat(r, s0 + t), x[t], a0);
+                        if (t + 1 < nbk) a1 = S::fma(Gat(r, s0 + t + 1), x[t + 1], a1);
                     }
                     Xs[r * k + cc] = S::sub(Xs[r * k + cc], S::add(a0, a1));
                 }
             }
             __syncthreads();
-        }
-    } else {
-        const int c = tid;
-        if (c < k) {
-            for (int s = c; s >= 0; --s) {
-                T a0 = S::zero();
-                for (int t = s + 1; t <= c; ++t) a0 = S::fma(G[(size_t)t * k + s], Xs[t * k + c], a0);
-                Xs[s * k + c] = S::mul(taus[s], S::sub(Xs[s * k + c], a0));
-            }
         }
     }
     __syncthreads();
@@ -869,10 +863,10 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
 
 void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V, const PtrBatch& X, int nb, int k,
                       int ldv, bool cplx, cudaStream_t stream) {
-    CTMB_CHECK(k <= 128, "wy_tsolve: k too large");
+    CTMB_CHECK(k <= 128 && (size_t)k * k * (cplx ? 16 : 8) <= 200 * 1024, "wy_tsolve: k too large");
     const size_t es = cplx ? 16 : 8;
     const int g_in_smem = 2 * (size_t)k * k * es <= 200 * 1024;
-    const size_t smem = (g_in_smem ? 2 : 1) * (size_t)k * k * es;
+    const size_t smem = g_in_smem ? 2 * (size_t)k * k * es : ((size_t)k * k + 16 * (size_t)k) * es;
     if (cplx) {
         auto kern = wy_tsolve_kernel<true>;
         static bool set = false;
@@ -1008,6 +1002,31 @@ void qr_copy_r_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& R,
     dim3 grid((unsigned)std::min(64, (b * k + 255) / 256), nb);
     if (cplx) qr_copy_r_kernel<true><<<grid, 256, 0, stream>>>(A, Rpp, R, k, j0, b, ld);
     else qr_copy_r_kernel<false><<<grid, 256, 0, stream>>>(A, Rpp, R, k, j0, b, ld);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// V[r, j0+c] (r >= J0) <- reflector entries of the leaf panel at columns j0..j0+bw of A: A below the leaf's
+// diagonal, 1 on it, 0 above (rows J0 .. j0+c-1 of A hold R entries of the enclosing super panel)
+template <bool CPLX>
+__global__ void qr_copy_v_kernel(PtrBatch Ab, PtrBatch Vb, int rows, int J0, int j0, int bw) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const T* A = reinterpret_cast<const T*>(Ab.p[blockIdx.y]);
+    T* V = reinterpret_cast<T*>(Vb.p[blockIdx.y]);
+    const int prow = rows - J0;
+    const long long n = (long long)prow * bw;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e / prow), r = J0 + (int)(e % prow);
+        const size_t idx = (size_t)(j0 + c) * rows + r;
+        V[idx] = r > j0 + c ? A[idx] : (r == j0 + c ? S::one() : S::zero());
+    }
+}
+void qr_copy_v_launch(const PtrBatch& A, const PtrBatch& V, int nb, int rows, int J0, int j0, int bw, bool cplx,
+                      cudaStream_t stream) {
+    const long long n = (long long)(rows - J0) * bw;
+    dim3 grid((unsigned)std::min<long long>(512, (n + 255) / 256), nb);
+    if (cplx) qr_copy_v_kernel<true><<<grid, 256, 0, stream>>>(A, V, rows, J0, j0, bw);
+    else qr_copy_v_kernel<false><<<grid, 256, 0, stream>>>(A, V, rows, J0, j0, bw);
     CTMB_CUDA(cudaGetLastError());
 }
 

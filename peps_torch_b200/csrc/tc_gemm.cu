@@ -420,16 +420,23 @@ static void tc_run_ws_t(const TcParams& p, cudaStream_t stream) {
     kern<<<grid, WS_THREADS, smem, stream>>>(p);
     CTMB_CUDA(cudaGetLastError());
 }
-// false if the loader flags differ inside the batch (the caller then uses the generic kernel)
+// the kernel is specialised on the operands' fast directions: a batch with mixed loader flags (the eight
+// corner x corner products of the halves have different transposes) is launched as one sub-batch per flag pair
 static bool tc_run_ws(const TcParams& p, cudaStream_t stream) {
-    const int lf = p.batch[0].flags & (TC_A_KFAST | TC_B_KFAST);
-    for (int i = 1; i < p.nbatch; ++i)
-        if ((p.batch[i].flags & (TC_A_KFAST | TC_B_KFAST)) != lf) return false;
-    const bool ak = (lf & TC_A_KFAST) != 0, bk = (lf & TC_B_KFAST) != 0;
-    if (ak && bk) tc_run_ws_t<true, true>(p, stream);
-    else if (ak) tc_run_ws_t<true, false>(p, stream);
-    else if (bk) tc_run_ws_t<false, true>(p, stream);
-    else tc_run_ws_t<false, false>(p, stream);
+    for (int lf = 0; lf < 4; ++lf) {
+        const bool ak = (lf & 1) != 0, bk = (lf & 2) != 0;
+        TcParams q = p;
+        q.nbatch = 0;
+        for (int i = 0; i < p.nbatch; ++i) {
+            const int f = p.batch[i].flags;
+            if (((f & TC_A_KFAST) != 0) == ak && ((f & TC_B_KFAST) != 0) == bk) q.batch[q.nbatch++] = p.batch[i];
+        }
+        if (q.nbatch == 0) continue;
+        if (ak && bk) tc_run_ws_t<true, true>(q, stream);
+        else if (ak) tc_run_ws_t<true, false>(q, stream);
+        else if (bk) tc_run_ws_t<false, true>(q, stream);
+        else tc_run_ws_t<false, false>(q, stream);
+    }
     return true;
 }
 

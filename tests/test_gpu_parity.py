@@ -332,3 +332,24 @@ def test_fused_double_layer_corner_D8(eng, dev, kind):
     out = eng.c2x2(kind, C.to(dev), T1.to(dev), T2.to(dev), a.to(dev), chi)
     assert out.shape == ref.shape
     assert H.maxrel(out.cpu(), ref) < 1e-13
+
+
+def test_tall_sketch_two_level_blocked_qr(eng, dev):
+    """4096 rows: a cluster holds only 32-column leaf panels, so the sketch (k = 200) goes through the two-level
+    blocked QR (leaf panels inside 128-column super panels) and the multi-CTA Jacobi.  The matrix is built from
+    known factors, so no reference SVD of a 4096^2 matrix is needed: sigma to 1e-10, singular vectors by overlap."""
+    n, chi = 4096, 100
+    g = torch.Generator(device='cpu').manual_seed(3)
+    U0, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64, generator=g).to(dev))
+    V0, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64, generator=g).to(dev))
+    s = torch.logspace(0, -40, n, dtype=torch.float64, device=dev)
+    M = (U0 * s) @ V0.t()
+    U, S, V = eng.truncated_svd(M, chi, rsvd_tol=1e-12)
+    assert float(((S - s[:chi]).abs() / s[:chi]).max()) < 1e-10
+    eye = torch.eye(chi, dtype=torch.float64, device=dev)
+    assert float((U.t() @ U - eye).abs().max()) < 1e-12
+    assert float((V.t() @ V - eye).abs().max()) < 1e-12
+    keep = s[:chi] / s[0] > 1e-8
+    ou = (U0[:, :chi].t() @ U).diagonal().abs()[keep]
+    ov = (V0[:, :chi].t() @ V).diagonal().abs()[keep]
+    assert float((1 - ou).max()) < 1e-9 and float((1 - ov).max()) < 1e-9
