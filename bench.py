@@ -150,6 +150,10 @@ def run_reference(args):
         return
     kind, D, chi, dt, fam, desc = CONFIGS[args.config]
     ncpu = os.cpu_count() or 1
+    if args.config == 'c5':
+        print(json.dumps({'impl': 'reference', 'unavailable': 'config c5 on CPU is four full 16384^2 LAPACK SVDs per ctm_MOVE '
+                          '(~56 min per move, SURVEY.md section 6); the default config c2 has a live reference arm'}))
+        return
     best = None
     for th in sorted({1, ncpu}):
         v, mps = cpu_moves_per_s(args.config, args.steps, min(args.warmup, 1), th)
@@ -158,8 +162,9 @@ def run_reference(args):
     v, th, mps = best
     line = {'impl': 'reference', 'metric': 'CTM moves/sec', 'value': v, 'unit': 'ctm_MOVE/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * mps / v, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'c128' if dt == 'complex128' else 'f64', 'data': 'synthetic',
-            'config': {'workload': desc, 'family': fam, 'seed': 123, 'moves_per_step': mps},
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c128' if dt == 'complex128' else 'f64', 'data': 'synthetic',
+            'config': {'workload': desc + f' ({"1 ctm_MOVE_sl" if kind == "c4v" else str(mps) + " ctm_MOVE"} per step)',
+                       'family': fam, 'seed': 123, 'moves_per_step': mps},
             'cpu_baseline': {'value': v, 'unit': 'ctm_MOVE/s', 'cores': th, 'kind': 'port',
                              'sample': f'{args.steps} timed CTMRG iterations, oracle port (torch CPU) of the reference path'},
             'e2e': {'value': v, 'unit': 'ctm_MOVE/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -278,14 +283,30 @@ def run_ours(args):
         init_env(st, env)
         p_phys = next(iter(sites_cpu.values())).shape[0]
 
+        # config c5 (n = 16384): a move takes seconds, so a STEP is ONE ctm_MOVE (directions cycle through the
+        # reference's sequence U,U,L,L,D,D,R,R) instead of a full iteration of eight
+        per_move = args.config == 'c5'
+        seq = [d for d in ctm_args.ctm_move_sequence for _ in range(lX if d in [(-1, 0), (1, 0)] else lY)]
+        cursor = [0]
+
+        def next_direction():
+            d = seq[cursor[0] % len(seq)]
+            cursor[0] += 1
+            return d
+
         def one_step(state, e):
-            if shard:
+            if per_move:
+                if shard:
+                    sharded.ctm_MOVE(next_direction(), state, e)
+                else:
+                    ctmrg.ctm_MOVE(next_direction(), state, e, ctm_args=ctm_args)
+            elif shard:
                 sharded.iteration(state, e, ctm_args.ctm_move_sequence)
             else:
                 ctmrg.run(state, e, ctm_args=ctm_args)
-        moves_per_step = 2 * (lX + lY)
+        moves_per_step = 1 if per_move else 2 * (lX + lY)
     # a few iterations so that the timed environment is not the zero-padded initial one
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(1 if args.config == 'c5' else max(args.warmup, 3)):
         one_step(st, env)
     torch.cuda.synchronize(dev)
 
@@ -313,6 +334,8 @@ def run_ours(args):
     def resident_step():
         if kind == 'c4v':
             ctmrg_c4v.ctm_MOVE_sl(st.site(), env, ctm_args=ctm_args)
+        elif per_move:
+            one_step(st, env)
         elif shard:
             sharded.iteration(st, env, ctm_args.ctm_move_sequence)
         else:
@@ -419,7 +442,12 @@ def run_ours(args):
 
     roof['kernel_level'] = kernel_level(eng, dev, fp64_peak)
     F_move = algorithmic_flops_per_move(kind, D, chi, p_phys, cplx)
-    base = cpu_baseline(args.config) if world == 1 or True else None
+    if args.config == 'c5':
+        base = {'value': None, 'unit': 'ctm_MOVE/s', 'cores': os.cpu_count(), 'kind': 'port',
+                'sample': 'not run: one reference move at n = 16384 is four full 16384^2 LAPACK SVDs (~56 min per ctm_MOVE '
+                          'extrapolated from DGEMM / gesdd timings, SURVEY.md section 6)'}
+    else:
+        base = cpu_baseline(args.config)
     line = {'metric': 'CTM moves/sec', 'value': value, 'unit': 'ctm_MOVE/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if shard else 'weak', 'vs_baseline': None, 'dtype': 'c128' if cplx else 'f64', 'data': 'synthetic',
@@ -431,7 +459,7 @@ def run_ours(args):
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': base,
             'flops': {'reference_algorithm_per_move': F_move, 'executed_per_move': flops_exec / (moves_per_step * args.steps),
                       'move_level_frac_of_fp64_peak': F_move * value / world / (fp64_peak * 1e12)}}
-    if world > 1:
+    if world > 1 and base.get('value') is not None:
         line['cpu_baseline']['note'] = 'measured on rank 0 host cores while the other ranks idle'
     print(json.dumps(line))
 

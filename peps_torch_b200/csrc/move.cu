@@ -409,6 +409,18 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         }
         std::swap(cur, pQ);
     };
+    if (eig_mode && !e.cplx && k == n) {
+        // small real symmetric problem decomposed exactly (config c1: n = 64): no sketch at all, the shifted
+        // one-sided Jacobi runs on M itself (row-major == column-major for a symmetric matrix)
+        e.flush();
+        for (int b = 0; b < nb; ++b)
+            CTMB_CUDA(cudaMemcpyAsync(R2[b], M[b], (size_t)k * k * es, cudaMemcpyDeviceToDevice, e.stream));
+        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 2.0 * es * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, chi, e.cplx, 1, e.stream); }
+        for (int b = 0; b < nb; ++b)
+            CTMB_CUDA(cudaMemcpyAsync(r.U[b], Uh[b], (size_t)k * chi * es, cudaMemcpyDeviceToDevice, e.stream));
+        return r;
+    }
     // Y = M * Omega
     for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, Om, false, tnY(b, "si"));
     qr(pY, pNull, m);
