@@ -64,6 +64,7 @@ public:
     cudaStream_t stream = nullptr;
     Workspace ws;
     long long launches = 0;        // kernels launched (our own), for bench accounting
+    std::map<std::string, int> iter_hint;   // adaptive range finder: power iterations that satisfied the residual test last time, per shape
     double flops = 0;              // algorithmic real flops enqueued
 
     // optional per-kernel-class timing with CUDA events on the launching stream

@@ -435,7 +435,15 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         hres = pinned;
     }
     int todo = complete ? 0 : o.rsvd_niter;               // full power iterations still to run
+    // Adaptive mode remembers, per problem shape, how many iterations passed the residual test last time and starts
+    // there (a CTM run decomposes a slowly changing matrix once per move): a failed first round costs a whole extra
+    // Rayleigh-Ritz / Jacobi pass.  Every result still satisfies the same residual bound.
+    char hkey[96];
+    snprintf(hkey, sizeof hkey, "%d:%d:%d:%d:%d", m, n, k, (int)eig_mode, (int)e.cplx);
+    if (adaptive) { auto it = e.iter_hint.find(hkey); if (it != e.iter_hint.end()) todo = std::max(todo, it->second); }
+    int used = 0;
     for (int round = 0;; ++round) {
+        used += todo;
         if (!eig_mode) {
             // power iterations Q <- orth(M (M^H Q)): ONE orthogonalisation per full iteration.  The
             // intermediate M^H Q is not re-orthogonalised: only directions with S/S0 > 1e-8 survive
@@ -496,7 +504,11 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         CTMB_CUDA(cudaMemcpyAsync(hres, dres, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
         CTMB_CUDA(cudaStreamSynchronize(e.stream));
         double res; memcpy(&res, hres, sizeof res);
-        if (res <= o.rsvd_tol) break;
+        if (res <= o.rsvd_tol) {
+            // three decades of margin are worth more than one iteration: probe one fewer next time
+            e.iter_hint[hkey] = (round == 0 && res <= 1.0e-3 * o.rsvd_tol) ? std::max(o.rsvd_niter, used - 1) : used;
+            break;
+        }
         todo = o.rsvd_niter << round;                     // q, 2q, 4q ... additional iterations
     }
     return r;
