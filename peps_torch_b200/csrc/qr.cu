@@ -454,16 +454,28 @@ __global__ void __launch_bounds__(QRC_THREADS) qr_reg_kernel(PtrBatch Ab, PtrBat
         const int off = par * 2 * cols;
         const int ncol = cols - cbeg;
         const int per = QRC_THREADS / CL;
-        for (int base = 0; base < ncol; base += per) {
-            const int ci = base + tid / CL, r = tid % CL;
+        // all remote (DSMEM) loads of the step are issued before anything consumes them: up to two column
+        // passes (cols <= 128, per >= 64) and the owner's row j -- one remote round trip instead of three
+        const int r = tid % CL;
+        const int ci0 = tid / CL, ci1 = per + tid / CL;
+        const T* rem = cluster.map_shared_rank(xbuf, r) + off + cbeg;
+        T v0 = S::zero(), v1 = S::zero(), rw = S::zero();
+        if (ci0 < ncol) v0 = rem[ci0];
+        if (ci1 < ncol) v1 = rem[ci1];
+        const int rc = cbeg + tid;
+        if (with_row && rc < cols) rw = (cluster.map_shared_rank(xbuf, owner) + off + cols)[rc];
+        for (int o = 1; o < CL; o <<= 1) { v0 = S::add(v0, S::shfl_xor(v0, o)); v1 = S::add(v1, S::shfl_xor(v1, o)); }
+        if (r == 0) {
+            if (ci0 < ncol) tot[cbeg + ci0] = v0;
+            if (ci1 < ncol) tot[cbeg + ci1] = v1;
+        }
+        if (with_row && rc < cols) tot[cols + rc] = rw;
+        for (int base = 2 * per; base < ncol; base += per) {      // (not reached for cols <= 128)
+            const int ci = base + tid / CL;
             T v = S::zero();
-            if (ci < ncol) v = cluster.map_shared_rank(xbuf, r)[off + cbeg + ci];
+            if (ci < ncol) v = rem[ci];
             for (int o = 1; o < CL; o <<= 1) v = S::add(v, S::shfl_xor(v, o));
             if (ci < ncol && r == 0) tot[cbeg + ci] = v;
-        }
-        if (with_row) {
-            const T* rowp = cluster.map_shared_rank(xbuf, owner) + off + cols;
-            for (int c = cbeg + tid; c < cols; c += QRC_THREADS) tot[cols + c] = rowp[c];
         }
         __syncthreads();
     };
