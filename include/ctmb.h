@@ -43,14 +43,18 @@ typedef struct {
     double eps_multiplet;      /* projector_eps_multiplet     (1e-8)  custom_svd.py:70-95; C4v: 1e-12 custom_eig.py:7-8 */
     double multiplet_abstol;   /* projector_multiplet_abstol  (1e-14) */
     double rsvd_rank_factor;   /* sketch width k = min(n, ceil(factor*chi)); default 2.0 */
-    int rsvd_niter;            /* power iterations q (projector_rsvd_niter); default 4 */
+    int rsvd_niter;            /* power iterations q of the first call with a new shape (later calls start from the count that
+                                  satisfied the residual test last time); default 4 */
     int jacobi_max_sweeps;     /* default 40 */
     int norm_type;             /* ctm_absorb_normalization: 0 = 'inf' (only value supported) */
-    int rsvd_max_rounds;       /* adaptive mode: at most this many doublings of the iteration count (default 3) */
+    int rsvd_max_rounds;       /* adaptive mode: at most this many rounds q, +q, +2q, +4q ... (default 5); a round that does not
+                                  halve the residual ends the iteration (rounding floor) */
     unsigned long long seed;   /* seed of the Gaussian sketch (deterministic) */
-    double rsvd_tol;           /* > 0: after the power iterations check max_j ||M v_j - s_j u_j|| / s_0 <= rsvd_tol on the
-                                  kept triplets (one host synchronisation) and iterate further if needed; 0 = fixed count.
-                                  Default: 0 for the generic SVD path, 1e-11 for the C4v eigen path. */
+    double rsvd_tol;           /* > 0 (default 2e-15): residual-checked range finder.  After the power iterations
+                                  max_j ||M v_j - s_j u_j|| / s_0 <= rsvd_tol * sqrt(n) is checked on the kept triplets (one host
+                                  synchronisation per call) and further rounds are run if needed: the bound is a few hundred
+                                  ulps, i.e. LAPACK-grade residuals, because the projectors amplify the error of a triplet by
+                                  s_0 / s_j.  0 = fixed iteration count, no synchronisation. */
 } ctmb_options;
 
 /* One unit-cell site: on-site tensor and its eight environment tensors. */

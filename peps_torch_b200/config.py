@@ -25,8 +25,8 @@ class CTMARGS:
         # engine-specific (no counterpart in the reference)
         self.b200_rsvd_niter = 4
         self.b200_rsvd_rank_factor = 2.0
-        self.b200_rsvd_tol = 0.0          # > 0: residual-checked (adaptive) range finder on the generic path
-        self.b200_rsvd_tol_c4v = 1.0e-11  # C4v eigen path: adaptive by default
+        self.b200_rsvd_tol = None         # None: library default 2e-15 (x sqrt(n)) residual bound; 0: fixed iteration count
+        self.b200_rsvd_tol_c4v = None     # C4v eigen path: same default
 
 
 class GLOBALARGS:

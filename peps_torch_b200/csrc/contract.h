@@ -64,7 +64,9 @@ public:
     cudaStream_t stream = nullptr;
     Workspace ws;
     long long launches = 0;        // kernels launched (our own), for bench accounting
-    std::map<std::string, int> iter_hint;   // adaptive range finder: power iterations that satisfied the residual test last time, per shape
+    struct IterHint { int q = 0; int cooldown = 0; };
+    std::map<std::string, IterHint> iter_hint;   // adaptive range finder, per problem shape: power iterations that satisfied
+                                                 // the residual test last time, and how long not to probe below them
     double flops = 0;              // algorithmic real flops enqueued
 
     // optional per-kernel-class timing with CUDA events on the launching stream

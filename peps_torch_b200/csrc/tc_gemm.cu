@@ -88,16 +88,6 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
     // split-K: this CTA reduces k in [kbeg, kend) only and writes a dense partial tile
     const int kbeg = p.ksplit > 1 ? blockIdx.y * p.kchunk : 0;
     const int kend = p.ksplit > 1 ? min(K, kbeg + p.kchunk) : K;
-    // The k-offset tables of this CTA's slice are staged in shared memory once: looked up from global memory they
-    // put an L2 round trip in front of every cp.async of every k-tile, which made the small contractions of a
-    // config-c2 move cost 1.2 us per k-tile (profiles/r1_launches_c2_v3.md: 23 us for K = 432).
-    constexpr int KTAB = 1024;
-    __shared__ int ks_a[KTAB], ks_b[KTAB];
-    const bool ktab = (kend - kbeg) <= KTAB;
-    if (ktab) {
-        for (int k = tid; k < kend - kbeg; k += 256) { ks_a[k] = tb.a_k[kbeg + k]; ks_b[k] = tb.b_k[kbeg + k]; }
-        __syncthreads();
-    }
     auto load_tile = [&](int kt, int stage) {
         const int k0 = kbeg + kt * BK;
         const int K = kend;                    // shadows the full extent: loads beyond the slice are zero-filled
@@ -107,7 +97,7 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
         for (int i = 0; i < A_PER; ++i) {
             int k = k0 + a_col[i];
             bool v = (a_off[i] >= 0) && (k < K);
-            const T* src = v ? (A + a_off[i] + (ktab ? ks_a[k - kbeg] : tb.a_k[k])) : A;
+            const T* src = v ? (A + a_off[i] + tb.a_k[k]) : A;
             if (CPLX) cp_async_16(as + a_row[i] * LDS + a_col[i], src, v);
             else cp_async_8(as + a_row[i] * LDS + a_col[i], src, v);
         }
@@ -115,7 +105,7 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
         for (int i = 0; i < B_PER; ++i) {
             int k = k0 + b_col[i];
             bool v = (b_off[i] >= 0) && (k < K);
-            const T* src = v ? (B + b_off[i] + (ktab ? ks_b[k - kbeg] : tb.b_k[k])) : B;
+            const T* src = v ? (B + b_off[i] + tb.b_k[k]) : B;
             if (CPLX) cp_async_16(bs + b_row[i] * LDS + b_col[i], src, v);
             else cp_async_8(bs + b_row[i] * LDS + b_col[i], src, v);
         }
@@ -133,16 +123,6 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
         }
 
     const int ktiles = (kend - kbeg + BK - 1) / BK;
-    constexpr bool PREFETCH_C = (TM * TN <= 8);
-    int cm_off[PREFETCH_C ? TM : 1], cn_off[PREFETCH_C ? TN : 1][2];
-    if constexpr (PREFETCH_C) {
-#pragma unroll
-        for (int i = 0; i < TM; ++i) { const int r = m0 + wm0 + i * 8 + (lane >> 2); cm_off[i] = r < M ? tb.c_m[r] : 0; }
-#pragma unroll
-        for (int j = 0; j < TN; ++j)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) { const int c = n0 + wn0 + j * 8 + (lane & 3) * 2 + h; cn_off[j][h] = c < N ? tb.c_n[c] : 0; }
-    }
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < ktiles) load_tile(s, s);
@@ -210,7 +190,7 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
         }
         return;
     }
-    // epilogue: registers -> global through the C offset tables (looked up before the k loop for the small tiles)
+    // epilogue: registers -> global through the C offset tables
     T* __restrict__ C = reinterpret_cast<T*>(be.C);
     const double alpha = p.alpha;
     const bool accum = (flags & TC_ACCUM) != 0;
@@ -219,23 +199,22 @@ __global__ void __launch_bounds__(256) tc_kernel(const __grid_constant__ TcParam
     for (int i = 0; i < TM; ++i) {
         const int r = m0 + wm0 + i * 8 + (lane >> 2);
         if (r >= M) continue;
-        const int ro = PREFETCH_C ? cm_off[i] : tb.c_m[r];
+        const int ro = tb.c_m[r];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c = n0 + wn0 + j * 8 + (lane & 3) * 2 + h;
                 if (c >= N) continue;
-                const int co = PREFETCH_C ? cn_off[j][h] : tb.c_n[c];
                 if constexpr (!CPLX) {
                     double v = alpha * acc[i][j][h];
-                    if (accum) v += C[ro + co];
-                    C[ro + co] = v;
+                    if (accum) v += C[ro + tb.c_n[c]];
+                    C[ro + tb.c_n[c]] = v;
                     lmax = fmax(lmax, fabs(v));
                 } else {
                     double2 v = make_double2(alpha * acc[i][j][h], alpha * acci[i][j][h]);
-                    if (accum) { const double2 o = C[ro + co]; v.x += o.x; v.y += o.y; }
-                    C[ro + co] = v;
+                    if (accum) { const double2 o = C[ro + tb.c_n[c]]; v.x += o.x; v.y += o.y; }
+                    C[ro + tb.c_n[c]] = v;
                     lmax = fmax(lmax, hypot(v.x, v.y));
                 }
             }
@@ -549,16 +528,14 @@ void tc_launch(const TcParams& p, bool cplx, cudaStream_t stream) {
     // a small contraction: prefer the tile that spreads the work over at least ~2 waves of CTAs.
     const int cfg = tc_config(p, cplx);
     if (!cplx) {
-        // deep cp.async rings: these small-tile launches run one or two CTAs per SM and were bound by the L2
-        // round trip of each k-tile (long_scoreboard 3.6-4.5 per issue, DMMA pipe 20 % busy with 2-3 tiles in flight)
-        if (cfg == 0) tc_run<128, 32, 16, 32, 16, 5, false>(p, stream);
+        if (cfg == 0) tc_run<128, 32, 16, 32, 16, 3, false>(p, stream);
         else if (cfg == 1) {
             static int ws_mode = -1;
             if (ws_mode < 0) { const char* ev = getenv("CTMB_GEMM_WS"); ws_mode = ev ? atoi(ev) : 1; }
             if (!ws_mode || !tc_run_ws(p, stream)) tc_run<128, 128, 16, 64, 32, 3, false>(p, stream);
         }
-        else if (cfg == 2) tc_run<64, 64, 16, 32, 16, 6, false>(p, stream);
-        else tc_run<32, 32, 32, 16, 8, 6, false>(p, stream);
+        else if (cfg == 2) tc_run<64, 64, 16, 32, 16, 4, false>(p, stream);
+        else tc_run<32, 32, 32, 16, 8, 3, false>(p, stream);
     } else {
         if (cfg == 0) tc_run<128, 32, 16, 32, 16, 3, true>(p, stream);
         else if (cfg == 2) tc_run<64, 64, 16, 32, 16, 3, true>(p, stream);

@@ -184,7 +184,6 @@ class CtmEngine:
         M = self._prep(M, self.device)
         n = M.shape[0]
         opt.setdefault('eps_multiplet', 1.0e-12)
-        opt.setdefault('rsvd_tol', 1.0e-11)
         o = self._opts(**opt)
         U = torch.empty((chi, n), dtype=M.dtype, device=self.device)
         D = torch.empty(chi, dtype=torch.float64, device=self.device)
@@ -340,7 +339,6 @@ class CtmEngine:
         a, C_, T = self._prep(a, self.device), self._prep(C_, self.device), self._prep(T, self.device)
         dt = _dt(a)
         opt.setdefault('eps_multiplet', 1.0e-12)      # truncated_eig_sym default (custom_eig.py:7-8)
-        opt.setdefault('rsvd_tol', 1.0e-11)           # residual-checked range finder (one host sync per move)
         o = self._opts(**opt)
         dims = (C.c_int * 5)(*a.shape)
         Co = torch.empty_like(C_)

@@ -289,7 +289,7 @@ def test_large_sketch_blocked_qr_and_multi_cta_jacobi(eng, dev, n, chi, dt):
     configs c3 and c5): sketch k = 2 chi > 128 columns -> blocked Householder QR, k x k Jacobi over several CTAs.
     Checked against the full LAPACK SVD: singular values to 1e-10 relative, U/V through the rank-chi projector."""
     M, s = _graded(n, dt, 12.0, 5)
-    U, S, V = eng.truncated_svd(M.to(dev), chi, rsvd_tol=1e-12)      # residual-checked range finder
+    U, S, V = eng.truncated_svd(M.to(dev), chi)      # residual-checked range finder (library default)
     Ur, Sr, Vhr = torch.linalg.svd(M)
     S, U, V = S.cpu(), U.cpu(), V.cpu()
     assert float(((S - Sr[:chi]).abs() / Sr[:chi]).max()) < 1e-10
@@ -344,7 +344,7 @@ def test_tall_sketch_two_level_blocked_qr(eng, dev):
     V0, _ = torch.linalg.qr(torch.randn(n, n, dtype=torch.float64, generator=g).to(dev))
     s = torch.logspace(0, -40, n, dtype=torch.float64, device=dev)
     M = (U0 * s) @ V0.t()
-    U, S, V = eng.truncated_svd(M, chi, rsvd_tol=1e-12)
+    U, S, V = eng.truncated_svd(M, chi)
     assert float(((S - s[:chi]).abs() / s[:chi]).max()) < 1e-10
     eye = torch.eye(chi, dtype=torch.float64, device=dev)
     assert float((U.t() @ U - eye).abs().max()) < 1e-12
@@ -353,3 +353,25 @@ def test_tall_sketch_two_level_blocked_qr(eng, dev):
     ou = (U0[:, :chi].t() @ U).diagonal().abs()[keep]
     ov = (V0[:, :chi].t() @ V).diagonal().abs()[keep]
     assert float((1 - ou).max()) < 1e-9 and float((1 - ov).max()) < 1e-9
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'])
+def test_matrix_free_projectors_match_reference_fixtures(eng, dev, name):
+    """The matrix-free projector path (M = R^T Rt applied as four corner factors, used when D^2 > 20: config c5)
+    forced on the small fixtures: every move must reproduce the reference's outputs like the explicit path."""
+    from peps_torch_b200 import _lib
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'mid_')
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    _lib.lib.ctmb_debug_set_matrix_free(2)
+    try:
+        for d in orc.DIRECTIONS:
+            env = H.Env(chi, H.to_dev(C, dev), H.to_dev(T, dev))
+            eng.move_generic(d, st, env)
+            Cg, Tg = H.golden_env(z, f'move_{d[0]}_{d[1]}_')
+            assert H.env_abs_diff(env.C, env.T, Cg, Tg) < 1e-8
+    finally:
+        _lib.lib.ctmb_debug_set_matrix_free(1)

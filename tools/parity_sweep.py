@@ -15,14 +15,16 @@ from peps_torch_b200.env import ENV, init_env
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device('cuda:0')
 eng = default_engine()
-D, chi = 3, 48
-for family in ('B', 'A'):
+if 'SWEEP_TOL' in os.environ:                 # default: the library's residual bound (2e-15 * sqrt(n)); 0 = fixed iteration count
+    eng.options.rsvd_tol = float(os.environ['SWEEP_TOL'])
+COMBOS = ((2.0, 4), (1.75, 4), (1.5, 4)) if eng.options.rsvd_tol > 0 else ((2.0, 4), (2.0, 3), (1.75, 4), (1.75, 3), (1.625, 4), (1.5, 5))
+for D, chi, family in ((3, 48, 'B'), (3, 48, 'A'), (4, 40, 'B'), (4, 64, 'B')):
     sites = orc.random_state_4site(D, family=family)
     C, T = orc.init_env(sites, orc.v2s_4site, chi)
     orc.run(sites, orc.v2s_4site, 2, 2, C, T, chi, iters)
     e_cpu = orc.energy_j1j2(sites, orc.v2s_4site, C, T, 1.0, 0.3)
     st = IPEPS(H.to_dev(sites, dev), orc.v2s_4site, 2, 2)
-    for rf, q in ((2.0, 4), (2.0, 3), (1.75, 4), (1.75, 5), (1.5, 4), (1.5, 5), (1.5, 6), (1.34, 6)):
+    for rf, q in COMBOS:
         eng.options.rsvd_rank_factor = rf
         eng.options.rsvd_niter = q
         env = ENV(chi, st)
@@ -36,6 +38,6 @@ for family in ('B', 'A'):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / (8 * iters)
         e_gpu = orc.energy_j1j2(sites, orc.v2s_4site, {k: v.cpu() for k, v in env.C.items()}, {k: v.cpu() for k, v in env.T.items()}, 1.0, 0.3)
-        print(json.dumps({'family': family, 'rank_factor': rf, 'niter': q, 'ms_per_move': 1e3 * dt,
+        print(json.dumps({'D': D, 'chi': chi, 'family': family, 'rank_factor': rf, 'niter': q, 'ms_per_move': 1e3 * dt,
                           'spectra_diff': H.spectra_diff(env.C, C), 'absCT_diff': H.env_abs_diff(env.C, env.T, C, T),
                           'energy_rel': abs(e_gpu - e_cpu) / abs(e_cpu)}), flush=True)
