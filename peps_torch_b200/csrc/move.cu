@@ -335,7 +335,7 @@ struct FactoredM {
 // M[b]: m x n row-major (or, with `fac`, given in factored form). eig_mode: M Hermitian (m == n), S receives signed eigenvalues.
 static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int n, int chi,
                        const ctmb_options& o, bool eig_mode, const std::vector<FactoredM>* fac = nullptr) {
-    Rsvd r; r.nb = (int)M.size(); r.m = m; r.n = n; r.chi = chi;
+    Rsvd r; r.nb = fac ? (int)fac->size() : (int)M.size(); r.m = m; r.n = n; r.chi = chi;
     const int nb = r.nb, k = sketch_width(m, n, chi, o);
     r.k = k;
     CTMB_CHECK(nb <= TC_MAX_BATCH, "too many problems in one batch");
@@ -561,19 +561,19 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         Engine::IterHint& hint = e.iter_hint[hkey];
         if (res <= tol_eff) {
             if (round == 0) {
-                // passed first time: occasionally probe one iteration fewer (a failed probe costs one extra
-                // Rayleigh-Ritz round, so it is retried only after a cool-down)
-                if (res <= 0.125 * tol_eff && hint.cooldown == 0 && used > 1) hint.q = used - 1;
-                else { hint.q = used; if (hint.cooldown > 0) --hint.cooldown; }
-            } else { hint.q = used; hint.cooldown = 64; }
+                // passed first time: probe one iteration fewer next time unless that count failed recently
+                if (++hint.age > 64) { hint.lo = 0; hint.age = 0; }
+                hint.q = (res <= 0.125 * tol_eff && used > 1 && used - 1 > hint.lo) ? used - 1 : used;
+            } else hint.q = used;
             break;
         }
+        if (round == 0) { hint.lo = std::max(hint.lo, used); hint.age = 0; }
         if (prev_res > 0.0 && res > 0.5 * prev_res) {         // rounding floor reached: more iterations do not help
-            hint.q = used - todo; hint.cooldown = 64;
+            hint.q = std::max(1, used - todo);
             break;
         }
         prev_res = res;
-        todo = o.rsvd_niter << round;                     // q, 2q, 4q ... additional iterations
+        todo = std::max(1, used);                         // double the total: q, 2q, 4q ...
     }
     return r;
 }
