@@ -440,12 +440,16 @@ def run_ours(args):
     roof['gemm_tflops_in_step'] = g['flops'] / max(g['ms'], 1e-9) / 1e9
     roof['fp64_dgemm_peak_tflops'] = fp64_peak
 
-    roof['kernel_level'] = kernel_level(eng, dev, fp64_peak)
+    # CTMB_BENCH_FAST=1 (profiling runs under ncu): skip the side measurements that are not part of the timed step
+    fast = bool(os.environ.get('CTMB_BENCH_FAST'))
+    roof['kernel_level'] = None if fast else kernel_level(eng, dev, fp64_peak)
     F_move = algorithmic_flops_per_move(kind, D, chi, p_phys, cplx)
     if args.config == 'c5':
         base = {'value': None, 'unit': 'ctm_MOVE/s', 'cores': os.cpu_count(), 'kind': 'port',
                 'sample': 'not run: one reference move at n = 16384 is four full 16384^2 LAPACK SVDs (~56 min per ctm_MOVE '
                           'extrapolated from DGEMM / gesdd timings, SURVEY.md section 6)'}
+    elif fast:
+        base = {'value': None, 'unit': 'ctm_MOVE/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'skipped (CTMB_BENCH_FAST)'}
     else:
         base = cpu_baseline(args.config)
     line = {'metric': 'CTM moves/sec', 'value': value, 'unit': 'ctm_MOVE/s', 'n_gpus': world, 'steps': args.steps,
