@@ -55,6 +55,9 @@ typedef struct {
                                   synchronisation per call) and further rounds are run if needed: the bound is a few hundred
                                   ulps, i.e. LAPACK-grade residuals, because the projectors amplify the error of a triplet by
                                   s_0 / s_j.  0 = fixed iteration count, no synchronisation. */
+    int projector_method;      /* CTMARGS.projector_method: 0 = '4X4' (halves of the 4x4 network, ctm_projectors.py:14-64; default),
+                                  1 = '4X2' (R, Rt = the two enlarged corners next to the bond, ctm_projectors.py:66-136) */
+    int pad2;
 } ctmb_options;
 
 /* One unit-cell site: on-site tensor and its eight environment tensors. */

@@ -41,6 +41,7 @@ class OracleArgs:
     projector_eps_multiplet = 1.0e-8
     projector_multiplet_abstol = 1.0e-14
     svd_driver = None            # LAPACK driver for torch.linalg.svd (None = gesdd)
+    projector_method = '4X4'     # or '4X2' (ctm_projectors.py:66-136)
     ctm_force_dl = False
 
     def __init__(self, **kw):
@@ -159,6 +160,17 @@ HALVES = {
     DOWN: ((('LD', 0, 0, True), ('LU', 0, -1, False)), (('RD', 1, 0, True), ('RU', 1, -1, True))),
     RIGHT: ((('RD', 0, 0, False), ('LD', -1, 0, True)), (('RU', 0, -1, True), ('LU', -1, -1, True))),
 }
+
+
+def corners_4x2(direction, coord, sites, v2s, C, T):
+    """ctm_get_projectors_4x2 (ctm_projectors.py:118-136): R and Rt are the first enlarged corner of each half
+    (same corner kinds, offsets and transpositions as the first factors of halves_of_4x4_CTM_MOVE_*)."""
+    res = []
+    for pair in HALVES[direction]:
+        kind, dx, dy, tr = pair[0]
+        m = corner_at(kind, (coord[0] + dx, coord[1] + dy), sites, v2s, C, T)
+        res.append(m.t() if tr else m)
+    return res[0], res[1]
 
 
 def halves(direction, coord, sites, v2s, C, T):
@@ -311,7 +323,12 @@ def ctm_move(direction, sites, v2s, C, T, chi, args=None, return_proj=False):
     args = args or OracleArgs()
     P, Pt = {}, {}
     for coord in sites.keys():
-        R, Rt = halves(direction, coord, sites, v2s, C, T)
+        if args.projector_method == '4X4':
+            R, Rt = halves(direction, coord, sites, v2s, C, T)
+        elif args.projector_method == '4X2':
+            R, Rt = corners_4x2(direction, coord, sites, v2s, C, T)
+        else:
+            raise ValueError("Invalid Projector method: " + str(args.projector_method))
         P[coord], Pt[coord] = projectors_from_matrices(R, Rt, chi, args)
     new = {}
     for coord in sites.keys():

@@ -20,7 +20,8 @@ LU, RU, RD, LD = 0, 1, 2, 3
 class Options(C.Structure):
     _fields_ = [('svd_reltol', C.c_double), ('eps_multiplet', C.c_double), ('multiplet_abstol', C.c_double),
                 ('rsvd_rank_factor', C.c_double), ('rsvd_niter', C.c_int), ('jacobi_max_sweeps', C.c_int),
-                ('norm_type', C.c_int), ('rsvd_max_rounds', C.c_int), ('seed', C.c_ulonglong), ('rsvd_tol', C.c_double)]
+                ('norm_type', C.c_int), ('rsvd_max_rounds', C.c_int), ('seed', C.c_ulonglong), ('rsvd_tol', C.c_double),
+                ('projector_method', C.c_int), ('pad2', C.c_int)]
 
 
 class Site(C.Structure):

@@ -599,14 +599,15 @@ struct MoveCtx {
 static void projectors_from_matrices(Engine& e, const std::vector<const void*>& R, const std::vector<const void*>& Rt,
                                      int n0, int n1, int chi, const ctmb_options& o,
                                      const std::vector<void*>& P, const std::vector<void*>& Pt,
-                                     const std::vector<double*>& Sout) {
+                                     const std::vector<double*>& Sout, bool trR = false, bool trRt = false) {
     const int nb = (int)R.size();
     const size_t mark = e.ws.mark();
     std::vector<const void*> Mp(nb);
     std::vector<Tn> Rtn(nb), Rttn(nb);
     for (int b = 0; b < nb; ++b) {
-        Rtn[b] = make_tn(const_cast<void*>(R[b]), "ki", {n0, n1});
-        Rttn[b] = make_tn(const_cast<void*>(Rt[b]), "kj", {n0, n1});
+        // (trR / trRt: the buffer holds the transpose -- the 4X2 method passes enlarged corners as they are stored)
+        Rtn[b] = trR ? make_tn(const_cast<void*>(R[b]), "ik", {n1, n0}) : make_tn(const_cast<void*>(R[b]), "ki", {n0, n1});
+        Rttn[b] = trRt ? make_tn(const_cast<void*>(Rt[b]), "jk", {n1, n0}) : make_tn(const_cast<void*>(Rt[b]), "kj", {n0, n1});
         Tn M = e.temp("ij", {n1, n1});
         Mp[b] = M.ptr;
         e.contract(Rtn[b], false, Rttn[b], false, M);           // M = R^T Rt  (plain transpose)
@@ -618,8 +619,8 @@ static void projectors_from_matrices(Engine& e, const std::vector<const void*>& 
         for (int b = 0; b < nb; ++b) { pU.p[b] = r.U[b]; pV.p[b] = r.V[b]; pS.p[b] = r.S[b]; pSo.p[b] = Sout.empty() ? nullptr : Sout[b]; }
         { ProfScope ps(e, Engine::CAT_MISC); proj_finalize_launch(pU, pV, pS, pSo, finalize_args(r, o, true, true), e.cplx, e.stream); }
         for (int b = 0; b < nb; ++b) {
-            e.contract(relabel(Rtn[b], "xi"), false, make_tn(r.U[b], "ci", {chi, n1}), false, make_tn(P[b], "xc", {n0, chi}));
-            e.contract(relabel(Rttn[b], "xi"), false, make_tn(r.V[b], "ci", {chi, n1}), false, make_tn(Pt[b], "xc", {n0, chi}));
+            e.contract(relabel(Rtn[b], trR ? "ix" : "xi"), false, make_tn(r.U[b], "ci", {chi, n1}), false, make_tn(P[b], "xc", {n0, chi}));
+            e.contract(relabel(Rttn[b], trRt ? "ix" : "xi"), false, make_tn(r.V[b], "ci", {chi, n1}), false, make_tn(Pt[b], "xc", {n0, chi}));
         }
         e.flush();
     }
@@ -691,6 +692,27 @@ static void move_projectors(MoveCtx& mc, const int* corner_site, const std::vect
         }
     int64_t n0 = 0, n1 = 0;
     half_shape(mc.dir, mc.chi, &corners[0], n0, n1);
+    CTMB_CHECK(mc.o.projector_method == 0 || mc.o.projector_method == 1, "Invalid Projector method");
+    if (mc.o.projector_method == 1) {
+        // '4X2' (ctm_projectors.py:66-136): R and Rt are the first enlarged corner of each half, transposed as there
+        const HalfSpec& hs = HALVES[mc.dir];
+        std::vector<CornerReq> cj;
+        std::vector<const void*> Rc(nj), Rtc(nj);
+        for (int j = 0; j < nj; ++j)
+            for (int q = 0; q < 4; q += 2) {
+                const ctmb_site& s = *corners[4 * j + q];
+                int64_t rows, cols;
+                corner_shape(hs.kind[q], s, mc.chi, rows, cols);
+                CTMB_CHECK(rows == n0 && cols == n0, "the 4X2 projectors need equal bond dimensions");
+                void* cm = e.ws.alloc((size_t)rows * cols * e.esize());
+                cj.push_back(CornerReq{hs.kind[q], &s, cm});
+                (q == 0 ? Rc[j] : Rtc[j]) = cm;
+            }
+        corners_run(e, mc.chi, cj);
+        projectors_from_matrices(e, Rc, Rtc, (int)n0, (int)n0, mc.chi, mc.o, P, Pt, {}, hs.tr[0], hs.tr[2]);
+        e.ws.release(mark);
+        return;
+    }
     if (use_matrix_free(n0, n1, mc.chi)) {
         const HalfSpec& hs = HALVES[mc.dir];
         const int n = (int)n0, chi = mc.chi;
@@ -866,7 +888,7 @@ void ctmb_default_options(ctmb_options* o) {
     if (!o) return;
     o->svd_reltol = 1.0e-8; o->eps_multiplet = 1.0e-8; o->multiplet_abstol = 1.0e-14;
     o->rsvd_rank_factor = 2.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->rsvd_max_rounds = 5;
-    o->seed = 0x5eed5eedull; o->rsvd_tol = 2.0e-15;
+    o->seed = 0x5eed5eedull; o->rsvd_tol = 2.0e-15; o->projector_method = 0; o->pad2 = 0;
 }
 
 int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops) {

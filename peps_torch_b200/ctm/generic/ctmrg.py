@@ -22,7 +22,11 @@ def _options(ctm_args):
     norm = getattr(ctm_args, 'ctm_absorb_normalization', 'inf')
     if norm != 'inf':
         raise ValueError("libctmb implements ctm_absorb_normalization='inf' only, got " + str(norm))
-    return dict(svd_reltol=ctm_args.projector_svd_reltol,
+    pm = getattr(ctm_args, 'projector_method', '4X4')
+    if pm not in ('4X4', '4X2'):
+        raise ValueError("Invalid Projector method: " + str(pm))
+    return dict(projector_method={'4X4': 0, '4X2': 1}[pm],
+                svd_reltol=ctm_args.projector_svd_reltol,
                 eps_multiplet=ctm_args.projector_eps_multiplet,
                 multiplet_abstol=ctm_args.projector_multiplet_abstol,
                 rsvd_niter=getattr(ctm_args, 'b200_rsvd_niter', None),
@@ -40,8 +44,6 @@ def ctm_MOVE(direction, state, env, ctm_args=cfg.ctm_args, global_args=cfg.globa
     truncation and normalisation for all sites) on the GPU.
     """
     eng = _engine()
-    if getattr(ctm_args, 'projector_method', '4X4') != '4X4':
-        raise ValueError("Invalid Projector method: " + str(ctm_args.projector_method))
     if direction not in ((0, -1), (-1, 0), (0, 1), (1, 0)):
         raise ValueError("Invalid direction: " + str(direction))
     eng.move_generic(direction, state, env, **_options(ctm_args))

@@ -400,3 +400,21 @@ def test_slowly_decaying_spectrum_against_live_oracle(eng, dev):
     e_gpu = orc.energy_j1j2(sites, orc.v2s_4site, cpu(env.C), cpu(env.T), 1.0, 0.3)
     e_cpu = orc.energy_j1j2(sites, orc.v2s_4site, C, T, 1.0, 0.3)
     assert abs(e_gpu - e_cpu) <= 1e-12 * abs(e_cpu)
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128'])
+def test_projector_method_4x2_against_oracle(eng, dev, name):
+    """CTMARGS.projector_method='4X2' (ctm_projectors.py:66-136): R, Rt are single enlarged corners.  The oracle's
+    4X2 restatement is pinned against the reference in tests/test_oracle_vs_reference_cpu.py."""
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C0, T0 = H.golden_env(z, 'mid_')
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    for d in orc.DIRECTIONS:
+        C, T = dict(C0), dict(T0)
+        orc.ctm_move(d, sites, v2s, C, T, chi, orc.OracleArgs(projector_method='4X2'))
+        env = H.Env(chi, H.to_dev(C0, dev), H.to_dev(T0, dev))
+        eng.move_generic(d, st, env, projector_method=1)
+        assert H.env_abs_diff(env.C, env.T, C, T) < 1e-8

@@ -24,11 +24,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from peps_torch_b200 import _lib
-    assert ctypes.sizeof(_lib.Options) == 64
+    assert ctypes.sizeof(_lib.Options) == 72      # 4 doubles, 4 ints, u64, double, 2 ints (include/ctmb.h)
     assert ctypes.sizeof(_lib.Site) == 8 + 24 + 32 + 32
     o = _lib.default_options()
     assert (o.svd_reltol, o.eps_multiplet, o.multiplet_abstol) == (1e-8, 1e-8, 1e-14)
     assert o.rsvd_niter >= 2 and o.rsvd_rank_factor >= 1.5
+    assert o.projector_method == 0 and 0.0 < o.rsvd_tol < 1e-13
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU error path')
