@@ -46,7 +46,8 @@ typedef struct {
     int rsvd_niter;            /* power iterations q of the first call with a new shape (later calls start from the count that
                                   satisfied the residual test last time); default 4 */
     int jacobi_max_sweeps;     /* default 40 */
-    int norm_type;             /* ctm_absorb_normalization: 0 = 'inf' (only value supported) */
+    int norm_type;             /* ctm_absorb_normalization (ctmrg.py:210-230): 0 = 'inf' (max |x|, default), 1 = any other value of
+                                  the reference = vector 2-norm (the C4v move scales C by |C[0,0]| either way, ctmrg_c4v.py:182-197) */
     int rsvd_max_rounds;       /* adaptive mode: at most this many rounds q, +q, +2q, +4q ... (default 5); a round that does not
                                   halve the residual ends the iteration (rounding floor) */
     unsigned long long seed;   /* seed of the Gaussian sketch (deterministic) */
@@ -62,8 +63,10 @@ typedef struct {
 
 /* One unit-cell site: on-site tensor and its eight environment tensors. */
 typedef struct {
-    const void* a;             /* a[p,Du,Dl,Dd,Dr] */
-    int dims[5];               /* p, Du, Dl, Dd, Dr */
+    const void* a;             /* a[p,Du,Dl,Dd,Dr]  -- or, with dims[0] == 0, the DOUBLE-LAYER tensor A[du,dl,dd,dr] whose legs
+                                  are the fused (ket,bra) pairs: what ctmrg.run builds under ctm_force_dl (ctmrg.py:51-61),
+                                  run_overlap (:137-147) and ctm_MOVE_dl (ctmrg_c4v.py:229-233) */
+    int dims[5];               /* p, Du, Dl, Dd, Dr      (double-layer: 0, du, dl, dd, dr = the fused extents) */
     int pad;
     const void* C[4];          /* C(-1,-1), C(1,-1), C(1,1), C(-1,1)   -- all chi x chi */
     const void* T[4];          /* T(0,-1), T(-1,0), T(0,1), T(1,0) */
@@ -151,12 +154,13 @@ int ctmb_move_generic_projectors(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction 
                                  void* ws, size_t ws_bytes, void* stream);
 int ctmb_move_generic_absorb(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
                              const ctmb_site* sites, const int* nb_site, int njobs, const int* jobs,
-                             const void* const* P, const void* const* Pt,
+                             const ctmb_options* opt, const void* const* P, const void* const* Pt,
                              void* const* nC1, void* const* nC2, void* const* nT,
                              void* ws, size_t ws_bytes, void* stream);
 
 /* One C4v move = ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463): a[p,D,D,D,D], C[chi,chi],
- * T[chi,chi,D^2] -> C_out, T_out (same shapes); D_out (may be NULL): the chi kept eigenvalues. */
+ * T[chi,chi,D^2] -> C_out, T_out (same shapes); D_out (may be NULL): the chi kept eigenvalues.
+ * With dims[0] == 0 `a` is the double-layer tensor A[D^2,D^2,D^2,D^2]: ctm_MOVE_dl (:200-322). */
 int ctmb_move_c4v(ctmb_handle_t h, ctmb_dtype dt, const void* a, const int dims[5], const void* C,
                   const void* T, int chi, const ctmb_options* opt, void* C_out, void* T_out, double* D_out,
                   void* ws, size_t ws_bytes, void* stream);

@@ -82,6 +82,14 @@ def sl_einsum(spec, ops, a, open_phys=False):
     assert len(a_pos) == 1
     a_pos = a_pos[0]
     a_idx = terms[a_pos][1:]
+    if a.dim() == 4:
+        # `a` IS the double-layer tensor A[u,l,d,r] (ctm_force_dl, ctmrg.py:51-61; run_overlap :137-147;
+        # ctm_MOVE_dl ctmrg_c4v.py:229-233): the reference's *_c functions contract it as one operand
+        # (ctm_components.py:321-370 "dl" branches)
+        assert not open_phys
+        xs = list(ops[:a_pos]) + [a] + list(ops[a_pos:])
+        subs = [t[1:] if t.startswith('@') else t for t in terms]
+        return _pairwise(subs, xs, out)
     assert len(a_idx) == 4 and 's' not in lhs
     D = {ch: a.shape[1 + i] for i, ch in enumerate(a_idx)}
     subs, xs = [], []
@@ -117,10 +125,12 @@ def sl_einsum(spec, ops, a, open_phys=False):
     return res.reshape(shape)
 
 
-def double_layer(a):
-    """A[u,l,d,r] with fused (ket,bra) legs (ctm/generic/ctmrg.py:51-61)."""
+def double_layer(a, bra=None):
+    """A[u,l,d,r] with fused (ket,bra) legs (ctm/generic/ctmrg.py:51-61); with `bra` the overlap tensor of
+    run_overlap (ctmrg.py:137-147: ket = state1, bra = state2)."""
+    bra = a if bra is None else bra
     d = a.shape
-    A = torch.einsum('mefgh,mabcd->eafbgchd', a, a.conj()).contiguous()
+    A = torch.einsum('mefgh,mabcd->eafbgchd', a, bra.conj()).contiguous()
     return A.view(d[1] ** 2, d[2] ** 2, d[3] ** 2, d[4] ** 2)
 
 
@@ -408,7 +418,8 @@ def c2x2_c4v(a, C, T):
 
 def ctm_move_c4v(a, C, T, chi, args=None, return_decomp=False):
     """Returns the new (C, T). eps_multiplet/abs_tol are the *function defaults* of
-    truncated_eig_sym (custom_eig.py:7-8), as used by ctmrg_c4v.py:50-52."""
+    truncated_eig_sym (custom_eig.py:7-8), as used by ctmrg_c4v.py:50-52.  With a rank-4 `a` (the double-layer
+    tensor) this is ctm_MOVE_dl (ctmrg_c4v.py:200-322)."""
     args = args or OracleArgs()
     C2X2 = c2x2_c4v(a, C, T)
     D, U = truncated_eig_sym(C2X2, chi)

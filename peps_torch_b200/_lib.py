@@ -60,7 +60,7 @@ SIGNATURES = {
     'ctmb_move_generic': (C.c_int, [_vp, _i, _i, _i, _i, _PS, _PI, _PI, _PO, _PVP, _PVP, _PVP, _vp, _sz, _vp]),
     'ctmb_move_generic_workspace': (_sz, [_vp, _i, _i, _i, _i, _PS, _PI, _PI, _PO]),
     'ctmb_move_generic_projectors': (C.c_int, [_vp, _i, _i, _i, _i, _PS, _PI, _i, _PI, _PO, _PVP, _PVP, _vp, _sz, _vp]),
-    'ctmb_move_generic_absorb': (C.c_int, [_vp, _i, _i, _i, _i, _PS, _PI, _i, _PI, _PVP, _PVP, _PVP, _PVP, _PVP,
+    'ctmb_move_generic_absorb': (C.c_int, [_vp, _i, _i, _i, _i, _PS, _PI, _i, _PI, _PO, _PVP, _PVP, _PVP, _PVP, _PVP,
                                            _vp, _sz, _vp]),
     'ctmb_move_c4v': (C.c_int, [_vp, _i, _vp, C.POINTER(C.c_int), _vp, _vp, _i, _PO, _vp, _vp, _vp, _vp, _sz, _vp]),
     'ctmb_move_c4v_workspace': (_sz, [_vp, _i, C.POINTER(C.c_int), _i, _PO]),

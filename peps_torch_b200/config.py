@@ -13,6 +13,7 @@ class CTMARGS:
         self.ctm_absorb_normalization = 'inf'
         self.projector_method = '4X4'
         self.projector_svd_method = 'DEFAULT'
+        self.warmup_projector_svd_method = self.projector_svd_method
         self.projector_svd_reltol = 1.0e-8
         self.projector_eps_multiplet = 1.0e-8
         self.projector_multiplet_abstol = 1.0e-14

@@ -126,7 +126,10 @@ void proj_finalize_launch(const PtrBatch& U, const PtrBatch& V, const PtrBatch& 
 
 // x /= amax (amax given as bits); count elements each
 struct ScaleBatch { void* p[TC_MAX_BATCH]; const unsigned long long* amax[TC_MAX_BATCH]; long long count[TC_MAX_BATCH]; };
-void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
+// sqrt_mode: the slot holds sum |x|^2 (sumsq_launch) instead of max |x|
+void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream, bool sqrt_mode = false);
+// slot (a double, zeroed by the caller) += sum |x|^2
+void sumsq_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
 // amax of |x|
 void absmax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
 

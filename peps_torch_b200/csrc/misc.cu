@@ -203,13 +203,36 @@ __global__ void __launch_bounds__(256) absmax_kernel(ScaleBatch b) {
     }
 }
 
+// sum |x|^2 into the slot (a double, zeroed by the caller): the 2-norm of ctm_absorb_normalization != 'inf'
+// (ctmrg.py:212-214).  Block partials are combined with atomicAdd: the last bits depend on the block order.
 template <bool CPLX>
-__global__ void __launch_bounds__(256) scale_kernel(ScaleBatch b) {
+__global__ void __launch_bounds__(256) sumsq_kernel(ScaleBatch b) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const T* x = reinterpret_cast<const T*>(b.p[blockIdx.y]);
+    const long long n = b.count[blockIdx.y];
+    double m = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m += S::abs2(x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m += red[w];
+        atomicAdd(reinterpret_cast<double*>(const_cast<unsigned long long*>(b.amax[blockIdx.y])), m);
+    }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) scale_kernel(ScaleBatch b, int sqrt_mode) {
     using S = Sc<CPLX>;
     using T = typename S::T;
     T* x = reinterpret_cast<T*>(b.p[blockIdx.y]);
     const long long n = b.count[blockIdx.y];
-    const double m = __longlong_as_double((long long)*b.amax[blockIdx.y]);
+    double m = __longlong_as_double((long long)*b.amax[blockIdx.y]);
+    if (sqrt_mode) m = sqrt(m);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         x[i] = CPLX ? S::make(S::re(x[i]) / m, S::im(x[i]) / m) : S::make(S::re(x[i]) / m, 0.0);
 }
@@ -228,10 +251,17 @@ void absmax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream) 
     CTMB_CUDA(cudaGetLastError());
 }
 
-void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream) {
+void sumsq_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream) {
     dim3 grid(blocks_for(b, nb), nb);
-    if (cplx) scale_kernel<true><<<grid, 256, 0, stream>>>(b);
-    else scale_kernel<false><<<grid, 256, 0, stream>>>(b);
+    if (cplx) sumsq_kernel<true><<<grid, 256, 0, stream>>>(b);
+    else sumsq_kernel<false><<<grid, 256, 0, stream>>>(b);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream, bool sqrt_mode) {
+    dim3 grid(blocks_for(b, nb), nb);
+    if (cplx) scale_kernel<true><<<grid, 256, 0, stream>>>(b, sqrt_mode ? 1 : 0);
+    else scale_kernel<false><<<grid, 256, 0, stream>>>(b, sqrt_mode ? 1 : 0);
     CTMB_CUDA(cudaGetLastError());
 }
 

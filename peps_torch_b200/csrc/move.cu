@@ -51,13 +51,20 @@ static const AbsorbSpec ABSORB[4] = {
     /* RIGHT */ {2, 2, 3, 0, 1, "ab", "feb", "afx", "xe", "ab", "eua", "bux", "ex", "arc", "aux", "uldr", "cdy", "xly", false},
 };
 
+// dims[0] == 0 marks a DOUBLE-LAYER on-site tensor A[u,l,d,r] whose legs are already the fused (ket,bra) pairs
+// (what ctmrg.run builds under ctm_force_dl, ctmrg.py:51-61, run_overlap :137-147 and ctm_MOVE_dl ctmrg_c4v.py:229-233)
+static inline bool is_dl(const ctmb_site& s) { return s.dims[0] == 0; }
+// extent of the environment leg facing auxiliary leg `leg` (0..3 = u,l,d,r)
+static inline int64_t aux2(const ctmb_site& s, int leg) {
+    const int64_t D = s.dims[1 + leg];
+    return is_dl(s) ? D : D * D;
+}
 static void t_dims(const ctmb_site& s, int which, int chi, int64_t d[3]) {
-    const int64_t Du = s.dims[1], Dl = s.dims[2], Dd = s.dims[3], Dr = s.dims[4];
     switch (which) {
-        case 0: d[0] = chi; d[1] = Du * Du; d[2] = chi; break;
-        case 1: d[0] = chi; d[1] = chi; d[2] = Dl * Dl; break;
-        case 2: d[0] = Dd * Dd; d[1] = chi; d[2] = chi; break;
-        default: d[0] = chi; d[1] = Dr * Dr; d[2] = chi; break;
+        case 0: d[0] = chi; d[1] = aux2(s, 0); d[2] = chi; break;
+        case 1: d[0] = chi; d[1] = chi; d[2] = aux2(s, 1); break;
+        case 2: d[0] = aux2(s, 2); d[1] = chi; d[2] = chi; break;
+        default: d[0] = chi; d[1] = aux2(s, 3); d[2] = chi; break;
     }
 }
 static Tn env_T(const ctmb_site& s, int which, int chi, const char* lab) {
@@ -74,6 +81,23 @@ static Tn env_C(const ctmb_site& s, int which, int chi, const char* lab) {
 static Engine::ChainJob sl_job(std::vector<Tn> ops, size_t apos, const char* la, const ctmb_site& s,
                                const char* out_lab, void* out_ptr, unsigned long long* amax) {
     Engine::ChainJob job;
+    if (is_dl(s)) {
+        // double-layer site: A enters as ONE operand with the fused labels, nothing is split
+        Tn A = make_tn(const_cast<void*>(s.a), la, {s.dims[1], s.dims[2], s.dims[3], s.dims[4]});
+        std::map<char, int64_t> ext;
+        for (int d = 0; d < A.nd; ++d) ext[A.idx[d]] = A.dim[d];
+        for (size_t i = 0; i < ops.size(); ++i) {
+            if (i == apos) { job.ops.push_back(A); job.conj.push_back(false); }
+            for (int d = 0; d < ops[i].nd; ++d) ext[ops[i].idx[d]] = ops[i].dim[d];
+            job.ops.push_back(ops[i]); job.conj.push_back(false);
+        }
+        if (apos >= ops.size()) { job.ops.push_back(A); job.conj.push_back(false); }
+        std::vector<int64_t> od;
+        for (const char* p = out_lab; *p; ++p) { CTMB_CHECK(ext.count(*p), "output label not found"); od.push_back(ext[*p]); }
+        job.out = make_tn(out_ptr, std::string(out_lab), od);
+        job.amax = amax;
+        return job;
+    }
     auto Dof = [&](char c) -> int64_t { const char* p = strchr(la, c); return p ? s.dims[1 + (p - la)] : 0; };
     std::string lab_a = std::string("s") + la, lab_ac = lab_a;
     for (size_t i = 1; i < lab_ac.size(); ++i) lab_ac[i] = (char)toupper(lab_ac[i]);
@@ -101,9 +125,9 @@ static Engine::ChainJob sl_job(std::vector<Tn> ops, size_t apos, const char* la,
 
 static void corner_shape(int kind, const ctmb_site& s, int chi, int64_t& rows, int64_t& cols) {
     const CornerSpec& cs = CORNERS[kind];
-    auto D = [&](char c) -> int64_t { const char* p = strchr(cs.la, c); return s.dims[1 + (p - cs.la)]; };
-    rows = chi * D(cs.out[1]) * D(cs.out[1]);
-    cols = chi * D(cs.out[3]) * D(cs.out[3]);
+    auto D2 = [&](char c) -> int64_t { const char* p = strchr(cs.la, c); return aux2(s, (int)(p - cs.la)); };
+    rows = chi * D2(cs.out[1]);
+    cols = chi * D2(cs.out[3]);
 }
 
 static Engine::ChainJob corner_job(int kind, const ctmb_site& s, int chi, void* out) {
@@ -126,6 +150,7 @@ static CornerRoles corner_roles(const CornerSpec& cs) {
 }
 
 static bool corner_fusable(const Engine& e, int kind, const ctmb_site& s) {
+    if (is_dl(s)) return false;
     const CornerSpec& cs = CORNERS[kind];
     const CornerRoles r = corner_roles(cs);
     auto D = [&](char c) { return s.dims[1 + (strchr(cs.la, c) - cs.la)]; };
@@ -765,7 +790,8 @@ static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>&
     Engine& e = mc.e;
     const int nj = (int)jobs.size();
     if (nj == 0) return;
-    CTMB_CHECK(mc.o.norm_type == 0, "only ctm_absorb_normalization='inf' is implemented");
+    CTMB_CHECK(mc.o.norm_type == 0 || mc.o.norm_type == 1, "norm_type must be 0 ('inf') or 1 (2-norm)");
+    const bool norm2 = mc.o.norm_type == 1;       // the slots then hold sum |x|^2, filled after the chains
     const AbsorbSpec& as = ABSORB[mc.dir];
     const int chi = mc.chi;
     unsigned long long* amax = nullptr;
@@ -789,13 +815,13 @@ static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>&
         a1.ops = {env_C(s, as.C1, chi, as.lC1), env_T(s, as.T1, chi, as.lT1), Pt1};
         a1.conj = {false, false, false};
         a1.out = make_tn(nC1[j], as.oC1, {chi, chi});
-        a1.amax = amax ? amax + 3 * j : nullptr;
+        a1.amax = (amax && !norm2) ? amax + 3 * j : nullptr;
         j1.push_back(a1);
         Engine::ChainJob a2;
         a2.ops = {env_C(s, as.C2, chi, as.lC2), env_T(s, as.T2, chi, as.lT2), P2};
         a2.conj = {false, false, false};
         a2.out = make_tn(nC2[j], as.oC2, {chi, chi});
-        a2.amax = amax ? amax + 3 * j + 1 : nullptr;
+        a2.amax = (amax && !norm2) ? amax + 3 * j + 1 : nullptr;
         j2.push_back(a2);
         // nT: the projector on the T1 side is P1 / Pt1 of the neighbour, on the T2 side P2 / Pt2 of this site
         const void* pa = as.pa_is_P1 ? Pall[sn] : Ptall[si];
@@ -803,7 +829,7 @@ static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>&
         const int64_t da = as.pa_is_P1 ? d1 : d2, db = as.pa_is_P1 ? d2 : d1;
         std::vector<Tn> ops = {env_T(s, as.T, chi, as.lT), make_tn(const_cast<void*>(pa), as.lPa, {chi, da, chi}),
                                make_tn(const_cast<void*>(pb), as.lPb, {chi, db, chi})};
-        j3.push_back(sl_job(ops, 2, as.lA, s, as.oT, nT[j], amax ? amax + 3 * j + 2 : nullptr));
+        j3.push_back(sl_job(ops, 2, as.lA, s, as.oT, nT[j], (amax && !norm2) ? amax + 3 * j + 2 : nullptr));
         int64_t td[3]; t_dims(s, as.T, chi, td);
         if (!amax) continue;
         sb.p[3 * j] = nC1[j]; sb.count[3 * j] = (long long)chi * chi; sb.amax[3 * j] = amax + 3 * j;
@@ -815,7 +841,10 @@ static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>&
     j12.insert(j12.end(), j2.begin(), j2.end());
     e.chain_multi(j12);
     e.chain_multi(j3);
-    if (!e.ws.dry()) { { ProfScope ps(e, Engine::CAT_MISC); scale_by_amax_launch(sb, 3 * nj, e.cplx, e.stream); } }
+    if (!e.ws.dry()) {
+        if (norm2) { ProfScope ps(e, Engine::CAT_MISC); sumsq_launch(sb, 3 * nj, e.cplx, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); scale_by_amax_launch(sb, 3 * nj, e.cplx, e.stream, norm2); }
+    }
 }
 
 static ctmb_options opts_or_default(const ctmb_options* o) {
@@ -1137,11 +1166,11 @@ int ctmb_move_generic_projectors(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction 
 
 int ctmb_move_generic_absorb(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir, int nsites, int chi,
                              const ctmb_site* sites, const int* nb_site, int njobs, const int* jobs,
-                             const void* const* P, const void* const* Pt, void* const* nC1, void* const* nC2,
-                             void* const* nT, void* ws, size_t ws_bytes, void* stream) {
+                             const ctmb_options* opt, const void* const* P, const void* const* Pt, void* const* nC1,
+                             void* const* nC2, void* const* nT, void* ws, size_t ws_bytes, void* stream) {
     CTMB_TRY
     begin_call(h, dt, ws, ws_bytes, stream);
-    ctmb_options o = opts_or_default(nullptr);
+    ctmb_options o = opts_or_default(opt);
     MoveCtx mc{h->h.eng, (int)dir, nsites, chi, sites, o};
     std::vector<const void*> Pc(P, P + nsites), Ptc(Pt, Pt + nsites);
     const int agroup = TC_MAX_BATCH / 3;
@@ -1158,9 +1187,9 @@ static void move_c4v_impl(ctmb_handle_t h, const void* a, const int dims[5], con
                           const ctmb_options& o, void* C_out, void* T_out, double* D_out) {
     Engine& e = h->h.eng;
     CTMB_CHECK(dims[1] == dims[2] && dims[2] == dims[3] && dims[3] == dims[4], "C4v needs equal bond dimensions");
-    const int64_t D = dims[1], d = D * D, n = (int64_t)chi * d;
     ctmb_site s{};
     s.a = a; for (int i = 0; i < 5; ++i) s.dims[i] = dims[i];
+    const int64_t d = aux2(s, 0), n = (int64_t)chi * d;
     // enlarged corner 'ab,xbu,ael,@uldr->edxr'  (ctm_components_c4v.py:52-130)
     Tn Ct = make_tn(const_cast<void*>(C), "ab", {chi, chi});
     void* c2 = e.ws.alloc((size_t)n * n * e.esize());
@@ -1188,11 +1217,14 @@ static void move_c4v_impl(ctmb_handle_t h, const void* a, const int dims[5], con
         e.chain_multi(jobs);
     }
     if (!e.ws.dry()) {
+        CTMB_CHECK(o.norm_type == 0 || o.norm_type == 1, "norm_type must be 0 ('inf') or 1 (2-norm)");
+        const bool norm2 = o.norm_type == 1;
         unsigned long long* amax = (unsigned long long*)e.persistent("amax", 3 * TC_MAX_BATCH * sizeof(unsigned long long));
-        CTMB_CUDA(cudaMemsetAsync(amax, 0, sizeof(unsigned long long), e.stream));
+        CTMB_CUDA(cudaMemsetAsync(amax, 0, 2 * sizeof(unsigned long long), e.stream));
         { ProfScope ps(e, Engine::CAT_MISC); c4v_sym_launch(nTraw, T_out, chi, (int)d, amax, e.cplx, e.stream); }
-        ScaleBatch sb{}; sb.p[0] = T_out; sb.count[0] = (long long)chi * chi * d; sb.amax[0] = amax;
-        { ProfScope ps(e, Engine::CAT_MISC); scale_by_amax_launch(sb, 1, e.cplx, e.stream); }
+        ScaleBatch sb{}; sb.p[0] = T_out; sb.count[0] = (long long)chi * chi * d; sb.amax[0] = norm2 ? amax + 1 : amax;
+        if (norm2) { ProfScope ps(e, Engine::CAT_MISC); sumsq_launch(sb, 1, e.cplx, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); scale_by_amax_launch(sb, 1, e.cplx, e.stream, norm2); }
         { ProfScope ps(e, Engine::CAT_MISC); c4v_diag_launch(Dv, C_out, chi, e.cplx, e.stream); }
         if (D_out) CTMB_CUDA(cudaMemcpyAsync(D_out, Dv, (size_t)chi * 8, cudaMemcpyDeviceToDevice, e.stream));
     }

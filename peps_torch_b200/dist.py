@@ -65,7 +65,7 @@ class ShardedCtm:
                 P_all[j] = blk[:n0 * chi].view(n0, chi)
                 Pt_all[j] = blk[n0 * chi:].view(n0, chi)
         # 2) absorption of my jobs, then all-gather of the new tensors
-        res = self.backend.move_generic_absorb(direction, state, env, mine, P_all, Pt_all) if mine else []
+        res = self.backend.move_generic_absorb(direction, state, env, mine, P_all, Pt_all, **opt) if mine else []
         flat = torch.cat([t.reshape(-1) for (_, c1, c2, t3) in res for t in (c1, c2, t3)]) if res else a0.new_zeros(0)
         shapes = {j: self.backend._nT_shape(direction, state.sites[coords[j]], chi) for j in range(n)}
         def job_len(j):

@@ -39,6 +39,16 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def aux2(a):
+    """Extents of the four environment legs facing the on-site tensor: D^2 per leg for a single-layer
+    a[s,u,l,d,r], the leg itself for a double-layer A[u,l,d,r] (ctm_force_dl / run_overlap / ctm_MOVE_dl)."""
+    if a.dim() == 5:
+        return [d * d for d in a.shape[1:]]
+    if a.dim() == 4:
+        return list(a.shape)
+    raise ValueError(f"on-site tensor must have rank 5 (single-layer) or 4 (double-layer), got rank {a.dim()}")
+
+
 class CtmEngine:
     """One engine (= one libctmb handle, one workspace) per process / GPU."""
 
@@ -111,8 +121,9 @@ class CtmEngine:
         s = _lib.Site()
         a = self._prep(a, self.device); keep.append(a)
         s.a = a.data_ptr()
+        dims = list(a.shape) if a.dim() == 5 else [0] + aux2(a)      # dims[0] == 0: double-layer tensor (include/ctmb.h)
         for i in range(5):
-            s.dims[i] = a.shape[i]
+            s.dims[i] = dims[i]
         for i, t in enumerate(Cs):
             if t is not None:
                 t = self._prep(t, self.device); keep.append(t); s.C[i] = t.data_ptr()
@@ -144,9 +155,9 @@ class CtmEngine:
         Cs[cslot], Ts[t1slot], Ts[t2slot] = C_, T1, T2
         keep = []
         s = self._site(a, Cs, Ts, keep)
-        D = a.shape[1:]
-        rows = chi * [D[2], D[1], D[0], D[0]][k] ** 2
-        cols = chi * [D[3], D[2], D[1], D[3]][k] ** 2
+        D = aux2(a)
+        rows = chi * [D[2], D[1], D[0], D[0]][k]
+        cols = chi * [D[3], D[2], D[1], D[3]][k]
         out = torch.empty((rows, cols), dtype=a.dtype, device=self.device)
         nb = lib.ctmb_c2x2_workspace(self._h, _dt(a), k, chi, C.byref(s))
         ws = self._workspace(nb)
@@ -215,14 +226,14 @@ class CtmEngine:
         return tab
 
     def _nT_shape(self, direction, a, chi):
-        D = a.shape[1:]
+        D = aux2(a)
         if direction == (0, -1):
-            return (chi, D[2] ** 2, chi)
+            return (chi, D[2], chi)
         if direction == (-1, 0):
-            return (chi, chi, D[3] ** 2)
+            return (chi, chi, D[3])
         if direction == (0, 1):
-            return (D[0] ** 2, chi, chi)
-        return (chi, D[1] ** 2, chi)
+            return (D[0], chi, chi)
+        return (chi, D[1], chi)
 
     def move_generic(self, direction, state, env, **opt):
         """One ctm_MOVE (ctm/generic/ctmrg.py:179-319): replaces the entries of env.C / env.T
@@ -238,8 +249,6 @@ class CtmEngine:
         a0 = None
         for i, c in enumerate(coords):
             a = state.sites[c]
-            if a.dim() != 5:
-                raise ValueError("libctmb contracts single-layer on-site tensors a[s,u,l,d,r] (ctm_force_dl is not supported)")
             a0 = a if a0 is None else a0
             sites[i] = self._site(a, [env.C[(c, k)] for k in C_KEYS], [env.T[(c, k)] for k in T_KEYS], keep)
         dt = _dt(a0)
@@ -252,7 +261,8 @@ class CtmEngine:
         p3 = (C.c_void_p * n)(*[t.data_ptr() for t in nT])
         o = self._opts(**opt)
         d = DIRECTIONS[direction]
-        wkey = ('ws', dt, d, n, chi, tuple(tuple(state.sites[c].shape) for c in coords), o.rsvd_rank_factor)
+        wkey = ('ws', dt, d, n, chi, tuple(tuple(state.sites[c].shape) for c in coords), o.rsvd_rank_factor,
+                o.projector_method)
         nbytes = self._tables.get(wkey)
         if nbytes is None:
             nbytes = lib.ctmb_move_generic_workspace(self._h, dt, d, n, chi, sites, corner, nb, C.byref(o))
@@ -280,10 +290,9 @@ class CtmEngine:
 
     def projector_shape(self, direction, state, env):
         """(n0, chi) of the projectors of `direction` (uniform bond dimensions)."""
-        a = next(iter(state.sites.values()))
-        D = a.shape[1:]
+        D = aux2(next(iter(state.sites.values())))
         leg = {(0, -1): D[1], (-1, 0): D[0], (0, 1): D[3], (1, 0): D[2]}[direction]   # bond being truncated
-        return env.chi * leg * leg, env.chi
+        return env.chi * leg, env.chi
 
     def move_generic_projectors(self, direction, state, env, jobs, **opt):
         """Projector pairs (P, Pt), each n0 x chi, of the listed site jobs (ctm_get_projectors_4x4)."""
@@ -307,7 +316,7 @@ class CtmEngine:
                                                _ptr(ws), ws.numel(), self._stream()))
         return P, Pt
 
-    def move_generic_absorb(self, direction, state, env, jobs, P_all, Pt_all):
+    def move_generic_absorb(self, direction, state, env, jobs, P_all, Pt_all, **opt):
         """Absorb + truncate + normalise the listed jobs given the projectors of ALL sites;
         returns [(dest_coord, nC1, nC2, nT)] without touching env."""
         keep = []
@@ -321,7 +330,7 @@ class CtmEngine:
         nT = [torch.empty(self._nT_shape(direction, state.sites[coords[j]], chi), dtype=a0.dtype, device=self.device)
               for j in jobs]
         d = DIRECTIONS[direction]
-        o = self._opts()
+        o = self._opts(**opt)
         nbytes = lib.ctmb_move_generic_workspace(self._h, dt, d, n, chi, sites, corner, nb, C.byref(o))
         ws = self._workspace(nbytes)
         jl = (C.c_int * len(jobs))(*jobs)
@@ -330,17 +339,18 @@ class CtmEngine:
         p1 = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in nC1])
         p2 = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in nC2])
         p3 = (C.c_void_p * len(jobs))(*[t.data_ptr() for t in nT])
-        check(lib.ctmb_move_generic_absorb(self._h, dt, d, n, chi, sites, nb, len(jobs), jl, pa, pta, p1, p2, p3,
+        check(lib.ctmb_move_generic_absorb(self._h, dt, d, n, chi, sites, nb, len(jobs), jl, C.byref(o), pa, pta, p1, p2, p3,
                                            _ptr(ws), ws.numel(), self._stream()))
         return [(dest[j], nC1[i], nC2[i], nT[i]) for i, j in enumerate(jobs)]
 
     def move_c4v(self, a, C_, T, chi, **opt):
-        """One ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463) -> (C', T', D)."""
+        """One ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463) or, with a double-layer A[u,l,d,r],
+        ctm_MOVE_dl (:200-322) -> (C', T', D)."""
         a, C_, T = self._prep(a, self.device), self._prep(C_, self.device), self._prep(T, self.device)
         dt = _dt(a)
         opt.setdefault('eps_multiplet', 1.0e-12)      # truncated_eig_sym default (custom_eig.py:7-8)
         o = self._opts(**opt)
-        dims = (C.c_int * 5)(*a.shape)
+        dims = (C.c_int * 5)(*(list(a.shape) if a.dim() == 5 else [0] + aux2(a)))
         Co = torch.empty_like(C_)
         To = torch.empty_like(T)
         Dv = torch.empty(chi, dtype=torch.float64, device=self.device)

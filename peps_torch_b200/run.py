@@ -44,8 +44,14 @@ def enable(engine_factory=None):
         return ours_c4v.ctm_MOVE_sl(a, env, f_c2x2_decomp, ctm_args=ctm_args, global_args=global_args,
                                     past_steps_data=past_steps_data)
 
+    def ctm_MOVE_dl(a, env, f_c2x2_decomp=None, ctm_args=ref_c4v.cfg.ctm_args, global_args=ref_c4v.cfg.global_args):
+        return ours_c4v.ctm_MOVE_dl(a, env, f_c2x2_decomp, ctm_args=ctm_args, global_args=global_args)
+
+    # the reference's own run / run_overlap / run_dl loops stay: they look these names up at call time, build the
+    # double-layer tensors themselves under ctm_force_dl and hand rank-4 sites to ctm_MOVE, which libctmb accepts
     ref.ctm_MOVE = ctm_MOVE
     ref_c4v.ctm_MOVE_sl = ctm_MOVE_sl
+    ref_c4v.ctm_MOVE_dl = ctm_MOVE_dl
     # Without opt_einsum the reference's generic rdm2x2 dispatch is broken (ctm/generic/rdm.py:1354-1362
     # passes force_cpu= to rdm2x2_legacy, which does not take it) and the 'sl' one/two-site RDMs need oe:
     # route them to the reference's own pure-torch implementations.

@@ -87,3 +87,33 @@ def spectra_diff(C1, C2):
     s1 = orc.corner_spectra({k: v.cpu() for k, v in C1.items()})
     s2 = orc.corner_spectra({k: v.cpu() for k, v in C2.items()})
     return max(float((s1[k] - s2[k]).abs().max()) for k in s2)
+
+
+class OracleEngine:
+    """HOST-LOGIC TESTS ONLY: an object with the three CtmEngine methods the drop-in modules call, computing with the
+    oracle on CPU tensors, so that the Python control flow of run / run_overlap / run_dl (double-layer construction,
+    warm-up, option mapping, conv_check protocol) is exercised without a GPU.  Never importable from the package."""
+    device = 'cpu'
+
+    def __init__(self):
+        self.calls = []
+
+    @staticmethod
+    def _args(opt):
+        return orc.OracleArgs(projector_method={0: '4X4', 1: '4X2', None: '4X4'}[opt.get('projector_method')],
+                              ctm_absorb_normalization='inf' if not opt.get('norm_type') else 'fro',
+                              projector_svd_reltol=opt.get('svd_reltol') or 1e-8,
+                              projector_eps_multiplet=opt.get('eps_multiplet') or 1e-8,
+                              projector_multiplet_abstol=opt.get('multiplet_abstol') or 1e-14)
+
+    def einsum2(self, spec, A, B, conjA=False, conjB=False):
+        return torch.einsum(spec, A.conj() if conjA else A, B.conj() if conjB else B).contiguous()
+
+    def move_generic(self, direction, state, env, **opt):
+        self.calls.append(('generic', direction, next(iter(state.sites.values())).dim()))
+        orc.ctm_move(direction, state.sites, state.vertexToSite, env.C, env.T, env.chi, self._args(opt))
+
+    def move_c4v(self, a, C_, T, chi, **opt):
+        self.calls.append(('c4v', a.dim()))
+        nC, nT = orc.ctm_move_c4v(a, C_, T, chi, self._args(opt))
+        return nC, nT, None

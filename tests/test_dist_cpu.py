@@ -32,7 +32,7 @@ class OracleBackend:
             P.append(p.contiguous()); Pt.append(pt.contiguous())
         return P, Pt
 
-    def move_generic_absorb(self, direction, state, env, jobs, P_all, Pt_all):
+    def move_generic_absorb(self, direction, state, env, jobs, P_all, Pt_all, **opt):
         coords = list(state.sites.keys())
         P = {coords[i]: p for i, p in enumerate(P_all)}
         Pt = {coords[i]: p for i, p in enumerate(Pt_all)}

@@ -418,3 +418,151 @@ def test_projector_method_4x2_against_oracle(eng, dev, name):
         env = H.Env(chi, H.to_dev(C0, dev), H.to_dev(T0, dev))
         eng.move_generic(d, st, env, projector_method=1)
         assert H.env_abs_diff(env.C, env.T, C, T) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------
+# non-default variants of the move: the oracle restatements used below are pinned against the
+# reference in tests/test_oracle_vs_reference_cpu.py
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'])
+def test_double_layer_sites_against_oracle(eng, dev, name):
+    """Rank-4 on-site tensors A = a (x) a* (ctm_force_dl, ctmrg.py:51-61): corners element-wise, moves through |.|."""
+    from peps_torch_b200.ctm.generic import ctmrg
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C0, T0 = H.golden_env(z, 'mid_')
+    dl_gpu = type(sites)((c, ctmrg.double_layer(eng, a.to(dev))) for c, a in sites.items())
+    dl = type(sites)((c, orc.double_layer(a)) for c, a in sites.items())
+    for c in sites:
+        assert H.maxrel(dl_gpu[c].cpu(), dl[c]) < 1e-14
+    coord = list(sites.keys())[-1]
+    for kind in orc.CORNERS:
+        kc, k1, k2, _ = orc.CORNERS[kind]
+        out = eng.c2x2(kind, C0[(coord, kc)].to(dev), T0[(coord, k1)].to(dev), T0[(coord, k2)].to(dev), dl_gpu[coord], chi)
+        assert H.maxrel(out.cpu(), torch.from_numpy(z['c2x2_' + kind])) < 1e-13
+    st = H.State(dl_gpu, v2s, lX, lY)
+    for d in orc.DIRECTIONS:
+        C, T = dict(C0), dict(T0)
+        orc.ctm_move(d, dl, v2s, C, T, chi)
+        env = H.Env(chi, H.to_dev(C0, dev), H.to_dev(T0, dev))
+        eng.move_generic(d, st, env)
+        assert H.env_abs_diff(env.C, env.T, C, T) < 1e-8
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128'])
+def test_2norm_normalisation_against_oracle(eng, dev, name):
+    """ctm_absorb_normalization != 'inf' -> vector 2-norm (ctmrg.py:210-230)."""
+    from peps_torch_b200.ctm.generic import ctmrg
+    from peps_torch_b200.config import CTMARGS
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C0, T0 = H.golden_env(z, 'mid_')
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    args = CTMARGS(); args.ctm_absorb_normalization = 'fro'
+    for d in orc.DIRECTIONS:
+        C, T = dict(C0), dict(T0)
+        orc.ctm_move(d, sites, v2s, C, T, chi, orc.OracleArgs(ctm_absorb_normalization='fro'))
+        env = H.Env(chi, H.to_dev(C0, dev), H.to_dev(T0, dev))
+        ctmrg.ctm_MOVE(d, st, env, ctm_args=args)
+        assert H.env_abs_diff(env.C, env.T, C, T) < 1e-8
+        kC1, kC2, kT = orc.ABSORB[d]['out']
+        for k, t in list(env.C.items()) + list(env.T.items()):
+            if k[1] in (kC1, kC2, kT):
+                assert abs(float(torch.linalg.vector_norm(t)) - 1.0) < 1e-13
+
+
+def test_run_overlap_against_oracle(eng, dev):
+    """run_overlap (ctmrg.py:112-175): double-layer tensors ket = state1, bra = state2 (not Hermitian)."""
+    from peps_torch_b200.ctm.generic import ctmrg
+    from peps_torch_b200.config import CTMARGS
+    from peps_torch_b200.ipeps import IPEPS
+    z, meta = H.load_golden('generic_4site_D2_chi8_B')
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C0, T0 = H.golden_env(z, 'mid_')
+    g = torch.Generator().manual_seed(7)
+    sites2 = type(sites)((c, a + 0.05 * (torch.rand(a.shape, generator=g, dtype=a.dtype) - 0.5)) for c, a in sites.items())
+    args = CTMARGS(); args.ctm_force_dl = True; args.ctm_max_iter = 2
+    env = H.Env(chi, H.to_dev(C0, dev), H.to_dev(T0, dev))
+    s1, s2 = IPEPS(H.to_dev(sites, dev), v2s, lX, lY), IPEPS(H.to_dev(sites2, dev), v2s, lX, lY)
+    calls = []
+    ctmrg.run_overlap(s1, s2, env, conv_check=lambda a, b, e, h, ctm_args=None: (calls.append(1) or False, h), ctm_args=args)
+    assert len(calls) == 2
+    with pytest.raises(AssertionError):
+        ctmrg.run_overlap(s1, s2, env, ctm_args=CTMARGS())
+    dl = type(sites)((c, orc.double_layer(sites[c], sites2[c])) for c in sites)
+    C, T = dict(C0), dict(T0)
+    for _ in range(2):
+        for d in orc.DIRECTIONS:
+            orc.ctm_move(d, dl, v2s, C, T, chi)
+    assert H.env_abs_diff(env.C, env.T, C, T) < 1e-8
+
+
+def test_run_force_dl_and_warmup_match_plain_run(eng, dev):
+    """ctmrg.run with ctm_force_dl (ctmrg.py:51-61) and with warm-up iterations (:76-86) against the oracle."""
+    from peps_torch_b200.ctm.generic import ctmrg
+    from peps_torch_b200.config import CTMARGS
+    from peps_torch_b200.ipeps import IPEPS
+    z, meta = H.load_golden('generic_4site_D2_chi8_B')
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C0, T0 = H.golden_env(z, 'init_')
+    st = IPEPS(H.to_dev(sites, dev), v2s, lX, lY)
+    C, T = dict(C0), dict(T0)
+    for _ in range(3):
+        orc.ctm_iteration(sites, v2s, lX, lY, C, T, chi)
+    e_ref = orc.energy_j1j2(sites, v2s, C, T, 1.0, 0.3)
+    for kw in (dict(ctm_force_dl=True, ctm_max_iter=3), dict(ctm_warmup_iter=1, ctm_max_iter=1)):
+        args = CTMARGS()
+        for k, v in kw.items():
+            setattr(args, k, v)
+        env = H.Env(chi, H.to_dev(C0, dev), H.to_dev(T0, dev))
+        _, _, t_ctm, _ = ctmrg.run(st, env, ctm_args=args)
+        assert t_ctm > 0
+        # warm-up: max(ctm_warmup_iter, ceil(chi / D^2)) = 2 iterations, then ctm_max_iter = 1
+        assert H.env_abs_diff(env.C, env.T, C, T) < 1e-8
+        e = orc.energy_j1j2(sites, v2s, cpu(env.C), cpu(env.T), 1.0, 0.3)
+        assert abs(e - e_ref) < 1e-10 * abs(e_ref)
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_c4v_double_layer_move_and_2norm(eng, dev, name):
+    """ctm_MOVE_dl / run_dl (ctmrg_c4v.py:110-176,200-322) and the 2-norm branch of _move_normalize_c (:182-197)."""
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v
+    from peps_torch_b200.config import CTMARGS
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    a = torch.from_numpy(z['site'])
+    A = orc.double_layer(a)
+    C0, T0 = torch.from_numpy(z['init_C']), torch.from_numpy(z['init_T'])
+    stc = IPEPS_C4V(a.to(dev))
+    for norm in ('inf', 'fro'):
+        args = CTMARGS(); args.ctm_absorb_normalization = norm; args.ctm_max_iter = 3
+        C, T = C0, T0
+        for _ in range(3):
+            C, T = orc.ctm_move_c4v(A, C, T, chi, orc.OracleArgs(ctm_absorb_normalization=norm))
+        # run_dl from the single-layer tensor (A built once on the GPU)
+        env = ENV_C4V(chi, stc)
+        env.C[env.keyC], env.T[env.keyT] = C0.to(dev), T0.to(dev)
+        ctmrg_c4v.run_dl(stc, env, ctm_args=args)
+        assert H.maxrel(env.get_C().cpu(), C) < 1e-10
+        assert H.maxrel(env.get_T().abs().cpu(), T.abs()) < 1e-8
+        # ctm_MOVE_dl handed the double-layer tensor itself
+        env2 = ENV_C4V(chi, stc)
+        env2.C[env2.keyC], env2.T[env2.keyT] = C0.to(dev), T0.to(dev)
+        for _ in range(3):
+            ctmrg_c4v.ctm_MOVE_dl(A.to(dev), env2, None, ctm_args=args)
+        assert H.maxrel(env2.get_C().cpu(), C) < 1e-10
+        assert H.maxrel(env2.get_T().abs().cpu(), T.abs()) < 1e-8
+        if norm == 'fro':
+            assert abs(float(torch.linalg.vector_norm(env2.get_T())) - 1.0) < 1e-13
+    with pytest.raises(ValueError):
+        ctmrg_c4v.ctm_MOVE_sl(A.to(dev), env2)

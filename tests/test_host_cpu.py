@@ -75,3 +75,85 @@ def test_host_env_init_matches_oracle_and_reference_fixture():
     init_env_c4v(st, env)
     assert H.maxrel(env.get_C(), torch.from_numpy(z['init_C'])) < 1e-14
     assert H.maxrel(env.get_T().abs(), torch.from_numpy(z['init_T']).abs()) < 1e-12
+
+
+@pytest.fixture()
+def oracle_engine(monkeypatch):
+    from peps_torch_b200.ctm.generic import ctmrg
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v
+    e = H.OracleEngine()
+    monkeypatch.setattr(ctmrg, '_engine', lambda: e)
+    monkeypatch.setattr(ctmrg_c4v, '_engine', lambda: e)
+    return e
+
+
+def test_host_run_variants_control_flow(oracle_engine):
+    """ctm_force_dl, warm-up, run_overlap (ctmrg.py:51-61,76-86,112-175): host logic with the oracle as engine."""
+    from peps_torch_b200.ctm.generic import ctmrg
+    from peps_torch_b200.config import CTMARGS
+    from peps_torch_b200.ipeps import IPEPS
+    z, meta = H.load_golden('generic_4site_D2_chi8_B')
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    C0, T0 = H.golden_env(z, 'init_')
+    st = IPEPS(sites, orc.v2s_4site, 2, 2)
+    C, T = dict(C0), dict(T0)
+    for _ in range(3):
+        orc.ctm_iteration(sites, orc.v2s_4site, 2, 2, C, T, chi)
+    # ctm_force_dl: every move sees rank-4 tensors, result = single-layer result
+    args = CTMARGS(); args.ctm_force_dl = True; args.ctm_max_iter = 3
+    env = H.Env(chi, dict(C0), dict(T0))
+    ctmrg.run(st, env, ctm_args=args)
+    assert len(oracle_engine.calls) == 24 and all(c[2] == 4 for c in oracle_engine.calls)
+    assert H.env_abs_diff(env.C, env.T, C, T) < 1e-9
+    # warm-up: max(ctm_warmup_iter, ceil(chi / D^2)) = 2 iterations before the ctm_max_iter = 1 of the main loop
+    oracle_engine.calls.clear()
+    args = CTMARGS(); args.ctm_warmup_iter = 1; args.ctm_max_iter = 1
+    env = H.Env(chi, dict(C0), dict(T0))
+    seen = []
+    ctmrg.run(st, env, conv_check=lambda s, e, h, ctm_args=None: (seen.append(1) or False, h), ctm_args=args)
+    assert len(oracle_engine.calls) == 24 and all(c[2] == 5 for c in oracle_engine.calls) and len(seen) == 1
+    assert H.env_abs_diff(env.C, env.T, C, T) < 1e-12
+    # option mapping
+    a2 = CTMARGS(); a2.ctm_absorb_normalization = 'fro'; a2.projector_method = '4X2'; a2.projector_svd_method = 'ARP'
+    o = ctmrg._options(a2)
+    assert (o['norm_type'], o['projector_method']) == (1, 1)
+    # run_overlap: needs ctm_force_dl, one move per direction and iteration, conv_check(state1, state2, env, history)
+    oracle_engine.calls.clear()
+    args = CTMARGS(); args.ctm_max_iter = 2
+    with pytest.raises(AssertionError):
+        ctmrg.run_overlap(st, st, env, ctm_args=args)
+    args.ctm_force_dl = True
+    env = H.Env(chi, dict(C0), dict(T0))
+    ctmrg.run_overlap(st, st, env, conv_check=lambda s1, s2, e, h, ctm_args=None: (False, h), ctm_args=args)
+    assert len(oracle_engine.calls) == 8 and all(c[2] == 4 for c in oracle_engine.calls)
+    Co, To = dict(C0), dict(T0)
+    for _ in range(2):
+        for d in orc.DIRECTIONS:
+            orc.ctm_move(d, sites, orc.v2s_4site, Co, To, chi)
+    assert H.env_abs_diff(env.C, env.T, Co, To) < 1e-9
+
+
+def test_host_c4v_run_dl_control_flow(oracle_engine):
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v
+    from peps_torch_b200.config import CTMARGS
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    z, meta = H.load_golden('c4v_D2_chi8_B')
+    chi = meta['chi']
+    a = torch.from_numpy(z['site'])
+    st = IPEPS_C4V(a)
+    C, T = torch.from_numpy(z['init_C']), torch.from_numpy(z['init_T'])
+    for _ in range(3):
+        C, T = orc.ctm_move_c4v(a, C, T, chi)
+    args = CTMARGS(); args.ctm_max_iter = 3
+    for runner, rank in ((ctmrg_c4v.run, 5), (ctmrg_c4v.run_dl, 4)):
+        oracle_engine.calls.clear()
+        env = ENV_C4V(chi, st)
+        env.C[env.keyC], env.T[env.keyT] = torch.from_numpy(z['init_C']), torch.from_numpy(z['init_T'])
+        runner(st, env, ctm_args=args)
+        assert oracle_engine.calls == [('c4v', rank)] * 3
+        assert H.maxrel(env.get_C(), C) < 1e-10 and H.maxrel(env.get_T().abs(), T.abs()) < 1e-9
+    bad = CTMARGS(); bad.projector_svd_method = 'GESDD'
+    with pytest.raises(Exception):
+        ctmrg_c4v.run(st, env, ctm_args=bad)
