@@ -74,6 +74,9 @@ typedef struct {
 
 int ctmb_version(void);
 const char* ctmb_last_error(void);
+/* device >= 0: a CUDA device of compute capability >= 10.0.  device == -1: planning-only handle -- the *_workspace
+ * queries run (they validate every contraction of the call and size its workspace without launching anything),
+ * every compute entry point fails with an error.  There is no CPU compute path. */
 int ctmb_create(ctmb_handle_t* h, int device);
 int ctmb_destroy(ctmb_handle_t h);
 void ctmb_default_options(ctmb_options* opt);
@@ -165,6 +168,21 @@ int ctmb_move_c4v(ctmb_handle_t h, ctmb_dtype dt, const void* a, const int dims[
                   const void* T, int chi, const ctmb_options* opt, void* C_out, void* T_out, double* D_out,
                   void* ws, size_t ws_bytes, void* stream);
 size_t ctmb_move_c4v_workspace(ctmb_handle_t h, ctmb_dtype dt, const int dims[5], int chi, const ctmb_options* opt);
+
+/* ---- observables on the converged environment --------------------------------------------------
+ * rdm2x2 (ctm/generic/rdm.py:1306-1592; contraction strategy of rdm2x2_legacy :1362): UN-normalised reduced density
+ * matrix of the 2x2 plaquette  s0 s1 / s2 s3.  sites[4] = the unit-cell sites (with their environment tensors) at
+ * coord, coord+(1,0), coord+(0,1), coord+(1,1); bit q of open_mask keeps site q open (`open_sites` of the reference),
+ * the others are traced.  rho: row-major [kets of the open sites in site order..., bras in the same order...]. */
+int ctmb_rdm2x2(ctmb_handle_t h, ctmb_dtype dt, int chi, const ctmb_site* const sites[4], int open_mask, void* rho,
+                void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_rdm2x2_workspace(ctmb_handle_t h, ctmb_dtype dt, int chi, const ctmb_site* const sites[4], int open_mask);
+
+/* _sym_pos_def_matrix (ctm/generic/rdm.py:38-57): out = (rdm + rdm^H)/2; with sym_pos_def != 0 and a negative
+ * eigenvalue, out = U max(D,0) U^H; finally out /= Re tr(out).  rdm, out: n x n row-major (may not alias). */
+int ctmb_sym_pos_def(ctmb_handle_t h, ctmb_dtype dt, const void* rdm, int n, int sym_pos_def, void* out,
+                     void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_sym_pos_def_workspace(ctmb_handle_t h, ctmb_dtype dt, int n, int sym_pos_def);
 
 #ifdef __cplusplus
 }

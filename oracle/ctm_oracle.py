@@ -480,19 +480,25 @@ def _sym_pos_def(rho, sym_pos_def=False):
     return m.reshape(shape)
 
 
-def rdm2x2(coord, sites, v2s, C, T, raw=False):
+def rdm2x2(coord, sites, v2s, C, T, raw=False, open_sites=(0, 1, 2, 3), sym_pos_def=False):
     """ctm/generic/rdm.py:1306-1675: rho(s0,s1,s2,s3; s0',s1',s2',s3') of the plaquette
     s0=coord, s1=coord+(1,0), s2=coord+(0,1), s3=coord+(1,1); hermitised, trace-normalised.
-    First index group = ket (the index of `a`), second = bra (conj(a))."""
+    First index group = ket (the index of `a`), second = bra (conj(a)).  Sites not in `open_sites` are traced
+    (their enlarged corner is the closed one); the remaining indices keep the order above (rdm.py:1352-1353)."""
     x, y = coord
-    LU = corner_at('LU', (x, y), sites, v2s, C, T, open_phys=True)          # [down,right,s,S]
-    RU = corner_at('RU', (x + 1, y), sites, v2s, C, T, open_phys=True)      # [left,down,s,S]
-    RD = corner_at('RD', (x + 1, y + 1), sites, v2s, C, T, open_phys=True)  # [up,left,s,S]
-    LD = corner_at('LD', (x, y + 1), sites, v2s, C, T, open_phys=True)      # [up,right,s,S]
-    upper = torch.einsum('abiI,bcjJ->aciIjJ', LU, RU)
-    lower = torch.einsum('abkK,cblL->ackKlL', LD, RD)
-    rho = torch.einsum('aciIjJ,ackKlL->ijklIJKL', upper, lower)
-    return rho if raw else _sym_pos_def(rho)
+    op = [q in open_sites for q in range(4)]
+    assert any(op)
+    LU = corner_at('LU', (x, y), sites, v2s, C, T, open_phys=op[0])          # [down,right,(s,S)]
+    RU = corner_at('RU', (x + 1, y), sites, v2s, C, T, open_phys=op[1])      # [left,down,(s,S)]
+    RD = corner_at('RD', (x + 1, y + 1), sites, v2s, C, T, open_phys=op[3])  # [up,left,(s,S)]
+    LD = corner_at('LD', (x, y + 1), sites, v2s, C, T, open_phys=op[2])      # [up,right,(s,S)]
+    p = ['iI' if op[0] else '', 'jJ' if op[1] else '', 'kK' if op[2] else '', 'lL' if op[3] else '']
+    upper = torch.einsum(f'ab{p[0]},bc{p[1]}->ac{p[0]}{p[1]}', LU, RU)
+    lower = torch.einsum(f'ab{p[2]},cb{p[3]}->ac{p[2]}{p[3]}', LD, RD)
+    kets = ''.join(s[0] for s in p if s)
+    bras = ''.join(s[1] for s in p if s)
+    rho = torch.einsum(f'ac{p[0]}{p[1]},ac{p[2]}{p[3]}->{kets}{bras}', upper, lower)
+    return rho if raw else _sym_pos_def(rho, sym_pos_def)
 
 
 def spin_half_ops(dtype=torch.float64):
@@ -536,6 +542,15 @@ def c4v_to_generic_env(C, T):
     Tg = {(s, (-1, 0)): T, (s, (0, 1)): T.permute(2, 0, 1), (s, (1, 0)): T.permute(1, 2, 0),
           (s, (0, -1)): T.permute(1, 2, 0)}
     return Cg, Tg
+
+
+def rdm2x2_c4v(a, C, T, open_sites=(0, 1, 2, 3), sym_pos_def=False):
+    """The 2x2 plaquette of the one-site C4v state through the generic construction: open_sites=(0,1) is
+    rdm2x2_NN_lowmem_sl, (0,3) rdm2x2_NNN_lowmem_sl, all four rdm2x2 (ctm/one_site_c4v/rdm_c4v.py:1160-1202,
+    1329-1371, 1446-1546; those rotate ONE enlarged corner, which C4v symmetry makes equivalent)."""
+    from collections import OrderedDict
+    Cg, Tg = c4v_to_generic_env(C, T)
+    return rdm2x2((0, 0), OrderedDict({(0, 0): a}), v2s_1site, Cg, Tg, open_sites=open_sites, sym_pos_def=sym_pos_def)
 
 
 def energy_j1j2_c4v(a, C, T, j1=1.0, j2=0.0):

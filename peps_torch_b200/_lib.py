@@ -64,6 +64,10 @@ SIGNATURES = {
                                            _vp, _sz, _vp]),
     'ctmb_move_c4v': (C.c_int, [_vp, _i, _vp, C.POINTER(C.c_int), _vp, _vp, _i, _PO, _vp, _vp, _vp, _vp, _sz, _vp]),
     'ctmb_move_c4v_workspace': (_sz, [_vp, _i, C.POINTER(C.c_int), _i, _PO]),
+    'ctmb_rdm2x2': (C.c_int, [_vp, _i, _i, C.POINTER(_PS), _i, _vp, _vp, _sz, _vp]),
+    'ctmb_rdm2x2_workspace': (_sz, [_vp, _i, _i, C.POINTER(_PS), _i]),
+    'ctmb_sym_pos_def': (C.c_int, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    'ctmb_sym_pos_def_workspace': (_sz, [_vp, _i, _i, _i]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)          # AttributeError if the library does not export it

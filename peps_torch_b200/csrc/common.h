@@ -130,6 +130,10 @@ struct ScaleBatch { void* p[TC_MAX_BATCH]; const unsigned long long* amax[TC_MAX
 void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream, bool sqrt_mode = false);
 // slot (a double, zeroed by the caller) += sum |x|^2
 void sumsq_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
+// reduced density matrices (ctm/generic/rdm.py:38-57): out = (raw + raw^H)/2 [/ Re tr raw]; positive part from eigenpairs
+void conj_inplace_launch(void* x, long long count, cudaStream_t stream);     // complex only: x <- conj(x)
+void rdm_herm_launch(const void* raw, void* out, int n, int normalize, bool cplx, cudaStream_t stream);
+void rdm_posdef_launch(void* out, const void* U, const double* D, int n, bool cplx, cudaStream_t stream);
 // amax of |x|
 void absmax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
 

@@ -77,7 +77,7 @@ void* Workspace::alloc(size_t bytes, bool back) {
 }
 
 Engine::Engine(int device) : device_(device) {
-    CTMB_CUDA(cudaSetDevice(device));
+    if (device >= 0) CTMB_CUDA(cudaSetDevice(device));      // device -1: planning-only engine (workspace queries)
 }
 
 Engine::~Engine() {
@@ -108,6 +108,35 @@ static void append_spec(std::ostringstream& os, const Tn& t) {
     os << t.idx << ':';
     for (int i = 0; i < t.nd; ++i) os << t.dim[i] << '/' << t.str[i] << ',';
     os << ';';
+}
+
+// The label / extent rules of a pairwise contraction, checked without touching the device: the workspace queries
+// (dry runs) call this, so a planning-only handle validates every chain of an entry point on a machine without a GPU.
+static void validate_contraction(const Tn& A, const Tn& B, const Tn& C) {
+    int64_t M = 1, N = 1, K = 1;
+    for (int i = 0; i < C.nd; ++i) {
+        char c = C.idx[i];
+        int pa = A.find(c), pb = B.find(c);
+        CTMB_CHECK((pa >= 0) != (pb >= 0), "output label must come from exactly one operand");
+        if (pa >= 0) { CTMB_CHECK(A.dim[pa] == C.dim[i], "extent mismatch (A,C)"); M *= C.dim[i]; }
+        else { CTMB_CHECK(B.dim[pb] == C.dim[i], "extent mismatch (B,C)"); N *= C.dim[i]; }
+        for (int q = 0; q < i; ++q) CTMB_CHECK(C.idx[q] != c, "repeated output label");
+    }
+    for (int i = 0; i < A.nd; ++i) {
+        char c = A.idx[i];
+        if (C.find(c) >= 0) continue;
+        int pb = B.find(c);
+        CTMB_CHECK(pb >= 0, "label of A neither in B nor in the output");
+        CTMB_CHECK(A.dim[i] == B.dim[pb], "extent mismatch (A,B)");
+        K *= A.dim[i];
+    }
+    for (int i = 0; i < B.nd; ++i) {
+        char c = B.idx[i];
+        CTMB_CHECK(C.find(c) >= 0 || A.find(c) >= 0, "label of B neither in A nor in the output");
+    }
+    CTMB_CHECK(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "GEMM extent overflow");
+    CTMB_CHECK(A.numel() < (1ll << 31) && B.numel() < (1ll << 31) && C.numel() < (1ll << 31),
+               "operand exceeds 2^31 elements (offset tables are 32-bit)");
 }
 
 const Plan& Engine::get_plan(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C) {
@@ -252,7 +281,7 @@ void Engine::flush() {
 
 void Engine::contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C,
                       unsigned long long* amax, double alpha, bool accumulate) {
-    if (ws.dry()) return;
+    if (ws.dry()) { validate_contraction(A, B, C); return; }
     const Plan& pl = get_plan(A, conjA && cplx, B, conjB && cplx, C);
     flops += 2.0 * pl.M * (double)pl.N * pl.K * (cplx ? 4.0 : 1.0);
     if (pend_active_) {

@@ -266,6 +266,83 @@ void scale_by_amax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t s
 }
 
 // ---------------------------------------------------------------------------------------------
+// reduced density matrices: _sym_pos_def_matrix (ctm/generic/rdm.py:38-57)
+//   out = (raw + raw^H) / 2 / Re tr(raw)                       (always)
+//   if min(D) < 0:  out = U max(D,0) U^H / sum max(D,0)        (sym_pos_def=True; D, U = eigenpairs of `out`)
+// ---------------------------------------------------------------------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) rdm_herm_kernel(const void* rawp, void* outp, int n, int normalize) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    const T* raw = reinterpret_cast<const T*>(rawp);
+    T* out = reinterpret_cast<T*>(outp);
+    // every block sums the diagonal in the same order: identical trace everywhere
+    double tr = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) tr += S::re(raw[(size_t)i * n + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    __shared__ double red[8];
+    __shared__ double sh_tr;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tr;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; sh_tr = t; }
+    __syncthreads();
+    const double sc = normalize ? 0.5 / sh_tr : 0.5;
+    const long long nn = (long long)n * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nn; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e % n);
+        out[e] = S::scale(S::add(raw[e], S::conj(raw[(size_t)j * n + i])), sc);
+    }
+}
+
+__global__ void conj_inplace_kernel(double2* x, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i].y = -x[i].y;
+}
+void conj_inplace_launch(void* x, long long count, cudaStream_t stream) {
+    int grid = (int)std::max(1ll, std::min((count + 255) / 256, 1184ll));
+    conj_inplace_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<double2*>(x), count);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+void rdm_herm_launch(const void* raw, void* out, int n, int normalize, bool cplx, cudaStream_t stream) {
+    long long nn = (long long)n * n;
+    int grid = (int)std::max(1ll, std::min((nn + 255) / 256, 1184ll));
+    if (cplx) rdm_herm_kernel<true><<<grid, 256, 0, stream>>>(raw, out, n, normalize);
+    else rdm_herm_kernel<false><<<grid, 256, 0, stream>>>(raw, out, n, normalize);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// U: n x n column-major (eigenvector k = U[k*n ..]), D: n eigenvalues in any order
+template <bool CPLX>
+__global__ void __launch_bounds__(256) rdm_posdef_kernel(void* outp, const void* Up, const double* D, int n) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    T* out = reinterpret_cast<T*>(outp);
+    const T* U = reinterpret_cast<const T*>(Up);
+    double dmin = 0.0, dsum = 0.0;
+    for (int k = 0; k < n; ++k) { dmin = fmin(dmin, D[k]); dsum += fmax(D[k], 0.0); }
+    if (!(dmin < 0.0)) return;                        // rdm.py:49: the matrix is replaced only if an eigenvalue is negative
+    const long long nn = (long long)n * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nn; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e % n);
+        T acc = S::zero();
+        for (int k = 0; k < n; ++k) {
+            const double d = fmax(D[k], 0.0);
+            if (d > 0.0) acc = S::add(acc, S::scale(S::mul(U[(size_t)k * n + i], S::conj(U[(size_t)k * n + j])), d));
+        }
+        out[e] = S::scale(acc, 1.0 / dsum);
+    }
+}
+
+void rdm_posdef_launch(void* out, const void* U, const double* D, int n, bool cplx, cudaStream_t stream) {
+    long long nn = (long long)n * n;
+    int grid = (int)std::max(1ll, std::min((nn + 255) / 256, 1184ll));
+    if (cplx) rdm_posdef_kernel<true><<<grid, 256, 0, stream>>>(out, U, D, n);
+    else rdm_posdef_kernel<false><<<grid, 256, 0, stream>>>(out, U, D, n);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
 // C4v epilogue (ctmrg_c4v.py:374,446,182-197): nT <- (nT + conj(nT)^T01)/2 with |.|max, C' = diag(D)/|D0|
 // ---------------------------------------------------------------------------------------------
 template <bool CPLX>

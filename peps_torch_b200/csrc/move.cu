@@ -78,10 +78,13 @@ static Tn env_C(const ctmb_site& s, int which, int chi, const char* lab) {
 // Build the single-layer chain for a double-layer spec: every label of `la` (the aux legs
 // u,l,d,r of the on-site tensor, in that order) found on an operand is split into (ket,bra) =
 // (lower, upper case); a and conj(a) are inserted at position `apos` of the operand list.
+// open_phys: the physical legs stay open (ket 's', bra 'S') and are appended to the output, as the
+// enlarged corners of the reduced density matrices need them (ctm/generic/rdm.py:1362-1592).
 static Engine::ChainJob sl_job(std::vector<Tn> ops, size_t apos, const char* la, const ctmb_site& s,
-                               const char* out_lab, void* out_ptr, unsigned long long* amax) {
+                               const char* out_lab, void* out_ptr, unsigned long long* amax, bool open_phys = false) {
     Engine::ChainJob job;
     if (is_dl(s)) {
+        CTMB_CHECK(!open_phys, "a double-layer on-site tensor has no open physical legs");
         // double-layer site: A enters as ONE operand with the fused labels, nothing is split
         Tn A = make_tn(const_cast<void*>(s.a), la, {s.dims[1], s.dims[2], s.dims[3], s.dims[4]});
         std::map<char, int64_t> ext;
@@ -100,7 +103,7 @@ static Engine::ChainJob sl_job(std::vector<Tn> ops, size_t apos, const char* la,
     }
     auto Dof = [&](char c) -> int64_t { const char* p = strchr(la, c); return p ? s.dims[1 + (p - la)] : 0; };
     std::string lab_a = std::string("s") + la, lab_ac = lab_a;
-    for (size_t i = 1; i < lab_ac.size(); ++i) lab_ac[i] = (char)toupper(lab_ac[i]);
+    for (size_t i = open_phys ? 0 : 1; i < lab_ac.size(); ++i) lab_ac[i] = (char)toupper(lab_ac[i]);
     Tn a = make_tn(const_cast<void*>(s.a), lab_a, {s.dims[0], s.dims[1], s.dims[2], s.dims[3], s.dims[4]});
     Tn ac = relabel(a, lab_ac.c_str());
     std::map<char, int64_t> ext;
@@ -118,6 +121,7 @@ static Engine::ChainJob sl_job(std::vector<Tn> ops, size_t apos, const char* la,
         if (strchr(la, *p)) { ol.push_back(*p); od.push_back(Dof(*p)); ol.push_back((char)toupper(*p)); od.push_back(Dof(*p)); }
         else { ol.push_back(*p); CTMB_CHECK(ext.count(*p), "output label not found"); od.push_back(ext[*p]); }
     }
+    if (open_phys) { ol += "sS"; od.push_back(s.dims[0]); od.push_back(s.dims[0]); }
     job.out = make_tn(out_ptr, ol, od);
     job.amax = amax;
     return job;
@@ -483,16 +487,19 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         }
         std::swap(cur, pQ);
     };
-    if (eig_mode && !e.cplx && k == n) {
-        // small real symmetric problem decomposed exactly (config c1: n = 64): no sketch at all, the shifted
-        // one-sided Jacobi runs on M itself (row-major == column-major for a symmetric matrix)
+    if (eig_mode && k == n) {
+        // small Hermitian problem decomposed exactly (config c1: n = 64; the 4 x 4 / 16 x 16 reduced density matrices):
+        // no sketch at all, the shifted one-sided Jacobi runs on M itself.  Row-major M read as column-major is M^T =
+        // conj(M): same eigenvalues, conjugated eigenvectors -- undone at the end in the complex case.
         e.flush();
         for (int b = 0; b < nb; ++b)
             CTMB_CUDA(cudaMemcpyAsync(R2[b], M[b], (size_t)k * k * es, cudaMemcpyDeviceToDevice, e.stream));
         { ProfScope ps(e, Engine::CAT_JACOBI, 0, 2.0 * es * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
         { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, chi, e.cplx, 1, e.stream); }
-        for (int b = 0; b < nb; ++b)
+        for (int b = 0; b < nb; ++b) {
             CTMB_CUDA(cudaMemcpyAsync(r.U[b], Uh[b], (size_t)k * chi * es, cudaMemcpyDeviceToDevice, e.stream));
+            if (e.cplx) { ProfScope ps(e, Engine::CAT_MISC); conj_inplace_launch(r.U[b], (long long)k * chi, e.stream); }
+        }
         return r;
     }
     // Y = M * Omega
@@ -847,6 +854,72 @@ static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>&
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// reduced density matrix of a 2x2 plaquette (ctm/generic/rdm.py:1306-1592, strategy of rdm2x2_legacy):
+// four enlarged corners -- with open physical legs at the sites kept open -- upper = LU.RU, lower = LD.RD, rho = upper.lower
+// ------------------------------------------------------------------------------------------
+static void rdm2x2_impl(Engine& e, int chi, const ctmb_site* const s4[4], int open_mask, void* rho) {
+    static const int kinds[4] = {CTMB_LU, CTMB_RU, CTMB_LD, CTMB_RD};       // s0 s1 / s2 s3
+    CTMB_CHECK(chi > 0 && s4 && open_mask > 0 && open_mask < 16, "bad arguments (at least one site must stay open)");
+    const size_t mark = e.ws.mark();
+    void* cm[4]; int64_t rows[4], cols[4], pd[4];
+    std::vector<CornerReq> closed;
+    std::vector<Engine::ChainJob> open;
+    for (int q = 0; q < 4; ++q) {
+        const ctmb_site& s = *s4[q];
+        corner_shape(kinds[q], s, chi, rows[q], cols[q]);
+        const bool op = (open_mask >> q) & 1;
+        pd[q] = op ? s.dims[0] : 1;
+        CTMB_CHECK(!op || s.dims[0] > 0, "open sites need the single-layer on-site tensor");
+        cm[q] = e.ws.alloc((size_t)rows[q] * cols[q] * pd[q] * pd[q] * e.esize());
+        if (!op) { closed.push_back(CornerReq{kinds[q], &s, cm[q]}); continue; }
+        const CornerSpec& cs = CORNERS[kinds[q]];
+        std::vector<Tn> ops = {env_C(s, cs.c, chi, cs.lc), env_T(s, cs.t1, chi, cs.l1), env_T(s, cs.t2, chi, cs.l2)};
+        open.push_back(sl_job(ops, 3, cs.la, s, cs.out, cm[q], nullptr, true));
+    }
+    if (!closed.empty()) corners_run(e, chi, closed);
+    if (!open.empty()) e.chain_multi(open);
+    CTMB_CHECK(cols[0] == rows[1] && cols[2] == cols[3] && rows[0] == rows[2] && cols[1] == rows[3],
+               "the four enlarged corners of the plaquette do not fit together");
+    // matrix views [row, col, s, S]: LU "ab iI", RU "bc jJ", LD "ad kK", RD "cd lL"  (oracle rdm2x2: same strings)
+    auto view = [&](int q, char r, char c, char k, char b) {
+        std::string lab{r, c}; std::vector<int64_t> d{rows[q], cols[q]};
+        if (pd[q] > 1 || ((open_mask >> q) & 1)) { lab.push_back(k); lab.push_back(b); d.push_back(pd[q]); d.push_back(pd[q]); }
+        return make_tn(cm[q], lab, d);
+    };
+    const Tn LU = view(0, 'a', 'b', 'i', 'I'), RU = view(1, 'b', 'c', 'j', 'J');
+    const Tn LD = view(2, 'a', 'd', 'k', 'K'), RD = view(3, 'c', 'd', 'l', 'L');
+    auto half = [&](const Tn& X, const Tn& Y, char r, char c) {
+        std::string lab{r, c}; std::vector<int64_t> d{X.dim[X.find(r)], Y.dim[Y.find(c)]};
+        for (const Tn* t : {&X, &Y}) for (int q = 2; q < t->nd; ++q) { lab.push_back(t->idx[q]); d.push_back(t->dim[q]); }
+        return e.temp(lab, d);
+    };
+    Tn upper = half(LU, RU, 'a', 'c'), lower = half(LD, RD, 'a', 'c');
+    e.contract(LU, false, RU, false, upper);
+    e.contract(LD, false, RD, false, lower);
+    e.flush();
+    // rho[kets..., bras...] in the site order s0 s1 s2 s3
+    std::string lab; std::vector<int64_t> d;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int q = 0; q < 4; ++q)
+            if ((open_mask >> q) & 1) { lab.push_back(pass ? "IJKL"[q] : "ijkl"[q]); d.push_back(pd[q]); }
+    e.contract(upper, false, lower, false, make_tn(rho, lab, d));
+    e.flush();
+    e.ws.release(mark);
+}
+
+// _sym_pos_def_matrix (ctm/generic/rdm.py:38-57)
+static void sym_pos_def_impl(Engine& e, const void* raw, int n, int sym_pos_def, const ctmb_options& o, void* out) {
+    CTMB_CHECK(n > 0, "bad arguments");
+    if (!e.ws.dry()) { ProfScope ps(e, Engine::CAT_MISC); rdm_herm_launch(raw, out, n, 1, e.cplx, e.stream); }
+    if (!sym_pos_def) return;
+    CTMB_CHECK(n <= 160, "sym_pos_def=True needs the complete eigendecomposition: supported for matrices up to 160 x 160");
+    const size_t mark = e.ws.mark();
+    Rsvd r = rsvd_batch(e, {out}, n, n, n, o, true);
+    if (!e.ws.dry()) { ProfScope ps(e, Engine::CAT_MISC); rdm_posdef_launch(out, r.U[0], (const double*)r.S[0], n, e.cplx, e.stream); }
+    e.ws.release(mark);
+}
+
 static ctmb_options opts_or_default(const ctmb_options* o) {
     ctmb_options d; ctmb_default_options(&d);
     return o ? *o : d;
@@ -870,6 +943,7 @@ static void begin_call(ctmb_handle_t h, ctmb_dtype dt, void* ws, size_t ws_bytes
     CTMB_CHECK(h != nullptr, "null handle");
     CTMB_CHECK(dt == CTMB_F64 || dt == CTMB_C128, "unsupported dtype");
     Engine& e = h->h.eng;
+    CTMB_CHECK(e.device() >= 0, "planning-only handle (device -1): no CUDA device, only the *_workspace queries are available");
     CTMB_CUDA(cudaSetDevice(e.device()));
     e.cplx = (dt == CTMB_C128);
     e.stream = (cudaStream_t)stream;
@@ -895,6 +969,10 @@ const char* ctmb_last_error(void) { return get_error().c_str(); }
 int ctmb_create(ctmb_handle_t* h, int device) {
     CTMB_TRY
     CTMB_CHECK(h != nullptr, "null out pointer");
+    if (device == -1) {          // planning-only handle: the *_workspace queries work (no kernel is ever launched), compute calls fail
+        *h = new ctmb_handle_s(-1);
+        return 0;
+    }
     int ndev = 0;
     CTMB_CUDA(cudaGetDeviceCount(&ndev));
     CTMB_CHECK(device >= 0 && device < ndev, "no such CUDA device");
@@ -1181,6 +1259,38 @@ int ctmb_move_generic_absorb(ctmb_handle_t h, ctmb_dtype dt, ctmb_direction dir,
     }
     return 0;
     CTMB_CATCH(-1)
+}
+
+int ctmb_rdm2x2(ctmb_handle_t h, ctmb_dtype dt, int chi, const ctmb_site* const sites[4], int open_mask, void* rho,
+                void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    rdm2x2_impl(h->h.eng, chi, sites, open_mask, rho);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_rdm2x2_workspace(ctmb_handle_t h, ctmb_dtype dt, int chi, const ctmb_site* const sites[4], int open_mask) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    rdm2x2_impl(h->h.eng, chi, sites, open_mask, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+int ctmb_sym_pos_def(ctmb_handle_t h, ctmb_dtype dt, const void* rdm, int n, int sym_pos_def, void* out,
+                     void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    sym_pos_def_impl(h->h.eng, rdm, n, sym_pos_def, opts_or_default(nullptr), out);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_sym_pos_def_workspace(ctmb_handle_t h, ctmb_dtype dt, int n, int sym_pos_def) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    sym_pos_def_impl(h->h.eng, nullptr, n, sym_pos_def, opts_or_default(nullptr), nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
 }
 
 static void move_c4v_impl(ctmb_handle_t h, const void* a, const int dims[5], const void* C, const void* T, int chi,

@@ -1,0 +1,44 @@
+"""Drop-in for the plaquette density matrices of ctm/one_site_c4v/rdm_c4v.py used by the C4v J1-J2 energy
+(models/j1j2.py:641-679): rdm2x2_NN_lowmem(_sl) :1117-1202, rdm2x2_NNN_lowmem(_sl) :1286-1371, rdm2x2 :1446-1546.
+The reference rotates ONE enlarged corner; here the single (C, T) pair is rotated into the eight tensors of a generic
+1x1-cell environment (env_c4v.py:25-45 vs env.py:57-77) and libctmb contracts the generic 2x2 network, tracing the
+sites that are not kept (closed corners)."""
+
+
+def _engine():
+    from ...engine import default_engine
+    return default_engine()
+
+
+def _generic_tensors(state, env):
+    a = next(iter(state.sites.values()))
+    C_, T = env.C[env.keyC], env.T[env.keyT]
+    # order of engine.C_KEYS = (-1,-1),(1,-1),(1,1),(-1,1) and engine.T_KEYS = (0,-1),(-1,0),(0,1),(1,0)
+    Cs = [C_, C_, C_, C_.t().contiguous()]
+    Tud = T.permute(1, 2, 0).contiguous()
+    Ts = [Tud, T, T.permute(2, 0, 1).contiguous(), Tud]
+    return [(a, Cs, Ts)] * 4, env.chi
+
+
+def _rdm(state, env, open_sites, sym_pos_def):
+    t4, chi = _generic_tensors(state, env)
+    return _engine().rdm2x2_sites(t4, chi, open_sites, sym_pos_def)
+
+
+def rdm2x2_NN_lowmem_sl(state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
+    r""":return: nearest-neighbour density matrix :math:`s_0s_1;s'_0s'_1` of the 2x2 plaquette (rdm_c4v.py:1160-1202)"""
+    return _rdm(state, env, (0, 1), sym_pos_def)
+
+
+def rdm2x2_NNN_lowmem_sl(state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
+    r""":return: next-nearest-neighbour (diagonal) density matrix :math:`s_0s_3;s'_0s'_3` (rdm_c4v.py:1329-1371)"""
+    return _rdm(state, env, (0, 3), sym_pos_def)
+
+
+rdm2x2_NN_lowmem = rdm2x2_NN_lowmem_sl          # the double-layer variants compute the same object
+rdm2x2_NNN_lowmem = rdm2x2_NNN_lowmem_sl
+
+
+def rdm2x2(state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
+    r""":return: 4-site density matrix :math:`s_0s_1s_2s_3;s'_0s'_1s'_2s'_3` (rdm_c4v.py:1446-1546)"""
+    return _rdm(state, env, (0, 1, 2, 3), sym_pos_def)

@@ -53,11 +53,17 @@ class CtmEngine:
     """One engine (= one libctmb handle, one workspace) per process / GPU."""
 
     def __init__(self, device=None):
-        if not torch.cuda.is_available():
-            raise RuntimeError("peps_torch_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
         self._h = C.c_void_p()
-        check(lib.ctmb_create(C.byref(self._h), self.device.index))
+        if device == 'plan':
+            # planning-only handle (include/ctmb.h: device -1): the workspace queries validate and size every call on a
+            # machine without a GPU; every compute call raises CtmbError.  Used by the CPU test-suite.
+            self.device = torch.device('cpu')
+            check(lib.ctmb_create(C.byref(self._h), -1))
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError("peps_torch_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+            check(lib.ctmb_create(C.byref(self._h), self.device.index))
         self._ws = None
         self._tables = {}
         self.options = _lib.default_options()
@@ -81,6 +87,8 @@ class CtmEngine:
         return self._ws
 
     def _stream(self):
+        if self.device.type != 'cuda':          # planning-only engine: the C call refuses to compute
+            return C.c_void_p(0)
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def counters(self):
@@ -365,6 +373,58 @@ class CtmEngine:
         check(lib.ctmb_move_c4v(self._h, dt, _ptr(a), dims, _ptr(C_), _ptr(T), chi, C.byref(o), _ptr(Co), _ptr(To),
                                 _ptr(Dv), _ptr(ws), ws.numel(), self._stream()))
         return Co, To, Dv
+
+
+    # ----------------------------------------------------------------------------------
+    # observables on the converged environment
+    # ----------------------------------------------------------------------------------
+    def sym_pos_def(self, rdm, sym_pos_def=False):
+        """_sym_pos_def_rdm (ctm/generic/rdm.py:38-68): hermitise, optionally project on the positive part, normalise the trace."""
+        shape = rdm.shape
+        assert len(shape) % 2 == 0, "invalid rank of RDM"
+        n = 1
+        for d in shape[:len(shape) // 2]:
+            n *= d
+        raw = self._prep(rdm, self.device)
+        out = torch.empty((n, n), dtype=raw.dtype, device=self.device)
+        dt = _dt(raw)
+        nbytes = lib.ctmb_sym_pos_def_workspace(self._h, dt, n, int(bool(sym_pos_def)))
+        if nbytes == 0:
+            raise _lib.CtmbError(lib.ctmb_last_error().decode())
+        ws = self._workspace(nbytes)
+        check(lib.ctmb_sym_pos_def(self._h, dt, _ptr(raw), n, int(bool(sym_pos_def)), _ptr(out), _ptr(ws), ws.numel(),
+                                   self._stream()))
+        return out.view(shape)
+
+    def rdm2x2_sites(self, tensors4, chi, open_sites=(0, 1, 2, 3), sym_pos_def=False, raw=False):
+        """2x2 reduced density matrix from explicit per-site data: tensors4[q] = (a, [C x4 in C_KEYS order], [T x4 in
+        T_KEYS order]) for the sites s0 s1 / s2 s3 of the plaquette."""
+        open_sites = sorted(set(int(q) for q in open_sites))
+        if not open_sites or open_sites[0] < 0 or open_sites[-1] > 3:
+            raise ValueError("open_sites must be a non-empty subset of [0,1,2,3]")
+        mask = sum(1 << q for q in open_sites)
+        keep = []
+        structs = [self._site(a, Cs, Ts, keep) for (a, Cs, Ts) in tensors4]
+        arr = (C.POINTER(_lib.Site) * 4)(*[C.pointer(s) for s in structs])
+        a0 = tensors4[0][0]
+        dt = _dt(a0)
+        dims = [tensors4[q][0].shape[0] for q in open_sites]
+        rho = torch.empty(dims + dims, dtype=a0.dtype, device=self.device)
+        nbytes = lib.ctmb_rdm2x2_workspace(self._h, dt, chi, arr, mask)
+        if nbytes == 0:
+            raise _lib.CtmbError(lib.ctmb_last_error().decode())
+        ws = self._workspace(nbytes)
+        check(lib.ctmb_rdm2x2(self._h, dt, chi, arr, mask, _ptr(rho), _ptr(ws), ws.numel(), self._stream()))
+        return rho if raw else self.sym_pos_def(rho, sym_pos_def)
+
+    def rdm2x2(self, coord, state, env, open_sites=(0, 1, 2, 3), sym_pos_def=False, raw=False):
+        """rdm2x2 (ctm/generic/rdm.py:1306-1592): rho[s0,s1,s2,s3; s0',s1',s2',s3'] of the plaquette with upper-left
+        vertex `coord` (s0 = coord, s1 = coord+(1,0), s2 = coord+(0,1), s3 = coord+(1,1))."""
+        t4 = []
+        for dx, dy in ((0, 0), (1, 0), (0, 1), (1, 1)):
+            c = state.vertexToSite((coord[0] + dx, coord[1] + dy))
+            t4.append((state.sites[c], [env.C[(c, k)] for k in C_KEYS], [env.T[(c, k)] for k in T_KEYS]))
+        return self.rdm2x2_sites(t4, env.chi, open_sites, sym_pos_def, raw)
 
 
 _default = None

@@ -28,9 +28,11 @@ def enable(engine_factory=None):
     from . import ctm as _pkg                                   # noqa: F401  (package import check)
     from .ctm.generic import ctmrg as ours
     from .ctm.one_site_c4v import ctmrg_c4v as ours_c4v
+    from .ctm.generic import rdm as ours_rdm
+    from .ctm.one_site_c4v import rdm_c4v as ours_rdm_c4v
     if engine_factory is not None:
-        ours._engine = engine_factory
-        ours_c4v._engine = engine_factory
+        for m in (ours, ours_c4v, ours_rdm, ours_rdm_c4v):
+            m._engine = engine_factory
     ref = importlib.import_module('ctm.generic.ctmrg')
     ref_c4v = importlib.import_module('ctm.one_site_c4v.ctmrg_c4v')
 
@@ -52,18 +54,19 @@ def enable(engine_factory=None):
     ref.ctm_MOVE = ctm_MOVE
     ref_c4v.ctm_MOVE_sl = ctm_MOVE_sl
     ref_c4v.ctm_MOVE_dl = ctm_MOVE_dl
-    # Without opt_einsum the reference's generic rdm2x2 dispatch is broken (ctm/generic/rdm.py:1354-1362
-    # passes force_cpu= to rdm2x2_legacy, which does not take it) and the 'sl' one/two-site RDMs need oe:
-    # route them to the reference's own pure-torch implementations.
+    # the plaquette density matrices behind the energies of the J1-J2 scripts (models/j1j2.py:223-247,641-679) run on
+    # libctmb as well
+    rdm = importlib.import_module('ctm.generic.rdm')
+    rdm.rdm2x2 = ours_rdm.rdm2x2
+    rdm.rdm2x2_legacy = ours_rdm.rdm2x2_legacy
+    rdm_c4v = importlib.import_module('ctm.one_site_c4v.rdm_c4v')
+    for name in ('rdm2x2_NN_lowmem_sl', 'rdm2x2_NNN_lowmem_sl', 'rdm2x2_NN_lowmem', 'rdm2x2_NNN_lowmem', 'rdm2x2'):
+        setattr(rdm_c4v, name, getattr(ours_rdm_c4v, name))
+    # Without opt_einsum the 'sl' one/two-site RDMs of the reference do not run (ctm/generic/rdm.py:107-112,292,
+    # 343-351,560): route them to the reference's own pure-torch double-layer implementations.
     try:
         import opt_einsum                                       # noqa: F401
     except ImportError:
-        rdm = importlib.import_module('ctm.generic.rdm')
-
-        def rdm2x2(coord, state, env, sym_pos_def=False, **kw):
-            return rdm.rdm2x2_legacy(coord, state, env, sym_pos_def=sym_pos_def,
-                                     **{k: v for k, v in kw.items() if k in ('verbosity',)})
-        rdm.rdm2x2 = rdm2x2
         def _dl(f):
             def wrapped(*a, mode='sl', unroll=False, checkpoint_unrolled=False, checkpoint_on_device=False, **kw):
                 return f(*a, **kw)

@@ -117,3 +117,15 @@ class OracleEngine:
         self.calls.append(('c4v', a.dim()))
         nC, nT = orc.ctm_move_c4v(a, C_, T, chi, self._args(opt))
         return nC, nT, None
+
+    def rdm2x2(self, coord, state, env, open_sites=(0, 1, 2, 3), sym_pos_def=False, raw=False):
+        return orc.rdm2x2(coord, state.sites, state.vertexToSite, env.C, env.T, raw=raw, open_sites=tuple(open_sites),
+                          sym_pos_def=sym_pos_def)
+
+    def rdm2x2_sites(self, tensors4, chi, open_sites=(0, 1, 2, 3), sym_pos_def=False, raw=False):
+        from peps_torch_b200.engine import C_KEYS, T_KEYS
+        coords = [(0, 0), (1, 0), (0, 1), (1, 1)]
+        sites = OrderedDict((c, t[0]) for c, t in zip(coords, tensors4))
+        C = {(c, k): t[1][i] for c, t in zip(coords, tensors4) for i, k in enumerate(C_KEYS)}
+        T = {(c, k): t[2][i] for c, t in zip(coords, tensors4) for i, k in enumerate(T_KEYS)}
+        return orc.rdm2x2((0, 0), sites, orc.v2s_4site, C, T, raw=raw, open_sites=tuple(open_sites), sym_pos_def=sym_pos_def)

@@ -7,7 +7,9 @@ import sys
 
 script = sys.argv[1]
 repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, repo)
+for p in (os.path.join(repo, 'oracle'), os.path.join(repo, 'tests'), repo):
+    sys.path.insert(0, p)
+import helpers as H   # noqa: E402
 from peps_torch_b200 import run as launcher   # noqa: E402
 
 root = launcher.find_reference_root(script)
@@ -18,10 +20,10 @@ import importlib   # noqa: E402
 ref = importlib.import_module('ctm.generic.ctmrg')
 ref_c4v = importlib.import_module('ctm.one_site_c4v.ctmrg_c4v')
 orig_move, orig_move_sl = ref.ctm_MOVE, ref_c4v.ctm_MOVE_sl
-calls = {'generic': 0, 'c4v': 0}
+calls = {'generic': 0, 'c4v': 0, 'rdm': 0}
 
 
-class RecordingEngine:
+class RecordingEngine(H.OracleEngine):          # density matrices: the oracle (host-logic test, no GPU here)
     device = 'cpu'
 
     def move_generic(self, direction, state, env, **opt):
@@ -30,6 +32,14 @@ class RecordingEngine:
 
     def move_c4v(self, a, C, T, chi, **opt):
         raise RuntimeError('not used: ctm_MOVE_sl is recorded at the module level below')
+
+    def rdm2x2(self, *a, **kw):
+        calls['rdm'] += 1
+        return super().rdm2x2(*a, **kw)
+
+    def rdm2x2_sites(self, *a, **kw):
+        calls['rdm'] += 1
+        return super().rdm2x2_sites(*a, **kw)
 
 
 launcher.enable(engine_factory=lambda: RecordingEngine())
@@ -48,4 +58,4 @@ sys.argv = [script] + sys.argv[2:]
 try:
     runpy.run_path(script, run_name='__main__')
 finally:
-    print('LAUNCHER_CALLS', calls['generic'], calls['c4v'])
+    print('LAUNCHER_CALLS', calls['generic'], calls['c4v'], calls['rdm'])

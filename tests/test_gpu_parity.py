@@ -566,3 +566,83 @@ def test_c4v_double_layer_move_and_2norm(eng, dev, name):
             assert abs(float(torch.linalg.vector_norm(env2.get_T())) - 1.0) < 1e-13
     with pytest.raises(ValueError):
         ctmrg_c4v.ctm_MOVE_sl(A.to(dev), env2)
+
+
+# ------------------------------------------------------------------------------------------
+# reduced density matrices / energy on the converged environment
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,dt', [(4, torch.float64), (4, torch.complex128), (16, torch.float64), (16, torch.complex128),
+                                  (64, torch.float64), (64, torch.complex128)])
+def test_sym_pos_def_matrix_against_oracle(eng, dev, n, dt):
+    """_sym_pos_def_matrix (ctm/generic/rdm.py:38-57) on an indefinite, slightly non-Hermitian matrix."""
+    g = torch.Generator().manual_seed(n)
+    Q, _ = torch.linalg.qr(torch.randn(n, n, dtype=dt, generator=g))
+    d = torch.linspace(1.0, -0.2, n, dtype=torch.float64)
+    M = (Q * d.to(dt)) @ Q.conj().t() + 1e-3 * torch.randn(n, n, dtype=dt, generator=g)
+    for spd in (False, True):
+        out = eng.sym_pos_def(M.to(dev), spd)
+        assert H.maxrel(out.cpu(), orc._sym_pos_def(M, spd)) < 1e-12
+    # nothing negative: sym_pos_def=True leaves the hermitised matrix alone (rdm.py:49)
+    P = (Q * torch.linspace(1.0, 0.01, n, dtype=torch.float64).to(dt)) @ Q.conj().t()
+    assert H.maxrel(eng.sym_pos_def(P.to(dev), True).cpu(), orc._sym_pos_def(P, True)) < 1e-13
+    # a 4-site RDM-shaped tensor keeps its shape
+    if n == 16:
+        t = eng.sym_pos_def(M.reshape((2,) * 8).to(dev), True)
+        assert t.shape == (2,) * 8 and H.maxrel(t.cpu().reshape(16, 16), orc._sym_pos_def(M, True)) < 1e-12
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128'])
+def test_rdm2x2_and_energy_against_oracle(eng, dev, name):
+    from peps_torch_b200.ctm.generic import rdm
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'mid_')
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    env = H.Env(chi, H.to_dev(C, dev), H.to_dev(T, dev))
+    hp = orc.j1j2_hp(1.0, 0.3, dtype=sites[(0, 0)].dtype)
+    e_gpu = 0.
+    for coord in sites:
+        r_ref = orc.rdm2x2(coord, sites, v2s, C, T)
+        r = rdm.rdm2x2(coord, st, env)
+        assert r.shape == r_ref.shape and float((r.cpu() - r_ref).abs().max()) < 1e-12
+        e_gpu = e_gpu + torch.einsum('ijklabcd,ijklabcd', r.cpu(), hp)
+    e_gpu = float((e_gpu / len(sites)).real)
+    e_ref = orc.energy_j1j2(sites, v2s, C, T, 1.0, 0.3)
+    assert abs(e_gpu - e_ref) < 1e-12 * max(1.0, abs(e_ref))
+    coord = list(sites)[1]
+    for open_sites in ([0, 1], [0, 3], [2], [1, 2, 3]):
+        for spd in (False, True):
+            r_ref = orc.rdm2x2(coord, sites, v2s, C, T, open_sites=tuple(open_sites), sym_pos_def=spd)
+            r = rdm.rdm2x2(coord, st, env, open_sites=open_sites, sym_pos_def=spd)
+            assert r.shape == r_ref.shape and float((r.cpu() - r_ref).abs().max()) < 1e-12, (open_sites, spd)
+    with pytest.raises(ValueError):
+        rdm.rdm2x2(coord, st, env, open_sites=[])
+
+
+@pytest.mark.parametrize('name', C4V)
+def test_c4v_rdms_and_energy_against_reference_fixture(eng, dev, name):
+    from peps_torch_b200.ctm.one_site_c4v import rdm_c4v
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    z, meta = H.load_golden(name)
+    a = torch.from_numpy(z['site'])
+    Cc, Tc = torch.from_numpy(z['final_C']), torch.from_numpy(z['final_T'])
+    stc = IPEPS_C4V(a.to(dev))
+    envc = ENV_C4V(meta['chi'], stc)
+    envc.C[envc.keyC], envc.T[envc.keyT] = Cc.to(dev), Tc.to(dev)
+    for spd in (False, True):
+        assert float((rdm_c4v.rdm2x2_NN_lowmem_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm2x2_c4v(a, Cc, Tc, (0, 1), spd)).abs().max()) < 1e-12
+        assert float((rdm_c4v.rdm2x2_NNN_lowmem_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm2x2_c4v(a, Cc, Tc, (0, 3), spd)).abs().max()) < 1e-12
+    assert float((rdm_c4v.rdm2x2(stc, envc).cpu() - orc.rdm2x2_c4v(a, Cc, Tc)).abs().max()) < 1e-12
+    # energy_1x1_lowmem (models/j1j2.py:641-679) from the GPU density matrices against the reference's own number
+    sz, sp, sm, I = orc.spin_half_ops(a.dtype)
+    SS = torch.einsum('ij,ab->iajb', sz, sz) + 0.5 * (torch.einsum('ij,ab->iajb', sp, sm) + torch.einsum('ij,ab->iajb', sm, sp))
+    rot = torch.tensor([[0., 1.], [-1., 0.]], dtype=a.dtype)
+    SS_rot = torch.einsum('ki,kjcb,ca->ijab', rot, SS, rot)
+    e = 2.0 * torch.einsum('ijab,ijab', rdm_c4v.rdm2x2_NN_lowmem_sl(stc, envc, sym_pos_def=True).cpu(), SS_rot)
+    if abs(meta['j2']) > 0:
+        e = e + 2.0 * meta['j2'] * torch.einsum('ijab,ijab', rdm_c4v.rdm2x2_NNN_lowmem_sl(stc, envc, sym_pos_def=True).cpu(), SS)
+    e_ref = float(z['energy'][0])
+    assert abs(float(e.real) - e_ref) < 1e-10 * abs(e_ref)

@@ -157,3 +157,83 @@ def test_host_c4v_run_dl_control_flow(oracle_engine):
     bad = CTMARGS(); bad.projector_svd_method = 'GESDD'
     with pytest.raises(Exception):
         ctmrg_c4v.run(st, env, ctm_args=bad)
+
+
+def test_planning_only_handle_validates_every_entry_point_and_never_computes():
+    """ctmb_create(device=-1): the *_workspace queries run the planner of every entry point (all contraction labels and
+    extents are validated) without a GPU; compute calls fail loudly."""
+    import ctypes as C
+    from peps_torch_b200 import _lib
+    from peps_torch_b200.engine import CtmEngine, C_KEYS, T_KEYS, DIRECTIONS
+    from peps_torch_b200.ipeps import IPEPS
+    lib = _lib.lib
+    eng = CtmEngine('plan')
+    for name in ('generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'):
+        z, meta = H.load_golden(name)
+        chi = meta['chi']
+        sites = H.golden_sites(z)
+        v2s, lX, lY = H.v2s_for(sites)
+        C0, T0 = H.golden_env(z, 'mid_')
+        for dl in (False, True):
+            ss = type(sites)((c, orc.double_layer(a)) for c, a in sites.items()) if dl else sites
+            st = IPEPS(ss, v2s, lX, lY)
+            env = H.Env(chi, C0, T0)
+            keep = []
+            coords, arr = eng._sites_array(st, env, keep)
+            dt = _lib.F64 if not ss[coords[0]].is_complex() else _lib.C128
+            for d, dcode in DIRECTIONS.items():
+                corner, nb, dest, _ = eng._move_tables(st, d)
+                for pm in (0, 1):
+                    o = eng._opts(projector_method=pm)
+                    assert lib.ctmb_move_generic_workspace(eng._h, dt, dcode, len(coords), chi, arr, corner, nb, C.byref(o)) > 0, \
+                        lib.ctmb_last_error()
+            for k in range(4):
+                assert lib.ctmb_c2x2_workspace(eng._h, dt, k, chi, C.byref(arr[0])) > 0, lib.ctmb_last_error()
+            # reduced density matrices: every subset of open sites (single-layer tensors only)
+            ptrs = (C.POINTER(_lib.Site) * 4)(*[C.pointer(arr[i % len(coords)]) for i in range(4)])
+            for mask in range(1, 16):
+                nbytes = lib.ctmb_rdm2x2_workspace(eng._h, dt, chi, ptrs, mask)
+                assert (nbytes > 0) == (not dl), (name, dl, mask, lib.ctmb_last_error())
+            assert lib.ctmb_rdm2x2_workspace(eng._h, dt, chi, ptrs, 0) == 0
+            # a compute call on the planning handle is an error, not a fallback
+            with pytest.raises(_lib.CtmbError):
+                eng.move_generic((0, -1), st, env)
+    for n, spd in ((4, 1), (16, 1), (256, 0)):
+        assert lib.ctmb_sym_pos_def_workspace(eng._h, _lib.C128, n, spd) > 0, lib.ctmb_last_error()
+    assert lib.ctmb_sym_pos_def_workspace(eng._h, _lib.F64, 256, 1) == 0          # complete eigendecomposition: n <= 160
+    for name in ('c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'):
+        z, meta = H.load_golden(name)
+        a = torch.from_numpy(z['site'])
+        dt = _lib.C128 if a.is_complex() else _lib.F64
+        for t in (a, orc.double_layer(a)):
+            dims = (C.c_int * 5)(*(list(t.shape) if t.dim() == 5 else [0] + list(t.shape)))
+            assert lib.ctmb_move_c4v_workspace(eng._h, dt, dims, meta['chi'], None) > 0, lib.ctmb_last_error()
+
+
+def test_host_rdm_modules_map_sites_and_env_correctly(monkeypatch):
+    """ctm/generic/rdm.py and ctm/one_site_c4v/rdm_c4v.py drop-ins: which site / which rotated env tensor goes where
+    (host logic, oracle as engine)."""
+    from peps_torch_b200.ctm.generic import rdm
+    from peps_torch_b200.ctm.one_site_c4v import rdm_c4v
+    from peps_torch_b200.ipeps import IPEPS, IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    e = H.OracleEngine()
+    monkeypatch.setattr(rdm, '_engine', lambda: e)
+    monkeypatch.setattr(rdm_c4v, '_engine', lambda: e)
+    z, meta = H.load_golden('generic_4site_D2_chi8_B')
+    sites = H.golden_sites(z)
+    C, T = H.golden_env(z, 'mid_')
+    st = IPEPS(sites, orc.v2s_4site, 2, 2)
+    env = H.Env(meta['chi'], C, T)
+    r = rdm.rdm2x2((1, 0), st, env)
+    assert r.shape == (2,) * 8 and abs(float(torch.einsum('ijklijkl', r)) - 1.0) < 1e-13
+    assert torch.equal(r, orc.rdm2x2((1, 0), sites, orc.v2s_4site, C, T))
+    z, meta = H.load_golden('c4v_D2_chi8_B_c128')
+    a = torch.from_numpy(z['site'])
+    stc = IPEPS_C4V(a)
+    envc = ENV_C4V(meta['chi'], stc)
+    Cc, Tc = torch.from_numpy(z['final_C']), torch.from_numpy(z['final_T'])
+    envc.C[envc.keyC], envc.T[envc.keyT] = Cc, Tc
+    assert H.maxrel(rdm_c4v.rdm2x2_NN_lowmem_sl(stc, envc, sym_pos_def=True), orc.rdm2x2_c4v(a, Cc, Tc, (0, 1), True)) < 1e-13
+    assert H.maxrel(rdm_c4v.rdm2x2_NNN_lowmem_sl(stc, envc), orc.rdm2x2_c4v(a, Cc, Tc, (0, 3))) < 1e-13
+    assert H.maxrel(rdm_c4v.rdm2x2(stc, envc), orc.rdm2x2_c4v(a, Cc, Tc)) < 1e-13

@@ -17,18 +17,18 @@ def _run(script, args, tmp_path):
                          cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith('LAUNCHER_CALLS')][-1].split()
-    return int(line[1]), int(line[2]), out.stdout
+    return int(line[1]), int(line[2]), int(line[3]), out.stdout
 
 
 def test_generic_script_calls_the_rebound_move(tmp_path):
-    g, c, out = _run('examples/j1j2/ctmrg_j1j2.py', ['--tiling', '4SITE', '--bond_dim', '2', '--chi', '8', '--seed', '123',
+    g, c, r, out = _run('examples/j1j2/ctmrg_j1j2.py', ['--tiling', '4SITE', '--bond_dim', '2', '--chi', '8', '--seed', '123',
                                                      '--j2', '0.3', '--CTMARGS_ctm_max_iter', '2'], tmp_path)
     assert g == 16 and c == 0          # 2 iterations x 2(lX+lY) moves of the 2x2 cell
-    assert 'FINAL' in out              # the energy evaluation ran (RDM dispatch fix without opt_einsum)
+    assert 'FINAL' in out and r >= 4   # the energy evaluation ran through the rebound rdm2x2 (one call per plaquette)
 
 
 def test_c4v_script_calls_the_rebound_move(tmp_path):
-    g, c, out = _run('examples/j1j2/ctmrg_j1j2_c4v.py', ['--bond_dim', '2', '--chi', '8', '--seed', '123', '--j2', '0.3',
+    g, c, r, out = _run('examples/j1j2/ctmrg_j1j2_c4v.py', ['--bond_dim', '2', '--chi', '8', '--seed', '123', '--j2', '0.3',
                                                          '--CTMARGS_ctm_max_iter', '3'], tmp_path)
     assert g == 0 and c >= 1
-    assert 'FINAL' in out
+    assert 'FINAL' in out and r >= 1   # energy_1x1_lowmem through the rebound rdm2x2_NN(N)_lowmem_sl

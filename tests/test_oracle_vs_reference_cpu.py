@@ -170,3 +170,58 @@ def test_oracle_c4v_double_layer_move_matches_reference(ref, name):
         C, T = orc.ctm_move_c4v(A, C, T, chi)
         assert float((env.C[env.keyC] - C).abs().max()) < 1e-12
         assert float((env.T[env.keyT].abs() - T.abs()).abs().max()) < 1e-10
+
+
+def test_oracle_rdm2x2_matches_reference_elementwise(ref):
+    """rdm2x2_legacy (ctm/generic/rdm.py:1362-1592) element-wise, plus the open_sites semantics (partial traces)."""
+    import helpers as H
+    import ctm_oracle as orc
+    from ipeps.ipeps import IPEPS
+    from ctm.generic.env import ENV
+    from ctm.generic import rdm
+    for name in ('generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128'):
+        z, meta = H.load_golden(name)
+        sites = H.golden_sites(z)
+        v2s, lX, lY = H.v2s_for(sites)
+        C, T = H.golden_env(z, 'final_') if 'final_C_00_-1_-1' in z.files else H.golden_env(z, 'mid_')
+        ref.global_args.dtype = 'complex128' if sites[(0, 0)].is_complex() else 'float64'
+        st = IPEPS(sites={c: t.clone() for c, t in sites.items()}, vertexToSite=v2s, lX=lX, lY=lY)
+        env = ENV(meta['chi'], st)
+        env.C, env.T = dict(C), dict(T)
+        for coord in sites:
+            for spd in (False, True):
+                r_ref = rdm.rdm2x2_legacy(coord, st, env, sym_pos_def=spd)
+                r_orc = orc.rdm2x2(coord, sites, v2s, C, T, sym_pos_def=spd)
+                assert float((r_ref - r_orc).abs().max()) < 1e-13
+        raw = orc.rdm2x2((0, 0), sites, v2s, C, T, raw=True)
+        tr = torch.einsum('ijklijkl', raw)
+        nn = orc.rdm2x2((0, 0), sites, v2s, C, T, raw=True, open_sites=(0, 1))
+        assert float((nn - torch.einsum('ijklabkl->ijab', raw)).abs().max()) < 1e-13 * abs(tr)
+        nnn = orc.rdm2x2((0, 0), sites, v2s, C, T, raw=True, open_sites=(0, 3))
+        assert float((nnn - torch.einsum('ijklajkd->ilad', raw)).abs().max()) < 1e-13 * abs(tr)
+        one = orc.rdm2x2((0, 0), sites, v2s, C, T, raw=True, open_sites=(2,))
+        assert float((one - torch.einsum('ijklijcl->kc', raw)).abs().max()) < 1e-13 * abs(tr)
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_oracle_c4v_rdms_match_reference_elementwise(ref, name):
+    """rdm2x2_NN_lowmem_sl / rdm2x2_NNN_lowmem_sl / rdm2x2 of ctm/one_site_c4v/rdm_c4v.py against the generic
+    construction on the rotated environment."""
+    import helpers as H
+    import ctm_oracle as orc
+    from ctm.one_site_c4v import rdm_c4v
+    from ctm.one_site_c4v.env_c4v import ENV_C4V
+    from ipeps.ipeps_c4v import IPEPS_C4V
+    z, meta = H.load_golden(name)
+    a = torch.from_numpy(z['site'])
+    ref.global_args.dtype = 'complex128' if a.is_complex() else 'float64'
+    C, T = torch.from_numpy(z['final_C']), torch.from_numpy(z['final_T'])
+    st = IPEPS_C4V(a.clone())
+    env = ENV_C4V(meta['chi'], st)
+    env.C[env.keyC], env.T[env.keyT] = C.clone(), T.clone()
+    for spd in (False, True):
+        assert float((rdm_c4v.rdm2x2_NN_lowmem_sl(st, env, sym_pos_def=spd)
+                      - orc.rdm2x2_c4v(a, C, T, (0, 1), spd)).abs().max()) < 1e-12
+        assert float((rdm_c4v.rdm2x2_NNN_lowmem_sl(st, env, sym_pos_def=spd)
+                      - orc.rdm2x2_c4v(a, C, T, (0, 3), spd)).abs().max()) < 1e-12
+        assert float((rdm_c4v.rdm2x2(st, env, sym_pos_def=spd) - orc.rdm2x2_c4v(a, C, T, (0, 1, 2, 3), spd)).abs().max()) < 1e-12
