@@ -32,7 +32,10 @@ CONFIGS = {
     'c3': ('c4v', 4, 96, 'complex128', 'B', 'J1-J2 one-site C4v complex128 D=4 chi=96'),
     'c4': ('kagome', 3, 64, 'float64', 'A', 'Kagome spin-1/2 iPESS D=3 chi=64 float64 (p=8, generic engine)'),
     'c5': ('4site', 8, 256, 'float64', 'B', 'J1-J2 generic 4SITE D=8 chi=256 float64'),
+    # one site of c5 (1x1 cell): the unit of the intra-site group split (G = 2N) that two GPUs can measure
+    'c5s': ('1site', 8, 256, 'float64', 'B', 'generic 1SITE D=8 chi=256 float64 (one site job of config 5)'),
 }
+BIG = ('c5', 'c5s')             # a move takes seconds: a step is ONE ctm_MOVE, no CPU arm
 
 
 def algorithmic_flops_per_move(kind, D, chi, p, cplx):
@@ -55,6 +58,9 @@ def make_state(cfg_name):
     dtype = torch.complex128 if dt == 'complex128' else torch.float64
     if kind == '4site':
         return kind, orc.random_state_4site(D, family=fam, dtype=dtype), orc.v2s_4site, 2, 2, chi
+    if kind == '1site':
+        a = orc.random_state_4site(D, family=fam, dtype=dtype)[(0, 0)]
+        return kind, OrderedDict({(0, 0): a}), orc.v2s_1site, 1, 1, chi
     if kind == 'kagome':
         return kind, OrderedDict({(0, 0): orc.random_state_kagome(D, family=fam, dtype=dtype)}), orc.v2s_1site, 1, 1, chi
     return kind, orc.random_state_c4v(D, family=fam, dtype=dtype), None, 1, 1, chi
@@ -150,7 +156,7 @@ def run_reference(args):
         return
     kind, D, chi, dt, fam, desc = CONFIGS[args.config]
     ncpu = os.cpu_count() or 1
-    if args.config == 'c5':
+    if args.config in BIG:
         print(json.dumps({'impl': 'reference', 'unavailable': 'config c5 on CPU is four full 16384^2 LAPACK SVDs per ctm_MOVE '
                           '(~56 min per move, SURVEY.md section 6); the default config c2 has a live reference arm'}))
         return
@@ -285,7 +291,7 @@ def run_ours(args):
 
         # config c5 (n = 16384): a move takes seconds, so a STEP is ONE ctm_MOVE (directions cycle through the
         # reference's sequence U,U,L,L,D,D,R,R) instead of a full iteration of eight
-        per_move = args.config == 'c5'
+        per_move = args.config in BIG
         seq = [d for d in ctm_args.ctm_move_sequence for _ in range(lX if d in [(-1, 0), (1, 0)] else lY)]
         cursor = [0]
 
@@ -306,7 +312,7 @@ def run_ours(args):
                 ctmrg.run(state, e, ctm_args=ctm_args)
         moves_per_step = 1 if per_move else 2 * (lX + lY)
     # a few iterations so that the timed environment is not the zero-padded initial one
-    for _ in range(1 if args.config == 'c5' else max(args.warmup, 3)):
+    for _ in range(1 if args.config in BIG else max(args.warmup, 3)):
         one_step(st, env)
     torch.cuda.synchronize(dev)
 
@@ -444,7 +450,7 @@ def run_ours(args):
     fast = bool(os.environ.get('CTMB_BENCH_FAST'))
     roof['kernel_level'] = None if fast else kernel_level(eng, dev, fp64_peak)
     F_move = algorithmic_flops_per_move(kind, D, chi, p_phys, cplx)
-    if args.config == 'c5':
+    if args.config in BIG:
         base = {'value': None, 'unit': 'ctm_MOVE/s', 'cores': os.cpu_count(), 'kind': 'port',
                 'sample': 'not run: one reference move at n = 16384 is four full 16384^2 LAPACK SVDs (~56 min per ctm_MOVE '
                           'extrapolated from DGEMM / gesdd timings, SURVEY.md section 6)'}
@@ -452,12 +458,23 @@ def run_ours(args):
         base = {'value': None, 'unit': 'ctm_MOVE/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'skipped (CTMB_BENCH_FAST)'}
     else:
         base = cpu_baseline(args.config)
+    if world == 1:
+        parallelism = 'single GPU'
+    elif not shard:
+        parallelism = f'{world} independent replicas (one CTM run per GPU)'
+    elif sharded._layout is not None and sharded._layout[1] > 1:
+        parallelism = (f'{sharded._layout[0]} site job(s) x groups of {sharded._layout[1]} GPUs: the n x n x k operator applications of the '
+                       f'range finder are split by sketch columns inside a group (in-place NCCL all-gather of the slabs, '
+                       f'{getattr(eng, "group_bytes", 0) / 1e6:.0f} MB received per rank in this run); NCCL all-gather of P/Pt and of '
+                       f'the new C/T per move')
+    else:
+        parallelism = f'per-site shard over {world} GPUs, NCCL all-gather of P/Pt and of the new C/T per move'
     line = {'metric': 'CTM moves/sec', 'value': value, 'unit': 'ctm_MOVE/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if shard else 'weak', 'vs_baseline': None, 'dtype': 'c128' if cplx else 'f64', 'data': 'synthetic',
             'config': {'workload': desc + f' ({"1 ctm_MOVE_sl" if kind == "c4v" else str(moves_per_step) + " ctm_MOVE"} per step)',
                        'family': fam, 'seed': 123, 'moves_per_step': moves_per_step, 'l2': 'flushed between timed steps (256 MiB write)',
-                       'parallelism': 'single GPU' if world == 1 else (f'per-site shard over {world} GPUs, NCCL all-gather of P/Pt and of the new C/T per move' if shard else f'{world} independent replicas (one CTM run per GPU)'),
+                       'parallelism': parallelism,
                        'rsvd': {'rank_factor': eng.options.rsvd_rank_factor, 'niter': eng.options.rsvd_niter}},
             'e2e': {'value': e2e_value, 'unit': 'ctm_MOVE/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': base,
@@ -482,7 +499,7 @@ def main():
                          'drop when a rank holds one site instead of four)')
     args = ap.parse_args()
     if args.parallel == 'auto':
-        args.parallel = 'shard' if args.config == 'c5' else 'replicas'
+        args.parallel = 'shard' if args.config in BIG else 'replicas'
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -80,6 +80,16 @@ const char* ctmb_last_error(void);
 int ctmb_create(ctmb_handle_t* h, int device);
 int ctmb_destroy(ctmb_handle_t h);
 void ctmb_default_options(ctmb_options* opt);
+/* Intra-site split over a group of GPUs (the "G = 2N" layout; yastn's device farm, _env_ctm_dist_mp.py:305-394,
+ * is the reference's counterpart).  Every member of the group makes the SAME ctmb_move_generic_projectors call on the
+ * same inputs; libctmb splits the n x n x k operator applications of the range finder by sketch columns and exchanges
+ * the slabs through `fn`: an IN-PLACE all-gather over the group, buf = [nranks][bytes_per_rank] with this rank's slot
+ * filled, ordered with `stream` (the host implements it with NCCL over NVLink, torch.distributed.all_gather_into_tensor).
+ * QR / Jacobi / truncation run redundantly on every member, which therefore all return identical projectors.
+ * nranks = 1 switches the group off. */
+typedef int (*ctmb_allgather_fn)(void* ctx, void* buf, size_t bytes_per_rank, void* stream);
+int ctmb_set_group(ctmb_handle_t h, int rank, int nranks, ctmb_allgather_fn fn, void* ctx);
+
 /* kernels launched / algorithmic real flops enqueued by this handle since the last reset */
 int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops);
 int ctmb_reset_counters(ctmb_handle_t h);

@@ -33,8 +33,11 @@ _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 _PS, _PO = C.POINTER(Site), C.POINTER(Options)
 _PI, _PVP = C.POINTER(C.c_int), C.POINTER(C.c_void_p)
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
 # every symbol include/ctmb.h declares, with its signature
 SIGNATURES = {
+    'ctmb_set_group': (C.c_int, [_vp, _i, _i, ALLGATHER_FN, _vp]),
     'ctmb_version': (C.c_int, []),
     'ctmb_last_error': (C.c_char_p, []),
     'ctmb_create': (C.c_int, [C.POINTER(_vp), _i]),

@@ -80,6 +80,20 @@ public:
 
     size_t esize() const { return cplx ? 16 : 8; }
 
+    // Intra-site split of the range finder over a GROUP of GPUs ("G = 2N"): every member of the group runs the
+    // same call on the same inputs; the n x n x k operator applications are split by sketch columns and the slabs are
+    // exchanged by an in-place all-gather that the host provides (NCCL over NVLink through torch.distributed).
+    // buf = [coll_n][bytes_per_rank], this rank's slot already filled; must be enqueued on / ordered with `stream`.
+    typedef int (*allgather_fn)(void* ctx, void* buf, size_t bytes_per_rank, void* stream);
+    int coll_rank = 0, coll_n = 1;
+    allgather_fn coll_fn = nullptr;
+    void* coll_ctx = nullptr;
+    bool coll_active() const { return coll_n > 1 && coll_fn != nullptr; }
+    void allgather(void* buf, size_t bytes_per_rank) {
+        flush();
+        CTMB_CHECK(coll_fn(coll_ctx, buf, bytes_per_rank, (void*)stream) == 0, "the host's all-gather callback failed");
+    }
+
     // C = A * B over shared labels not in C; C's labels/strides define the output layout.
     // Enqueued into the pending batch; flushed when incompatible or on flush().
     void contract(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C,

@@ -414,17 +414,32 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         pS.p[b] = r.S[b]; pUh.p[b] = Uh[b]; pWs.p[b] = Ws[b];
     }
     if (e.ws.dry()) return r;
-    Tn Om = make_tn(omega, "sj", {k, n});
     auto tnY = [&](int b, const char* lab) { return make_tn(pY.p[b], lab, {k, m}); };
     auto tnZ = [&](int b, const char* lab) { return make_tn(pZ.p[b], lab, {k, n}); };
     const double cf = e.cplx ? 4.0 : 1.0;
     // Y[s,i] = sum_j M[i,j] X[s,j]  (adjoint: Z[s,j] = sum_i conj(M[i,j]) Y[s,i]) for `cols` vectors per matrix
-    auto apply_op = [&](const PtrBatch& in, const PtrBatch& out, int cols, bool adjoint) {
+    auto apply_op = [&](const PtrBatch& in_full, const PtrBatch& out_full, int cols_full, bool adjoint) {
+        // group mode: this rank applies the operator to its slab of columns (vectors are contiguous: column-major
+        // storage), then the slabs are all-gathered in place; every member ends with the full, identical result
+        const bool split = e.coll_active() && cols_full % e.coll_n == 0 && !e.ws.dry();
+        const int cols = split ? cols_full / e.coll_n : cols_full;
+        const int64_t in_len = adjoint ? m : n, out_len = adjoint ? n : m;
+        PtrBatch in = in_full, out = out_full;
+        if (split)
+            for (int b = 0; b < nb; ++b) {
+                in.p[b] = (char*)in_full.p[b] + (size_t)e.coll_rank * cols * in_len * es;
+                out.p[b] = (char*)out_full.p[b] + (size_t)e.coll_rank * cols * out_len * es;
+            }
+        auto gather = [&]() {
+            if (!split) return;
+            for (int b = 0; b < nb; ++b) e.allgather(out_full.p[b], (size_t)cols * out_len * es);
+        };
         if (!fac) {
             for (int b = 0; b < nb; ++b)
                 e.contract(Mt[b], adjoint, make_tn(in.p[b], adjoint ? "si" : "sj", {cols, adjoint ? m : n}), false,
                            make_tn(out.p[b], adjoint ? "sj" : "si", {cols, adjoint ? n : m}));
             e.flush();
+            gather();
             return;
         }
         // M = H1^T H0^T H2 H3 :  M X = H1^T (H0^T (H2 (H3 X))),   M^H Y = H3^H (H2^H (conj(H0) (conj(H1) Y)))
@@ -452,6 +467,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             }
             e.flush();
         }
+        gather();
     };
     // orthonormalise the columns of the matrices in `cur` (rows x k, column-major); on return `cur`
     // holds the explicit thin Q (the buffers of `cur` and pQ are swapped in the WY form)
@@ -503,17 +519,16 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         return r;
     }
     // Y = M * Omega
-    if (!fac) { for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, Om, false, tnY(b, "si")); }
-    else { PtrBatch pOm{}; for (int b = 0; b < nb; ++b) pOm.p[b] = omega; apply_op(pOm, pY, k, false); }
+    { PtrBatch pOm{}; for (int b = 0; b < nb; ++b) pOm.p[b] = omega; apply_op(pOm, pY, k, false); }
     qr(pY, pNull, m);
     const bool complete = (k == std::min(m, n));          // the sketch spans everything: exact, no iteration
     const bool adaptive = o.rsvd_tol > 0.0 && !complete;
     unsigned long long* dres = nullptr;
     unsigned long long* hres = nullptr;
     if (adaptive) {
-        dres = (unsigned long long*)e.persistent("resid", sizeof(unsigned long long));
+        dres = (unsigned long long*)e.persistent("resid", 32 * sizeof(unsigned long long));    // [0]: mine, [1..]: the group's
         static unsigned long long* pinned = nullptr;
-        if (!pinned) CTMB_CUDA(cudaMallocHost(&pinned, sizeof(unsigned long long)));
+        if (!pinned) CTMB_CUDA(cudaMallocHost(&pinned, 32 * sizeof(unsigned long long)));
         hres = pinned;
     }
     int todo = complete ? 0 : o.rsvd_niter;               // full power iterations still to run
@@ -584,9 +599,18 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         { PtrBatch pXin{}; for (int b = 0; b < nb; ++b) pXin.p[b] = eig_mode ? r.U[b] : r.V[b]; apply_op(pXin, pMX, chi, false); }
         CTMB_CUDA(cudaMemsetAsync(dres, 0, sizeof(unsigned long long), e.stream));
         { ProfScope ps(e, Engine::CAT_MISC); resid_launch(pMX, pYv, pS, nb, m, chi, o.svd_reltol, dres, e.cplx, e.stream); }
-        CTMB_CUDA(cudaMemcpyAsync(hres, dres, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
+        if (e.coll_active()) {
+            // every member of the group must take the same decision below: exchange the residuals (rounding may differ
+            // between devices only through non-deterministic reduction orders, but a split decision would dead-lock)
+            CTMB_CHECK(e.coll_n <= 16, "group too large");
+            CTMB_CUDA(cudaMemcpyAsync(dres + 1 + e.coll_rank, dres, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e.stream));
+            e.allgather(dres + 1, sizeof(unsigned long long));
+            CTMB_CUDA(cudaMemcpyAsync(hres, dres + 1, e.coll_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
+        } else
+            CTMB_CUDA(cudaMemcpyAsync(hres, dres, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
         CTMB_CUDA(cudaStreamSynchronize(e.stream));
         double res; memcpy(&res, hres, sizeof res);
+        for (int g = 1; e.coll_active() && g < e.coll_n; ++g) { double rg; memcpy(&rg, hres + g, sizeof rg); res = std::max(res, rg); }
         static int dbg = -1;
         if (dbg < 0) { const char* ev = getenv("CTMB_DEBUG_RESID"); dbg = ev ? atoi(ev) : 0; }
         if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d k=%d round %d iterations %d residual %.3e (tol %.1e)\n", m, n, k, round, used, res, tol_eff);
@@ -996,6 +1020,17 @@ void ctmb_default_options(ctmb_options* o) {
     o->svd_reltol = 1.0e-8; o->eps_multiplet = 1.0e-8; o->multiplet_abstol = 1.0e-14;
     o->rsvd_rank_factor = 2.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->rsvd_max_rounds = 5;
     o->seed = 0x5eed5eedull; o->rsvd_tol = 2.0e-15; o->projector_method = 0; o->pad2 = 0;
+}
+
+int ctmb_set_group(ctmb_handle_t h, int rank, int nranks, ctmb_allgather_fn fn, void* ctx) {
+    CTMB_TRY
+    CTMB_CHECK(h != nullptr, "null handle");
+    CTMB_CHECK(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks, "bad group");
+    CTMB_CHECK(nranks == 1 || fn != nullptr, "a group needs an all-gather callback");
+    Engine& e = h->h.eng;
+    e.coll_rank = rank; e.coll_n = nranks; e.coll_fn = nranks > 1 ? fn : nullptr; e.coll_ctx = ctx;
+    return 0;
+    CTMB_CATCH(-1)
 }
 
 int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops) {

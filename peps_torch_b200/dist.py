@@ -1,9 +1,17 @@
-"""Per-site sharding of one CTM move over the GPUs of a node (one process per GPU).
+"""Sharding of one CTM move over the GPUs of a node (one process per GPU).
 
 Inside ctm_MOVE all N projector pairs are computed from the same environment snapshot, then
 all N absorptions from that snapshot plus the projectors, and results are written only
-afterwards (ctm/generic/ctmrg.py:246-275,313-319).  Rank r therefore owns the site jobs
-r, r+W, r+2W, ...; the move has exactly two exchange steps:
+afterwards (ctm/generic/ctmrg.py:246-275,313-319).
+
+* world <= N: rank r owns the site jobs r, r+W, r+2W, ...
+* world >= 2N (config 5 on 8 GPUs: N = 4): the ranks form N GROUPS of g = world // N members; a group shares the
+  projector job of one site -- libctmb splits the n x n x k operator applications of the range finder by sketch
+  columns over the group and all-gathers the slabs in place over NVLink (engine.set_group / ctmb_set_group), so
+  every member ends with identical projectors; the group's first rank (leader) does the absorption.  Ranks beyond
+  g*N stay idle.
+
+Either way the move has two exchange steps over ALL ranks:
 
   1. all-gather of (P, Pt) of every job   -- the absorption at `coord` needs the projectors of
      the neighbouring site coord+shift (ctmrg.py:326-334), which another rank may own;
@@ -11,7 +19,7 @@ r, r+W, r+2W, ...; the move has exactly two exchange steps:
      environment, as the next move reads all of it.
 
 Collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).
-The compute backend is anything with the two methods of CtmEngine used below, so the same
+The compute backend is anything with the methods of CtmEngine used below, so the same
 code is exercised on CPU with the oracle as backend (tests/test_dist_cpu.py).
 """
 import torch
@@ -24,12 +32,21 @@ def partition_jobs(nsites, world):
     return [list(range(r, nsites, world)) for r in range(world)]
 
 
+def group_layout(nsites, world):
+    """(members per group g, [ranks of group j]) when the ranks outnumber the sites at least 2:1, else (1, None)."""
+    g = world // nsites if nsites > 0 else 1
+    if g < 2:
+        return 1, None
+    return g, [list(range(j * g, (j + 1) * g)) for j in range(nsites)]
+
+
 class ShardedCtm:
     def __init__(self, backend, group=None):
         self.backend = backend
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._layout = None         # (nsites, g, my group index or None, parts)
 
     def _all_gather(self, flat, counts):
         """all-gather of ragged per-rank 1-D tensors (padded to the maximum count)."""
@@ -40,19 +57,45 @@ class ShardedCtm:
         dist.all_gather(out, buf, group=self.group)
         return [o[:c] for o, c in zip(out, counts)]
 
+    def _setup(self, nsites):
+        """Decide the layout for `nsites` jobs once; in group mode create the process groups (a collective call: every
+        rank creates every group, in the same order) and hand this rank's group to the backend."""
+        if self._layout is not None and self._layout[0] == nsites:
+            return self._layout
+        g, groups = group_layout(nsites, self.world)
+        if groups is None:
+            parts = partition_jobs(nsites, self.world)
+            self._layout = (nsites, 1, None, parts, parts)
+            return self._layout
+        base = list(range(self.world)) if self.group is None else dist.get_process_group_ranks(self.group)
+        mine, my_pg = None, None
+        for j, members in enumerate(groups):
+            pg = dist.new_group([base[r] for r in members])
+            if self.rank in members:
+                mine, my_pg = j, pg
+        if mine is not None:
+            self.backend.set_group(my_pg, groups[mine].index(self.rank), g)
+        # compute: every member of group j runs job j; exchange: only the leader contributes
+        compute = [[r // g] if r < g * nsites else [] for r in range(self.world)]
+        contribute = [[r // g] if (r < g * nsites and r % g == 0) else [] for r in range(self.world)]
+        self._layout = (nsites, g, mine, compute, contribute)
+        return self._layout
+
     def ctm_MOVE(self, direction, state, env, **opt):
         """Same contract as ctm.generic.ctmrg.ctm_MOVE; every rank ends with the same env."""
         if direction not in DIRECTIONS:
             raise ValueError("Invalid direction: " + str(direction))
         coords = list(state.sites.keys())
         n = len(coords)
-        parts = partition_jobs(n, self.world)
-        mine = parts[self.rank]
+        _, g, _, compute, parts = self._setup(n)
+        mine = compute[self.rank]
+        contributes = bool(parts[self.rank])
         n0, chi = self.backend.projector_shape(direction, state, env)
         a0 = state.sites[coords[0]]
-        # 1) projectors of my jobs, then all-gather
+        # 1) projectors of my jobs (in group mode: shared with the other members of my group), then all-gather
         if mine:
             P, Pt = self.backend.move_generic_projectors(direction, state, env, mine, **opt)
+        if contributes:
             flat = torch.cat([t.reshape(-1) for pair in zip(P, Pt) for t in pair])
         else:
             flat = a0.new_zeros(0)
@@ -64,8 +107,9 @@ class ShardedCtm:
                 blk = gathered[r][i * per_job:(i + 1) * per_job]
                 P_all[j] = blk[:n0 * chi].view(n0, chi)
                 Pt_all[j] = blk[n0 * chi:].view(n0, chi)
-        # 2) absorption of my jobs, then all-gather of the new tensors
-        res = self.backend.move_generic_absorb(direction, state, env, mine, P_all, Pt_all, **opt) if mine else []
+        # 2) absorption of my jobs (group mode: by the leader), then all-gather of the new tensors
+        todo = parts[self.rank]
+        res = self.backend.move_generic_absorb(direction, state, env, todo, P_all, Pt_all, **opt) if todo else []
         flat = torch.cat([t.reshape(-1) for (_, c1, c2, t3) in res for t in (c1, c2, t3)]) if res else a0.new_zeros(0)
         shapes = {j: self.backend._nT_shape(direction, state.sites[coords[j]], chi) for j in range(n)}
         def job_len(j):

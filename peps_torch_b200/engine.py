@@ -91,6 +91,41 @@ class CtmEngine:
             return C.c_void_p(0)
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # ----------------------------------------------------------------------------------
+    # intra-site split over a group of GPUs (include/ctmb.h: ctmb_set_group)
+    # ----------------------------------------------------------------------------------
+    def set_group(self, group=None, rank=0, nranks=1):
+        """Make this engine one member of a group that shares every projector job: libctmb splits the operator
+        applications of the range finder by sketch columns and calls back for an in-place all-gather over `group`
+        (a torch.distributed process group on NCCL).  nranks=1 switches it off."""
+        import torch.distributed as dist
+
+        class _Raw:                       # zero-copy view of device memory owned by libctmb's caller
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+        def _allgather(ctx, buf, bytes_per_rank, stream):
+            try:
+                whole = torch.as_tensor(_Raw(buf, bytes_per_rank * nranks), device=self.device)
+                mine = whole[rank * bytes_per_rank:(rank + 1) * bytes_per_rank]
+                # libctmb launches on torch's current stream (self._stream()); c10d orders the NCCL kernel after the work
+                # queued there and makes the stream wait for it on return (async_op=False)
+                dist.all_gather_into_tensor(whole, mine, group=group)
+                self.group_bytes += bytes_per_rank * (nranks - 1)
+                return 0
+            except Exception as ex:       # never let an exception cross the C boundary
+                self._group_error = ex
+                return -1
+
+        self.group_bytes = 0
+        self._group_error = None
+        if nranks <= 1:
+            self._group_cb = _lib.ALLGATHER_FN()      # NULL function pointer
+            check(lib.ctmb_set_group(self._h, 0, 1, self._group_cb, None))
+            return
+        self._group_cb = _lib.ALLGATHER_FN(_allgather)    # keep a reference: ctypes callbacks die with their object
+        check(lib.ctmb_set_group(self._h, rank, nranks, self._group_cb, None))
+
     def counters(self):
         n, f = C.c_longlong(), C.c_double()
         check(lib.ctmb_get_counters(self._h, C.byref(n), C.byref(f)))

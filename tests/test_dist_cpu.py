@@ -23,6 +23,13 @@ class OracleBackend:
         return {(0, -1): (chi, D[2] ** 2, chi), (-1, 0): (chi, chi, D[3] ** 2),
                 (0, 1): (D[0] ** 2, chi, chi), (1, 0): (chi, D[1] ** 2, chi)}[direction]
 
+    grp = None
+
+    def set_group(self, group, rank, nranks):
+        """Group mode: libctmb would split the range finder over the members; the oracle backend simply computes the
+        whole job on every member (same result on all of them, which is what the sharding logic relies on)."""
+        self.grp = (rank, nranks, dist.get_world_size(group))
+
     def move_generic_projectors(self, direction, state, env, jobs, **opt):
         coords = list(state.sites.keys())
         P, Pt = [], []
@@ -87,3 +94,47 @@ def test_sharded_move_world2_gloo():
         assert moves == 8
         assert worst < 1e-12, worst          # same arithmetic as the single-process oracle, job order aside
         assert same
+
+
+def _worker_group(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from peps_torch_b200.dist import ShardedCtm
+        torch.set_num_threads(2)
+        z, meta = H.load_golden('kagome_1site_D2_chi8_A')
+        sites = H.golden_sites(z)
+        v2s, lX, lY = H.v2s_for(sites)
+        C, T = H.golden_env(z, 'mid_')
+        st = H.State(sites, v2s, lX, lY)
+        env = H.Env(meta['chi'], C, T)
+        be = OracleBackend()
+        sh = ShardedCtm(be)
+        moves = sh.iteration(st, env)
+        C2, T2 = H.golden_env(z, 'mid_')
+        orc.ctm_iteration(sites, v2s, lX, lY, C2, T2, meta['chi'])
+        worst = max([float((env.C[k] - C2[k]).abs().max()) for k in C2] + [float((env.T[k] - T2[k]).abs().max()) for k in T2])
+        flat = torch.cat([env.C[k].reshape(-1) for k in sorted(env.C)] + [env.T[k].reshape(-1) for k in sorted(env.T)])
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        ret[rank] = (moves, worst, all(torch.equal(other[0], o) for o in other), be.grp)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_group_mode_world2_one_site_gloo():
+    """world >= 2 N: the ranks form groups that share a site job (SURVEY 8e, G = 2N); here N = 1, one group of two."""
+    from peps_torch_b200.dist import group_layout
+    assert group_layout(4, 8) == (2, [[0, 1], [2, 3], [4, 5], [6, 7]])
+    assert group_layout(4, 4) == (1, None) and group_layout(4, 7) == (1, None) and group_layout(1, 2) == (2, [[0, 1]])
+    assert group_layout(2, 8)[0] == 4
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_group, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        moves, worst, same, grp = ret[r]
+        assert moves == 4 and worst < 1e-12 and same
+        assert grp == (r, 2, 2)
