@@ -270,6 +270,9 @@ def run_ours(args):
     cplx = dt == 'complex128'
     ctm_args = pcfg.CTMARGS()
     ctm_args.ctm_max_iter = 1
+    if args.rank_factor is not None:            # experiments: sketch width k = ceil(rank_factor * chi)
+        eng.options.rsvd_rank_factor = args.rank_factor
+    ctm_args.b200_rsvd_rank_factor = eng.options.rsvd_rank_factor if args.rank_factor is not None else None
 
     # pinned host copies (e2e) and device-resident state (value)
     if kind == 'c4v':
@@ -475,7 +478,8 @@ def run_ours(args):
             'config': {'workload': desc + f' ({"1 ctm_MOVE_sl" if kind == "c4v" else str(moves_per_step) + " ctm_MOVE"} per step)',
                        'family': fam, 'seed': 123, 'moves_per_step': moves_per_step, 'l2': 'flushed between timed steps (256 MiB write)',
                        'parallelism': parallelism,
-                       'rsvd': {'rank_factor': eng.options.rsvd_rank_factor, 'niter': eng.options.rsvd_niter}},
+                       'rsvd': {'rank_factor': eng.options.rsvd_rank_factor or 'auto (1.75 for n <= 1024, else 2.0)',
+                                'niter_first_call': eng.options.rsvd_niter, 'iterations': 'residual-checked (rsvd_tol 2e-15 sqrt(n))'}},
             'e2e': {'value': e2e_value, 'unit': 'ctm_MOVE/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': base,
             'flops': {'reference_algorithm_per_move': F_move, 'executed_per_move': flops_exec / (moves_per_step * args.steps),
@@ -492,6 +496,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--rank-factor', type=float, default=None, dest='rank_factor',
+                    help='sketch width of the range finder in units of chi (default: the library default)')
     ap.add_argument('--parallel', default='auto', choices=['auto', 'shard', 'replicas'],
                     help='N>1: "shard" = per-site shard of ONE CTM run with NCCL all-gathers of P/Pt and C/T (strong scaling; '
                          'default for c5, whose move is FLOP-bound); "replicas" = one independent CTM run per GPU (weak scaling; '

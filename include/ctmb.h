@@ -42,7 +42,8 @@ typedef struct {
     double svd_reltol;         /* projector_svd_reltol        (1e-8)  ctm_projectors.py:266 */
     double eps_multiplet;      /* projector_eps_multiplet     (1e-8)  custom_svd.py:70-95; C4v: 1e-12 custom_eig.py:7-8 */
     double multiplet_abstol;   /* projector_multiplet_abstol  (1e-14) */
-    double rsvd_rank_factor;   /* sketch width k = min(n, ceil(factor*chi)); default 2.0 */
+    double rsvd_rank_factor;   /* sketch width k = min(n, ceil(factor*chi)); default 0 = automatic: 1.75 for n <= 1024 (latency-bound
+                                  QR / Jacobi steps), 2.0 above (bound by the n x n x k products); measured, profiles/r1_sketch_width.md */
     int rsvd_niter;            /* power iterations q of the first call with a new shape (later calls start from the count that
                                   satisfied the residual test last time); default 4 */
     int jacobi_max_sweeps;     /* default 40 */

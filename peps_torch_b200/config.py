@@ -24,8 +24,8 @@ class CTMARGS:
         self.fpcm_init_iter = 1
         self.fpcm_freq = -1
         # engine-specific (no counterpart in the reference)
-        self.b200_rsvd_niter = 4
-        self.b200_rsvd_rank_factor = 2.0
+        self.b200_rsvd_niter = None       # None: library default (ctmb_default_options, include/ctmb.h)
+        self.b200_rsvd_rank_factor = None  # None: library default; sketch width k = ceil(rank_factor * chi)
         self.b200_rsvd_tol = None         # None: library default 2e-15 (x sqrt(n)) residual bound; 0: fixed iteration count
         self.b200_rsvd_tol_c4v = None     # C4v eigen path: same default
 

@@ -245,7 +245,14 @@ struct Rsvd {
 static int sketch_width(int m, int n, int chi, const ctmb_options& o) {
     int mn = std::min(m, n);
     if (mn <= 160) return mn;
-    int k = (int)std::ceil(o.rsvd_rank_factor * chi);
+    // rank factor 0 = automatic.  Measured on B200 (profiles/r1_sketch_width.md): where the move is bound by the serial
+    // column steps of the QR and the Jacobi rounds (n <= 1024: config c2, 432 x 432) a narrower sketch with one more
+    // power iteration is faster (k = 1.75 chi, q = 3: 333 moves/s; 2 chi, q = 2: 296; 1.5 chi, q = 5: 314); where it is
+    // bound by the n x n x k products (config c5) the iteration count explodes below 2 chi (1.5 chi: q = 11, 10 % slower).
+    // Accuracy does not depend on the choice: the residual test decides the number of iterations.
+    double f = o.rsvd_rank_factor;
+    if (!(f > 0.0)) f = std::max(m, n) <= 1024 ? 1.75 : 2.0;
+    int k = (int)std::ceil(f * chi);
     k = std::max(k, chi + 1);
     return std::min(k, mn);
 }
@@ -1018,7 +1025,7 @@ int ctmb_destroy(ctmb_handle_t h) {
 void ctmb_default_options(ctmb_options* o) {
     if (!o) return;
     o->svd_reltol = 1.0e-8; o->eps_multiplet = 1.0e-8; o->multiplet_abstol = 1.0e-14;
-    o->rsvd_rank_factor = 2.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->rsvd_max_rounds = 5;
+    o->rsvd_rank_factor = 0.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->rsvd_max_rounds = 5;
     o->seed = 0x5eed5eedull; o->rsvd_tol = 2.0e-15; o->projector_method = 0; o->pad2 = 0;
 }
 

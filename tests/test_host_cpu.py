@@ -28,7 +28,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.Site) == 8 + 24 + 32 + 32
     o = _lib.default_options()
     assert (o.svd_reltol, o.eps_multiplet, o.multiplet_abstol) == (1e-8, 1e-8, 1e-14)
-    assert o.rsvd_niter >= 2 and o.rsvd_rank_factor >= 1.5
+    assert o.rsvd_niter >= 2 and o.rsvd_rank_factor == 0.0      # 0 = automatic sketch width
     assert o.projector_method == 0 and 0.0 < o.rsvd_tol < 1e-13
 
 
