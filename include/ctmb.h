@@ -189,6 +189,14 @@ int ctmb_rdm2x2(ctmb_handle_t h, ctmb_dtype dt, int chi, const ctmb_site* const 
                 void* ws, size_t ws_bytes, void* stream);
 size_t ctmb_rdm2x2_workspace(ctmb_handle_t h, ctmb_dtype dt, int chi, const ctmb_site* const sites[4], int open_mask);
 
+/* rdm1x1 / rdm2x1 / rdm1x2 (ctm/generic/rdm.py:114-258, 352-500, 672-826; C4v: rdm1x1(_sl), rdm2x1(_sl) of
+ * ctm/one_site_c4v/rdm_c4v.py:168-392, 394-665 on the rotated environment): UN-normalised one- and two-site density
+ * matrices.  kind 0: sites[0] = site at coord, rho[s;s'];  kind 1: sites = coord, coord+(1,0), rho[s0,s1;s0',s1'];
+ * kind 2: sites = coord, coord+(0,1), rho[s0,s1;s0',s1']. */
+int ctmb_rdm_small(ctmb_handle_t h, ctmb_dtype dt, int kind, int chi, const ctmb_site* const sites[2], void* rho,
+                   void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_rdm_small_workspace(ctmb_handle_t h, ctmb_dtype dt, int kind, int chi, const ctmb_site* const sites[2]);
+
 /* _sym_pos_def_matrix (ctm/generic/rdm.py:38-57): out = (rdm + rdm^H)/2; with sym_pos_def != 0 and a negative
  * eigenvalue, out = U max(D,0) U^H; finally out /= Re tr(out).  rdm, out: n x n row-major (may not alias). */
 int ctmb_sym_pos_def(ctmb_handle_t h, ctmb_dtype dt, const void* rdm, int n, int sym_pos_def, void* out,

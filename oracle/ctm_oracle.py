@@ -544,6 +544,51 @@ def c4v_to_generic_env(C, T):
     return Cg, Tg
 
 
+def rdm1x1(coord, sites, v2s, C, T, raw=False, sym_pos_def=False):
+    """ctm/generic/rdm.py:114-258 (rdm1x1_dl): rho(s;s') of the site at `coord`: open enlarged LU corner closed by
+    C(1,-1) T(1,0) C(1,1) T(0,1) C(-1,1) of the same site."""
+    s = v2s(coord)
+    LU = corner_at('LU', coord, sites, v2s, C, T, open_phys=True)            # [(l,D),(x,R),s,S]
+    E = torch.einsum('xa,aRb,bc,Dec,le->lDxR', C[(s, (1, -1))], T[(s, (1, 0))], C[(s, (1, 1))], T[(s, (0, 1))], C[(s, (-1, 1))])
+    rho = torch.einsum('yzsS,yz->sS', LU, E.reshape(LU.shape[0], LU.shape[1]))
+    return rho if raw else _sym_pos_def(rho, sym_pos_def)
+
+
+def rdm2x1(coord, sites, v2s, C, T, raw=False, sym_pos_def=False):
+    """ctm/generic/rdm.py:352-500 (rdm2x1_dl): rho(s0,s1;s0',s1'), s0 = coord, s1 = coord+(1,0)."""
+    c0, c1 = v2s(coord), v2s((coord[0] + 1, coord[1]))
+    LU = corner_at('LU', coord, sites, v2s, C, T, open_phys=True)                        # [(l,D),(x,R),s,S]
+    RU = corner_at('RU', (coord[0] + 1, coord[1]), sites, v2s, C, T, open_phys=True)     # [(e,l),(c,f),j,J]
+    B0 = torch.einsum('le,Dec->lDc', C[(c0, (-1, 1))], T[(c0, (0, 1))])
+    B1 = torch.einsum('fEb,cb->cfE', T[(c1, (0, 1))], C[(c1, (1, 1))])
+    L = torch.einsum('yzsS,yc->czsS', LU, B0.reshape(LU.shape[0], -1))
+    R = torch.einsum('tqjJ,qE->tEjJ', RU, B1.reshape(RU.shape[1], -1))
+    rho = torch.einsum('czsS,zcjJ->sjSJ', L, R)
+    return rho if raw else _sym_pos_def(rho, sym_pos_def)
+
+
+def rdm1x2(coord, sites, v2s, C, T, raw=False, sym_pos_def=False):
+    """ctm/generic/rdm.py:672-826 (rdm1x2_dl): rho(s0,s1;s0',s1'), s0 = coord, s1 = coord+(0,1)."""
+    c0, c1 = v2s(coord), v2s((coord[0], coord[1] + 1))
+    LU = corner_at('LU', coord, sites, v2s, C, T, open_phys=True)                        # [(l,D),(x,R),s,S]
+    LD = corner_at('LD', (coord[0], coord[1] + 1), sites, v2s, C, T, open_phys=True)     # [(c,u),(e,r),k,K]
+    Rr = torch.einsum('xa,aRb->xRb', C[(c0, (1, -1))], T[(c0, (1, 0))])
+    Rb = torch.einsum('Brc,ce->erB', T[(c1, (1, 0))], C[(c1, (1, 1))])
+    Tp = torch.einsum('yzsS,zb->ybsS', LU, Rr.reshape(LU.shape[1], -1))
+    Bt = torch.einsum('tqkK,qB->tBkK', LD, Rb.reshape(LD.shape[1], -1))
+    rho = torch.einsum('ybsS,ybkK->skSK', Tp, Bt)
+    return rho if raw else _sym_pos_def(rho, sym_pos_def)
+
+
+def rdm_small_c4v(kind, a, C, T, sym_pos_def=False):
+    """rdm1x1_sl / rdm2x1_sl of ctm/one_site_c4v/rdm_c4v.py:266-392,530-665 through the generic construction on the
+    rotated environment (kind '1x1' or '2x1')."""
+    from collections import OrderedDict
+    Cg, Tg = c4v_to_generic_env(C, T)
+    f = {'1x1': rdm1x1, '2x1': rdm2x1, '1x2': rdm1x2}[kind]
+    return f((0, 0), OrderedDict({(0, 0): a}), v2s_1site, Cg, Tg, sym_pos_def=sym_pos_def)
+
+
 def rdm2x2_c4v(a, C, T, open_sites=(0, 1, 2, 3), sym_pos_def=False):
     """The 2x2 plaquette of the one-site C4v state through the generic construction: open_sites=(0,1) is
     rdm2x2_NN_lowmem_sl, (0,3) rdm2x2_NNN_lowmem_sl, all four rdm2x2 (ctm/one_site_c4v/rdm_c4v.py:1160-1202,

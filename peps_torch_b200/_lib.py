@@ -69,6 +69,8 @@ SIGNATURES = {
     'ctmb_move_c4v_workspace': (_sz, [_vp, _i, C.POINTER(C.c_int), _i, _PO]),
     'ctmb_rdm2x2': (C.c_int, [_vp, _i, _i, C.POINTER(_PS), _i, _vp, _vp, _sz, _vp]),
     'ctmb_rdm2x2_workspace': (_sz, [_vp, _i, _i, C.POINTER(_PS), _i]),
+    'ctmb_rdm_small': (C.c_int, [_vp, _i, _i, _i, C.POINTER(_PS), _vp, _vp, _sz, _vp]),
+    'ctmb_rdm_small_workspace': (_sz, [_vp, _i, _i, _i, C.POINTER(_PS)]),
     'ctmb_sym_pos_def': (C.c_int, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     'ctmb_sym_pos_def_workspace': (_sz, [_vp, _i, _i, _i]),
 }

@@ -939,6 +939,79 @@ static void rdm2x2_impl(Engine& e, int chi, const ctmb_site* const s4[4], int op
     e.ws.release(mark);
 }
 
+// One- and two-site density matrices (ctm/generic/rdm.py: rdm1x1_dl :114-258, rdm2x1_dl :352-500, rdm1x2_dl :672-826), built
+// from OPEN enlarged corners closed by the remaining edge tensors; the strings are those of oracle/ctm_oracle.py
+// (rdm1x1 / rdm2x1 / rdm1x2), which is pinned element-wise against the reference.   kind: 0 = 1x1, 1 = 2x1, 2 = 1x2.
+static void rdm_small_impl(Engine& e, int kind, int chi, const ctmb_site* const s2[2], void* rho) {
+    CTMB_CHECK(kind >= 0 && kind <= 2 && chi > 0 && s2 && s2[0] && (kind == 0 || s2[1]), "bad arguments");
+    const size_t mark = e.ws.mark();
+    const ctmb_site& s0 = *s2[0];
+    const ctmb_site& s1 = kind == 0 ? s0 : *s2[1];
+    CTMB_CHECK(s0.dims[0] > 0 && s1.dims[0] > 0, "density matrices need the single-layer on-site tensors");
+    const int64_t p0 = s0.dims[0], p1 = s1.dims[0];
+    auto open_corner = [&](int ck, const ctmb_site& s, int64_t& rows, int64_t& cols) {
+        corner_shape(ck, s, chi, rows, cols);
+        void* buf = e.ws.alloc((size_t)rows * cols * s.dims[0] * s.dims[0] * e.esize());
+        const CornerSpec& cs = CORNERS[ck];
+        std::vector<Tn> ops = {env_C(s, cs.c, chi, cs.lc), env_T(s, cs.t1, chi, cs.l1), env_T(s, cs.t2, chi, cs.l2)};
+        std::vector<Engine::ChainJob> jobs = {sl_job(ops, 3, cs.la, s, cs.out, buf, nullptr, true)};
+        e.chain_multi(jobs);
+        return buf;
+    };
+    // edge pieces: chains of plain environment tensors into a contiguous buffer with the given output labels
+    auto edge = [&](std::vector<Tn> ops, const char* out_lab) {
+        std::map<char, int64_t> ext;
+        for (const Tn& t : ops) for (int d = 0; d < t.nd; ++d) ext[t.idx[d]] = t.dim[d];
+        std::vector<int64_t> od; size_t count = 1;
+        for (const char* q = out_lab; *q; ++q) { od.push_back(ext[*q]); count *= (size_t)ext[*q]; }
+        void* buf = e.ws.alloc(count * e.esize());
+        Engine::ChainJob job;
+        job.ops = ops; job.conj.assign(ops.size(), false);
+        job.out = make_tn(buf, std::string(out_lab), od);
+        std::vector<Engine::ChainJob> jobs = {job};
+        e.chain_multi(jobs);
+        return job.out;
+    };
+    int64_t r0, c0;
+    void* LU = open_corner(CTMB_LU, s0, r0, c0);                              // [(l,D),(x,R),s,S]
+    if (kind == 0) {
+        Tn E = edge({env_C(s0, 1, chi, "xa"), env_T(s0, 3, chi, "aRb"), env_C(s0, 2, chi, "bc"), env_T(s0, 2, chi, "Dec"),
+                     env_C(s0, 3, chi, "le")}, "lDxR");
+        CTMB_CHECK(E.dim[0] * E.dim[1] == r0 && E.dim[2] * E.dim[3] == c0, "the edge of the site does not fit its enlarged corner");
+        // (dummy mode w of extent 1: every output label comes from one operand, the second contributes none otherwise)
+        e.contract(make_tn(LU, "yzsS", {r0, c0, p0, p0}), false, make_tn(E.ptr, "yzw", {r0, c0, 1}), false,
+                   make_tn(rho, "sSw", {p0, p0, 1}));
+    } else if (kind == 1) {
+        int64_t r1, c1;
+        void* RU = open_corner(CTMB_RU, s1, r1, c1);                          // [(e,l),(c,f),j,J]
+        Tn B0 = edge({env_C(s0, 3, chi, "le"), env_T(s0, 2, chi, "Dec")}, "lDc");
+        Tn B1 = edge({env_T(s1, 2, chi, "fEb"), env_C(s1, 2, chi, "cb")}, "cfE");
+        CTMB_CHECK(B0.dim[0] * B0.dim[1] == r0 && B1.dim[0] * B1.dim[1] == c1 && c0 == r1 && B0.dim[2] == B1.dim[2],
+                   "the two sites of the 2x1 patch do not fit together");
+        Tn L = e.temp("czsS", {B0.dim[2], c0, p0, p0});
+        Tn R = e.temp("tEjJ", {r1, B1.dim[2], p1, p1});
+        e.contract(make_tn(LU, "yzsS", {r0, c0, p0, p0}), false, make_tn(B0.ptr, "yc", {r0, B0.dim[2]}), false, L);
+        e.contract(make_tn(RU, "tqjJ", {r1, c1, p1, p1}), false, make_tn(B1.ptr, "qE", {c1, B1.dim[2]}), false, R);
+        e.flush();
+        e.contract(L, false, relabel(R, "zcjJ"), false, make_tn(rho, "sjSJ", {p0, p1, p0, p1}));
+    } else {
+        int64_t r1, c1;
+        void* LD = open_corner(CTMB_LD, s1, r1, c1);                          // [(c,u),(e,r),k,K]
+        Tn Rr = edge({env_C(s0, 1, chi, "xa"), env_T(s0, 3, chi, "aRb")}, "xRb");
+        Tn Rb = edge({env_T(s1, 3, chi, "Brc"), env_C(s1, 2, chi, "ce")}, "erB");
+        CTMB_CHECK(Rr.dim[0] * Rr.dim[1] == c0 && Rb.dim[0] * Rb.dim[1] == c1 && r0 == r1 && Rr.dim[2] == Rb.dim[2],
+                   "the two sites of the 1x2 patch do not fit together");
+        Tn Tp = e.temp("ybsS", {r0, Rr.dim[2], p0, p0});
+        Tn Bt = e.temp("tBkK", {r1, Rb.dim[2], p1, p1});
+        e.contract(make_tn(LU, "yzsS", {r0, c0, p0, p0}), false, make_tn(Rr.ptr, "zb", {c0, Rr.dim[2]}), false, Tp);
+        e.contract(make_tn(LD, "tqkK", {r1, c1, p1, p1}), false, make_tn(Rb.ptr, "qB", {c1, Rb.dim[2]}), false, Bt);
+        e.flush();
+        e.contract(Tp, false, relabel(Bt, "ybkK"), false, make_tn(rho, "skSK", {p0, p1, p0, p1}));
+    }
+    e.flush();
+    e.ws.release(mark);
+}
+
 // _sym_pos_def_matrix (ctm/generic/rdm.py:38-57)
 static void sym_pos_def_impl(Engine& e, const void* raw, int n, int sym_pos_def, const ctmb_options& o, void* out) {
     CTMB_CHECK(n > 0, "bad arguments");
@@ -1315,6 +1388,22 @@ size_t ctmb_rdm2x2_workspace(ctmb_handle_t h, ctmb_dtype dt, int chi, const ctmb
     CTMB_TRY
     begin_dry(h, dt);
     rdm2x2_impl(h->h.eng, chi, sites, open_mask, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+int ctmb_rdm_small(ctmb_handle_t h, ctmb_dtype dt, int kind, int chi, const ctmb_site* const sites[2], void* rho,
+                   void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    rdm_small_impl(h->h.eng, kind, chi, sites, rho);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_rdm_small_workspace(ctmb_handle_t h, ctmb_dtype dt, int kind, int chi, const ctmb_site* const sites[2]) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    rdm_small_impl(h->h.eng, kind, chi, sites, nullptr);
     return h->h.eng.ws.peak() + 256;
     CTMB_CATCH(0)
 }

@@ -1,6 +1,8 @@
-"""Drop-in for the 2x2 reduced density matrix of ctm/generic/rdm.py (rdm2x2 :1306-1360, rdm2x2_legacy :1362-1592):
-the energy of the J1-J2 scripts is tr(rho_2x2 h_p) over the plaquettes of the unit cell (models/j1j2.py:223-247).
-The network -- four enlarged corners with open physical legs, two halves, one trace -- is contracted by libctmb."""
+"""Drop-in for the reduced density matrices of ctm/generic/rdm.py that the J1-J2 scripts evaluate: rdm2x2 (:1306-1360,
+rdm2x2_legacy :1362-1592) -- the energy is tr(rho_2x2 h_p) over the plaquettes of the unit cell (models/j1j2.py:223-247)
+-- and rdm1x1 / rdm2x1 / rdm1x2 (:71-112, 304-350, 622-670) behind the magnetisations and nearest-neighbour correlations
+(models/j1j2.py eval_obs).  The networks -- enlarged corners with open physical legs closed by the remaining edge
+tensors -- are contracted by libctmb."""
 from ... import config as cfg
 
 
@@ -23,3 +25,43 @@ def rdm2x2(coord, state, env, open_sites=[0, 1, 2, 3], unroll=[], checkpoint_unr
 
 def rdm2x2_legacy(coord, state, env, sym_pos_def=False, verbosity=0):
     return _engine().rdm2x2(coord, state, env, sym_pos_def=sym_pos_def)
+
+
+def _no_operator(operator):
+    if operator is not None:
+        raise NotImplementedError("libctmb returns the density matrix; contract it with the operator on the caller's side")
+
+
+def rdm1x1(coord, state, env, mode='sl', operator=None, sym_pos_def=False, force_cpu=False, verbosity=0):
+    r""":return: 1-site reduced density matrix with indices :math:`s;s'` (ctm/generic/rdm.py:71-112); ``mode`` selects
+    between equivalent contraction orders in the reference and is ignored"""
+    _no_operator(operator)
+    return _engine().rdm_small('1x1', coord, state, env, sym_pos_def=sym_pos_def)
+
+
+def rdm2x1(coord, state, env, mode='sl', sym_pos_def=False, force_cpu=False, unroll=False, checkpoint_unrolled=False,
+           checkpoint_on_device=False, verbosity=0):
+    r""":return: 2-site reduced density matrix :math:`s_0s_1;s'_0s'_1`, s1 at ``coord+(1,0)`` (rdm.py:304-350)"""
+    return _engine().rdm_small('2x1', coord, state, env, sym_pos_def=sym_pos_def)
+
+
+def rdm1x2(coord, state, env, mode='sl', sym_pos_def=False, force_cpu=False, unroll=False, checkpoint_unrolled=False,
+           checkpoint_on_device=False, verbosity=0):
+    r""":return: 2-site reduced density matrix :math:`s_0s_1;s'_0s'_1`, s1 at ``coord+(0,1)`` (rdm.py:622-670)"""
+    return _engine().rdm_small('1x2', coord, state, env, sym_pos_def=sym_pos_def)
+
+
+def rdm1x1_dl(coord, state, env, operator=None, sym_pos_def=False, force_cpu=False, verbosity=0):
+    _no_operator(operator)
+    return _engine().rdm_small('1x1', coord, state, env, sym_pos_def=sym_pos_def)
+
+
+def rdm2x1_dl(coord, state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
+    return _engine().rdm_small('2x1', coord, state, env, sym_pos_def=sym_pos_def)
+
+
+def rdm1x2_dl(coord, state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
+    return _engine().rdm_small('1x2', coord, state, env, sym_pos_def=sym_pos_def)
+
+
+rdm1x1_sl, rdm2x1_sl, rdm1x2_sl = rdm1x1_dl, rdm2x1_dl, rdm1x2_dl

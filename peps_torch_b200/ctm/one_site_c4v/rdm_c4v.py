@@ -1,5 +1,6 @@
-"""Drop-in for the plaquette density matrices of ctm/one_site_c4v/rdm_c4v.py used by the C4v J1-J2 energy
-(models/j1j2.py:641-679): rdm2x2_NN_lowmem(_sl) :1117-1202, rdm2x2_NNN_lowmem(_sl) :1286-1371, rdm2x2 :1446-1546.
+"""Drop-in for the density matrices of ctm/one_site_c4v/rdm_c4v.py used by the C4v J1-J2 energy and observables
+(models/j1j2.py:641-679, eval_obs): rdm2x2_NN_lowmem(_sl) :1117-1202, rdm2x2_NNN_lowmem(_sl) :1286-1371, rdm2x2 :1446-1546,
+rdm1x1(_sl) :168-392, rdm2x1(_sl) :394-665.
 The reference rotates ONE enlarged corner; here the single (C, T) pair is rotated into the eight tensors of a generic
 1x1-cell environment (env_c4v.py:25-45 vs env.py:57-77) and libctmb contracts the generic 2x2 network, tracing the
 sites that are not kept (closed corners)."""
@@ -42,3 +43,19 @@ rdm2x2_NNN_lowmem = rdm2x2_NNN_lowmem_sl
 def rdm2x2(state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
     r""":return: 4-site density matrix :math:`s_0s_1s_2s_3;s'_0s'_1s'_2s'_3` (rdm_c4v.py:1446-1546)"""
     return _rdm(state, env, (0, 1, 2, 3), sym_pos_def)
+
+
+def rdm1x1_sl(state, env, sym_pos_def=False, verbosity=0):
+    r""":return: 1-site density matrix :math:`s;s'` (rdm_c4v.py:266-392)"""
+    t4, chi = _generic_tensors(state, env)
+    return _engine().rdm_small_sites('1x1', t4[:1], chi, sym_pos_def)
+
+
+def rdm2x1_sl(state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
+    r""":return: 2-site density matrix :math:`s_0s_1;s'_0s'_1` of a nearest-neighbour pair (rdm_c4v.py:530-665)"""
+    t4, chi = _generic_tensors(state, env)
+    return _engine().rdm_small_sites('2x1', t4[:2], chi, sym_pos_def)
+
+
+rdm1x1 = rdm1x1_sl
+rdm2x1 = rdm2x1_sl

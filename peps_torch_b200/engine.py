@@ -452,6 +452,35 @@ class CtmEngine:
         check(lib.ctmb_rdm2x2(self._h, dt, chi, arr, mask, _ptr(rho), _ptr(ws), ws.numel(), self._stream()))
         return rho if raw else self.sym_pos_def(rho, sym_pos_def)
 
+    def rdm_small_sites(self, kind, tensors2, chi, sym_pos_def=False, raw=False):
+        """One- / two-site density matrix from explicit per-site data (see rdm2x2_sites); kind '1x1', '2x1' (second site
+        to the right) or '1x2' (second site below)."""
+        k = {'1x1': 0, '2x1': 1, '1x2': 2}[kind]
+        keep = []
+        structs = [self._site(a, Cs, Ts, keep) for (a, Cs, Ts) in tensors2]
+        if len(structs) == 1:
+            structs = structs * 2
+        arr = (C.POINTER(_lib.Site) * 2)(*[C.pointer(s) for s in structs[:2]])
+        a0 = tensors2[0][0]
+        dt = _dt(a0)
+        dims = [t[0].shape[0] for t in tensors2[:1 if k == 0 else 2]]
+        rho = torch.empty(dims + dims, dtype=a0.dtype, device=self.device)
+        nbytes = lib.ctmb_rdm_small_workspace(self._h, dt, k, chi, arr)
+        if nbytes == 0:
+            raise _lib.CtmbError(lib.ctmb_last_error().decode())
+        ws = self._workspace(nbytes)
+        check(lib.ctmb_rdm_small(self._h, dt, k, chi, arr, _ptr(rho), _ptr(ws), ws.numel(), self._stream()))
+        return rho if raw else self.sym_pos_def(rho, sym_pos_def)
+
+    def rdm_small(self, kind, coord, state, env, sym_pos_def=False, raw=False):
+        """rdm1x1 / rdm2x1 / rdm1x2 (ctm/generic/rdm.py:71-112, 304-350, 622-670) at vertex `coord`."""
+        shifts = {'1x1': [(0, 0)], '2x1': [(0, 0), (1, 0)], '1x2': [(0, 0), (0, 1)]}[kind]
+        t2 = []
+        for dx, dy in shifts:
+            c = state.vertexToSite((coord[0] + dx, coord[1] + dy))
+            t2.append((state.sites[c], [env.C[(c, k)] for k in C_KEYS], [env.T[(c, k)] for k in T_KEYS]))
+        return self.rdm_small_sites(kind, t2, env.chi, sym_pos_def, raw)
+
     def rdm2x2(self, coord, state, env, open_sites=(0, 1, 2, 3), sym_pos_def=False, raw=False):
         """rdm2x2 (ctm/generic/rdm.py:1306-1592): rho[s0,s1,s2,s3; s0',s1',s2',s3'] of the plaquette with upper-left
         vertex `coord` (s0 = coord, s1 = coord+(1,0), s2 = coord+(0,1), s3 = coord+(1,1))."""

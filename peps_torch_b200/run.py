@@ -57,23 +57,15 @@ def enable(engine_factory=None):
     # the plaquette density matrices behind the energies of the J1-J2 scripts (models/j1j2.py:223-247,641-679) run on
     # libctmb as well
     rdm = importlib.import_module('ctm.generic.rdm')
-    rdm.rdm2x2 = ours_rdm.rdm2x2
-    rdm.rdm2x2_legacy = ours_rdm.rdm2x2_legacy
+    for name in ('rdm2x2', 'rdm2x2_legacy', 'rdm1x1', 'rdm2x1', 'rdm1x2', 'rdm1x1_dl', 'rdm2x1_dl', 'rdm1x2_dl',
+                 'rdm1x1_sl', 'rdm2x1_sl', 'rdm1x2_sl'):
+        setattr(rdm, name, getattr(ours_rdm, name))
     rdm_c4v = importlib.import_module('ctm.one_site_c4v.rdm_c4v')
-    for name in ('rdm2x2_NN_lowmem_sl', 'rdm2x2_NNN_lowmem_sl', 'rdm2x2_NN_lowmem', 'rdm2x2_NNN_lowmem', 'rdm2x2'):
+    for name in ('rdm2x2_NN_lowmem_sl', 'rdm2x2_NNN_lowmem_sl', 'rdm2x2_NN_lowmem', 'rdm2x2_NNN_lowmem', 'rdm2x2',
+                 'rdm1x1', 'rdm1x1_sl', 'rdm2x1', 'rdm2x1_sl'):
         setattr(rdm_c4v, name, getattr(ours_rdm_c4v, name))
-    # Without opt_einsum the 'sl' one/two-site RDMs of the reference do not run (ctm/generic/rdm.py:107-112,292,
-    # 343-351,560): route them to the reference's own pure-torch double-layer implementations.
-    try:
-        import opt_einsum                                       # noqa: F401
-    except ImportError:
-        def _dl(f):
-            def wrapped(*a, mode='sl', unroll=False, checkpoint_unrolled=False, checkpoint_on_device=False, **kw):
-                return f(*a, **kw)
-            return wrapped
-        for name in ('rdm1x1', 'rdm2x1', 'rdm1x2'):
-            if hasattr(rdm, name + '_dl'):
-                setattr(rdm, name, _dl(getattr(rdm, name + '_dl')))
+    # (this also removes the reference's dependence on opt_einsum for these functions: without it its 'sl' one- and
+    # two-site RDMs and the rdm2x2 dispatch do not run at all, ctm/generic/rdm.py:107-112,292,343-351,560,1354-1362)
     return ref, ref_c4v
 
 

@@ -129,3 +129,18 @@ class OracleEngine:
         C = {(c, k): t[1][i] for c, t in zip(coords, tensors4) for i, k in enumerate(C_KEYS)}
         T = {(c, k): t[2][i] for c, t in zip(coords, tensors4) for i, k in enumerate(T_KEYS)}
         return orc.rdm2x2((0, 0), sites, orc.v2s_4site, C, T, raw=raw, open_sites=tuple(open_sites), sym_pos_def=sym_pos_def)
+
+    def rdm_small(self, kind, coord, state, env, sym_pos_def=False, raw=False):
+        f = {'1x1': orc.rdm1x1, '2x1': orc.rdm2x1, '1x2': orc.rdm1x2}[kind]
+        return f(coord, state.sites, state.vertexToSite, env.C, env.T, raw=raw, sym_pos_def=sym_pos_def)
+
+    def rdm_small_sites(self, kind, tensors2, chi, sym_pos_def=False, raw=False):
+        from peps_torch_b200.engine import C_KEYS, T_KEYS
+        coords = [(0, 0), (1, 0)] if kind != '1x2' else [(0, 0), (0, 1)]
+        t2 = list(tensors2) if len(tensors2) > 1 else [tensors2[0], tensors2[0]]
+        sites = OrderedDict((c, t[0]) for c, t in zip(coords, t2))
+        C = {(c, k): t[1][i] for c, t in zip(coords, t2) for i, k in enumerate(C_KEYS)}
+        T = {(c, k): t[2][i] for c, t in zip(coords, t2) for i, k in enumerate(T_KEYS)}
+        v2s = (lambda c: (c[0] % 2, 0)) if kind != '1x2' else (lambda c: (0, c[1] % 2))
+        f = {'1x1': orc.rdm1x1, '2x1': orc.rdm2x1, '1x2': orc.rdm1x2}[kind]
+        return f((0, 0), sites, v2s, C, T, raw=raw, sym_pos_def=sym_pos_def)

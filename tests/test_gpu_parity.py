@@ -646,3 +646,41 @@ def test_c4v_rdms_and_energy_against_reference_fixture(eng, dev, name):
         e = e + 2.0 * meta['j2'] * torch.einsum('ijab,ijab', rdm_c4v.rdm2x2_NNN_lowmem_sl(stc, envc, sym_pos_def=True).cpu(), SS)
     e_ref = float(z['energy'][0])
     assert abs(float(e.real) - e_ref) < 1e-10 * abs(e_ref)
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128',
+                                  'kagome_1site_D2_chi8_A'])
+def test_small_rdms_against_oracle(eng, dev, name):
+    """rdm1x1 / rdm2x1 / rdm1x2 (ctm/generic/rdm.py:71-112,304-350,622-670): deterministic contractions, element-wise."""
+    from peps_torch_b200.ctm.generic import rdm
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'mid_')
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    env = H.Env(chi, H.to_dev(C, dev), H.to_dev(T, dev))
+    for coord in sites:
+        for f, g in ((rdm.rdm1x1, orc.rdm1x1), (rdm.rdm2x1, orc.rdm2x1), (rdm.rdm1x2, orc.rdm1x2)):
+            for spd in (False, True):
+                if spd and sites[coord].shape[0] ** 2 > 160 and f is not rdm.rdm1x1:
+                    continue                                   # kagome p = 8: 64 x 64 is fine, 4096 x 4096 is not needed
+                r_ref = g(coord, sites, v2s, C, T, sym_pos_def=spd)
+                r = f(coord, st, env, sym_pos_def=spd)
+                assert r.shape == r_ref.shape and float((r.cpu() - r_ref).abs().max()) < 1e-12, (f.__name__, coord, spd)
+
+
+@pytest.mark.parametrize('name', C4V)
+def test_c4v_small_rdms_against_oracle(eng, dev, name):
+    from peps_torch_b200.ctm.one_site_c4v import rdm_c4v
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    z, meta = H.load_golden(name)
+    a = torch.from_numpy(z['site'])
+    Cc, Tc = torch.from_numpy(z['final_C']), torch.from_numpy(z['final_T'])
+    stc = IPEPS_C4V(a.to(dev))
+    envc = ENV_C4V(meta['chi'], stc)
+    envc.C[envc.keyC], envc.T[envc.keyT] = Cc.to(dev), Tc.to(dev)
+    for spd in (False, True):
+        assert float((rdm_c4v.rdm1x1_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm_small_c4v('1x1', a, Cc, Tc, spd)).abs().max()) < 1e-12
+        assert float((rdm_c4v.rdm2x1_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm_small_c4v('2x1', a, Cc, Tc, spd)).abs().max()) < 1e-12

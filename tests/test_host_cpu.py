@@ -195,6 +195,11 @@ def test_planning_only_handle_validates_every_entry_point_and_never_computes():
                 nbytes = lib.ctmb_rdm2x2_workspace(eng._h, dt, chi, ptrs, mask)
                 assert (nbytes > 0) == (not dl), (name, dl, mask, lib.ctmb_last_error())
             assert lib.ctmb_rdm2x2_workspace(eng._h, dt, chi, ptrs, 0) == 0
+            two = (C.POINTER(_lib.Site) * 2)(C.pointer(arr[0]), C.pointer(arr[1 % len(coords)]))
+            for kind in range(3):
+                # the sites of the fixtures have equal bond dimensions, so any pair of them plans
+                nbytes = lib.ctmb_rdm_small_workspace(eng._h, dt, kind, chi, two)
+                assert (nbytes > 0) == (not dl), (name, dl, kind, lib.ctmb_last_error())
             # a compute call on the planning handle is an error, not a fallback
             with pytest.raises(_lib.CtmbError):
                 eng.move_generic((0, -1), st, env)
@@ -237,3 +242,9 @@ def test_host_rdm_modules_map_sites_and_env_correctly(monkeypatch):
     assert H.maxrel(rdm_c4v.rdm2x2_NN_lowmem_sl(stc, envc, sym_pos_def=True), orc.rdm2x2_c4v(a, Cc, Tc, (0, 1), True)) < 1e-13
     assert H.maxrel(rdm_c4v.rdm2x2_NNN_lowmem_sl(stc, envc), orc.rdm2x2_c4v(a, Cc, Tc, (0, 3))) < 1e-13
     assert H.maxrel(rdm_c4v.rdm2x2(stc, envc), orc.rdm2x2_c4v(a, Cc, Tc)) < 1e-13
+    assert H.maxrel(rdm_c4v.rdm1x1_sl(stc, envc), orc.rdm_small_c4v('1x1', a, Cc, Tc)) < 1e-13
+    assert H.maxrel(rdm_c4v.rdm2x1_sl(stc, envc, sym_pos_def=True), orc.rdm_small_c4v('2x1', a, Cc, Tc, True)) < 1e-13
+    for f, g in ((rdm.rdm1x1, orc.rdm1x1), (rdm.rdm2x1, orc.rdm2x1), (rdm.rdm1x2, orc.rdm1x2)):
+        assert torch.equal(f((0, 1), st, env), g((0, 1), sites, orc.v2s_4site, C, T))
+    with pytest.raises(NotImplementedError):
+        rdm.rdm1x1((0, 0), st, env, operator=torch.eye(2))

@@ -225,3 +225,50 @@ def test_oracle_c4v_rdms_match_reference_elementwise(ref, name):
         assert float((rdm_c4v.rdm2x2_NNN_lowmem_sl(st, env, sym_pos_def=spd)
                       - orc.rdm2x2_c4v(a, C, T, (0, 3), spd)).abs().max()) < 1e-12
         assert float((rdm_c4v.rdm2x2(st, env, sym_pos_def=spd) - orc.rdm2x2_c4v(a, C, T, (0, 1, 2, 3), spd)).abs().max()) < 1e-12
+
+
+def test_oracle_small_rdms_match_reference_elementwise(ref):
+    """rdm1x1_dl / rdm2x1_dl / rdm1x2_dl (ctm/generic/rdm.py:114-258,352-500,672-826) element-wise."""
+    import helpers as H
+    import ctm_oracle as orc
+    from ipeps.ipeps import IPEPS
+    from ctm.generic.env import ENV
+    from ctm.generic import rdm
+    for name in ('generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128', 'generic_4site_D3_chi12_B'):
+        z, meta = H.load_golden(name)
+        sites = H.golden_sites(z)
+        v2s, lX, lY = H.v2s_for(sites)
+        C, T = H.golden_env(z, 'mid_')
+        ref.global_args.dtype = 'complex128' if sites[(0, 0)].is_complex() else 'float64'
+        st = IPEPS(sites={c: t.clone() for c, t in sites.items()}, vertexToSite=v2s, lX=lX, lY=lY)
+        env = ENV(meta['chi'], st)
+        env.C, env.T = dict(C), dict(T)
+        for coord in sites:
+            for spd in (False, True):
+                for f_ref, f_orc in ((rdm.rdm1x1_dl, orc.rdm1x1), (rdm.rdm2x1_dl, orc.rdm2x1), (rdm.rdm1x2_dl, orc.rdm1x2)):
+                    r_ref = f_ref(coord, st, env, sym_pos_def=spd)
+                    r_orc = f_orc(coord, sites, v2s, C, T, sym_pos_def=spd)
+                    assert r_ref.shape == r_orc.shape
+                    assert float((r_ref - r_orc).abs().max()) < 1e-13, (name, coord, spd, f_orc.__name__)
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_oracle_c4v_small_rdms_match_reference_elementwise(ref, name):
+    import helpers as H
+    import ctm_oracle as orc
+    from ctm.one_site_c4v import rdm_c4v
+    from ctm.one_site_c4v.env_c4v import ENV_C4V
+    from ipeps.ipeps_c4v import IPEPS_C4V
+    z, meta = H.load_golden(name)
+    a = torch.from_numpy(z['site'])
+    ref.global_args.dtype = 'complex128' if a.is_complex() else 'float64'
+    C, T = torch.from_numpy(z['final_C']), torch.from_numpy(z['final_T'])
+    st = IPEPS_C4V(a.clone())
+    env = ENV_C4V(meta['chi'], st)
+    env.C[env.keyC], env.T[env.keyT] = C.clone(), T.clone()
+    for spd in (False, True):
+        for f_ref, kind in ((rdm_c4v.rdm1x1_sl, '1x1'), (rdm_c4v.rdm1x1, '1x1'), (rdm_c4v.rdm2x1_sl, '2x1'), (rdm_c4v.rdm2x1, '2x1')):
+            r_ref = f_ref(st, env, sym_pos_def=spd)
+            r_orc = orc.rdm_small_c4v(kind, a, C, T, spd)
+            assert r_ref.shape == r_orc.shape
+            assert float((r_ref - r_orc).abs().max()) < 1e-12, (kind, spd, f_ref.__name__)
