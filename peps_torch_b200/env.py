@@ -1,8 +1,16 @@
-"""Environment containers and 'CTMRG' initialisation with the reference's layout
-(ctm/generic/env.py:14-109,367-536; ctm/one_site_c4v/env_c4v.py:7-76,257-311).
-Initialisation runs once per CTM run on a handful of D^2-sized tensors; it uses torch ops
-on the state's device and is not part of the timed hot path."""
+"""Environment containers with the reference's layout and API (ctm/generic/env.py:14-233: ENV with clone / detach /
+extend / min_chi / get_spectra / get_site_env_t; ctm/one_site_c4v/env_c4v.py:7-164: ENV_C4V), the 'CTMRG' and 'RANDOM'
+initialisations (env.py:235-272,367-536; env_c4v.py:166-311) and the corner-spectrum convergence criterion
+(env.py:816-875).  Initialisation runs once per CTM run on a handful of D^2-sized tensors; it uses torch ops on the
+state's device and is not part of the timed hot path."""
+from math import sqrt
 import torch
+from . import config as cfg
+
+
+class EnvError(RuntimeError):
+    def __init__(self, message="Environment error"):
+        super().__init__(message)
 
 _INIT_C = {(-1, -1): ('mijef,mijab->eafb', (3, 4)), (1, -1): ('miefj,miabj->eafb', (2, 3)),
            (1, 1): ('mefij,mabij->eafb', (1, 2)), (-1, 1): ('meijf,maijb->eafb', (1, 4))}
@@ -27,11 +35,67 @@ class ENV:
                 for vec in [(-1, -1), (-1, 1), (1, -1), (1, 1)]:
                     self.C[(coord, vec)] = torch.empty((chi, chi), dtype=self.dtype, device=self.device)
 
-    def clone(self):
-        e = ENV(self.chi)
+    def _like(self, chi=None):
+        e = ENV(self.chi if chi is None else chi)
+        if hasattr(self, 'dtype'):
+            e.dtype, e.device = self.dtype, self.device
+        return e
+
+    def __str__(self):
+        lines = [f"ENV chi={self.chi}"]
+        lines += [f"C({k[0]} {k[1]}): {tuple(t.shape)}" for k, t in self.C.items()]
+        lines += [f"T({k[0]} {k[1]}): {tuple(t.shape)}" for k, t in self.T.items()]
+        return "\n".join(lines)
+
+    def clone(self, ctm_args=None, global_args=None):
+        """Copy of the environment (env.py:118-133; keeps gradient tracking)."""
+        e = self._like()
         e.C = {k: v.clone() for k, v in self.C.items()}
         e.T = {k: v.clone() for k, v in self.T.items()}
         return e
+
+    def detach(self, ctm_args=None, global_args=None):
+        """Detached view of the environment (env.py:135-151)."""
+        e = self._like()
+        e.C = {k: v.detach() for k, v in self.C.items()}
+        e.T = {k: v.detach() for k, v in self.T.items()}
+        return e
+
+    def detach_(self):
+        for t in list(self.C.values()) + list(self.T.values()):
+            t.detach_()
+
+    def min_chi(self):
+        """Smallest environment bond dimension over all corners (env.py:157-162)."""
+        return min(min(c.shape) for c in self.C.values())
+
+    def extend(self, new_chi, ctm_args=None, global_args=None):
+        """New environment of dimension ``new_chi``: the leading min(chi, new_chi) block of every environment leg is
+        kept, the rest is zero (env.py:164-202).  Environment legs: both of C; legs (0,2) of T(0,-1) and T(1,0),
+        (0,1) of T(-1,0), (1,2) of T(0,1)."""
+        e = self._like(new_chi)
+        x = min(self.chi, new_chi)
+        env_legs = {(0, -1): (0, 2), (1, 0): (0, 2), (-1, 0): (0, 1), (0, 1): (1, 2)}
+        for k, c in self.C.items():
+            out = c.new_zeros((new_chi, new_chi))
+            out[:x, :x] = c[:x, :x].detach()
+            e.C[k] = out
+        for k, t in self.T.items():
+            if k[1] not in env_legs:
+                raise Exception(f"Unexpected direction {k[1]}")
+            shape = [new_chi if i in env_legs[k[1]] else t.shape[i] for i in range(3)]
+            sl = tuple(slice(0, x) if i in env_legs[k[1]] else slice(None) for i in range(3))
+            out = t.new_zeros(shape)
+            out[sl] = t[sl].detach()
+            e.T[k] = out
+        return e
+
+    def get_site_env_t(self, coord, state):
+        """(C1, C2, C3, C4, T1, T2, T3, T4) of the site at ``coord``: corners clockwise from the upper left, half-row /
+        column tensors clockwise from the top (env.py:211-233)."""
+        s = state.vertexToSite(coord)
+        return tuple(self.C[(s, v)] for v in ((-1, -1), (1, -1), (1, 1), (-1, 1))) \
+            + tuple(self.T[(s, v)] for v in ((0, -1), (1, 0), (0, 1), (-1, 0)))
 
     def get_spectra(self):
         out = {}
@@ -41,8 +105,31 @@ class ENV:
         return out
 
 
-def init_env(state, env):
-    """'CTMRG' initialisation: partial traces of a (x) a*, /max|.|, zero-padded to chi."""
+def init_random(env, verbosity=0):
+    """All C and T uniform in [0,1) (env.py:268-272)."""
+    for key, t in env.C.items():
+        env.C[key] = torch.rand(t.shape, dtype=t.dtype, device=t.device)
+    for key, t in env.T.items():
+        env.T[key] = torch.rand(t.shape, dtype=t.dtype, device=t.device)
+
+
+def init_env(state, env, ctm_args=None):
+    """Initialise ``env`` as CTMARGS.ctm_env_init_type says (env.py:235-265): 'CTMRG' (default) or 'RANDOM'; the
+    product-state and open-boundary variants ('PROD', 'CTMRG_OBC') are not built here."""
+    kind = getattr(ctm_args if ctm_args is not None else cfg.ctm_args, 'ctm_env_init_type', 'CTMRG')
+    if next(iter(state.sites.values())).dim() == 4 and kind not in ('PROD', 'CTMRG_OBC', 'RANDOM'):
+        raise RuntimeError("Incompatible ENV initialization")
+    if kind == 'RANDOM':
+        return init_random(env)
+    if kind in ('PROD', 'CTMRG_OBC'):
+        raise NotImplementedError(f"ctm_env_init_type='{kind}' is not built in peps_torch_b200; use the reference's init_env")
+    if kind != 'CTMRG':
+        raise ValueError("Invalid environment initialization: " + str(kind))
+    init_from_ipeps_pbc(state, env)
+
+
+def init_from_ipeps_pbc(state, env, verbosity=0):
+    """'CTMRG' initialisation: partial traces of a (x) a*, /max|.|, zero-padded to chi (env.py:367-536)."""
     chi = env.chi
     for coord in state.sites.keys():
         for vec, (ein, legs) in _INIT_C.items():
@@ -66,6 +153,38 @@ def init_env(state, env):
             env.T[(coord, vec)] = out
 
 
+@torch.no_grad()
+def ctmrg_conv_specC(state, env, history, p='inf', ctm_args=None):
+    """Convergence criterion on the normalised singular spectra of all corners (env.py:816-875): conv_crit = sqrt of the
+    largest (p='inf') or of the summed (p='fro' / 2) squared 2-norm difference between the spectra of consecutive
+    iterations.  Same history dict ('spec', 'diffs', 'conv_crit') and return value as the reference; the differences are
+    reduced on the device and read back with ONE host synchronisation per call (the reference synchronises once per
+    corner)."""
+    ctm_args = ctm_args if ctm_args is not None else cfg.ctm_args
+    if not history:
+        history = {'spec': [], 'diffs': [], 'conv_crit': []}
+    spec = {k: s.sort(descending=True)[0] for k, s in env.get_spectra().items()}
+    conv_crit, diffs = float('inf'), None
+    if history['spec']:
+        old = history['spec'][-1]
+        per_corner = []
+        for k, s in spec.items():
+            o = old[k]
+            m = min(s.shape[0], o.shape[0])
+            # spectra of different length: the missing tail counts as zeros
+            per_corner.append(((s[:m] - o[:m]) ** 2).sum() + (s[m:] ** 2).sum() + (o[m:] ** 2).sum())
+        diffs = torch.stack(per_corner).tolist()                 # the one synchronisation
+        if p in ('fro', 2):
+            conv_crit = sqrt(sum(diffs))
+        elif p in (float('inf'), 'inf'):
+            conv_crit = sqrt(max(diffs))
+    history['spec'].append(spec)
+    history['diffs'].append(diffs)
+    history['conv_crit'].append(conv_crit)
+    done = (len(history['diffs']) > 1 and conv_crit < ctm_args.ctm_conv_tol) or len(history['diffs']) >= ctm_args.ctm_max_iter
+    return bool(done), history
+
+
 class ENV_C4V:
     def __init__(self, chi, state=None, bond_dim=None):
         assert state is not None or bond_dim, "either state or bond_dim must be supplied"
@@ -87,10 +206,85 @@ class ENV_C4V:
     def get_T(self):
         return self.T[self.keyT]
 
+    def _like(self, chi=None):
+        e = ENV_C4V(self.chi if chi is None else chi, bond_dim=self.bond_dim)
+        if hasattr(self, 'dtype'):
+            e.dtype, e.device = self.dtype, self.device
+        return e
 
-def init_env_c4v(state, env):
-    """env_c4v.py:257-311: C = diag(eig of the D^2 x D^2 corner), T rotated into its eigenbasis."""
+    def clone(self, ctm_args=None, global_args=None):
+        """env_c4v.py:92-108"""
+        e = self._like()
+        e.C[e.keyC], e.T[e.keyT] = self.get_C().clone(), self.get_T().clone()
+        return e
+
+    def detach(self, ctm_args=None, global_args=None):
+        """env_c4v.py:110-127"""
+        e = self._like()
+        e.C[e.keyC], e.T[e.keyT] = self.get_C().detach(), self.get_T().detach()
+        return e
+
+    def detach_(self):
+        self.get_C().detach_()
+        self.get_T().detach_()
+
+    def extend(self, new_chi, ctm_args=None, global_args=None):
+        """Zero-padded (or cut) copy with environment dimension ``new_chi`` (env_c4v.py:133-153)."""
+        e = self._like(new_chi)
+        x = min(self.chi, new_chi)
+        C_, T = self.get_C(), self.get_T()
+        nC, nT = C_.new_zeros((new_chi, new_chi)), T.new_zeros((new_chi, new_chi, T.shape[2]))
+        nC[:x, :x] = C_[:x, :x]
+        nT[:x, :x, :] = T[:x, :x, :]
+        e.C[e.keyC], e.T[e.keyT] = nC, nT
+        return e
+
+
+def compute_multiplets(env, eps_multiplet_gap=1.0e-10):
+    """Sizes of the groups of (numerically) degenerate |eigenvalues| of the C4v corner, largest first
+    (env_c4v.py:401-418): a group ends where the gap to the next magnitude exceeds ``eps_multiplet_gap``."""
+    D = torch.linalg.eigvalsh(env.C[env.keyC]).abs().sort(descending=True)[0]
+    D = torch.cat([D, D.new_zeros(1)])
+    gaps = (D[:-1] - D[1:] > eps_multiplet_gap).tolist()
+    sizes, run = [], 0
+    for big in gaps:
+        run += 1
+        if big:
+            sizes.append(run)
+            run = 0
+    return sizes
+
+
+def init_random_c4v(env, verbosity=0):
+    """Hermitian random C, random T (env_c4v.py:249-255)."""
+    C_ = torch.rand(env.get_C().shape, dtype=env.get_C().dtype, device=env.get_C().device)
+    env.C[env.keyC] = 0.5 * (C_ + C_.conj().t())
+    env.T[env.keyT] = torch.rand(env.get_T().shape, dtype=env.get_T().dtype, device=env.get_T().device)
+
+
+def init_env_c4v(state, env, C_and_T=None, ctm_args=None):
+    """init_env of env_c4v.py:166-213: custom (C, T), 'RANDOM', or 'CTMRG' (default; :257-311: C = diag(eig of the
+    D^2 x D^2 corner), T rotated into its eigenbasis)."""
+    if C_and_T:
+        assert len(C_and_T) == 2 and all(isinstance(t, torch.Tensor) for t in C_and_T), "Invalid C and T. Expects tuple (C, T)."
+        C0, T0 = C_and_T
+        x = C0.shape[0]
+        nC = env.get_C().new_zeros((env.chi, env.chi)) if env.keyC in env.C else C0.new_zeros((env.chi, env.chi))
+        nT = C0.new_zeros((env.chi, env.chi, T0.shape[2]))
+        nC[:x, :x] = C0
+        nT[:x, :x, :] = T0
+        env.C[env.keyC], env.T[env.keyT] = nC, nT
+        return
+    kind = getattr(ctm_args if ctm_args is not None else cfg.ctm_args, 'ctm_env_init_type', 'CTMRG')
     a = next(iter(state.sites.values()))
+    if a.dim() == 4 and kind in ('CTMRG', 'CTMRG_OBC'):
+        raise RuntimeError("Incompatible ENV_C4V initialization")
+    if kind == 'RANDOM':
+        return init_random_c4v(env)
+    if kind in ('PROD', 'CTMRG_OBC', 'CTMRG_OBC_SL'):
+        raise NotImplementedError(f"ctm_env_init_type='{kind}' is not built in peps_torch_b200; use the reference's init_env")
+    if kind != 'CTMRG':
+        raise ValueError("Invalid environment initialization: " + str(kind))
     chi = env.chi
     d = a.shape
     dk = [d[i + 1] ** 2 for i in range(4)]
