@@ -10,7 +10,11 @@ algorithm the reference implements in
   * linalg/custom_eig.py, linalg/eig_sym.py     (truncated_eig_sym)
   * ctm/one_site_c4v/ctmrg_c4v.py, ctm_components_c4v.py (ctm_MOVE_sl, c2x2_sl)
   * ctm/generic/env.py, ctm/one_site_c4v/env_c4v.py (init_from_ipeps_pbc)
-  * ctm/generic/rdm.py (rdm2x2) + models/j1j2.py (get_hp, energy_per_site)
+  * ctm/generic/rdm.py (rdm2x2 incl. open_sites, rdm1x1, rdm2x1, rdm1x2, _sym_pos_def_matrix)
+    + models/j1j2.py (get_hp, energy_per_site, energy_1x1_lowmem)
+  * ctm/one_site_c4v/rdm_c4v.py (rdm2x2_NN/NNN_lowmem_sl, rdm2x2, rdm1x1_sl, rdm2x1_sl), ctmrg_c4v.py (ctm_MOVE_dl)
+  * the non-default variants of the move: projector_method='4X2' (ctm_projectors.py:66-136), double-layer on-site
+    tensors (ctm_force_dl, run_overlap), 2-norm normalisation
 
 It exists to CHECK the CUDA path (tests/, __graft_entry__.smoke(), and the
 cpu_baseline / --impl reference legs of bench.py).  Nothing under
@@ -19,7 +23,10 @@ peps_torch_b200/ may import it; the product path has no CPU fallback.
 Parity pin: every function here is compared against the reference itself
 (imported from /root/reference in the build container) by oracle/gen_golden.py,
 which also writes the fixtures under tests/golden/ that the CPU test-suite
-re-checks without the reference being present.
+re-checks without the reference being present.  The restatements added after the
+fixtures were generated (variants of the move, density matrices) are compared with
+the unmodified reference by tests/test_oracle_vs_reference_cpu.py -- element-wise for
+the deterministic parts -- every time the CPU suite runs where /root/reference exists.
 
 Conventions (ctm/generic/env.py:57-77): on-site a[s,u,l,d,r]; C(-1,-1)[down,right],
 C(1,-1)[left,down], C(1,1)[up,left], C(-1,1)[up,right]; T(0,-1)[l,d,r], T(-1,0)[u,d,r],
