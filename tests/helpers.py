@@ -144,3 +144,86 @@ class OracleEngine:
         v2s = (lambda c: (c[0] % 2, 0)) if kind != '1x2' else (lambda c: (0, c[1] % 2))
         f = {'1x1': orc.rdm1x1, '2x1': orc.rdm2x1, '1x2': orc.rdm1x2}[kind]
         return f((0, 0), sites, v2s, C, T, raw=raw, sym_pos_def=sym_pos_def)
+
+
+# ----------------------------------------------------------------------------------------------
+# tests/golden/variants_*.npz (oracle/gen_golden_variants.py): outputs of the UNMODIFIED reference for the variants of
+# the move and for the density matrices.  The same checks run on CPU with OracleEngine patched into the drop-in modules
+# (pins the oracle and the host logic without the reference being present) and on the GPU box with libctmb.
+# ----------------------------------------------------------------------------------------------
+def check_generic_variants(name, dev, tol_move=1e-8, tol_rdm=1e-12, tol_rdm_spd=1e-10):
+    from peps_torch_b200.ctm.generic import ctmrg, rdm
+    from peps_torch_b200.config import CTMARGS
+    z, meta = load_golden(name)
+    v, vmeta = load_golden('variants_' + name)
+    assert vmeta['source'] == name
+    chi = meta['chi']
+    sites = golden_sites(z)
+    v2s, lX, lY = v2s_for(sites)
+    C0, T0 = golden_env(z, 'mid_')
+    sites_dev = to_dev(sites, dev)
+    dl_dev = type(sites)((c, ctmrg.double_layer(ctmrg._engine(), a)) for c, a in sites_dev.items())
+    n_checked = 0
+    for tag, kw, ss in (('4x2', dict(projector_method='4X2'), sites_dev), ('dl', dict(ctm_force_dl=True), dl_dev),
+                        ('fro', dict(ctm_absorb_normalization='fro'), sites_dev)):
+        args = CTMARGS()
+        for k, val in kw.items():
+            setattr(args, k, val)
+        st = State(ss, v2s, lX, lY)
+        for d in orc.DIRECTIONS:
+            env = Env(chi, to_dev(C0, dev), to_dev(T0, dev))
+            ctmrg.ctm_MOVE(d, st, env, ctm_args=args)
+            prefix = f'move_{tag}_{d[0]}_{d[1]}_'
+            keys = [k for k in v.files if k.startswith(prefix)]
+            assert len(keys) == 3 * len(sites), (prefix, len(keys))
+            for k in keys:
+                kind, body = k[len(prefix)], k[len(prefix) + 2:]
+                c, vx, vy = body.split('_')
+                key = ((int(c[0]), int(c[1])), (int(vx), int(vy)))
+                got = (env.C if kind == 'C' else env.T)[key].cpu()
+                want = torch.from_numpy(v[k])
+                assert got.shape == want.shape, k
+                assert maxrel(got.abs(), want.abs()) < tol_move, (k, maxrel(got.abs(), want.abs()))
+                n_checked += 1
+    st = State(sites_dev, v2s, lX, lY)
+    env = Env(chi, to_dev(C0, dev), to_dev(T0, dev))
+    for coord in sites:
+        for spd in (False, True):
+            for fname, f in (('rdm2x2', rdm.rdm2x2), ('rdm1x1', rdm.rdm1x1), ('rdm2x1', rdm.rdm2x1), ('rdm1x2', rdm.rdm1x2)):
+                want = torch.from_numpy(v[f'{fname}_{coord[0]}{coord[1]}_{int(spd)}'])
+                got = f(coord, st, env, sym_pos_def=spd).cpu()
+                assert got.shape == want.shape, fname
+                err = float((got - want).abs().max())
+                assert err < (tol_rdm_spd if spd else tol_rdm), (fname, coord, spd, err)
+                n_checked += 1
+    return n_checked
+
+
+def check_c4v_variants(name, dev, tol_C=1e-10, tol_T=1e-8, tol_rdm=1e-12, tol_rdm_spd=1e-10):
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v, rdm_c4v
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    z, meta = load_golden(name)
+    v, vmeta = load_golden('variants_' + name)
+    assert vmeta['source'] == name
+    chi = meta['chi']
+    a = torch.from_numpy(z['site']).to(dev)
+    stc = IPEPS_C4V(a)
+    env = ENV_C4V(chi, stc)
+    env.C[env.keyC], env.T[env.keyT] = torch.from_numpy(z['init_C']).to(dev), torch.from_numpy(z['init_T']).to(dev)
+    for _ in range(vmeta['n_moves_dl']):
+        ctmrg_c4v.ctm_MOVE_dl(a, env, None)
+    assert maxrel(env.get_C().cpu(), torch.from_numpy(v['dl3_C'])) < tol_C
+    assert maxrel(env.get_T().abs().cpu(), torch.from_numpy(v['dl3_T']).abs()) < tol_T
+    env.C[env.keyC], env.T[env.keyT] = torch.from_numpy(z['final_C']).to(dev), torch.from_numpy(z['final_T']).to(dev)
+    n_checked = 2
+    for spd in (False, True):
+        for fname, f in (('rdm2x2_NN', rdm_c4v.rdm2x2_NN_lowmem_sl), ('rdm2x2_NNN', rdm_c4v.rdm2x2_NNN_lowmem_sl),
+                         ('rdm2x2', rdm_c4v.rdm2x2), ('rdm1x1', rdm_c4v.rdm1x1_sl), ('rdm2x1', rdm_c4v.rdm2x1_sl)):
+            want = torch.from_numpy(v[f'{fname}_{int(spd)}'])
+            got = f(stc, env, sym_pos_def=spd).cpu()
+            assert got.shape == want.shape, fname
+            err = float((got - want).abs().max())
+            assert err < (tol_rdm_spd if spd else tol_rdm), (fname, spd, err)
+            n_checked += 1
+    return n_checked

@@ -690,3 +690,18 @@ def test_c4v_small_rdms_against_oracle(eng, dev, name):
     for spd in (False, True):
         assert float((rdm_c4v.rdm1x1_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm_small_c4v('1x1', a, Cc, Tc, spd)).abs().max()) < 1e-12
         assert float((rdm_c4v.rdm2x1_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm_small_c4v('2x1', a, Cc, Tc, spd)).abs().max()) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------
+# libctmb against outputs of the UNMODIFIED reference for the variants and the density matrices
+# (tests/golden/variants_*.npz, oracle/gen_golden_variants.py)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128'])
+def test_variants_against_reference_fixtures_generic(eng, dev, name):
+    # (bounds: libctmb-vs-oracle of the tests above plus oracle-vs-reference of the generator, 1.4e-10 / 1e-13)
+    assert H.check_generic_variants(name, dev, tol_move=1e-8, tol_rdm=5e-12, tol_rdm_spd=1e-10) == 3 * 4 * 12 + 4 * 2 * 4
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_variants_against_reference_fixtures_c4v(eng, dev, name):
+    assert H.check_c4v_variants(name, dev, tol_C=1e-10, tol_T=1e-8, tol_rdm=5e-12, tol_rdm_spd=1e-10) == 12

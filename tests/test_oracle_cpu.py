@@ -135,3 +135,28 @@ def test_multiplet_rule_edge_cases():
     # values below abs_tol count as zero
     s = torch.tensor([1.0, 1e-15, 1e-15, 0.0], dtype=torch.float64)
     assert orc.multiplet_chi(s, 2, 1e-8, 1e-14) == 0
+
+
+# ------------------------------------------------------------------------------------------
+# variants of the move and density matrices: reference outputs in tests/golden/variants_*.npz
+# (oracle/gen_golden_variants.py) against the oracle, through the drop-in modules with the oracle as engine
+# ------------------------------------------------------------------------------------------
+@pytest.fixture()
+def oracle_engine_everywhere(monkeypatch):
+    from peps_torch_b200.ctm.generic import ctmrg, rdm
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v, rdm_c4v
+    e = H.OracleEngine()
+    for m in (ctmrg, rdm, ctmrg_c4v, rdm_c4v):
+        monkeypatch.setattr(m, '_engine', lambda: e)
+    return e
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128'])
+def test_oracle_against_reference_variant_fixtures_generic(oracle_engine_everywhere, name):
+    n = H.check_generic_variants(name, torch.device('cpu'), tol_move=1e-9, tol_rdm=1e-13, tol_rdm_spd=1e-13)
+    assert n == 3 * 4 * 12 + 4 * 2 * 4
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_oracle_against_reference_variant_fixtures_c4v(oracle_engine_everywhere, name):
+    assert H.check_c4v_variants(name, torch.device('cpu'), tol_C=1e-12, tol_T=1e-10, tol_rdm=1e-12, tol_rdm_spd=1e-12) == 12
