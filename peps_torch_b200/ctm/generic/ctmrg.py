@@ -100,7 +100,10 @@ def run(state, env, conv_check=None, ctm_args=cfg.ctm_args, global_args=cfg.glob
         warmup_ctm_args = copy.deepcopy(ctm_args)
         warmup_ctm_args.projector_svd_method = getattr(ctm_args, 'warmup_projector_svd_method',
                                                        ctm_args.projector_svd_method)
-        maxD = max(max(t.shape[1:]) if t.dim() == 5 else ceil(max(t.shape) ** 0.5) for t in state.sites.values())
+        if hasattr(state, 'get_aux_bond_dims'):
+            maxD = max(state.get_aux_bond_dims())       # as the reference (ctmrg.py:80); for rank-4 sites these are D^2
+        else:
+            maxD = max(max(t.shape[1:]) if t.dim() == 5 else max(t.shape) for t in state.sites.values())
         for i in range(max(ctm_args.ctm_warmup_iter, ceil(env.chi / maxD ** 2))):
             _sync(dev)
             t0_ctm = time.perf_counter()

@@ -19,6 +19,24 @@ class IPEPS:
     def site(self, coord):
         return self.sites[self.vertexToSite(coord)]
 
+    def get_parameters(self):
+        """The on-site tensors (ipeps/ipeps.py:249-256)."""
+        return self.sites.values()
+
+    def get_aux_bond_dims(self):
+        """All auxiliary bond dimensions of all sites, site by site in (u, l, d, r) order (ipeps/ipeps.py:306-307)."""
+        return [d for t in self.sites.values() for d in t.shape[1:]]
+
+    def normalize_(self):
+        """Every on-site tensor divided by its largest magnitude (ipeps/ipeps.py:331-333)."""
+        for c in self.sites:
+            self.sites[c] = self.sites[c] / self.sites[c].abs().max()
+
+    def __str__(self):
+        lines = [f"lX x lY: {self.lX} x {self.lY}"]
+        lines += [f"a{i} {c}: {tuple(t.shape)}" for i, (c, t) in enumerate(self.sites.items())]
+        return "\n".join(lines)
+
     def to(self, device):
         return IPEPS(OrderedDict((c, t.to(device)) for c, t in self.sites.items()), self.vertexToSite, self.lX, self.lY)
 
