@@ -32,3 +32,13 @@ def test_c4v_script_calls_the_rebound_move(tmp_path):
                                                          '--CTMARGS_ctm_max_iter', '3'], tmp_path)
     assert g == 0 and c >= 1
     assert 'FINAL' in out and r >= 1   # energy_1x1_lowmem through the rebound rdm2x2_NN(N)_lowmem_sl
+
+
+def test_kagome_script_calls_the_rebound_move(tmp_path):
+    """BASELINE config 4: the kagome iPESS script drives ctm.generic.ctmrg.run on a 1x1 cell with a p = 8 on-site tensor
+    (SURVEY 3.3); complex128 because the CLI's --jperm is complex (caveat 2)."""
+    g, c, r, out = _run('examples/kagome/ctmrg_spin_half_kagome.py', ['--ansatz', 'IPESS', '--bond_dim', '2', '--chi', '8',
+                                                                      '--seed', '123', '--CTMARGS_ctm_max_iter', '2',
+                                                                      '--GLOBALARGS_dtype', 'complex128'], tmp_path)
+    assert g == 8 and c == 0           # 2 iterations x 2(lX+lY) moves of the 1x1 cell
+    assert 'spectrum(T)' in out        # the script ran to its end (observables, transfer-matrix spectra)
