@@ -138,3 +138,47 @@ def test_group_mode_world2_one_site_gloo():
         moves, worst, same, grp = ret[r]
         assert moves == 4 and worst < 1e-12 and same
         assert grp == (r, 2, 2)
+
+
+def _worker_two_groups(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from peps_torch_b200.dist import ShardedCtm
+        torch.set_num_threads(1)
+        z, meta = H.load_golden('generic_4site_D2_chi8_B')
+        # a 2-site cell (2x1) cut out of the 4-site fixture: sites (0,0) and (1,0), 2SITE tiling
+        all_sites = H.golden_sites(z)
+        from collections import OrderedDict
+        sites = OrderedDict([((0, 0), all_sites[(0, 0)]), ((1, 0), all_sites[(1, 0)])])
+        C, T = orc.init_env(sites, orc.v2s_2site, meta['chi'])
+        st = H.State(sites, orc.v2s_2site, 2, 1)
+        env = H.Env(meta['chi'], dict(C), dict(T))
+        be = OracleBackend()
+        sh = ShardedCtm(be)
+        moves = sh.iteration(st, env)
+        C2, T2 = dict(C), dict(T)
+        orc.ctm_iteration(sites, orc.v2s_2site, 2, 1, C2, T2, meta['chi'])
+        worst = max([float((env.C[k] - C2[k]).abs().max()) for k in C2] + [float((env.T[k] - T2[k]).abs().max()) for k in T2])
+        flat = torch.cat([env.C[k].reshape(-1) for k in sorted(env.C)] + [env.T[k].reshape(-1) for k in sorted(env.T)])
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        ret[rank] = (moves, worst, all(torch.equal(other[0], o) for o in other), be.grp, sh._layout[2])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_group_mode_world4_two_sites_gloo():
+    """Two sites on four ranks: two groups of two (ranks {0,1} share site 0, {2,3} site 1); every rank creates both
+    process groups in the same order, only the leaders contribute to the exchanges."""
+    world = 4
+    port = 33700 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_two_groups, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        moves, worst, same, grp, mine = ret[r]
+        assert moves == 6                       # 2(lX + lY) with lX = 2, lY = 1
+        assert worst < 1e-12 and same
+        assert grp == (r % 2, 2, 2) and mine == r // 2
