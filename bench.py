@@ -441,7 +441,8 @@ def run_ours(args):
                            'jacobi': 'jacobi_kernel (one-sided Jacobi SVD of the k x k factor in shared memory; shared-memory-bandwidth bound)',
                            'misc': 'misc kernels'}[dom], 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': ach / hbm_peak, 'traffic': traffic,
-                'note': 'the step is latency-bound (2.8 GFLOP per move); the FLOP-bound kernels of the path are reported under kernel_level'}
+                'note': 'the step is latency-bound (2.8 GFLOP per move); the FLOP-bound kernels of the path are reported under kernel_level; '
+                        'traffic is the ncu capture of the k = 96 build (profiles/r1_c2_qr_tsolve_metrics.csv), the sketches are 84 columns wide since'}
     roof['peak_source'] = ('cuBLAS DGEMM 8192^3 measured in this run' if roof['bound'] == 'tensor'
                            else ('MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'))
     roof['avg_launch_us'] = 1e3 * prof[dom]['ms'] / max(1, prof[dom]['launches'])
