@@ -248,3 +248,45 @@ def test_host_rdm_modules_map_sites_and_env_correctly(monkeypatch):
         assert torch.equal(f((0, 1), st, env), g((0, 1), sites, orc.v2s_4site, C, T))
     with pytest.raises(NotImplementedError):
         rdm.rdm1x1((0, 0), st, env, operator=torch.eye(2))
+
+
+def test_anisotropic_and_ragged_unit_cells_plan_or_fail_loudly():
+    """Edge cases of the unit cell, checked with the planning-only handle: (1) bond dimensions that differ between the
+    horizontal and the vertical bonds but are the same for every site plan in all four directions; (2) a consistent cell
+    whose vertical bonds alternate D = 2 / 3 between the rows (the reference handles it, and so does the oracle): the
+    moves along the uniform direction plan, the others are refused with an explicit message -- libctmb batches the site
+    jobs of a move and needs equal projector shapes -- never a silent wrong result."""
+    import ctypes as C
+    from collections import OrderedDict
+    from peps_torch_b200 import _lib
+    from peps_torch_b200.engine import CtmEngine, DIRECTIONS
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    eng = CtmEngine('plan')
+    g = torch.Generator().manual_seed(3)
+    chi = 6
+
+    def plan(shapes):
+        sites = OrderedDict((c, torch.rand(s, dtype=torch.float64, generator=g) - 0.5) for c, s in shapes.items())
+        st = IPEPS(sites, orc.v2s_4site, 2, 2)
+        env = ENV(chi, st)
+        init_env(st, env)
+        Cc, Tc = orc.init_env(sites, orc.v2s_4site, chi)
+        orc.ctm_iteration(sites, orc.v2s_4site, 2, 2, Cc, Tc, chi)          # the oracle (= the reference algorithm) runs
+        keep = []
+        coords, arr = eng._sites_array(st, env, keep)
+        out = {}
+        for d, dc in DIRECTIONS.items():
+            corner, nb, dest, _ = eng._move_tables(st, d)
+            o = eng._opts()
+            n = _lib.lib.ctmb_move_generic_workspace(eng._h, _lib.F64, dc, 4, chi, arr, corner, nb, C.byref(o))
+            out[d] = (n, _lib.lib.ctmb_last_error().decode())
+        return out
+
+    cells = [(0, 0), (1, 0), (0, 1), (1, 1)]
+    res = plan({c: (2, 2, 3, 2, 3) for c in cells})
+    assert all(n > 0 for n, _ in res.values()), res
+    res = plan({(0, 0): (2, 2, 2, 3, 2), (1, 0): (2, 2, 2, 3, 2), (0, 1): (2, 3, 2, 2, 2), (1, 1): (2, 3, 2, 2, 2)})
+    assert res[(0, -1)][0] > 0 and res[(0, 1)][0] > 0
+    for d in ((-1, 0), (1, 0)):
+        assert res[d][0] == 0 and 'non-uniform bond dimensions' in res[d][1]
