@@ -705,3 +705,27 @@ def test_variants_against_reference_fixtures_generic(eng, dev, name):
 @pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
 def test_variants_against_reference_fixtures_c4v(eng, dev, name):
     assert H.check_c4v_variants(name, dev, tol_C=1e-10, tol_T=1e-8, tol_rdm=5e-12, tol_rdm_spd=1e-10) == 12
+
+
+def test_config1_script_known_answer_on_gpu(eng, dev):
+    """BASELINE.json configs[0] (J1-J2 one-site C4v D=2 chi=16 float64): the reference script
+    `ctmrg_j1j2_c4v.py --bond_dim 2 --chi 16 --seed 123 --j2 0.3` stops after four moves and prints
+    FINAL -0.35003258049356745.  Same state, four moves through the drop-in `run`, energy_1x1_lowmem
+    (models/j1j2.py:641-679) from the GPU density matrices."""
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v, rdm_c4v
+    from peps_torch_b200.config import CTMARGS
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V, init_env_c4v
+    a = orc.random_state_c4v(2, family='A')
+    stc = IPEPS_C4V(a.to(dev))
+    env = ENV_C4V(16, stc)
+    init_env_c4v(stc, env)
+    args = CTMARGS(); args.ctm_max_iter = 4
+    ctmrg_c4v.run(stc, env, ctm_args=args)
+    sz, sp, sm, I = orc.spin_half_ops(a.dtype)
+    SS = torch.einsum('ij,ab->iajb', sz, sz) + 0.5 * (torch.einsum('ij,ab->iajb', sp, sm) + torch.einsum('ij,ab->iajb', sm, sp))
+    rot = torch.tensor([[0., 1.], [-1., 0.]], dtype=a.dtype)
+    SS_rot = torch.einsum('ki,kjcb,ca->ijab', rot, SS, rot)
+    e = 2.0 * torch.einsum('ijab,ijab', rdm_c4v.rdm2x2_NN_lowmem_sl(stc, env, sym_pos_def=True).cpu(), SS_rot) \
+        + 2.0 * 0.3 * torch.einsum('ijab,ijab', rdm_c4v.rdm2x2_NNN_lowmem_sl(stc, env, sym_pos_def=True).cpu(), SS)
+    assert abs(float(e) - (-0.35003258049356745)) < 1e-10 * 0.35

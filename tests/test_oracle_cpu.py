@@ -160,3 +160,16 @@ def test_oracle_against_reference_variant_fixtures_generic(oracle_engine_everywh
 @pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
 def test_oracle_against_reference_variant_fixtures_c4v(oracle_engine_everywhere, name):
     assert H.check_c4v_variants(name, torch.device('cpu'), tol_C=1e-12, tol_T=1e-10, tol_rdm=1e-12, tol_rdm_spd=1e-12) == 12
+
+
+C1_FINAL_ENERGY = -0.35003258049356745      # `ctmrg_j1j2_c4v.py --bond_dim 2 --chi 16 --seed 123 --j2 0.3` run here
+
+
+def test_config1_script_known_answer_oracle():
+    """BASELINE.json configs[0]: the reference script converges in four moves (rdm2x1 distance 7.2e-9 < ctm_conv_tol) and
+    prints FINAL -0.35003258049356745; the oracle on the script-exact state (seed 123, family A) reproduces it."""
+    a = orc.random_state_c4v(2, family='A')
+    C, T = orc.init_env_c4v(a, 16)
+    for _ in range(4):
+        C, T = orc.ctm_move_c4v(a, C, T, 16)
+    assert abs(orc.energy_j1j2_c4v(a, C, T, 1.0, 0.3) - C1_FINAL_ENERGY) < 1e-13
