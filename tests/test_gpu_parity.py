@@ -729,3 +729,23 @@ def test_config1_script_known_answer_on_gpu(eng, dev):
     e = 2.0 * torch.einsum('ijab,ijab', rdm_c4v.rdm2x2_NN_lowmem_sl(stc, env, sym_pos_def=True).cpu(), SS_rot) \
         + 2.0 * 0.3 * torch.einsum('ijab,ijab', rdm_c4v.rdm2x2_NNN_lowmem_sl(stc, env, sym_pos_def=True).cpu(), SS)
     assert abs(float(e) - (-0.35003258049356745)) < 1e-10 * 0.35
+
+
+def test_config2_script_known_answer_on_gpu(eng, dev):
+    """BASELINE.json configs[1] (J1-J2 generic 4SITE D=3 chi=48 float64) on the script-exact state: the reference script
+    `ctmrg_j1j2.py --tiling 4SITE --bond_dim 3 --chi 48 --seed 123 --j2 0.3` converges in three iterations and prints
+    FINAL 0.6424192641900255 (energy per site, models/j1j2.py:223-247).  Same state, three iterations through the drop-in
+    `run`, energy from the GPU rdm2x2 of every plaquette."""
+    from peps_torch_b200.ctm.generic import ctmrg, rdm
+    from peps_torch_b200.config import CTMARGS
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    sites = orc.random_state_4site(3, family='A')
+    st = IPEPS(H.to_dev(sites, dev), orc.v2s_4site, 2, 2)
+    env = ENV(48, st)
+    init_env(st, env)
+    args = CTMARGS(); args.ctm_max_iter = 3
+    ctmrg.run(st, env, ctm_args=args)
+    hp = orc.j1j2_hp(1.0, 0.3)
+    e = sum(torch.einsum('ijklabcd,ijklabcd', rdm.rdm2x2(c, st, env).cpu(), hp) for c in sites) / len(sites)
+    assert abs(float(e) - 0.6424192641900255) < 1e-10 * 0.64

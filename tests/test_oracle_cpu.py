@@ -173,3 +173,17 @@ def test_config1_script_known_answer_oracle():
     for _ in range(4):
         C, T = orc.ctm_move_c4v(a, C, T, 16)
     assert abs(orc.energy_j1j2_c4v(a, C, T, 1.0, 0.3) - C1_FINAL_ENERGY) < 1e-13
+
+
+C2_FINAL_ENERGY = 0.6424192641900255    # `ctmrg_j1j2.py --tiling 4SITE --bond_dim 3 --chi 48 --seed 123 --j2 0.3`, three iterations
+
+
+def test_config2_script_known_answer_oracle():
+    """BASELINE.json configs[1] on the script-exact state (seed 123, family A): the reference script (moves of the
+    reference, energy through rdm2x2 -- tests/launcher_probe.py, which has to supply rdm2x2 because the reference's own
+    dispatch needs opt_einsum) converges in three iterations and prints FINAL 0.6424192641900255."""
+    sites = orc.random_state_4site(3, family='A')
+    C, T = orc.init_env(sites, orc.v2s_4site, 48)
+    for _ in range(3):
+        orc.ctm_iteration(sites, orc.v2s_4site, 2, 2, C, T, 48)
+    assert abs(orc.energy_j1j2(sites, orc.v2s_4site, C, T, 1.0, 0.3) - C2_FINAL_ENERGY) < 1e-13
