@@ -119,6 +119,8 @@ class OracleEngine:
         return nC, nT, None
 
     def rdm2x2(self, coord, state, env, open_sites=(0, 1, 2, 3), sym_pos_def=False, raw=False):
+        if not list(open_sites):
+            raise ValueError("open_sites must be a non-empty subset of [0,1,2,3]")      # as CtmEngine.rdm2x2_sites
         return orc.rdm2x2(coord, state.sites, state.vertexToSite, env.C, env.T, raw=raw, open_sites=tuple(open_sites),
                           sym_pos_def=sym_pos_def)
 
@@ -144,6 +146,26 @@ class OracleEngine:
         v2s = (lambda c: (c[0] % 2, 0)) if kind != '1x2' else (lambda c: (0, c[1] % 2))
         f = {'1x1': orc.rdm1x1, '2x1': orc.rdm2x1, '1x2': orc.rdm1x2}[kind]
         return f((0, 0), sites, v2s, C, T, raw=raw, sym_pos_def=sym_pos_def)
+
+    # ---- the piecewise entry points of CtmEngine, for the CPU dry run of the GPU suite (tests/test_gpu_dryrun_cpu.py) ----
+    def c2x2(self, kind, C_, T1, T2, a, chi):
+        if a.dim() == 4:
+            t = orc.sl_einsum(orc.CORNERS[kind][3], (C_, T1, T2), a)
+            return t.reshape(t.shape[0] * t.shape[1], t.shape[2] * t.shape[3])
+        return orc.c2x2(kind, C_, T1, T2, a)
+
+    def projectors(self, R, Rt, chi, **opt):
+        P, Pt, (M, U, S, V) = orc.projectors_from_matrices(R, Rt, chi, self._args(opt), return_svd=True)
+        return P, Pt, S
+
+    def truncated_svd(self, M, chi, **opt):
+        return orc.truncated_svd(M, chi, opt.get('eps_multiplet') or 1e-8, opt.get('multiplet_abstol') or 1e-14)
+
+    def truncated_eig_sym(self, M, chi, **opt):
+        return orc.truncated_eig_sym(M, chi)
+
+    def sym_pos_def(self, rdm, sym_pos_def=False):
+        return orc._sym_pos_def(rdm, sym_pos_def)
 
 
 # ----------------------------------------------------------------------------------------------
