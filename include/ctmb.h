@@ -59,7 +59,9 @@ typedef struct {
                                   s_0 / s_j.  0 = fixed iteration count, no synchronisation. */
     int projector_method;      /* CTMARGS.projector_method: 0 = '4X4' (halves of the 4x4 network, ctm_projectors.py:14-64; default),
                                   1 = '4X2' (R, Rt = the two enlarged corners next to the bond, ctm_projectors.py:66-136) */
-    int pad2;
+    int rsvd_stateless;        /* 0 (default): the handle remembers, per problem shape, the iteration count that passed the residual
+                                  test last time and starts there (a CTM run decomposes a slowly changing matrix once per move);
+                                  1: every call starts from rsvd_niter, so its result does not depend on the handle's history */
 } ctmb_options;
 
 /* One unit-cell site: on-site tensor and its eight environment tensors. */
@@ -90,6 +92,12 @@ void ctmb_default_options(ctmb_options* opt);
  * nranks = 1 switches the group off. */
 typedef int (*ctmb_allgather_fn)(void* ctx, void* buf, size_t bytes_per_rank, void* stream);
 int ctmb_set_group(ctmb_handle_t h, int rank, int nranks, ctmb_allgather_fn fn, void* ctx);
+
+/* Status of the residual-checked range finder since the last reset: number of residual checks, number of decompositions
+ * that were RETURNED ALTHOUGH they missed the bound rsvd_tol * sqrt(n) (the residual stopped improving -- rounding floor --
+ * or rsvd_max_rounds was reached) and the worst residual / bound ratio among those.  The host wrappers turn missed > 0 into
+ * a Python warning.  (The reference's LAPACK SVD has no such diagnostic: svd_gesdd.py:77-96.) */
+int ctmb_get_rsvd_status(ctmb_handle_t h, long long* checks, long long* missed, double* worst_ratio, int reset);
 
 /* kernels launched / algorithmic real flops enqueued by this handle since the last reset */
 int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops);

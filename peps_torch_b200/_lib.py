@@ -21,7 +21,7 @@ class Options(C.Structure):
     _fields_ = [('svd_reltol', C.c_double), ('eps_multiplet', C.c_double), ('multiplet_abstol', C.c_double),
                 ('rsvd_rank_factor', C.c_double), ('rsvd_niter', C.c_int), ('jacobi_max_sweeps', C.c_int),
                 ('norm_type', C.c_int), ('rsvd_max_rounds', C.c_int), ('seed', C.c_ulonglong), ('rsvd_tol', C.c_double),
-                ('projector_method', C.c_int), ('pad2', C.c_int)]
+                ('projector_method', C.c_int), ('rsvd_stateless', C.c_int)]
 
 
 class Site(C.Structure):
@@ -43,6 +43,7 @@ SIGNATURES = {
     'ctmb_create': (C.c_int, [C.POINTER(_vp), _i]),
     'ctmb_destroy': (C.c_int, [_vp]),
     'ctmb_default_options': (None, [_PO]),
+    'ctmb_get_rsvd_status': (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double), _i]),
     'ctmb_get_counters': (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     'ctmb_reset_counters': (C.c_int, [_vp]),
     'ctmb_profile_enable': (C.c_int, [_vp, _i]),

@@ -85,6 +85,12 @@ Engine::~Engine() {
     for (auto& kv : persist_) if (kv.second.first) cudaFree(kv.second.first);
     prof_reset();
     for (auto e : ev_pool_) cudaEventDestroy(e);
+    if (pinned_) cudaFreeHost(pinned_);
+}
+
+unsigned long long* Engine::pinned_words() {
+    if (!pinned_) CTMB_CUDA(cudaMallocHost(&pinned_, 32 * sizeof(unsigned long long)));
+    return pinned_;
 }
 
 void* Engine::persistent(const std::string& key, size_t bytes, bool* created) {

@@ -68,6 +68,12 @@ public:
     std::map<std::string, IterHint> iter_hint;   // adaptive range finder, per problem shape: power iterations that satisfied
                                                  // the residual test last time, and how long not to probe below them
     double flops = 0;              // algorithmic real flops enqueued
+    // residual-checked range finder: how many checks ran, how many results were returned although they missed the bound
+    // (rounding floor / rsvd_max_rounds), and the worst residual / bound ratio among those (ctmb_get_rsvd_status)
+    struct RsvdStatus { long long checks = 0, missed = 0; double worst_ratio = 0.0; };
+    RsvdStatus rsvd_status;
+    unsigned long long* pinned_words();     // 32 pinned host words owned by this engine (read-back of device scalars)
+    void drop_pending() { pend_active_ = false; pend_plans_.clear(); }
 
     // optional per-kernel-class timing with CUDA events on the launching stream
     enum Cat { CAT_GEMM = 0, CAT_QR = 1, CAT_JACOBI = 2, CAT_MISC = 3, CAT_COUNT = 4 };
@@ -127,6 +133,7 @@ private:
     std::vector<cudaEvent_t> ev_pool_;
     cudaEvent_t prof_open_ = nullptr;
     cudaEvent_t get_event();
+    unsigned long long* pinned_ = nullptr;
 };
 
 // RAII helper: times one launch of class `cat` when profiling is on

@@ -17,12 +17,12 @@
 namespace ctmb {
 
 // When may the sweep loop stop without a verification sweep?  Cyclic Jacobi converges quadratically once every rotation
-// of a sweep was small.  Shipped test: the COSINE between the two columns, |g|^2 <= 1e-16 a b.  Inside a tight cluster of
-// singular values (a ~ b) a tiny cosine can still mean a large rotation ANGLE, the quadratic argument does not apply, and
-// the cluster is left orthogonal to ~1e-11 only (measured through sym_pos_def on a nearly rank-one density matrix: 3.1e-12,
-// DESIGN.md section 9).  Building with -DCTMB_JACOBI_EXIT_ANGLE tests sin^2(theta) = |g|^2 r^2 rc^2 <= 1e-16 instead.
-// STAGED, not the default: the hot kernel could not be re-validated on a GPU at the end of round 1; without the macro the
-// preprocessed source is identical to the validated build.
+// of a sweep was by a small ANGLE: sin^2(theta) = |g|^2 r^2 rc^2 <= 1e-16.  (Round 1 tested the cosine between the two
+// columns, |g|^2 <= 1e-16 a b; inside a tight cluster of singular values, a ~ b, a tiny cosine can still mean a large
+// rotation angle, the quadratic argument does not apply and the cluster was left orthogonal to ~1e-11 only.)  A pair
+// whose cosine is already below 1e-13 is rotated (to ~1e-16) but does not ask for another sweep either, whatever its
+// angle: a rotation inside the pair preserves the magnitudes of its inner products with every other column, so exactly
+// degenerate multiplets (angle 45 degrees at rounding-level cosines) cannot keep the loop alive.
 // diagnostics: total sweeps executed / matrices processed since the last read (tools/ only)
 __device__ unsigned long long g_jac_stats[2];
 
@@ -129,16 +129,11 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
                         }
                         const double ag2 = g * g;
                         if (ag2 > tol2 * a * b && ag2 > 0.0) {
-#ifndef CTMB_JACOBI_EXIT_ANGLE
-                            if (gl == 0) { rotated = 1; if (ag2 > 1.0e-16 * a * b) notsmall = 1; }
-#endif
                             const double d = b - a;
                             const double r = rsqrt(d * d + 4.0 * ag2);
                             const double c2 = 0.5 + 0.5 * fabs(d) * r;
                             const double rc = rsqrt(c2);
-#ifdef CTMB_JACOBI_EXIT_ANGLE
-                            if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16) notsmall = 1; }
-#endif
+                            if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 1.0e-26 * a * b) notsmall = 1; }
                             const double c = c2 * rc;
                             const double al = g * copysign(r * rc, d);
 #pragma unroll
@@ -195,9 +190,6 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
                 }
                 const double ag2 = S::abs2(g);
                 if (ag2 > tol2 * a * b && ag2 > 0.0) {
-#ifndef CTMB_JACOBI_EXIT_ANGLE
-                    if (gl == 0) { rotated = 1; if (ag2 > 1.0e-16 * a * b) notsmall = 1; }
-#endif
                     // Rotation [x y] <- [x y] [[c, conj(al)], [-al, c]] that makes the columns orthogonal:
                     //   tan(2 theta) = 2|g| / |b-a|,  c = cos(theta) >= 1/sqrt(2),  al = sign(b-a) conj(g) sin(theta)/|g|.
                     // Written with two reciprocal square roots and no division / square root:
@@ -207,9 +199,7 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
                     const double r = rsqrt(d * d + 4.0 * ag2);
                     const double c2 = 0.5 + 0.5 * fabs(d) * r;
                     const double rc = rsqrt(c2);
-#ifdef CTMB_JACOBI_EXIT_ANGLE
-                    if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16) notsmall = 1; }
-#endif
+                    if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 1.0e-26 * a * b) notsmall = 1; }
                     const double c = c2 * rc;
                     const T al = S::scale(S::conj(g), copysign(r * rc, d));
                     const T cal = S::conj(al);
@@ -377,18 +367,12 @@ __global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, Pt
                 a = warp_sum(a); b = warp_sum(b); g = warp_sum_t<CPLX>(g);
                 const double ag2 = S::abs2(g);
                 if (ag2 > tol2 * a * b && ag2 > 0.0) {
-#ifndef CTMB_JACOBI_EXIT_ANGLE
-                    rot = 1; if (ag2 > 1.0e-16 * a * b) big = 1;
-#else
-                    rot = 1;
-#endif
                     const double d = b - a;
                     const double r = rsqrt(d * d + 4.0 * ag2);
                     const double c2 = 0.5 + 0.5 * fabs(d) * r;
                     const double rc = rsqrt(c2);
-#ifdef CTMB_JACOBI_EXIT_ANGLE
-                    if (ag2 * r * r * rc * rc > 1.0e-16) big = 1;
-#endif
+                    rot = 1;
+                    if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 1.0e-26 * a * b) big = 1;
                     const double c = c2 * rc;
                     const T al = S::scale(S::conj(g), copysign(r * rc, d));
                     const T cal = S::conj(al);

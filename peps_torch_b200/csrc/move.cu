@@ -534,9 +534,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     unsigned long long* hres = nullptr;
     if (adaptive) {
         dres = (unsigned long long*)e.persistent("resid", 32 * sizeof(unsigned long long));    // [0]: mine, [1..]: the group's
-        static unsigned long long* pinned = nullptr;
-        if (!pinned) CTMB_CUDA(cudaMallocHost(&pinned, 32 * sizeof(unsigned long long)));
-        hres = pinned;
+        hres = e.pinned_words();                          // per-engine pinned read-back buffer (32 words)
     }
     int todo = complete ? 0 : o.rsvd_niter;               // full power iterations still to run
     // Adaptive mode remembers, per problem shape, how many iterations passed the residual test last time and starts
@@ -547,7 +545,8 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     // residual bound: rsvd_tol * sqrt(n) relative to the largest singular value (the rounding floor of the residual
     // itself grows like eps * sqrt(n))
     const double tol_eff = o.rsvd_tol * std::sqrt((double)std::max(m, n));
-    if (adaptive) { auto it = e.iter_hint.find(hkey); if (it != e.iter_hint.end() && it->second.q > 0) todo = it->second.q; }
+    // (ctmb_options.rsvd_stateless: every call starts from rsvd_niter, so its result does not depend on the handle's history)
+    if (adaptive && !o.rsvd_stateless) { auto it = e.iter_hint.find(hkey); if (it != e.iter_hint.end() && it->second.q > 0) todo = it->second.q; }
     int used = 0;
     double prev_res = -1.0;
     for (int round = 0;; ++round) {
@@ -596,8 +595,9 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
                 e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
             e.flush();
         }
-        if (!adaptive || round + 1 >= std::max(1, o.rsvd_max_rounds)) break;
-        // residual of the kept triplets; pZ is free at this point and serves as scratch for M X
+        if (!adaptive) break;
+        // residual of the kept triplets -- evaluated after EVERY round, the last one included, so that a result that misses
+        // the bound is never returned silently (Engine::rsvd_status); pZ is free at this point and serves as scratch for M X
         PtrBatch pMX{}, pYv{};
         for (int b = 0; b < nb; ++b) {
             pMX.p[b] = pZ.p[b];
@@ -622,6 +622,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         if (dbg < 0) { const char* ev = getenv("CTMB_DEBUG_RESID"); dbg = ev ? atoi(ev) : 0; }
         if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d k=%d round %d iterations %d residual %.3e (tol %.1e)\n", m, n, k, round, used, res, tol_eff);
         Engine::IterHint& hint = e.iter_hint[hkey];
+        ++e.rsvd_status.checks;
         if (res <= tol_eff) {
             if (round == 0) {
                 // passed first time: probe one iteration fewer next time unless that count failed recently
@@ -631,8 +632,16 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             break;
         }
         if (round == 0) { hint.lo = std::max(hint.lo, used); hint.age = 0; }
-        if (prev_res > 0.0 && res > 0.5 * prev_res) {         // rounding floor reached: more iterations do not help
-            hint.q = std::max(1, used - todo);
+        const bool floor_reached = prev_res > 0.0 && res > 0.5 * prev_res;    // rounding floor: more iterations do not help
+        const bool out_of_rounds = round + 1 >= std::max(1, o.rsvd_max_rounds);
+        if (floor_reached || out_of_rounds) {
+            // the result is returned although it misses the bound: say so (ctmb_get_rsvd_status), and remember the count
+            // so that later calls do not walk through all the rounds again
+            hint.q = floor_reached ? std::max(1, used - todo) : used;
+            ++e.rsvd_status.missed;
+            e.rsvd_status.worst_ratio = std::max(e.rsvd_status.worst_ratio, res / tol_eff);
+            if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d: residual %.3e stays above the bound %.1e (%s)\n", m, n, res, tol_eff,
+                             floor_reached ? "rounding floor" : "rsvd_max_rounds");
             break;
         }
         prev_res = res;
@@ -1052,6 +1061,7 @@ static void begin_call(ctmb_handle_t h, ctmb_dtype dt, void* ws, size_t ws_bytes
     e.cplx = (dt == CTMB_C128);
     e.stream = (cudaStream_t)stream;
     e.ws.reset(ws, ws_bytes);
+    e.drop_pending();          // a previous call that threw between contract() and flush() must not leak its batch into this one
 }
 // dry run: measure the workspace the same call would use
 static void begin_dry(ctmb_handle_t h, ctmb_dtype dt) {
@@ -1059,6 +1069,7 @@ static void begin_dry(ctmb_handle_t h, ctmb_dtype dt) {
     Engine& e = h->h.eng;
     e.cplx = (dt == CTMB_C128);
     e.ws.reset(nullptr, 0);
+    e.drop_pending();
 }
 
 extern "C" {
@@ -1068,6 +1079,8 @@ int ctmb_version(void) { return 100; }
 void ctmb_debug_jacobi_stats(unsigned long long* out) { ctmb::jacobi_stats(out); }
 // tests: force (2) / forbid (0) / auto (1) the matrix-free projector path regardless of the problem size
 void ctmb_debug_set_matrix_free(int mode) { ctmb::g_matrix_free_mode = mode; }
+// tests: 1 if square halves of extent n with environment dimension chi take the matrix-free projector path
+int ctmb_debug_uses_matrix_free(int n, int chi) { return ctmb::use_matrix_free(n, n, chi) ? 1 : 0; }
 const char* ctmb_last_error(void) { return get_error().c_str(); }
 
 int ctmb_create(ctmb_handle_t* h, int device) {
@@ -1099,7 +1112,7 @@ void ctmb_default_options(ctmb_options* o) {
     if (!o) return;
     o->svd_reltol = 1.0e-8; o->eps_multiplet = 1.0e-8; o->multiplet_abstol = 1.0e-14;
     o->rsvd_rank_factor = 0.0; o->rsvd_niter = 4; o->jacobi_max_sweeps = 40; o->norm_type = 0; o->rsvd_max_rounds = 5;
-    o->seed = 0x5eed5eedull; o->rsvd_tol = 2.0e-15; o->projector_method = 0; o->pad2 = 0;
+    o->seed = 0x5eed5eedull; o->rsvd_tol = 2.0e-15; o->projector_method = 0; o->rsvd_stateless = 0;
 }
 
 int ctmb_set_group(ctmb_handle_t h, int rank, int nranks, ctmb_allgather_fn fn, void* ctx) {
@@ -1109,6 +1122,18 @@ int ctmb_set_group(ctmb_handle_t h, int rank, int nranks, ctmb_allgather_fn fn, 
     CTMB_CHECK(nranks == 1 || fn != nullptr, "a group needs an all-gather callback");
     Engine& e = h->h.eng;
     e.coll_rank = rank; e.coll_n = nranks; e.coll_fn = nranks > 1 ? fn : nullptr; e.coll_ctx = ctx;
+    return 0;
+    CTMB_CATCH(-1)
+}
+
+int ctmb_get_rsvd_status(ctmb_handle_t h, long long* checks, long long* missed, double* worst_ratio, int reset) {
+    CTMB_TRY
+    CTMB_CHECK(h != nullptr, "null handle");
+    Engine& e = h->h.eng;
+    if (checks) *checks = e.rsvd_status.checks;
+    if (missed) *missed = e.rsvd_status.missed;
+    if (worst_ratio) *worst_ratio = e.rsvd_status.worst_ratio;
+    if (reset) e.rsvd_status = Engine::RsvdStatus{};
     return 0;
     CTMB_CATCH(-1)
 }

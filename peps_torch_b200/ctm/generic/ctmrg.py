@@ -12,6 +12,7 @@ log = logging.getLogger(__name__)
 # every value the reference dispatches on (ctm_projectors.py:213-257) asks for the same object -- the leading chi
 # singular triplets of M -- from a different LAPACK / ARPACK / randomised driver; here all of them run the
 # residual-checked randomised decomposition of libctmb
+_announced = set()
 _SUPPORTED_SVD = ('DEFAULT', 'GESDD', 'GESDD_CPU', 'AF', 'ARP', 'PROPACK', 'RSVD', 'RSVD_CUSTOM')
 
 
@@ -25,6 +26,12 @@ def _options(ctm_args):
     if method not in _SUPPORTED_SVD:
         # the reference raises a bare string here (ctm_projectors.py:257), i.e. a TypeError
         raise TypeError(f'Projector svd method "{method}" not implemented')
+    if method not in ('DEFAULT', 'RSVD', 'RSVD_CUSTOM') and method not in _announced \
+            and getattr(ctm_args, 'verbosity_projectors', 0) + getattr(ctm_args, 'verbosity_ctm_move', 0) > 0:
+        # no multi-backend dispatch here: say so once instead of silently serving a different driver
+        _announced.add(method)
+        log.info(f"projector_svd_method={method}: libctmb serves every method with its residual-checked randomised "
+                 "decomposition (leading chi triplets to LAPACK-grade residuals); the named driver is not called")
     # ctmrg.py:212-214: 'inf' is the infinity norm, every other value the vector 2-norm
     norm = 0 if getattr(ctm_args, 'ctm_absorb_normalization', 'inf') == 'inf' else 1
     pm = getattr(ctm_args, 'projector_method', '4X4')

@@ -39,6 +39,15 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def refuse_autograd(what, tensors):
+    """libctmb's kernels are invisible to autograd: a result computed from tensors that require grad would come back
+    detached and an optimiser would silently lose the CTM contribution to the gradient.  Fail loudly instead (reverse-mode
+    AD through the move is SURVEY 8f row 2; use torch.no_grad() / detached tensors for forward-only evaluation)."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError(f"{what}: an input requires grad, but the libctmb move is forward-only (no autograd graph is "
+                           "recorded through it); call it under torch.no_grad() or detach the state and the environment")
+
+
 def aux2(a):
     """Extents of the four environment legs facing the on-site tensor: D^2 per leg for a single-layer
     a[s,u,l,d,r], the leg itself for a double-layer A[u,l,d,r] (ctm_force_dl / run_overlap / ctm_MOVE_dl)."""
@@ -66,6 +75,7 @@ class CtmEngine:
             check(lib.ctmb_create(C.byref(self._h), self.device.index))
         self._ws = None
         self._tables = {}
+        self._rsvd_missed_seen = 0
         self.options = _lib.default_options()
 
     def close(self):
@@ -125,6 +135,27 @@ class CtmEngine:
             return
         self._group_cb = _lib.ALLGATHER_FN(_allgather)    # keep a reference: ctypes callbacks die with their object
         check(lib.ctmb_set_group(self._h, rank, nranks, self._group_cb, None))
+
+    def debug_set_matrix_free(self, mode):
+        """Tests only: 0 = never, 1 = by size (default), 2 = always use the matrix-free projector path; the cached
+        workspace sizes depend on it."""
+        lib.ctmb_debug_set_matrix_free(int(mode))
+        self._tables = {k: v for k, v in self._tables.items() if not (isinstance(k, tuple) and k and k[0] in ('ws', 'wsc4v'))}
+
+    def rsvd_status(self, reset=False):
+        """(residual checks, decompositions returned although they missed the residual bound, worst residual / bound)."""
+        a, b, w = C.c_longlong(), C.c_longlong(), C.c_double()
+        check(lib.ctmb_get_rsvd_status(self._h, C.byref(a), C.byref(b), C.byref(w), int(bool(reset))))
+        return a.value, b.value, w.value
+
+    def _warn_rsvd(self):
+        _, missed, worst = self.rsvd_status()
+        if missed > self._rsvd_missed_seen:
+            import warnings
+            self._rsvd_missed_seen = missed
+            warnings.warn(f"libctmb: a truncated decomposition was returned with a residual {worst:.1f}x above the bound "
+                          "rsvd_tol*sqrt(n) (rounding floor or rsvd_max_rounds reached); the projectors amplify this by S0/Sj",
+                          RuntimeWarning, stacklevel=3)
 
     def counters(self):
         n, f = C.c_longlong(), C.c_double()
@@ -207,6 +238,32 @@ class CtmEngine:
         check(lib.ctmb_c2x2(self._h, _dt(a), k, chi, C.byref(s), _ptr(out), _ptr(ws), ws.numel(), self._stream()))
         return out
 
+    def halves(self, direction, coord, state, env):
+        """halves_of_4x4_CTM_MOVE_{UP,LEFT,DOWN,RIGHT} (ctm/generic/ctm_components.py:10-265): the pair (R, Rt) of the
+        projector job at `coord`, built from the four enlarged corners of its 2x2 patch."""
+        if direction not in DIRECTIONS:
+            raise ValueError("Invalid direction: " + str(direction))
+        keep, structs = [], []
+        for dx, dy in PATCH[direction]:
+            c = state.vertexToSite((coord[0] + dx, coord[1] + dy))
+            structs.append(self._site(state.sites[c], [env.C[(c, k)] for k in C_KEYS], [env.T[(c, k)] for k in T_KEYS], keep))
+        arr = (C.POINTER(_lib.Site) * 4)(*[C.pointer(s) for s in structs])
+        a0 = state.sites[state.vertexToSite(coord)]
+        dt = _dt(a0)
+        # rows: the bond being truncated, at the first corner's site; columns: the same leg at the second corner's site
+        leg = {(0, -1): 1, (-1, 0): 2, (0, 1): 3, (1, 0): 0}[direction]
+        c1 = state.vertexToSite((coord[0] + PATCH[direction][1][0], coord[1] + PATCH[direction][1][1]))
+        n0, n1 = env.chi * aux2(a0)[leg], env.chi * aux2(state.sites[c1])[leg]
+        R = torch.empty((n0, n1), dtype=a0.dtype, device=self.device)
+        Rt = torch.empty((n0, n1), dtype=a0.dtype, device=self.device)
+        d = DIRECTIONS[direction]
+        nb = lib.ctmb_halves_workspace(self._h, dt, d, env.chi, arr)
+        if nb == 0:
+            raise _lib.CtmbError(lib.ctmb_last_error().decode())
+        ws = self._workspace(nb)
+        check(lib.ctmb_halves(self._h, dt, d, env.chi, arr, _ptr(R), _ptr(Rt), _ptr(ws), ws.numel(), self._stream()))
+        return R, Rt
+
     def projectors(self, R, Rt, chi, **opt):
         R, Rt = self._prep(R, self.device), self._prep(Rt, self.device)
         n0, n1 = R.shape
@@ -286,6 +343,7 @@ class CtmEngine:
         coords = list(state.sites.keys())
         n = len(coords)
         chi = env.chi
+        refuse_autograd('ctm_MOVE', list(state.sites.values()) + list(env.C.values()) + list(env.T.values()))
         corner, nb, dest, _ = self._move_tables(state, direction)
         keep = []
         sites = (_lib.Site * n)()
@@ -315,6 +373,7 @@ class CtmEngine:
         ws = self._workspace(nbytes)
         check(lib.ctmb_move_generic(self._h, dt, d, n, chi, sites, corner, nb, C.byref(o), p1, p2, p3,
                                     _ptr(ws), ws.numel(), self._stream()))
+        self._warn_rsvd()
         kC1, kC2, kT = OUT_KEYS[direction]
         for i in range(n):
             env.C[(dest[i], kC1)] = nC1[i]
@@ -334,7 +393,7 @@ class CtmEngine:
     def projector_shape(self, direction, state, env):
         """(n0, chi) of the projectors of `direction` (uniform bond dimensions)."""
         D = aux2(next(iter(state.sites.values())))
-        leg = {(0, -1): D[1], (-1, 0): D[0], (0, 1): D[3], (1, 0): D[2]}[direction]   # bond being truncated
+        leg = {(0, -1): D[1], (-1, 0): D[2], (0, 1): D[3], (1, 0): D[0]}[direction]   # bond being truncated (row index of R)
         return env.chi * leg, env.chi
 
     def move_generic_projectors(self, direction, state, env, jobs, **opt):
@@ -389,6 +448,7 @@ class CtmEngine:
     def move_c4v(self, a, C_, T, chi, **opt):
         """One ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463) or, with a double-layer A[u,l,d,r],
         ctm_MOVE_dl (:200-322) -> (C', T', D)."""
+        refuse_autograd('ctm_MOVE_sl / ctm_MOVE_dl', (a, C_, T))
         a, C_, T = self._prep(a, self.device), self._prep(C_, self.device), self._prep(T, self.device)
         dt = _dt(a)
         opt.setdefault('eps_multiplet', 1.0e-12)      # truncated_eig_sym default (custom_eig.py:7-8)
@@ -407,6 +467,7 @@ class CtmEngine:
         ws = self._workspace(nbytes)
         check(lib.ctmb_move_c4v(self._h, dt, _ptr(a), dims, _ptr(C_), _ptr(T), chi, C.byref(o), _ptr(Co), _ptr(To),
                                 _ptr(Dv), _ptr(ws), ws.numel(), self._stream()))
+        self._warn_rsvd()
         return Co, To, Dv
 
 
@@ -438,6 +499,7 @@ class CtmEngine:
         if not open_sites or open_sites[0] < 0 or open_sites[-1] > 3:
             raise ValueError("open_sites must be a non-empty subset of [0,1,2,3]")
         mask = sum(1 << q for q in open_sites)
+        refuse_autograd('rdm2x2', [t for (a, Cs, Ts) in tensors4 for t in [a] + list(Cs) + list(Ts)])
         keep = []
         structs = [self._site(a, Cs, Ts, keep) for (a, Cs, Ts) in tensors4]
         arr = (C.POINTER(_lib.Site) * 4)(*[C.pointer(s) for s in structs])
@@ -456,6 +518,7 @@ class CtmEngine:
         """One- / two-site density matrix from explicit per-site data (see rdm2x2_sites); kind '1x1', '2x1' (second site
         to the right) or '1x2' (second site below)."""
         k = {'1x1': 0, '2x1': 1, '1x2': 2}[kind]
+        refuse_autograd('rdm' + kind, [t for (a, Cs, Ts) in tensors2 for t in [a] + list(Cs) + list(Ts)])
         keep = []
         structs = [self._site(a, Cs, Ts, keep) for (a, Cs, Ts) in tensors2]
         if len(structs) == 1:

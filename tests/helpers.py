@@ -148,6 +148,29 @@ class OracleEngine:
         return f((0, 0), sites, v2s, C, T, raw=raw, sym_pos_def=sym_pos_def)
 
     # ---- the piecewise entry points of CtmEngine, for the CPU dry run of the GPU suite (tests/test_gpu_dryrun_cpu.py) ----
+    def debug_set_matrix_free(self, mode):
+        pass
+
+    def halves(self, direction, coord, state, env):
+        return orc.halves(direction, coord, state.sites, state.vertexToSite, env.C, env.T)
+
+    def move_generic_projectors(self, direction, state, env, jobs, **opt):
+        coords = list(state.sites.keys())
+        out = [orc.projectors_from_matrices(*orc.halves(direction, coords[j], state.sites, state.vertexToSite, env.C, env.T),
+                                            env.chi, self._args(opt)) for j in jobs]
+        return [p.contiguous() for p, _ in out], [pt.contiguous() for _, pt in out]
+
+    def move_generic_absorb(self, direction, state, env, jobs, P_all, Pt_all, **opt):
+        coords = list(state.sites.keys())
+        P = {coords[i]: p for i, p in enumerate(P_all)}
+        Pt = {coords[i]: p for i, p in enumerate(Pt_all)}
+        out = []
+        for j in jobs:
+            c = coords[j]
+            nC1, nC2, nT = orc.absorb(direction, c, state.sites, state.vertexToSite, env.C, env.T, P, Pt, self._args(opt))
+            out.append((state.vertexToSite((c[0] - direction[0], c[1] - direction[1])), nC1, nC2, nT))
+        return out
+
     def c2x2(self, kind, C_, T1, T2, a, chi):
         if a.dim() == 4:
             t = orc.sl_einsum(orc.CORNERS[kind][3], (C_, T1, T2), a)

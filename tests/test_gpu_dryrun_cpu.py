@@ -8,6 +8,7 @@ import pytest
 import torch
 import helpers as H
 import test_gpu_parity as G
+import test_gpu_parity_sizes as GS
 
 DRY = ['test_pieces_against_reference_fixtures', 'test_run_energy_and_spectra_against_reference',
        'test_c4v_against_reference_fixtures', 'test_known_answer_rvb_c4v_on_gpu', 'test_known_answer_j1j2_2site_on_gpu',
@@ -18,13 +19,20 @@ DRY = ['test_pieces_against_reference_fixtures', 'test_run_energy_and_spectra_ag
        'test_c4v_rdms_and_energy_against_reference_fixture', 'test_small_rdms_against_oracle',
        'test_c4v_small_rdms_against_oracle', 'test_variants_against_reference_fixtures_generic',
        'test_variants_against_reference_fixtures_c4v', 'test_config1_script_known_answer_on_gpu',
-       'test_config2_script_known_answer_on_gpu']
+       'test_config2_script_known_answer_on_gpu',
+       # tests/test_gpu_parity_sizes.py
+       'test_config3_size_c4v_complex_against_live_oracle', 'test_config4_size_kagome_against_live_oracle',
+       'test_shard_entry_points_on_one_gpu', 'test_halves_against_reference_fixtures', 'test_clustered_spectrum_orthogonality']
+
+
+def _find(name):
+    return getattr(G, name, None) or getattr(GS, name)
 
 
 def _cases():
     out = []
     for name in DRY:
-        f = getattr(G, name)
+        f = _find(name)
         marks = [m for m in getattr(f, 'pytestmark', []) if m.name == 'parametrize']
         if not marks:
             out.append(pytest.param(name, {}, id=name))
@@ -49,7 +57,7 @@ def oracle_everywhere(monkeypatch):
 
 @pytest.mark.parametrize('name,kw', _cases())
 def test_gpu_test_body_runs_with_the_oracle_as_engine(oracle_everywhere, name, kw):
-    f = getattr(G, name)
+    f = _find(name)
     params = inspect.signature(f).parameters
     args = dict(kw)
     if 'eng' in params:
