@@ -1,18 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- CTM moves/sec of the B200-native engine (and of the reference CPU path).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c5]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], named in config.workload): J1-J2 generic 4SITE iPEPS,
-D=3, chi=48, float64, synthetic random state (family B: rand-0.5, seed 123),
-environment from the 'CTMRG' initialisation.  One STEP = one full CTMRG iteration
-= 2(lX+lY) = 8 calls of ctm_MOVE (ctm/generic/ctmrg.py:63-69); metric = ctm_MOVE calls / s,
-timed on the device with CUDA events (conv_check excluded, as the reference's t_ctm).
+Default workload for EVERY N (BASELINE.json: "CTM moves/sec (4SITE, D,chi named) at 1/2/4/8 B200", configs[4]):
+J1-J2 generic 4SITE iPEPS, D=8, chi=256, float64 (n = chi D^2 = 16384), synthetic random state (family B: rand-0.5,
+seed 123), environment from the 'CTMRG' initialisation.  One STEP = ONE ctm_MOVE (ctm/generic/ctmrg.py:179-319;
+the directions cycle through the reference's sequence U,U,L,L,D,D,R,R): a move is 1.13e14 reference-algorithm FLOP and
+takes seconds.  N > 1: ONE CTM run sharded per site over the ranks (N = 2, 4) and, on 8 GPUs, 4 site jobs x groups of 2
+(peps_torch_b200/dist.py), `scaling: strong`.  `--config c1..c4` select the other BASELINE configs (a step is then one
+full CTMRG iteration, N > 1 runs replicas); the c2 line with its live reference arm is recorded in profiles/.
+metric = ctm_MOVE calls / s, timed on the device with CUDA events (conv_check excluded, as the reference's t_ctm).
 Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -35,7 +40,7 @@ CONFIGS = {
     # one site of c5 (1x1 cell): the unit of the intra-site group split (G = 2N) that two GPUs can measure
     'c5s': ('1site', 8, 256, 'float64', 'B', 'generic 1SITE D=8 chi=256 float64 (one site job of config 5)'),
 }
-BIG = ('c5', 'c5s')             # a move takes seconds: a step is ONE ctm_MOVE, no CPU arm
+BIG = ('c5', 'c5s')             # a move takes seconds: a step is ONE ctm_MOVE
 
 
 def algorithmic_flops_per_move(kind, D, chi, p, cplx):
@@ -111,43 +116,166 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's CPU path on host cores
+# reference arm / cpu baseline on the host cores: the UNMODIFIED reference through its own library API when a copy
+# of it travelled with the repo (baseline/_ref, written by __graft_entry__.build() where /root/reference exists:
+# kind "reference"), else the oracle port (kind "port").  Never reads /root/reference at run time.
 # ------------------------------------------------------------------------------------------
-def cpu_moves_per_s(cfg_name, steps, warmup, threads):
-    import ctm_oracle as orc
-    kind, sites, v2s, lX, lY, chi = make_state(cfg_name)
-    torch.set_num_threads(threads)
-    if kind == 'c4v':
-        a = sites
-        C, T = orc.init_env_c4v(a, chi)
+REF_ROOT = os.path.join(ROOT, 'baseline', '_ref')
+
+
+class RefArm:
+    def __init__(self):
+        self.kind = 'port'
+        self.ref = None
+        if os.path.isfile(os.path.join(REF_ROOT, 'ctm', 'generic', 'ctmrg.py')):
+            try:
+                self.ref = self._import_reference()
+                self.kind = 'reference'
+            except Exception as ex:                # an unimportable copy must not take the bench line down
+                self.import_error = repr(ex)[:200]
+
+    @staticmethod
+    def _import_reference():
+        sys.dont_write_bytecode = True
+        if REF_ROOT not in sys.path:
+            sys.path.insert(0, REF_ROOT)
+        import contextlib
+        import importlib
+        cwd = os.getcwd()
+        os.chdir('/tmp')                           # config.configure / logging write into cwd (config.py:129)
+        try:
+            with contextlib.redirect_stdout(sys.stderr):       # the reference prints warnings about optional back-ends at import
+                m = {name: importlib.import_module(name) for name in
+                     ('config', 'ipeps.ipeps', 'ipeps.ipeps_c4v', 'ctm.generic.env', 'ctm.generic.ctmrg',
+                      'ctm.generic.ctm_components', 'ctm.one_site_c4v.env_c4v', 'ctm.one_site_c4v.ctmrg_c4v',
+                      'linalg.custom_svd')}
+        finally:
+            os.chdir(cwd)
+        return m
+
+    def describe(self):
+        return ('the unmodified reference (baseline/_ref) through its library API: ENV, init_env, ctmrg.run(conv_check=None), t_ctm'
+                if self.kind == 'reference' else 'oracle/ctm_oracle.py, the port of the reference CPU path (torch CPU, LAPACK gesdd/syevd)')
+
+    # ---- configs c1-c4: whole iterations -------------------------------------------------
+    def _moves_per_s_once(self, cfg_name, steps, warmup):
+        import ctm_oracle as orc
+        kind, sites, v2s, lX, lY, chi = make_state(cfg_name)
+        if self.kind == 'reference':
+            m = self.ref
+            cfg = m['config']
+            dt = sites.dtype if kind == 'c4v' else next(iter(sites.values())).dtype
+            cfg.global_args.torch_dtype = dt
+            cfg.global_args.dtype = 'complex128' if dt.is_complex else 'float64'
+            cfg.global_args.device = 'cpu'
+            if kind == 'c4v':
+                state = m['ipeps.ipeps_c4v'].IPEPS_C4V(sites)
+                env = m['ctm.one_site_c4v.env_c4v'].ENV_C4V(chi, state)
+                m['ctm.one_site_c4v.env_c4v'].init_env(state, env)
+                run, mps = m['ctm.one_site_c4v.ctmrg_c4v'].run, 1
+            else:
+                state = m['ipeps.ipeps'].IPEPS(sites, vertexToSite=v2s, lX=lX, lY=lY)
+                env = m['ctm.generic.env'].ENV(chi, state)
+                m['ctm.generic.env'].init_env(state, env)
+                run, mps = m['ctm.generic.ctmrg'].run, 2 * (lX + lY)
+            if warmup > 0:
+                cfg.ctm_args.ctm_max_iter = warmup
+                run(state, env, conv_check=None)
+            cfg.ctm_args.ctm_max_iter = steps
+            _, _, t_ctm, _ = run(state, env, conv_check=None)
+            return steps * mps / t_ctm, mps
+        if kind == 'c4v':
+            a = sites
+            C, T = orc.init_env_c4v(a, chi)
+            for _ in range(warmup):
+                C, T = orc.ctm_move_c4v(a, C, T, chi)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                C, T = orc.ctm_move_c4v(a, C, T, chi)
+            return steps / (time.perf_counter() - t0), 1
+        C, T = orc.init_env(sites, v2s, chi)
         for _ in range(warmup):
-            C, T = orc.ctm_move_c4v(a, C, T, chi)
+            orc.ctm_iteration(sites, v2s, lX, lY, C, T, chi)
         t0 = time.perf_counter()
+        moves = 0
         for _ in range(steps):
-            C, T = orc.ctm_move_c4v(a, C, T, chi)
-        return steps / (time.perf_counter() - t0), 1
-    C, T = orc.init_env(sites, v2s, chi)
-    for _ in range(warmup):
-        orc.ctm_iteration(sites, v2s, lX, lY, C, T, chi)
-    t0 = time.perf_counter()
-    moves = 0
-    for _ in range(steps):
-        moves += orc.ctm_iteration(sites, v2s, lX, lY, C, T, chi)
-    return moves / (time.perf_counter() - t0), moves // steps
+            moves += orc.ctm_iteration(sites, v2s, lX, lY, C, T, chi)
+        return moves / (time.perf_counter() - t0), moves // steps
 
+    def moves_per_s(self, cfg_name, steps, warmup, repeats=3):
+        """thread sweep {1, all host cores} (MKL threading can cost 20x on small problems), median
+        of `repeats` repeats per thread count, best median reported."""
+        ncpu = os.cpu_count() or 1
+        best = None
+        for th in sorted({1, ncpu}):
+            torch.set_num_threads(th)
+            vals, mps = [], 1
+            for _ in range(repeats):
+                v, mps = self._moves_per_s_once(cfg_name, steps, warmup)
+                vals.append(v)
+            med = statistics.median(vals)
+            if best is None or med > best[0]:
+                best = (med, th, mps, vals)
+        v, th, mps, vals = best
+        return {'value': v, 'unit': 'ctm_MOVE/s', 'cores': th, 'kind': self.kind, 'moves_per_step': mps,
+                'sample': f'{warmup} warm-up + {steps} timed CTMRG iterations ({mps} ctm_MOVE each) of the same workload, median of '
+                          f'{repeats} repeats ({", ".join(f"{x:.3g}" for x in vals)}), best of thread counts {{1,{ncpu}}} on {ncpu} host cores; '
+                          + self.describe()}
 
-def cpu_baseline(cfg_name, steps=3, warmup=1):
-    """Thread sweep {1, all host cores} (MKL threading can cost 20x on small problems,
-    BASELINE.md section 5): report the best."""
-    ncpu = os.cpu_count() or 1
-    best = None
-    for th in sorted({1, ncpu}):
-        v, mps = cpu_moves_per_s(cfg_name, steps, warmup, th)
-        if best is None or v > best[0]:
-            best = (v, th, mps)
-    return {'value': best[0], 'unit': 'ctm_MOVE/s', 'cores': best[1], 'kind': 'port',
-            'sample': f'{warmup} warm-up + {steps} timed CTMRG iterations ({best[2]} ctm_MOVE each) of the same workload; '
-                      f'oracle/ctm_oracle.py (torch CPU, LAPACK gesdd/syevd) on {ncpu} host cores, best of thread counts {{1,{ncpu}}}'}
+    # ---- config c5: phases of one site, SVD extrapolated (BASELINE.md section 4.3) --------
+    def c5_sample(self, cfg_name, repeats=1):
+        """One reference ctm_MOVE at n = 16384 is four full 16384^2 LAPACK SVDs (tens of minutes per move).  Bounded
+        sample, timed with the reference's own functions on the workload's own tensors: ONE enlarged corner at full size
+        (c2x2_LU, ctm_components.py:314-434), ONE n x n x n product at full size (the halves and M = R^T Rt are three of
+        these per site, ctm_components.py:55-75, ctm_projectors.py:260-263), and ONE truncated_svd_gesdd
+        (custom_svd.py:38-101) at n/4 = 4096 scaled by 4^3 (gesdd is O(n^3)) -- the only extrapolated phase, stated as
+        such.  Projector products and the absorption (< 1 % of the FLOPs) are left out, which favours the CPU."""
+        import ctm_oracle as orc
+        kind, sites, v2s, lX, lY, chi = make_state(cfg_name)
+        nsites = len(sites)
+        ncpu = os.cpu_count() or 1
+        torch.set_num_threads(ncpu)
+        D = next(iter(sites.values())).shape[1]
+        n = chi * D * D
+        if self.kind == 'reference':
+            m = self.ref
+            cfg = m['config']
+            cfg.global_args.torch_dtype, cfg.global_args.dtype, cfg.global_args.device = torch.float64, 'float64', 'cpu'
+            state = m['ipeps.ipeps'].IPEPS(sites, vertexToSite=v2s, lX=lX, lY=lY)
+            env = m['ctm.generic.env'].ENV(chi, state)
+            m['ctm.generic.env'].init_env(state, env)
+            corner = lambda: m['ctm.generic.ctm_components'].c2x2_LU((0, 0), state, env, mode='sl')     # noqa: E731
+            svd = lambda M: m['linalg.custom_svd'].truncated_svd_gesdd(M, chi // 4)                       # noqa: E731
+        else:
+            C, T = orc.init_env(sites, v2s, chi)
+            corner = lambda: orc.corner_at('LU', (0, 0), sites, v2s, C, T)                                # noqa: E731
+            svd = lambda M: orc.truncated_svd(M, chi // 4, 1e-8, 1e-14)                                   # noqa: E731
+        g = torch.Generator().manual_seed(123)
+        A = torch.rand(n, n, dtype=torch.float64, generator=g) - 0.5
+        ns = n // 4
+        Ms = (torch.rand(ns, ns, dtype=torch.float64, generator=g) - 0.5) * torch.logspace(0, -12, ns, dtype=torch.float64)
+        tc, tg, ts = [], [], []
+        for _ in range(repeats):
+            t0 = time.perf_counter(); X = corner(); tc.append(time.perf_counter() - t0)
+            assert X.shape == (n, n)
+            t0 = time.perf_counter(); torch.mm(A.t(), X); tg.append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); svd(Ms); ts.append(time.perf_counter() - t0)
+        t_corner, t_gemm, t_svd_s = statistics.median(tc), statistics.median(tg), statistics.median(ts)
+        t_svd = t_svd_s * (n / ns) ** 3
+        per_site = 4 * t_corner + 3 * t_gemm + t_svd
+        return {'value': 1.0 / (nsites * per_site), 'unit': 'ctm_MOVE/s', 'cores': ncpu, 'kind': self.kind, 'extrapolated': True,
+                'phases_s': {'enlarged_corner_full_size': t_corner, 'gemm_n3_full_size': t_gemm,
+                             f'svd_gesdd_n{ns}': t_svd_s, f'svd_gesdd_n{n}_extrapolated_x{int((n / ns) ** 3)}': t_svd},
+                'seconds_per_move_extrapolated': nsites * per_site,
+                'sample': f'phases of ONE site job timed once each on {ncpu} host cores (median of {repeats}): one enlarged corner at full '
+                          f'size ({t_corner:.2f} s), one {n}^3 DGEMM ({t_gemm:.2f} s), one truncated_svd_gesdd at n = {ns} ({t_svd_s:.2f} s) '
+                          f'scaled by {int((n / ns) ** 3)} to n = {n} (EXTRAPOLATED, O(n^3)); move = {nsites} sites x (4 corners + 3 GEMMs + 1 SVD), '
+                          'projector products and absorption left out (BASELINE.md section 4.3); ' + self.describe()}
+
+    def baseline(self, cfg_name, steps=3, warmup=1, repeats=3):
+        if cfg_name in BIG:
+            return self.c5_sample(cfg_name, repeats=1)
+        return self.moves_per_s(cfg_name, steps, warmup, repeats)
 
 
 def run_reference(args):
@@ -155,26 +283,28 @@ def run_reference(args):
     if rank != 0:
         return
     kind, D, chi, dt, fam, desc = CONFIGS[args.config]
-    ncpu = os.cpu_count() or 1
+    arm = RefArm()
     if args.config in BIG:
-        print(json.dumps({'impl': 'reference', 'unavailable': 'config c5 on CPU is four full 16384^2 LAPACK SVDs per ctm_MOVE '
-                          '(~56 min per move, SURVEY.md section 6); the default config c2 has a live reference arm'}))
-        return
-    best = None
-    for th in sorted({1, ncpu}):
-        v, mps = cpu_moves_per_s(args.config, args.steps, min(args.warmup, 1), th)
-        if best is None or v > best[0]:
-            best = (v, th, mps)
-    v, th, mps = best
+        base = arm.c5_sample(args.config, repeats=min(max(args.steps, 1), 3))
+        mps = 1
+        steps_done = min(max(args.steps, 1), 3)
+    else:
+        steps_done = max(1, min(args.steps, 20))
+        base = arm.moves_per_s(args.config, steps_done, min(args.warmup, 1), repeats=3)
+        mps = base['moves_per_step']
+    v = base['value']
+    per_step = f'{"1 ctm_MOVE_sl" if kind == "c4v" else str(mps) + " ctm_MOVE"} per step'
     line = {'impl': 'reference', 'metric': 'CTM moves/sec', 'value': v, 'unit': 'ctm_MOVE/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 * mps / v, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c128' if dt == 'complex128' else 'f64', 'data': 'synthetic',
-            'config': {'workload': desc + f' ({"1 ctm_MOVE_sl" if kind == "c4v" else str(mps) + " ctm_MOVE"} per step)',
-                       'family': fam, 'seed': 123, 'moves_per_step': mps},
-            'cpu_baseline': {'value': v, 'unit': 'ctm_MOVE/s', 'cores': th, 'kind': 'port',
-                             'sample': f'{args.steps} timed CTMRG iterations, oracle port (torch CPU) of the reference path'},
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * mps / v, 'higher_is_better': True,
+            'scaling': 'strong' if args.config in BIG else 'weak', 'vs_baseline': None,
+            'dtype': 'c128' if dt == 'complex128' else 'f64', 'data': 'synthetic',
+            'config': {'workload': desc + f' ({per_step})', 'family': fam, 'seed': 123, 'moves_per_step': mps},
+            'cpu_baseline': base,
             'e2e': {'value': v, 'unit': 'ctm_MOVE/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+            'gpu_launches': 0,
+            'note': (f'the CPU arm timed {steps_done} bounded sample(s), not {args.steps} whole moves: one reference ctm_MOVE at n = 16384 takes '
+                     'tens of minutes (four full 16384^2 gesdd); value is an explicit extrapolation from timed phases, see cpu_baseline.sample'
+                     if args.config in BIG else f'{steps_done} timed iterations per repeat')}
     print(json.dumps(line))
 
 
@@ -197,10 +327,9 @@ def measure_fp64_peak(dev):
 
 
 def kernel_level(eng, dev, fp64_peak):
-    """FLOP-bound evidence next to the (latency-bound) c2 step: the enlarged corner at config-5 size
-    (D=8, chi=256, float64: the north star's named kernel, F_c = 2.77e11 FLOP, 2.1 GB output) and the
-    n x n x n contraction that carries 94 % of a config-5 move, timed alone with CUDA events (best of 3,
-    warm; inputs 2-4 GB >> L2)."""
+    """Kernel-level FLOP-bound evidence: the enlarged corner at config-5 size (D=8, chi=256, float64: the north star's
+    named kernel, F_c = 2.77e11 FLOP, 2.1 GB output) and an n x n x n contraction, timed alone with CUDA events (best of
+    3, warm; inputs 2-4 GB >> L2)."""
     out = {}
 
     def best_ms(fn, reps=3):
@@ -229,7 +358,6 @@ def kernel_level(eng, dev, fp64_peak):
         ms = best_ms(lambda: eng.einsum2('ki,kj->ij', A, B))
         out['gemm_RtR_8192'] = {'ms': ms, 'flops': 2.0 * n ** 3, 'tflops': 2.0 * n ** 3 / ms / 1e9, 'frac_of_fp64_dgemm_peak': 2.0 * n ** 3 / ms / 1e9 / fp64_peak}
         del A, B
-        eng._ws = None
         torch.cuda.empty_cache()
     except Exception as ex:          # never lose the bench line over the side measurement
         out['error'] = str(ex)[:200]
@@ -238,7 +366,6 @@ def kernel_level(eng, dev, fp64_peak):
 
 def run_ours(args):
     import torch.distributed as dist
-    import ctm_oracle as orc
     from peps_torch_b200.engine import default_engine
     from peps_torch_b200.ipeps import IPEPS, IPEPS_C4V
     from peps_torch_b200.env import ENV, init_env, ENV_C4V, init_env_c4v
@@ -273,6 +400,7 @@ def run_ours(args):
     if args.rank_factor is not None:            # experiments: sketch width k = ceil(rank_factor * chi)
         eng.options.rsvd_rank_factor = args.rank_factor
     ctm_args.b200_rsvd_rank_factor = eng.options.rsvd_rank_factor if args.rank_factor is not None else None
+    per_move = args.config in BIG
 
     # pinned host copies (e2e) and device-resident state (value)
     if kind == 'c4v':
@@ -294,7 +422,6 @@ def run_ours(args):
 
         # config c5 (n = 16384): a move takes seconds, so a STEP is ONE ctm_MOVE (directions cycle through the
         # reference's sequence U,U,L,L,D,D,R,R) instead of a full iteration of eight
-        per_move = args.config in BIG
         seq = [d for d in ctm_args.ctm_move_sequence for _ in range(lX if d in [(-1, 0), (1, 0)] else lY)]
         cursor = [0]
 
@@ -314,8 +441,8 @@ def run_ours(args):
             else:
                 ctmrg.run(state, e, ctm_args=ctm_args)
         moves_per_step = 1 if per_move else 2 * (lX + lY)
-    # a few iterations so that the timed environment is not the zero-padded initial one
-    for _ in range(1 if args.config in BIG else max(args.warmup, 3)):
+    # a few moves so that the timed environment is not the zero-padded initial one
+    for _ in range(1 if per_move else max(args.warmup, 3)):
         one_step(st, env)
     torch.cuda.synchronize(dev)
 
@@ -358,8 +485,11 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     eng.reset_counters()
+    if sharded is not None:
+        sharded.comm_reset()
     ms = timed_region(resident_step, args.steps)
     launches, flops_exec = eng.counters()
+    comm = sharded.comm_totals() if sharded is not None else None
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -370,12 +500,8 @@ def run_ours(args):
     value = mult * moves_per_step * args.steps / (ms * 1e-3)
 
     # ------------------------------------------------------------------ e2e (host buffers)
-    if kind == 'c4v':
-        hostC = {k: v.cpu().pin_memory() for k, v in env.C.items()}
-        hostT = {k: v.cpu().pin_memory() for k, v in env.T.items()}
-    else:
-        hostC = {k: v.cpu().pin_memory() for k, v in env.C.items()}
-        hostT = {k: v.cpu().pin_memory() for k, v in env.T.items()}
+    hostC = {k: v.cpu().pin_memory() for k, v in env.C.items()}
+    hostT = {k: v.cpu().pin_memory() for k, v in env.T.items()}
     h2d = sum(t_.numel() * t_.element_size() for t_ in list(hostC.values()) + list(hostT.values()))
     h2d += (a_host.numel() * a_host.element_size()) if kind == 'c4v' else sum(t_.numel() * t_.element_size() for t_ in host_sites.values())
     d2h = sum(t_.numel() * t_.element_size() for t_ in list(hostC.values()) + list(hostT.values()))
@@ -390,13 +516,13 @@ def run_ours(args):
             e2 = ENV(chi)
         e2.C = {k: v.to(dev, non_blocking=True) for k, v in hostC.items()}
         e2.T = {k: v.to(dev, non_blocking=True) for k, v in hostT.items()}
-        one_step(s2, e2)                       # the public drop-in API: ctmrg.run(state, env)
+        one_step(s2, e2)                       # the public drop-in API: ctmrg.run(state, env) / ctm_MOVE(direction, state, env)
         for k, v in e2.C.items():
             hostC[k].copy_(v, non_blocking=True)
         for k, v in e2.T.items():
             hostT[k].copy_(v, non_blocking=True)
 
-    for _ in range(min(args.warmup, 3)):
+    for _ in range(min(args.warmup, 1 if per_move else 3)):
         e2e_step()
     ms_e2e = timed_region(e2e_step, args.steps)
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
@@ -406,11 +532,14 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ roofline of the dominant kernel
     # (all ranks take part: in shard mode a step contains collectives)
+    prof_steps = max(1, min(args.steps, 4)) if per_move else args.steps
     eng.profile(True)
     eng.reset_counters()
-    timed_region(resident_step, args.steps)
+    timed_region(resident_step, prof_steps)
     prof = eng.profile_totals()
     eng.profile(False)
+    rsvd_checks, rsvd_missed, rsvd_worst = eng.rsvd_status()
+    rsvd_calls, rsvd_iters = eng.rsvd_iterations()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -422,28 +551,35 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    # capture of the same config (profiles/traffic.json: {config: {class: {"bytes_per_launch": ..., "source": ...}}})
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    except Exception:
+        traffic_tab = {}
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     total_ms = sum(v['ms'] for v in prof.values()) or 1.0
     dom = max(prof, key=lambda k_: prof[k_]['ms'])
     g = prof['tc_gemm']
     share = {k_: round(v['ms'] / total_ms, 4) for k_, v in prof.items()}
+    tr = traffic_tab.get(args.config, {}).get(dom, {})
     if dom == 'tc_gemm':
         ach = g['flops'] / (g['ms'] * 1e-3) / 1e12
-        roof = {'kernel': 'tc_kernel / tc_kernel_ws (DMMA tensor-contraction GEMM)', 'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak,
-                'unit': 'TFLOP/s', 'frac': ach / fp64_peak, 'traffic': None}
+        roof = {'kernel': 'tc_kernel_ws / tc_kernel (DMMA tensor-contraction GEMM: corners, operator applications of the range finder, '
+                          'projector products, absorption)', 'bound': 'tensor', 'achieved': ach, 'peak': fp64_peak,
+                'unit': 'TFLOP/s', 'frac': ach / fp64_peak, 'traffic': tr.get('bytes_per_launch'),
+                'algorithmic_bytes_per_launch': g['bytes'] / max(1, g['launches'])}
     else:
         v = prof[dom]
         ach = v['bytes'] / (v['ms'] * 1e-3) / 1e9
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-        # (profiles/r1_c2_qr_tsolve_metrics.csv: qr_reg_kernel reads 1.37 MB = the four 432x96 sketches, writes stay in L2)
-        traffic = {'qr': 1.370624e6 if args.config == 'c2' else None, 'jacobi': None, 'misc': None}[dom]
-        roof = {'kernel': {'qr': 'qr_reg_kernel + wy_tsolve_kernel (Householder QR of the range-finder sketches, register-resident over a cluster of 8 CTAs per matrix; latency-bound: one cluster barrier per column)',
-                           'jacobi': 'jacobi_kernel (one-sided Jacobi SVD of the k x k factor in shared memory; shared-memory-bandwidth bound)',
+        roof = {'kernel': {'qr': 'Householder QR of the range-finder sketches (qr.cu)',
+                           'jacobi': 'jacobi_kernel (one-sided Jacobi SVD of the k x k factor in shared memory)',
                            'misc': 'misc kernels'}[dom], 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': ach / hbm_peak, 'traffic': traffic,
-                'note': 'the step is latency-bound (2.8 GFLOP per move); the FLOP-bound kernels of the path are reported under kernel_level; '
-                        'traffic is the ncu capture of the k = 96 build (profiles/r1_c2_qr_tsolve_metrics.csv), the sketches are 84 columns wide since'}
-    roof['peak_source'] = ('cuBLAS DGEMM 8192^3 measured in this run' if roof['bound'] == 'tensor'
+                'frac': ach / hbm_peak, 'traffic': tr.get('bytes_per_launch'),
+                'note': 'this config is latency-bound (a few GFLOP per move); the FLOP-bound kernels of the path are reported under kernel_level'}
+    if tr.get('source'):
+        roof['traffic_source'] = tr['source']
+    roof['peak_source'] = ('cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor path = DMMA; tcgen05 has no f64 kind)' if roof['bound'] == 'tensor'
                            else ('MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650 GB/s'))
     roof['avg_launch_us'] = 1e3 * prof[dom]['ms'] / max(1, prof[dom]['launches'])
     roof['time_share_by_kernel_class'] = share
@@ -452,41 +588,45 @@ def run_ours(args):
 
     # CTMB_BENCH_FAST=1 (profiling runs under ncu): skip the side measurements that are not part of the timed step
     fast = bool(os.environ.get('CTMB_BENCH_FAST'))
+    eng._ws = None
+    torch.cuda.empty_cache()
     roof['kernel_level'] = None if fast else kernel_level(eng, dev, fp64_peak)
     F_move = algorithmic_flops_per_move(kind, D, chi, p_phys, cplx)
-    if args.config in BIG:
+    if fast or world > 1:
         base = {'value': None, 'unit': 'ctm_MOVE/s', 'cores': os.cpu_count(), 'kind': 'port',
-                'sample': 'not run: one reference move at n = 16384 is four full 16384^2 LAPACK SVDs (~56 min per ctm_MOVE '
-                          'extrapolated from DGEMM / gesdd timings, SURVEY.md section 6)'}
-    elif fast:
-        base = {'value': None, 'unit': 'ctm_MOVE/s', 'cores': os.cpu_count(), 'kind': 'port', 'sample': 'skipped (CTMB_BENCH_FAST)'}
+                'sample': 'skipped (CTMB_BENCH_FAST)' if fast else 'reported at N = 1 only (rank 0 host cores)'}
     else:
-        base = cpu_baseline(args.config)
+        base = RefArm().baseline(args.config)
     if world == 1:
         parallelism = 'single GPU'
     elif not shard:
         parallelism = f'{world} independent replicas (one CTM run per GPU)'
     elif sharded._layout is not None and sharded._layout[1] > 1:
-        parallelism = (f'{sharded._layout[0]} site job(s) x groups of {sharded._layout[1]} GPUs: the n x n x k operator applications of the '
-                       f'range finder are split by sketch columns inside a group (in-place NCCL all-gather of the slabs, '
-                       f'{getattr(eng, "group_bytes", 0) / 1e6:.0f} MB received per rank in this run); NCCL all-gather of P/Pt and of '
-                       f'the new C/T per move')
+        parallelism = (f'shard: {sharded._layout[0]} site job(s) x groups of {sharded._layout[1]} GPUs -- the n x n x k operator applications of the '
+                       f'range finder are split by sketch columns inside a group (in-place NCCL all-gather of the slabs); NCCL all-gather of P/Pt '
+                       f'and of the new C/T per move')
     else:
-        parallelism = f'per-site shard over {world} GPUs, NCCL all-gather of P/Pt and of the new C/T per move'
+        parallelism = f'shard: per-site shard of ONE CTM run over {world} GPUs, NCCL all-gather of P/Pt and of the new C/T per move'
     line = {'metric': 'CTM moves/sec', 'value': value, 'unit': 'ctm_MOVE/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'strong' if shard else 'weak', 'vs_baseline': None, 'dtype': 'c128' if cplx else 'f64', 'data': 'synthetic',
+            'scaling': 'strong' if (shard or (per_move and world == 1)) else 'weak', 'vs_baseline': None, 'dtype': 'c128' if cplx else 'f64',
+            'data': 'synthetic',
             'config': {'workload': desc + f' ({"1 ctm_MOVE_sl" if kind == "c4v" else str(moves_per_step) + " ctm_MOVE"} per step)',
                        'family': fam, 'seed': 123, 'moves_per_step': moves_per_step, 'l2': 'flushed between timed steps (256 MiB write)',
                        'parallelism': parallelism,
                        'rsvd': {'rank_factor': eng.options.rsvd_rank_factor or 'auto (1.75 for n <= 1024, else 2.0)',
-                                'niter_first_call': eng.options.rsvd_niter, 'iterations': 'residual-checked (rsvd_tol 2e-15 sqrt(n))'}},
+                                'niter_first_call': eng.options.rsvd_niter, 'iterations': 'residual-checked (rsvd_tol 2e-15 sqrt(n))',
+                                'residual_checks': rsvd_checks, 'results_above_bound': rsvd_missed,
+                                'power_iterations_per_decomposition': (rsvd_iters / rsvd_calls) if rsvd_calls else None}},
             'e2e': {'value': e2e_value, 'unit': 'ctm_MOVE/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': base,
-            'flops': {'reference_algorithm_per_move': F_move, 'executed_per_move': flops_exec / (moves_per_step * args.steps),
+            'flops': {'reference_algorithm_per_move': F_move, 'executed_per_move': flops_exec / (moves_per_step * prof_steps),
                       'move_level_frac_of_fp64_peak': F_move * value / world / (fp64_peak * 1e12)}}
-    if world > 1 and base.get('value') is not None:
-        line['cpu_baseline']['note'] = 'measured on rank 0 host cores while the other ranks idle'
+    if comm is not None:
+        moves = moves_per_step * args.steps
+        line['collectives'] = {'nccl_bytes_received_per_move': comm['bytes'] / moves, 'ms_in_collectives_per_move': comm['ms'] / moves,
+                               'share_of_step': comm['ms'] / ms if ms else None, 'by_kind_ms_per_move': {k_: v / moves for k_, v in comm['by_kind'].items()},
+                               'note': 'CUDA events around every NCCL call on rank 0 (includes waiting for the slowest rank)'}
     print(json.dumps(line))
 
 
@@ -496,7 +636,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--config', default='c5', choices=sorted(CONFIGS))
     ap.add_argument('--rank-factor', type=float, default=None, dest='rank_factor',
                     help='sketch width of the range finder in units of chi (default: the library default)')
     ap.add_argument('--parallel', default='auto', choices=['auto', 'shard', 'replicas'],

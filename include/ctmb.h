@@ -96,8 +96,10 @@ int ctmb_set_group(ctmb_handle_t h, int rank, int nranks, ctmb_allgather_fn fn, 
 /* Status of the residual-checked range finder since the last reset: number of residual checks, number of decompositions
  * that were RETURNED ALTHOUGH they missed the bound rsvd_tol * sqrt(n) (the residual stopped improving -- rounding floor --
  * or rsvd_max_rounds was reached) and the worst residual / bound ratio among those.  The host wrappers turn missed > 0 into
- * a Python warning.  (The reference's LAPACK SVD has no such diagnostic: svd_gesdd.py:77-96.) */
-int ctmb_get_rsvd_status(ctmb_handle_t h, long long* checks, long long* missed, double* worst_ratio, int reset);
+ * a Python warning; calls / iterations: iterative decompositions run and power iterations they took in total.
+ * (The reference's LAPACK SVD has no such diagnostic: svd_gesdd.py:77-96.) */
+int ctmb_get_rsvd_status(ctmb_handle_t h, long long* checks, long long* missed, double* worst_ratio, long long* calls,
+                         long long* iterations, int reset);
 
 /* kernels launched / algorithmic real flops enqueued by this handle since the last reset */
 int ctmb_get_counters(ctmb_handle_t h, long long* launches, double* flops);

@@ -43,7 +43,8 @@ SIGNATURES = {
     'ctmb_create': (C.c_int, [C.POINTER(_vp), _i]),
     'ctmb_destroy': (C.c_int, [_vp]),
     'ctmb_default_options': (None, [_PO]),
-    'ctmb_get_rsvd_status': (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double), _i]),
+    'ctmb_get_rsvd_status': (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                             C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
     'ctmb_get_counters': (C.c_int, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     'ctmb_reset_counters': (C.c_int, [_vp]),
     'ctmb_profile_enable': (C.c_int, [_vp, _i]),

@@ -94,6 +94,11 @@ void add_identity_launch(const PtrBatch& Q, int nb, int k, int ld, bool cplx, cu
 int qr_panel_width(int rows, int cols, bool cplx);
 void qr_panel_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& Tau, int nb, int rows, int b, int ld,
                      bool cplx, cudaStream_t stream);
+// tall panels (qr_tall.cu): rows split over up to 148 co-resident CTAs, 32 columns per leaf; width 0 = does not apply
+int qr_tall_panel_width(int nb, int rows, int cols, bool cplx);
+size_t qr_tall_scratch_bytes(int nb);
+bool qr_tall_panel_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& Tau, int nb, int rows, int b, int ld, bool cplx,
+                          void* scratch, cudaStream_t stream);
 void qr_copy_r_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& R, int nb, int k, int j0, int b, int ld,
                       bool cplx, cudaStream_t stream);
 void set_identity_launch(const PtrBatch& Q, int nb, int rows, int k, bool cplx, cudaStream_t stream);

@@ -70,7 +70,7 @@ public:
     double flops = 0;              // algorithmic real flops enqueued
     // residual-checked range finder: how many checks ran, how many results were returned although they missed the bound
     // (rounding floor / rsvd_max_rounds), and the worst residual / bound ratio among those (ctmb_get_rsvd_status)
-    struct RsvdStatus { long long checks = 0, missed = 0; double worst_ratio = 0.0; };
+    struct RsvdStatus { long long checks = 0, missed = 0, calls = 0, iterations = 0; double worst_ratio = 0.0; };
     RsvdStatus rsvd_status;
     unsigned long long* pinned_words();     // 32 pinned host words owned by this engine (read-back of device scalars)
     void drop_pending() { pend_active_ = false; pend_plans_.clear(); }

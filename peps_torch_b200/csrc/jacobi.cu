@@ -253,6 +253,15 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
         if (gl == 0) sig[c] = nrm - mu;
         const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
         for (int r = gl; r < k; r += gs) G[(size_t)c * k + r] = S::scale(G[(size_t)c * k + r], inv);
+        if (accw) {
+            // W is a product of ~sweeps * k plane rotations per column: its column norms drift by a few tens of ulps
+            // (1.4e-14 measured at k = 96); renormalise, so that V = Q2 W has unit columns like U = Q Uhat
+            double w2 = 0.0;
+            for (int r = gl; r < k; r += gs) w2 += S::abs2(W[(size_t)c * k + r]);
+            for (int o = gs >> 1; o > 0; o >>= 1) w2 += __shfl_xor_sync(gmask, w2, o);
+            const double winv = w2 > 0.0 ? rsqrt(w2) : 0.0;
+            for (int r = gl; r < k; r += gs) W[(size_t)c * k + r] = S::scale(W[(size_t)c * k + r], winv);
+        }
     }
     if (use_smem) {
         __syncthreads();
@@ -412,6 +421,13 @@ __global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, Pt
         if (lane == 0) sig[c] = nrm - mu;
         const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
         for (int r = lane; r < k; r += 32) G[(size_t)c * k + r] = S::scale(ldcg_t(G + (size_t)c * k + r), inv);
+        if (accw) {                                     // renormalise the accumulated rotations (see jacobi_kernel)
+            double w2 = 0.0;
+            for (int r = lane; r < k; r += 32) w2 += S::abs2(ldcg_t(W + (size_t)c * k + r));
+            w2 = warp_sum(w2);
+            const double winv = w2 > 0.0 ? rsqrt(w2) : 0.0;
+            for (int r = lane; r < k; r += 32) W[(size_t)c * k + r] = S::scale(ldcg_t(W + (size_t)c * k + r), winv);
+        }
     }
 }
 

@@ -265,7 +265,7 @@ static int sketch_width(int m, int n, int chi, const ctmb_options& o) {
 // Q = H_1 .. H_P E is accumulated backwards per super panel the same way.  (With leaf panels only, the
 // 16384 x 512 sketch of config c5 paid 64 full-width trailing updates with K = 8 per QR: 1.4 s per move.)
 // V is kept in its own buffer (zeros above each leaf's diagonal), the factor R stays in the upper part of A.
-struct QrBlockedWs { PtrBatch Q{}, V{}, Tau{}, Rpp{}, G{}, Tl{}, T{}, W{}, W2{}; int b = 0, B = 0; };
+struct QrBlockedWs { PtrBatch Q{}, V{}, Tau{}, Rpp{}, G{}, Tl{}, T{}, W{}, W2{}; int b = 0, B = 0; void* tall = nullptr; };
 
 static void qr_blocked_alloc(Engine& e, QrBlockedWs& w, int bidx, int rows_max, int k, int b) {
     const size_t es = e.esize();
@@ -330,7 +330,9 @@ static void qr_blocked(Engine& e, PtrBatch& cur, const PtrBatch& Rout, int nb, i
             const int bw = std::min(b, J1 - j0), prow = rows - j0;
             PtrBatch Ap = sub(cur, (size_t)j0 * rows + j0), Rp = sub(w.Rpp, (size_t)(j0 / b) * b * b);
             { ProfScope ps(e, Engine::CAT_QR, (e.cplx ? 4.0 : 1.0) * nb * 2.0 * prow * bw * bw, 2.0 * es * nb * (double)prow * bw);
-              qr_panel_launch(Ap, Rp, sub(w.Tau, j0), nb, prow, bw, rows, e.cplx, e.stream); }
+              // tall panels: rows split over the SMs (qr_tall.cu); the cluster kernel takes over where that does not apply
+              if (!(w.tall && qr_tall_panel_launch(Ap, Rp, sub(w.Tau, j0), nb, prow, bw, rows, e.cplx, w.tall, e.stream)))
+                  qr_panel_launch(Ap, Rp, sub(w.Tau, j0), nb, prow, bw, rows, e.cplx, e.stream); }
             { ProfScope ps(e, Engine::CAT_MISC);          // V buffer <- the leaf's reflectors, zeros above its diagonal (rows J0..)
               qr_copy_v_launch(cur, w.V, nb, rows, J0, j0, bw, e.cplx, e.stream); }
             if (b < B || J1 < k) {
@@ -392,10 +394,18 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     const int mx = std::max(m, n);
     const bool wy = qr_wy_supported(m, k, e.cplx) && qr_wy_supported(n, k, e.cplx);
     // neither the register / WY path nor one cluster holds the whole sketch: blocked factorisation
-    const int pw = std::min(std::min(qr_panel_width(m, k, e.cplx), qr_panel_width(n, k, e.cplx)), e.cplx ? 64 : 128);
+    int pw = std::min(std::min(qr_panel_width(m, k, e.cplx), qr_panel_width(n, k, e.cplx)), e.cplx ? 64 : 128);
     const bool blocked = !wy && pw < k;
-    CTMB_CHECK(!blocked || pw >= 4, "sketch too tall for the panel kernels");
     QrBlockedWs qbw;
+    if (blocked) {
+        // tall sketches (config 5: 16384 x 512): 32-column leaf panels factored with the rows split over the SMs
+        const int tw = std::min(qr_tall_panel_width(nb, m, k, e.cplx), qr_tall_panel_width(nb, n, k, e.cplx));
+        if (tw > pw) {
+            pw = tw;
+            if (!e.ws.dry()) qbw.tall = e.persistent("qrtall", qr_tall_scratch_bytes(TC_MAX_BATCH));
+        }
+    }
+    CTMB_CHECK(!blocked || pw >= 4, "sketch too tall for the panel kernels");
     for (int b = 0; b < nb; ++b) {
         if (!fac) Mt[b] = make_tn(const_cast<void*>(M[b]), "ij", {m, n});
         // (the QR drivers swap these with their Q scratch, so all of them are sized for the taller side)
@@ -647,6 +657,8 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         prev_res = res;
         todo = std::max(1, used);                         // double the total: q, 2q, 4q ...
     }
+    ++e.rsvd_status.calls;
+    e.rsvd_status.iterations += used;
     return r;
 }
 
@@ -1126,13 +1138,16 @@ int ctmb_set_group(ctmb_handle_t h, int rank, int nranks, ctmb_allgather_fn fn, 
     CTMB_CATCH(-1)
 }
 
-int ctmb_get_rsvd_status(ctmb_handle_t h, long long* checks, long long* missed, double* worst_ratio, int reset) {
+int ctmb_get_rsvd_status(ctmb_handle_t h, long long* checks, long long* missed, double* worst_ratio, long long* calls,
+                         long long* iterations, int reset) {
     CTMB_TRY
     CTMB_CHECK(h != nullptr, "null handle");
     Engine& e = h->h.eng;
     if (checks) *checks = e.rsvd_status.checks;
     if (missed) *missed = e.rsvd_status.missed;
     if (worst_ratio) *worst_ratio = e.rsvd_status.worst_ratio;
+    if (calls) *calls = e.rsvd_status.calls;
+    if (iterations) *iterations = e.rsvd_status.iterations;
     if (reset) e.rsvd_status = Engine::RsvdStatus{};
     return 0;
     CTMB_CATCH(-1)

@@ -22,6 +22,7 @@ Collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the 
 The compute backend is anything with the methods of CtmEngine used below, so the same
 code is exercised on CPU with the oracle as backend (tests/test_dist_cpu.py).
 """
+import time
 import torch
 import torch.distributed as dist
 from .engine import OUT_KEYS, DIRECTIONS
@@ -47,15 +48,58 @@ class ShardedCtm:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._layout = None         # (nsites, g, my group index or None, parts)
+        self._comm = []             # (kind, bytes received, start, end): CUDA events on the current stream (CPU: seconds)
 
-    def _all_gather(self, flat, counts):
-        """all-gather of ragged per-rank 1-D tensors (padded to the maximum count)."""
+    # ---- accounting of the exchange steps (bench.py: NCCL bytes and time in collectives per move) ----
+    def comm_reset(self):
+        self._comm = []
+        if hasattr(self.backend, 'group_reset'):
+            self.backend.group_reset()
+
+    def comm_totals(self):
+        """Synchronises the recorded events.  {'bytes', 'ms', 'by_kind': {kind: ms}}; the slab gathers of the intra-site
+        group split are reported by the backend (CtmEngine.group_totals)."""
+        tot = {'bytes': 0, 'ms': 0.0, 'by_kind': {}}
+        recs = list(self._comm)
+        if hasattr(self.backend, 'group_totals'):
+            recs += self.backend.group_totals()
+        for kind, nbytes, a, b in recs:
+            if isinstance(a, float):
+                ms = 1e3 * (b - a)
+            else:
+                b.synchronize()
+                ms = a.elapsed_time(b)
+            tot['bytes'] += nbytes
+            tot['ms'] += ms
+            tot['by_kind'][kind] = tot['by_kind'].get(kind, 0.0) + ms
+        return tot
+
+    def _all_gather(self, flat, counts, kind='gather'):
+        """all-gather of per-rank 1-D tensors: one in-place NCCL all-gather into a [world, m] buffer (ragged counts are
+        padded to the maximum m; with equal counts -- the per-site shard with N | 4 -- nothing is padded or copied twice)."""
         m = max(counts)
-        buf = flat.new_zeros(m)
-        buf[:flat.numel()] = flat
-        out = [torch.empty_like(buf) for _ in range(self.world)]
-        dist.all_gather(out, buf, group=self.group)
-        return [o[:c] for o, c in zip(out, counts)]
+        whole = flat.new_empty((self.world, m))
+        mine = whole[self.rank]
+        mine[:flat.numel()] = flat
+        cuda = flat.is_cuda
+        if cuda:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        else:
+            a = time.perf_counter()
+        if cuda:
+            dist.all_gather_into_tensor(whole, mine, group=self.group)
+        else:                       # gloo (CPU tests) has no all_gather_into_tensor
+            out = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(out, mine.clone(), group=self.group)
+            for r, o in enumerate(out):
+                whole[r] = o
+        if cuda:
+            b.record()
+        else:
+            b = time.perf_counter()
+        self._comm.append((kind, flat.element_size() * (sum(counts) - counts[self.rank]), a, b))
+        return [whole[r, :c] for r, c in enumerate(counts)]
 
     def _setup(self, nsites):
         """Decide the layout for `nsites` jobs once; in group mode create the process groups (a collective call: every
@@ -100,7 +144,7 @@ class ShardedCtm:
         else:
             flat = a0.new_zeros(0)
         per_job = 2 * n0 * chi
-        gathered = self._all_gather(flat, [len(p) * per_job for p in parts])
+        gathered = self._all_gather(flat, [len(p) * per_job for p in parts], 'allgather_P_Pt')
         P_all, Pt_all = [None] * n, [None] * n
         for r, jobs in enumerate(parts):
             for i, j in enumerate(jobs):
@@ -115,7 +159,7 @@ class ShardedCtm:
         def job_len(j):
             s = shapes[j]
             return 2 * chi * chi + s[0] * s[1] * s[2]
-        gathered = self._all_gather(flat, [sum(job_len(j) for j in p) for p in parts])
+        gathered = self._all_gather(flat, [sum(job_len(j) for j in p) for p in parts], 'allgather_C_T')
         kC1, kC2, kT = OUT_KEYS[direction]
         v2s = state.vertexToSite
         for r, jobs in enumerate(parts):
@@ -124,11 +168,11 @@ class ShardedCtm:
                 c = coords[j]
                 dest = v2s((c[0] - direction[0], c[1] - direction[1]))
                 blk = gathered[r]
-                env.C[(dest, kC1)] = blk[off:off + chi * chi].view(chi, chi).clone(); off += chi * chi
-                env.C[(dest, kC2)] = blk[off:off + chi * chi].view(chi, chi).clone(); off += chi * chi
+                env.C[(dest, kC1)] = blk[off:off + chi * chi].view(chi, chi); off += chi * chi
+                env.C[(dest, kC2)] = blk[off:off + chi * chi].view(chi, chi); off += chi * chi
                 s = shapes[j]
                 ln = s[0] * s[1] * s[2]
-                env.T[(dest, kT)] = blk[off:off + ln].view(*s).clone(); off += ln
+                env.T[(dest, kT)] = blk[off:off + ln].view(*s); off += ln
 
     def iteration(self, state, env, move_sequence=((0, -1), (-1, 0), (0, 1), (1, 0)), **opt):
         n = 0

@@ -118,16 +118,21 @@ class CtmEngine:
             try:
                 whole = torch.as_tensor(_Raw(buf, bytes_per_rank * nranks), device=self.device)
                 mine = whole[rank * bytes_per_rank:(rank + 1) * bytes_per_rank]
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
                 # libctmb launches on torch's current stream (self._stream()); c10d orders the NCCL kernel after the work
                 # queued there and makes the stream wait for it on return (async_op=False)
                 dist.all_gather_into_tensor(whole, mine, group=group)
+                b.record()
                 self.group_bytes += bytes_per_rank * (nranks - 1)
+                self._group_recs.append(('allgather_sketch_slabs', bytes_per_rank * (nranks - 1), a, b))
                 return 0
             except Exception as ex:       # never let an exception cross the C boundary
                 self._group_error = ex
                 return -1
 
         self.group_bytes = 0
+        self._group_recs = []
         self._group_error = None
         if nranks <= 1:
             self._group_cb = _lib.ALLGATHER_FN()      # NULL function pointer
@@ -142,11 +147,23 @@ class CtmEngine:
         lib.ctmb_debug_set_matrix_free(int(mode))
         self._tables = {k: v for k, v in self._tables.items() if not (isinstance(k, tuple) and k and k[0] in ('ws', 'wsc4v'))}
 
+    def group_reset(self):
+        self._group_recs = []
+
+    def group_totals(self):
+        return list(getattr(self, '_group_recs', []))
+
     def rsvd_status(self, reset=False):
         """(residual checks, decompositions returned although they missed the residual bound, worst residual / bound)."""
         a, b, w = C.c_longlong(), C.c_longlong(), C.c_double()
-        check(lib.ctmb_get_rsvd_status(self._h, C.byref(a), C.byref(b), C.byref(w), int(bool(reset))))
+        check(lib.ctmb_get_rsvd_status(self._h, C.byref(a), C.byref(b), C.byref(w), None, None, int(bool(reset))))
         return a.value, b.value, w.value
+
+    def rsvd_iterations(self):
+        """(iterative decompositions run, power iterations they took in total) since the last reset."""
+        c, i = C.c_longlong(), C.c_longlong()
+        check(lib.ctmb_get_rsvd_status(self._h, None, None, None, C.byref(c), C.byref(i), 0))
+        return c.value, i.value
 
     def _warn_rsvd(self):
         _, missed, worst = self.rsvd_status()

@@ -1,0 +1,48 @@
+"""The drop-in claim on the GPU: UNMODIFIED example scripts of the reference, driven through the launcher
+(python -m peps_torch_b200.run <script> ... --GLOBALARGS_device cuda:0), with libctmb as the CTM engine, must print the
+FINAL energies the reference itself prints on CPU for BASELINE configs 1 and 2 (the numbers were produced
+by running the unmodified scripts in the build container).
+
+Needs the staged copy of the reference under baseline/_ref/ (git-ignored; written by __graft_entry__.build() where the
+reference tree exists, travels to the GPU box with the snapshot): skipped where it is absent."""
+import os
+import subprocess
+import sys
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def _final(script, args, tmp_path):
+    if not os.path.isfile(os.path.join(REF, script)):
+        pytest.skip('baseline/_ref (staged copy of the reference) not present')
+    if not torch.cuda.is_available():
+        pytest.skip('GPU tests need a CUDA device')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    out = subprocess.run([sys.executable, '-m', 'peps_torch_b200.run', os.path.join(REF, script)] + args
+                         + ['--GLOBALARGS_device', 'cuda:0'], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('FINAL')]
+    assert lines, out.stdout[-2000:]
+    return [float(x) for x in lines[-1][len('FINAL'):].split(',')], out.stdout
+
+
+def test_config1_script_unmodified_on_gpu(tmp_path):
+    """BASELINE configs[0]: examples/j1j2/ctmrg_j1j2_c4v.py --bond_dim 2 --chi 16 --seed 123 --j2 0.3 (converges at the fourth
+    move by its own rdm2x1 criterion, ctmrg_j1j2_c4v.py:101-129) -> FINAL -0.35003258049356745, ..."""
+    vals, out = _final('examples/j1j2/ctmrg_j1j2_c4v.py', ['--bond_dim', '2', '--chi', '16', '--seed', '123', '--j2', '0.3'], tmp_path)
+    assert abs(vals[0] - (-0.35003258049356745)) < 1e-10 * 0.35, vals[0]
+    # the script's own convergence history: four moves, as on CPU
+    iters = [ln for ln in out.splitlines() if ln[:1].isdigit() and ', ' in ln and len(ln.split(', ')) == 2]
+    assert len(iters) == 4, iters
+
+
+def test_config2_script_unmodified_on_gpu(tmp_path):
+    """BASELINE configs[1]: examples/j1j2/ctmrg_j1j2.py --tiling 4SITE --bond_dim 3 --chi 48 --seed 123 --j2 0.3 -> FINAL
+    0.6424192641900255, ... (energy per site from rdm2x2 of every plaquette, models/j1j2.py:223-247)."""
+    vals, _ = _final('examples/j1j2/ctmrg_j1j2.py', ['--tiling', '4SITE', '--bond_dim', '3', '--chi', '48', '--seed', '123',
+                                                   '--j2', '0.3'], tmp_path)
+    assert abs(vals[0] - 0.6424192641900255) < 1e-10 * 0.64, vals[0]
