@@ -323,7 +323,10 @@ __global__ void __launch_bounds__(1024) jacobi_prep_kernel(PtrBatch Gb, PtrBatch
     }
 }
 
-template <bool CPLX>
+// NR = register-cached rows per lane (k <= 32 NR): the two columns of a pair are loaded ONCE, with all loads in flight
+// together, rotated in registers and stored; W likewise.  (Round 1 walked the columns with a run-time loop, one L2 round
+// trip per 32 rows and two passes: 17 us per round at k = 512, 52 ms per 512 x 512 factor -- profiles/r2_c5s_launches.md.)
+template <bool CPLX, int NR>
 __global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch Sb, int k, int cpm,
                                                                    int max_sweeps) {
     using S = Sc<CPLX>;
@@ -368,10 +371,17 @@ __global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, Pt
                 T* gq = G + (size_t)q * k;
                 double a = 0.0, b = 0.0;
                 T g = S::zero();
-                for (int r = lane; r < k; r += 32) {
-                    const T x = ldcg_t(gp + r), y = ldcg_t(gq + r);
-                    a += S::abs2(x); b += S::abs2(y);
-                    g = S::fma(S::conj(x), y, g);
+                T xr[NR], yr[NR];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int r = lane + 32 * i;
+                    xr[i] = r < k ? ldcg_t(gp + r) : S::zero();
+                    yr[i] = r < k ? ldcg_t(gq + r) : S::zero();
+                }
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    a += S::abs2(xr[i]); b += S::abs2(yr[i]);
+                    g = S::fma(S::conj(xr[i]), yr[i], g);
                 }
                 a = warp_sum(a); b = warp_sum(b); g = warp_sum_t<CPLX>(g);
                 const double ag2 = S::abs2(g);
@@ -385,18 +395,40 @@ __global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, Pt
                     const double c = c2 * rc;
                     const T al = S::scale(S::conj(g), copysign(r * rc, d));
                     const T cal = S::conj(al);
-                    for (int rr = lane; rr < k; rr += 32) {
-                        const T x = ldcg_t(gp + rr), y = ldcg_t(gq + rr);
-                        gp[rr] = S::sub(S::scale(x, c), S::mul(al, y));
-                        gq[rr] = S::add(S::mul(cal, x), S::scale(y, c));
-                    }
-                    if (accw) {
+                    if (accw) {                             // W columns: loads in flight while G is rotated
                         T* wp = W + (size_t)p * k;
                         T* wq = W + (size_t)q * k;
-                        for (int rr = lane; rr < k; rr += 32) {
-                            const T u = ldcg_t(wp + rr), v = ldcg_t(wq + rr);
-                            wp[rr] = S::sub(S::scale(u, c), S::mul(al, v));
-                            wq[rr] = S::add(S::mul(cal, u), S::scale(v, c));
+                        T ur[NR], vr[NR];
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int rr = lane + 32 * i;
+                            ur[i] = rr < k ? ldcg_t(wp + rr) : S::zero();
+                            vr[i] = rr < k ? ldcg_t(wq + rr) : S::zero();
+                        }
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int rr = lane + 32 * i;
+                            if (rr < k) {
+                                gp[rr] = S::sub(S::scale(xr[i], c), S::mul(al, yr[i]));
+                                gq[rr] = S::add(S::mul(cal, xr[i]), S::scale(yr[i], c));
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int rr = lane + 32 * i;
+                            if (rr < k) {
+                                wp[rr] = S::sub(S::scale(ur[i], c), S::mul(al, vr[i]));
+                                wq[rr] = S::add(S::mul(cal, ur[i]), S::scale(vr[i], c));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int rr = lane + 32 * i;
+                            if (rr < k) {
+                                gp[rr] = S::sub(S::scale(xr[i], c), S::mul(al, yr[i]));
+                                gq[rr] = S::add(S::mul(cal, xr[i]), S::scale(yr[i], c));
+                            }
                         }
                     }
                 }
@@ -468,7 +500,11 @@ void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, in
         CTMB_CUDA(cudaGetLastError());
         PtrBatch g = G, w = W, sg = sig;
         void* args[] = {&g, &w, &sg, &kk_, &cpm, &mxs};
-        const void* kern = cplx ? (const void*)jacobi_coop_kernel<true> : (const void*)jacobi_coop_kernel<false>;
+        CTMB_CHECK(k <= 512, "the multi-CTA Jacobi kernel caches columns of up to 512 rows in registers");
+        const void* kern;
+        if (k <= 128) kern = cplx ? (const void*)jacobi_coop_kernel<true, 4> : (const void*)jacobi_coop_kernel<false, 4>;
+        else if (k <= 256) kern = cplx ? (const void*)jacobi_coop_kernel<true, 8> : (const void*)jacobi_coop_kernel<false, 8>;
+        else kern = cplx ? (const void*)jacobi_coop_kernel<true, 16> : (const void*)jacobi_coop_kernel<false, 16>;
         CTMB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nb * cpm), dim3(JC_THREADS), args, 0, stream));
         return;
     }

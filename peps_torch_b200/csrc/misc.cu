@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(256) resid_kernel(PtrBatch MXb, PtrBatch Yb, P
     const double* Sv = reinterpret_cast<const double*>(Sb.p[b]);
     const double s0 = fabs(Sv[0]), sj = Sv[j];
     if (!(fabs(sj) > reltol * s0) || s0 == 0.0) return;
+    // out[1]: dynamic range S_0 / S_j of the kept triplets (decides how many operator applications the range finder may
+    // chain between two orthogonalisations, move.cu)
+    if (threadIdx.x == 0) atomicMax(out + 1, (unsigned long long)__double_as_longlong(s0 / fabs(sj)));
     double acc = 0.0;
     for (int r = threadIdx.x; r < rows; r += blockDim.x) acc += S::abs2(S::sub(mx[r], S::scale(y[r], sj)));
     acc = warp_sum(acc);

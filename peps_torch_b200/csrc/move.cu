@@ -556,7 +556,22 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     // itself grows like eps * sqrt(n))
     const double tol_eff = o.rsvd_tol * std::sqrt((double)std::max(m, n));
     // (ctmb_options.rsvd_stateless: every call starts from rsvd_niter, so its result does not depend on the handle's history)
-    if (adaptive && !o.rsvd_stateless) { auto it = e.iter_hint.find(hkey); if (it != e.iter_hint.end() && it->second.q > 0) todo = it->second.q; }
+    // Orthogonalisation interval.  Between two QRs the component of a column along the dominant direction grows, relative to
+    // the column's own direction j, by S_0 / S_j per operator application; rounding noise (1e-16) injected at the first of m
+    // chained applications therefore reaches 1e-16 (S_0/S_j)^(m-1).  With the full dynamic range the projectors use
+    // (S_0/S_chi up to 1e8, ctm_projectors.py:266-270) that allows two applications -- the shipped default: one QR per
+    // M M^H in the SVD branch, per M M in the Hermitian branch.  Where the kept spectrum is flat (C4v corner of config 3:
+    // lambda_0/lambda_chi = 25, so the iteration converges slowly AND needs few orthogonalisations) the measured range of
+    // the previous decomposition of the same shape allows more: (m-1) log10(range) <= 12.
+    int orth = 2;
+    if (adaptive && !o.rsvd_stateless) {
+        auto it = e.iter_hint.find(hkey);
+        if (it != e.iter_hint.end()) {
+            if (it->second.q > 0) todo = it->second.q;
+            if (it->second.range > 1.0) orth = std::max(2, std::min(8, 1 + (int)(12.0 / std::log10(it->second.range * 1.5))));
+        }
+    }
+    const int orth_iter = std::max(1, orth / 2);          // SVD branch: whole iterations (two applications each) per QR
     int used = 0;
     double prev_res = -1.0;
     for (int round = 0;; ++round) {
@@ -570,7 +585,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             for (int it = 0; it < todo; ++it) {
                 apply_op(pY, pZ, k, true);                                                                       // Z = M^H Q
                 apply_op(pZ, pY, k, false);                                                                      // Y = M Z
-                qr(pY, pNull, m);
+                if ((it + 1) % orth_iter == 0 || it + 1 == todo) qr(pY, pNull, m);
             }
             // Bt = M^H Q = Q2 R2  =>  M ~ Q R2^H Q2^H.  One-sided Jacobi on G = R2^H:  G W = Uh Sigma, so
             // U = Q Uh (normalised columns of the rotated G) and V = Q2 W (accumulated rotations); both come
@@ -590,7 +605,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             // Rayleigh-Ritz; the eigenvectors are the normalised columns of the rotated (T + mu).
             for (int it = 0; it < 4 * todo; ++it) {
                 for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));
-                if (it & 1) qr(pZ, pNull, n);
+                if ((it + 1) % orth == 0 || it + 1 == 4 * todo) qr(pZ, pNull, n);
                 else e.flush();
                 std::swap(pY, pZ);
             }
@@ -614,24 +629,30 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             pYv.p[b] = r.U[b];
         }
         { PtrBatch pXin{}; for (int b = 0; b < nb; ++b) pXin.p[b] = eig_mode ? r.U[b] : r.V[b]; apply_op(pXin, pMX, chi, false); }
-        CTMB_CUDA(cudaMemsetAsync(dres, 0, sizeof(unsigned long long), e.stream));
+        CTMB_CUDA(cudaMemsetAsync(dres, 0, 2 * sizeof(unsigned long long), e.stream));       // [0] residual, [1] range S_0 / S_chi
         { ProfScope ps(e, Engine::CAT_MISC); resid_launch(pMX, pYv, pS, nb, m, chi, o.svd_reltol, dres, e.cplx, e.stream); }
+        int nwords = 2;
         if (e.coll_active()) {
-            // every member of the group must take the same decision below: exchange the residuals (rounding may differ
-            // between devices only through non-deterministic reduction orders, but a split decision would dead-lock)
-            CTMB_CHECK(e.coll_n <= 16, "group too large");
-            CTMB_CUDA(cudaMemcpyAsync(dres + 1 + e.coll_rank, dres, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e.stream));
-            e.allgather(dres + 1, sizeof(unsigned long long));
-            CTMB_CUDA(cudaMemcpyAsync(hres, dres + 1, e.coll_n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
+            // every member of the group must take the same decisions below: exchange residual and range (rounding may
+            // differ between devices through non-deterministic reduction orders, and a split decision would dead-lock)
+            CTMB_CHECK(e.coll_n <= 14, "group too large");
+            CTMB_CUDA(cudaMemcpyAsync(dres + 2 + 2 * e.coll_rank, dres, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e.stream));
+            e.allgather(dres + 2, 2 * sizeof(unsigned long long));
+            nwords = 2 * e.coll_n;
+            CTMB_CUDA(cudaMemcpyAsync(hres, dres + 2, nwords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
         } else
-            CTMB_CUDA(cudaMemcpyAsync(hres, dres, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
+            CTMB_CUDA(cudaMemcpyAsync(hres, dres, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
         CTMB_CUDA(cudaStreamSynchronize(e.stream));
-        double res; memcpy(&res, hres, sizeof res);
-        for (int g = 1; e.coll_active() && g < e.coll_n; ++g) { double rg; memcpy(&rg, hres + g, sizeof rg); res = std::max(res, rg); }
+        double res = 0.0, range = 0.0;
+        for (int g = 0; g < nwords / 2; ++g) {
+            double rg, sg; memcpy(&rg, hres + 2 * g, sizeof rg); memcpy(&sg, hres + 2 * g + 1, sizeof sg);
+            res = std::max(res, rg); range = std::max(range, sg);
+        }
         static int dbg = -1;
         if (dbg < 0) { const char* ev = getenv("CTMB_DEBUG_RESID"); dbg = ev ? atoi(ev) : 0; }
-        if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d k=%d round %d iterations %d residual %.3e (tol %.1e)\n", m, n, k, round, used, res, tol_eff);
+        if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d k=%d round %d iterations %d (QR every %d applications) residual %.3e (tol %.1e) range %.2e\n", m, n, k, round, used, orth, res, tol_eff, range);
         Engine::IterHint& hint = e.iter_hint[hkey];
+        hint.range = range;
         ++e.rsvd_status.checks;
         if (res <= tol_eff) {
             if (round == 0) {

@@ -149,6 +149,18 @@ def test_config5_full_size_matrix_free_vs_explicit(eng, dev):
             eng.debug_set_matrix_free(1)
     m['spectra'] = H.spectra_diff(res[1].C, cpu(res[0].C))
     m['absCT'] = H.env_abs_diff(res[1].C, res[1].T, res[0].C, res[0].T)
+    # noise floor of the reference algorithm itself at this size: the explicit path again with another sketch seed -- both
+    # runs satisfy the same residual bound, so they differ by rounding-level perturbations of the triplets only, which the
+    # projectors amplify by S0/Sj (the analogue of the reference's gesdd-vs-gesvd floor of SURVEY 8c, which was measured
+    # at n = 432; no CPU can produce it at n = 16384)
+    eng.debug_set_matrix_free(0)
+    try:
+        e3 = H.Env(chi, dict(env.C), dict(env.T))
+        eng.move_generic(d, st, e3, seed=0xabcdef12345)
+    finally:
+        eng.debug_set_matrix_free(1)
+    m['floor_absCT'] = H.env_abs_diff(e3.C, e3.T, res[0].C, res[0].T)
+    m['floor_spectra'] = H.spectra_diff(e3.C, cpu(res[0].C))
     m['rsvd_status'] = eng.rsvd_status()
     import json
     import os
@@ -160,8 +172,8 @@ def test_config5_full_size_matrix_free_vs_explicit(eng, dev):
     assert m['biorth_matrix_free'] < 1e-7 and m['biorth_explicit'] < 1e-7, m
     # P Pt^T carries S^-1: its rounding floor is eps * S0 / S_min ~ 1e-8 when the kept spectrum reaches the 1e-8 cut
     assert m['P_PtT_probe'] < 1e-7, m
-    assert m['spectra'] < 1e-10, m
-    assert m['absCT'] < 1.2e-8, m
+    assert m['spectra'] < max(1e-10, 3 * m['floor_spectra']), m
+    assert m['absCT'] < max(1.2e-8, 3 * m['floor_absCT']), m       # max(gate, 3 x measured floor): the rule of SURVEY 8c
 
 
 @pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D3_chi12_B', 'generic_4site_D2_chi8_B_c128'])
