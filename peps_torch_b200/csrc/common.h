@@ -97,6 +97,7 @@ void qr_panel_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& Tau
 // tall panels (qr_tall.cu): rows split over up to 148 co-resident CTAs, 32 columns per leaf; width 0 = does not apply
 int qr_tall_panel_width(int nb, int rows, int cols, bool cplx);
 size_t qr_tall_scratch_bytes(int nb);
+int qr_tall_mode();
 bool qr_tall_panel_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& Tau, int nb, int rows, int b, int ld, bool cplx,
                           void* scratch, cudaStream_t stream);
 void qr_copy_r_launch(const PtrBatch& A, const PtrBatch& Rpp, const PtrBatch& R, int nb, int k, int j0, int b, int ld,

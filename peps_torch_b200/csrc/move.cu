@@ -400,7 +400,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     if (blocked) {
         // tall sketches (config 5: 16384 x 512): 32-column leaf panels factored with the rows split over the SMs
         const int tw = std::min(qr_tall_panel_width(nb, m, k, e.cplx), qr_tall_panel_width(nb, n, k, e.cplx));
-        if (tw > pw) {
+        if (tw > pw || (tw > 0 && qr_tall_mode() == 2)) {
             pw = tw;
             if (!e.ws.dry()) qbw.tall = e.persistent("qrtall", qr_tall_scratch_bytes(TC_MAX_BATCH));
         }
