@@ -656,10 +656,23 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         ++e.rsvd_status.checks;
         if (res <= tol_eff) {
             if (round == 0) {
-                // passed first time: probe one iteration fewer next time unless that count failed recently
+                // passed first time: probe fewer iterations next time (two fewer with a margin of 64x, one with 8x) unless
+                // that count failed recently
                 if (++hint.age > 64) { hint.lo = 0; hint.age = 0; }
-                hint.q = (res <= 0.125 * tol_eff && used > 1 && used - 1 > hint.lo) ? used - 1 : used;
-            } else hint.q = used;
+                int dec = res <= tol_eff / 64.0 ? 2 : (res <= 0.125 * tol_eff ? 1 : 0);
+                while (dec > 0 && !(used - dec >= 1 && used - dec > hint.lo)) --dec;
+                hint.q = used - dec;
+            } else {
+                // passed after an extra round: the decay rate measured between the last two rounds says how many of the
+                // extra iterations were needed (a later call starts there instead of walking down one by one)
+                int need = used;
+                if (prev_res > res && res > 0.0 && todo > 0) {
+                    const double per_iter = std::log(prev_res / res) / todo;             // decades (natural log) per iteration
+                    const int spare = (int)std::floor(std::log(0.25 * tol_eff / res) / per_iter);
+                    need = std::max(used - todo + 1, used - std::max(0, spare));
+                }
+                hint.q = need;
+            }
             break;
         }
         if (round == 0) { hint.lo = std::max(hint.lo, used); hint.age = 0; }
@@ -675,8 +688,15 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
                              floor_reached ? "rounding floor" : "rsvd_max_rounds");
             break;
         }
+        // next round: from the second round on the measured decay rate predicts the missing iterations; until then double
+        int next = std::max(1, used);
+        if (prev_res > res && res > 0.0 && todo > 0) {
+            const double per_iter = std::log(prev_res / res) / todo;
+            const int want = (int)std::ceil(std::log(res / (0.25 * tol_eff)) / per_iter);
+            next = std::max(1, std::min(want, used));
+        }
         prev_res = res;
-        todo = std::max(1, used);                         // double the total: q, 2q, 4q ...
+        todo = next;
     }
     ++e.rsvd_status.calls;
     e.rsvd_status.iterations += used;

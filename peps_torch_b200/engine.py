@@ -35,6 +35,25 @@ def _dt(t):
     raise TypeError(f"libctmb computes in float64/complex128 (as the reference CLI, config.py:113-118); got {t.dtype}")
 
 
+# float32 / complex64 (reachable in the reference through the library API only: the generic ENV takes its dtype from the
+# state, ctm/generic/env.py:78-83; the CLI accepts float64 / complex128, config.py:113-118).  The moves and the density
+# matrices accept them: operands are widened on entry, the kernels run in float64 / complex128 (DMMA), results are rounded
+# to the input precision on exit -- inside the 1e-4 gate of the north star by construction.  There is no native
+# single-precision kernel (tcgen05.mma kind::tf32 + 3xTF32 compensation would be the Blackwell route).
+_WIDE = {torch.float32: torch.float64, torch.complex64: torch.complex128}
+
+
+def _widen(t):
+    return t.to(_WIDE[t.dtype]) if (t is not None and t.dtype in _WIDE) else t
+
+
+class _Shadow:
+    """state / environment stand-in holding widened copies (sites, vertexToSite, lX, lY / chi, C, T)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
@@ -227,6 +246,8 @@ class CtmEngine:
     # piecewise entry points (parity tests mirror the reference's *_c functions)
     # ----------------------------------------------------------------------------------
     def einsum2(self, spec, A, B, conjA=False, conjB=False):
+        if A.dtype in _WIDE and B.dtype == A.dtype:
+            return self.einsum2(spec, _widen(A), _widen(B), conjA, conjB).to(A.dtype)
         lhs, out = spec.split('->')
         la, lb = lhs.split(',')
         A, B = self._prep(A, self.device), self._prep(B, self.device)
@@ -352,6 +373,16 @@ class CtmEngine:
             return (D[0], chi, chi)
         return (chi, D[1], chi)
 
+    def _wide_state(self, state):
+        key = ('wide', id(state), tuple(id(t) for t in state.sites.values()))
+        st2 = self._tables.get(key)
+        if st2 is None:
+            self._tables = {k: v for k, v in self._tables.items() if not (isinstance(k, tuple) and k and k[0] == 'wide')}
+            st2 = _Shadow(sites=type(state.sites)((c, _widen(t)) for c, t in state.sites.items()),
+                          vertexToSite=state.vertexToSite, lX=getattr(state, 'lX', None), lY=getattr(state, 'lY', None))
+            self._tables[key] = st2
+        return st2
+
     def move_generic(self, direction, state, env, **opt):
         """One ctm_MOVE (ctm/generic/ctmrg.py:179-319): replaces the entries of env.C / env.T
         at coord-direction by freshly allocated tensors; inputs are never modified."""
@@ -361,6 +392,20 @@ class CtmEngine:
         n = len(coords)
         chi = env.chi
         refuse_autograd('ctm_MOVE', list(state.sites.values()) + list(env.C.values()) + list(env.T.values()))
+        low = next(iter(state.sites.values())).dtype
+        if low in _WIDE:
+            st2 = self._wide_state(state)
+            env2 = _Shadow(chi=chi, C={k: _widen(v) for k, v in env.C.items()}, T={k: _widen(v) for k, v in env.T.items()})
+            before = {('C',) + k: v for k, v in env2.C.items()}
+            before.update({('T',) + k: v for k, v in env2.T.items()})
+            self.move_generic(direction, st2, env2, **opt)
+            for k, v in env2.C.items():
+                if v is not before[('C',) + k]:
+                    env.C[k] = v.to(low)
+            for k, v in env2.T.items():
+                if v is not before[('T',) + k]:
+                    env.T[k] = v.to(low)
+            return
         corner, nb, dest, _ = self._move_tables(state, direction)
         keep = []
         sites = (_lib.Site * n)()
@@ -466,6 +511,9 @@ class CtmEngine:
         """One ctm_MOVE_sl (ctm/one_site_c4v/ctmrg_c4v.py:325-463) or, with a double-layer A[u,l,d,r],
         ctm_MOVE_dl (:200-322) -> (C', T', D)."""
         refuse_autograd('ctm_MOVE_sl / ctm_MOVE_dl', (a, C_, T))
+        if a.dtype in _WIDE:
+            Co, To, Dv = self.move_c4v(_widen(a), _widen(C_), _widen(T), chi, **opt)
+            return Co.to(C_.dtype), To.to(T.dtype), Dv
         a, C_, T = self._prep(a, self.device), self._prep(C_, self.device), self._prep(T, self.device)
         dt = _dt(a)
         opt.setdefault('eps_multiplet', 1.0e-12)      # truncated_eig_sym default (custom_eig.py:7-8)
@@ -493,6 +541,8 @@ class CtmEngine:
     # ----------------------------------------------------------------------------------
     def sym_pos_def(self, rdm, sym_pos_def=False):
         """_sym_pos_def_rdm (ctm/generic/rdm.py:38-68): hermitise, optionally project on the positive part, normalise the trace."""
+        if rdm.dtype in _WIDE:
+            return self.sym_pos_def(_widen(rdm), sym_pos_def).to(rdm.dtype)
         shape = rdm.shape
         assert len(shape) % 2 == 0, "invalid rank of RDM"
         n = 1
@@ -517,6 +567,9 @@ class CtmEngine:
             raise ValueError("open_sites must be a non-empty subset of [0,1,2,3]")
         mask = sum(1 << q for q in open_sites)
         refuse_autograd('rdm2x2', [t for (a, Cs, Ts) in tensors4 for t in [a] + list(Cs) + list(Ts)])
+        if tensors4[0][0].dtype in _WIDE:
+            wide = [(_widen(a), [_widen(t) for t in Cs], [_widen(t) for t in Ts]) for (a, Cs, Ts) in tensors4]
+            return self.rdm2x2_sites(wide, chi, open_sites, sym_pos_def, raw).to(tensors4[0][0].dtype)
         keep = []
         structs = [self._site(a, Cs, Ts, keep) for (a, Cs, Ts) in tensors4]
         arr = (C.POINTER(_lib.Site) * 4)(*[C.pointer(s) for s in structs])
@@ -536,6 +589,9 @@ class CtmEngine:
         to the right) or '1x2' (second site below)."""
         k = {'1x1': 0, '2x1': 1, '1x2': 2}[kind]
         refuse_autograd('rdm' + kind, [t for (a, Cs, Ts) in tensors2 for t in [a] + list(Cs) + list(Ts)])
+        if tensors2[0][0].dtype in _WIDE:
+            wide = [(_widen(a), [_widen(t) for t in Cs], [_widen(t) for t in Ts]) for (a, Cs, Ts) in tensors2]
+            return self.rdm_small_sites(kind, wide, chi, sym_pos_def, raw).to(tensors2[0][0].dtype)
         keep = []
         structs = [self._site(a, Cs, Ts, keep) for (a, Cs, Ts) in tensors2]
         if len(structs) == 1:
