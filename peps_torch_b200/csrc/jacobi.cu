@@ -20,8 +20,9 @@ namespace ctmb {
 // of a sweep was by a small ANGLE: sin^2(theta) = |g|^2 r^2 rc^2 <= 1e-16.  (Round 1 tested the cosine between the two
 // columns, |g|^2 <= 1e-16 a b; inside a tight cluster of singular values, a ~ b, a tiny cosine can still mean a large
 // rotation angle, the quadratic argument does not apply and the cluster was left orthogonal to ~1e-11 only.)  A pair
-// whose cosine is already below 1e-13 is rotated (to ~1e-16) but does not ask for another sweep either, whatever its
-// angle: a rotation inside the pair preserves the magnitudes of its inner products with every other column, so exactly
+// whose cosine is already below 2 tol (tol = eps sqrt(k), the threshold under which a pair is not rotated at all) is rotated
+// but does not ask for another sweep either, whatever its angle (with 1e-13 here, a large-angle rotation inside a cluster
+// late in the last sweep left the pair's partners of earlier rounds at cosines of a few 1e-13: test_clustered_spectrum_*): a rotation inside the pair preserves the magnitudes of its inner products with every other column, so exactly
 // degenerate multiplets (angle 45 degrees at rounding-level cosines) cannot keep the loop alive.
 // diagnostics: total sweeps executed / matrices processed since the last read (tools/ only)
 __device__ unsigned long long g_jac_stats[2];
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
                             const double r = rsqrt(d * d + 4.0 * ag2);
                             const double c2 = 0.5 + 0.5 * fabs(d) * r;
                             const double rc = rsqrt(c2);
-                            if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 1.0e-26 * a * b) notsmall = 1; }
+                            if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 4.0 * tol2 * a * b) notsmall = 1; }
                             const double c = c2 * rc;
                             const double al = g * copysign(r * rc, d);
 #pragma unroll
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(THREADS) jacobi_kernel(PtrBatch Gb, PtrBatch W
                     const double r = rsqrt(d * d + 4.0 * ag2);
                     const double c2 = 0.5 + 0.5 * fabs(d) * r;
                     const double rc = rsqrt(c2);
-                    if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 1.0e-26 * a * b) notsmall = 1; }
+                    if (gl == 0) { rotated = 1; if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 4.0 * tol2 * a * b) notsmall = 1; }
                     const double c = c2 * rc;
                     const T al = S::scale(S::conj(g), copysign(r * rc, d));
                     const T cal = S::conj(al);
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, Pt
                     const double c2 = 0.5 + 0.5 * fabs(d) * r;
                     const double rc = rsqrt(c2);
                     rot = 1;
-                    if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 1.0e-26 * a * b) big = 1;
+                    if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 4.0 * tol2 * a * b) big = 1;
                     const double c = c2 * rc;
                     const T al = S::scale(S::conj(g), copysign(r * rc, d));
                     const T cal = S::conj(al);

@@ -371,11 +371,24 @@ struct FactoredM {
 };
 
 // M[b]: m x n row-major (or, with `fac`, given in factored form). eig_mode: M Hermitian (m == n), S receives signed eigenvalues.
+//
+// WARM START (`slots`: one tag per problem, or nullptr).  A CTM run decomposes, move after move, a slowly changing matrix
+// per (direction, site): the leading kw = k - r Ritz vectors of the previous decomposition of the same slot (right singular
+// vectors / eigenvectors, ordered) replace the first kw columns of the Gaussian sketch; the last r columns stay Gaussian, so
+// that every direction keeps a generic component in the start block (a direction that is new to the dominant subspace is
+// found at the rate of an r-column random sketch and shows up in the residual of the kept triplets until it has converged).
+// Only the NUMBER of power iterations changes -- the residual test below accepts exactly the same results -- and near the
+// fixed point of a CTM run it drops to zero.  ctmb_options.rsvd_stateless = 1 switches warm start (and the iteration-count
+// memory) off; the piecewise entry points (ctmb_truncated_svd, ctmb_projectors, ...) never use it.
 static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int n, int chi,
-                       const ctmb_options& o, bool eig_mode, const std::vector<FactoredM>* fac = nullptr) {
+                       const ctmb_options& o, bool eig_mode, const std::vector<FactoredM>* fac = nullptr,
+                       const std::vector<std::string>* slots = nullptr) {
     Rsvd r; r.nb = fac ? (int)fac->size() : (int)M.size(); r.m = m; r.n = n; r.chi = chi;
     const int nb = r.nb, k = sketch_width(m, n, chi, o);
     r.k = k;
+    // warm start: kw ordered Ritz vectors are kept per slot (kw = chi when there is none: nothing below changes then)
+    const bool warm = slots != nullptr && !o.rsvd_stateless && o.rsvd_tol > 0.0 && k < std::min(m, n) && k > chi + 1;
+    const int kw = warm ? std::max(chi + 1, k - std::max(4, k / 8)) : chi;
     CTMB_CHECK(nb <= TC_MAX_BATCH, "too many problems in one batch");
     CTMB_CHECK(chi <= std::min(m, n), "chi exceeds matrix size");
     const size_t es = e.esize();
@@ -423,10 +436,11 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         W[b] = e.ws.alloc((size_t)k * k * es);
         sig[b] = e.ws.alloc((size_t)k * 8);
         r.S.push_back(e.ws.alloc((size_t)k * 8));
-        Uh[b] = e.ws.alloc((size_t)k * chi * es);
-        Ws[b] = e.ws.alloc((size_t)k * chi * es);
-        r.U.push_back(e.ws.alloc((size_t)m * chi * es));
-        r.V.push_back(eig_mode ? nullptr : e.ws.alloc((size_t)n * chi * es));
+        // (warm start: kw >= chi columns are gathered / formed on the side that is remembered; callers use the first chi)
+        Uh[b] = e.ws.alloc((size_t)k * kw * es);
+        Ws[b] = e.ws.alloc((size_t)k * kw * es);
+        r.U.push_back(e.ws.alloc((size_t)m * (eig_mode ? kw : chi) * es));
+        r.V.push_back(eig_mode ? nullptr : e.ws.alloc((size_t)n * kw * es));
         pR.p[b] = R2[b]; pW.p[b] = W[b]; pSig.p[b] = sig[b];
         pS.p[b] = r.S[b]; pUh.p[b] = Uh[b]; pWs.p[b] = Ws[b];
     }
@@ -535,8 +549,21 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         }
         return r;
     }
-    // Y = M * Omega
-    { PtrBatch pOm{}; for (int b = 0; b < nb; ++b) pOm.p[b] = omega; apply_op(pOm, pY, k, false); }
+    // Y = M * Omega  (Omega: the shared Gaussian sketch, or the slot's warm block [previous Ritz vectors | Gaussian columns])
+    std::vector<void*> slot(nb, nullptr);
+    bool all_warm = warm;
+    if (warm)
+        for (int b = 0; b < nb; ++b) {
+            char sk[160];
+            snprintf(sk, sizeof sk, "warm:%s:%d:%d:%d:%d:%d", (*slots)[b].c_str(), m, n, k, (int)eig_mode, (int)e.cplx);
+            bool created = false;
+            slot[b] = e.persistent(sk, (size_t)n * k * es, &created);
+            if (created) {      // first decomposition of this slot: plain Gaussian sketch
+                CTMB_CUDA(cudaMemcpyAsync(slot[b], omega, (size_t)n * k * es, cudaMemcpyDeviceToDevice, e.stream));
+                all_warm = false;
+            }
+        }
+    { PtrBatch pOm{}; for (int b = 0; b < nb; ++b) pOm.p[b] = warm ? slot[b] : omega; apply_op(pOm, pY, k, false); }
     qr(pY, pNull, m);
     const bool complete = (k == std::min(m, n));          // the sketch spans everything: exact, no iteration
     const bool adaptive = o.rsvd_tol > 0.0 && !complete;
@@ -551,7 +578,8 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     // there (a CTM run decomposes a slowly changing matrix once per move): a failed first round costs a whole extra
     // Rayleigh-Ritz / Jacobi pass.  Every result still satisfies the same residual bound.
     char hkey[96];
-    snprintf(hkey, sizeof hkey, "%d:%d:%d:%d:%d", m, n, k, (int)eig_mode, (int)e.cplx);
+    snprintf(hkey, sizeof hkey, "%d:%d:%d:%d:%d:%s", m, n, k, (int)eig_mode, (int)e.cplx, all_warm ? "warm" : "cold");
+    const int q_min = all_warm ? 0 : 1;                   // a warm block may need no power iteration at all
     // residual bound: rsvd_tol * sqrt(n) relative to the largest singular value (the rounding floor of the residual
     // itself grows like eps * sqrt(n))
     const double tol_eff = o.rsvd_tol * std::sqrt((double)std::max(m, n));
@@ -567,7 +595,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     if (adaptive && !o.rsvd_stateless) {
         auto it = e.iter_hint.find(hkey);
         if (it != e.iter_hint.end()) {
-            if (it->second.q > 0) todo = it->second.q;
+            if (it->second.known) todo = it->second.q;
             if (it->second.range > 1.0) orth = std::max(2, std::min(8, 1 + (int)(12.0 / std::log10(it->second.range * 1.5))));
         }
     }
@@ -593,11 +621,12 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             apply_op(pY, pZ, k, true);
             qr(pZ, pR, n);
             { ProfScope ps(e, Engine::CAT_JACOBI, 0, 4.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pW, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, 1, e.stream); }
-            { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, chi, e.cplx, 0, e.stream); }
-            for (int b = 0; b < nb; ++b) {
+            { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pW, pSig, pS, pUh, pWs, nb, k, kw, e.cplx, 0, e.stream); }
+            for (int b = 0; b < nb; ++b)
                 e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
-                e.contract(tnZ(b, "sj"), false, make_tn(Ws[b], "cs", {chi, k}), false, make_tn(r.V[b], "cj", {chi, n}));
-            }
+            e.flush();
+            for (int b = 0; b < nb; ++b)         // (warm start: kw >= chi ordered right vectors, the first chi are the result)
+                e.contract(tnZ(b, "sj"), false, make_tn(Ws[b], "cs", {kw, k}), false, make_tn(r.V[b], "cj", {kw, n}));
             e.flush();
         } else {
             // Hermitian: subspace iteration with M itself (4 applications per "iteration": the spectrum of
@@ -615,9 +644,9 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
                 e.contract(tnY(b, "si"), true, tnZ(b, "ti"), false, make_tn(R2[b], "ts", {k, k}));       // Tm = Q^H Z
             e.flush();
             { ProfScope ps(e, Engine::CAT_JACOBI, 0, 2.0 * e.esize() * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
-            { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, chi, e.cplx, 1, e.stream); }
+            { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, kw, e.cplx, 1, e.stream); }
             for (int b = 0; b < nb; ++b)
-                e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {chi, k}), false, make_tn(r.U[b], "ci", {chi, m}));
+                e.contract(tnY(b, "si"), false, make_tn(Uh[b], "cs", {kw, k}), false, make_tn(r.U[b], "ci", {kw, m}));
             e.flush();
         }
         if (!adaptive) break;
@@ -658,9 +687,9 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             if (round == 0) {
                 // passed first time: probe fewer iterations next time (two fewer with a margin of 64x, one with 8x) unless
                 // that count failed recently
-                if (++hint.age > 64) { hint.lo = 0; hint.age = 0; }
+                if (++hint.age > 64) { hint.lo = -1; hint.age = 0; }
                 int dec = res <= tol_eff / 64.0 ? 2 : (res <= 0.125 * tol_eff ? 1 : 0);
-                while (dec > 0 && !(used - dec >= 1 && used - dec > hint.lo)) --dec;
+                while (dec > 0 && !(used - dec >= q_min && used - dec > hint.lo)) --dec;
                 hint.q = used - dec;
             } else {
                 // passed after an extra round: the decay rate measured between the last two rounds says how many of the
@@ -673,6 +702,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
                 }
                 hint.q = need;
             }
+            hint.known = true;
             break;
         }
         if (round == 0) { hint.lo = std::max(hint.lo, used); hint.age = 0; }
@@ -682,6 +712,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             // the result is returned although it misses the bound: say so (ctmb_get_rsvd_status), and remember the count
             // so that later calls do not walk through all the rounds again
             hint.q = floor_reached ? std::max(1, used - todo) : used;
+            hint.known = true;
             ++e.rsvd_status.missed;
             e.rsvd_status.worst_ratio = std::max(e.rsvd_status.worst_ratio, res / tol_eff);
             if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d: residual %.3e stays above the bound %.1e (%s)\n", m, n, res, tol_eff,
@@ -700,6 +731,9 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     }
     ++e.rsvd_status.calls;
     e.rsvd_status.iterations += used;
+    if (warm)        // remember the ordered Ritz vectors (before the caller's sign fixing / scaling touches the first chi of them)
+        for (int b = 0; b < nb; ++b)
+            CTMB_CUDA(cudaMemcpyAsync(slot[b], eig_mode ? r.U[b] : r.V[b], (size_t)n * kw * es, cudaMemcpyDeviceToDevice, e.stream));
     return r;
 }
 
@@ -724,7 +758,8 @@ struct MoveCtx {
 static void projectors_from_matrices(Engine& e, const std::vector<const void*>& R, const std::vector<const void*>& Rt,
                                      int n0, int n1, int chi, const ctmb_options& o,
                                      const std::vector<void*>& P, const std::vector<void*>& Pt,
-                                     const std::vector<double*>& Sout, bool trR = false, bool trRt = false) {
+                                     const std::vector<double*>& Sout, bool trR = false, bool trRt = false,
+                                     const std::vector<std::string>* slots = nullptr) {
     const int nb = (int)R.size();
     const size_t mark = e.ws.mark();
     std::vector<const void*> Mp(nb);
@@ -738,7 +773,7 @@ static void projectors_from_matrices(Engine& e, const std::vector<const void*>& 
         e.contract(Rtn[b], false, Rttn[b], false, M);           // M = R^T Rt  (plain transpose)
     }
     e.flush();
-    Rsvd r = rsvd_batch(e, Mp, n1, n1, chi, o, false);
+    Rsvd r = rsvd_batch(e, Mp, n1, n1, chi, o, false, nullptr, slots);
     if (!e.ws.dry()) {
         PtrBatch pU{}, pV{}, pS{}, pSo{};
         for (int b = 0; b < nb; ++b) { pU.p[b] = r.U[b]; pV.p[b] = r.V[b]; pS.p[b] = r.S[b]; pSo.p[b] = Sout.empty() ? nullptr : Sout[b]; }
@@ -818,6 +853,12 @@ static void move_projectors(MoveCtx& mc, const int* corner_site, const std::vect
     int64_t n0 = 0, n1 = 0;
     half_shape(mc.dir, mc.chi, &corners[0], n0, n1);
     CTMB_CHECK(mc.o.projector_method == 0 || mc.o.projector_method == 1, "Invalid Projector method");
+    // warm-start slots of the decompositions: one per (direction, projector method, site job)
+    std::vector<std::string> slots(nj);
+    for (int j = 0; j < nj; ++j) {
+        char t[48]; snprintf(t, sizeof t, "d%d:p%d:j%d", mc.dir, mc.o.projector_method, jobs[j]);
+        slots[j] = t;
+    }
     if (mc.o.projector_method == 1) {
         // '4X2' (ctm_projectors.py:66-136): R and Rt are the first enlarged corner of each half, transposed as there
         const HalfSpec& hs = HALVES[mc.dir];
@@ -834,7 +875,7 @@ static void move_projectors(MoveCtx& mc, const int* corner_site, const std::vect
                 (q == 0 ? Rc[j] : Rtc[j]) = cm;
             }
         corners_run(e, mc.chi, cj);
-        projectors_from_matrices(e, Rc, Rtc, (int)n0, (int)n0, mc.chi, mc.o, P, Pt, {}, hs.tr[0], hs.tr[2]);
+        projectors_from_matrices(e, Rc, Rtc, (int)n0, (int)n0, mc.chi, mc.o, P, Pt, {}, hs.tr[0], hs.tr[2], &slots);
         e.ws.release(mark);
         return;
     }
@@ -854,7 +895,7 @@ static void move_projectors(MoveCtx& mc, const int* corner_site, const std::vect
                 fac[j].H[q] = cm; fac[j].tr[q] = hs.tr[q];
             }
         corners_run(e, chi, cj);
-        Rsvd r = rsvd_batch(e, {}, n, n, chi, mc.o, false, &fac);
+        Rsvd r = rsvd_batch(e, {}, n, n, chi, mc.o, false, &fac, &slots);
         std::vector<void*> T1(nj), T2(nj);
         for (int j = 0; j < nj; ++j) { T1[j] = e.ws.alloc((size_t)chi * n * e.esize()); T2[j] = e.ws.alloc((size_t)chi * n * e.esize()); }
         if (!e.ws.dry()) {
@@ -880,7 +921,7 @@ static void move_projectors(MoveCtx& mc, const int* corner_site, const std::vect
     for (int j = 0; j < nj; ++j) { R[j] = e.ws.alloc((size_t)n0 * n1 * e.esize()); Rt[j] = e.ws.alloc((size_t)n0 * n1 * e.esize()); }
     halves_jobs(e, mc.dir, mc.chi, corners, R, Rt, n0, n1);
     std::vector<const void*> Rc(R.begin(), R.end()), Rtc(Rt.begin(), Rt.end());
-    projectors_from_matrices(e, Rc, Rtc, (int)n0, (int)n1, mc.chi, mc.o, P, Pt, {});
+    projectors_from_matrices(e, Rc, Rtc, (int)n0, (int)n1, mc.chi, mc.o, P, Pt, {}, false, false, &slots);
     e.ws.release(mark);
 }
 
@@ -1520,7 +1561,8 @@ static void move_c4v_impl(ctmb_handle_t h, const void* a, const int dims[5], con
         std::vector<Engine::ChainJob> jobs = {sl_job(ops, 3, "uldr", s, "edxr", c2, nullptr)};
         e.chain_multi(jobs);
     }
-    Rsvd r = rsvd_batch(e, {c2}, (int)n, (int)n, chi, o, true);
+    const std::vector<std::string> slots = {"c4v"};
+    Rsvd r = rsvd_batch(e, {c2}, (int)n, (int)n, chi, o, true, nullptr, &slots);
     double* Dv = (double*)e.ws.alloc((size_t)chi * 8);
     void* nTraw = e.ws.alloc((size_t)chi * chi * d * e.esize());
     if (!e.ws.dry()) {

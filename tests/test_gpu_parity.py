@@ -118,6 +118,40 @@ def test_run_energy_and_spectra_against_reference(eng, dev, name):
     assert t_ctm > 0
 
 
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128'])
+def test_single_precision_move_within_1e4(eng, dev, name):
+    """float32 / complex64 (ENV takes its dtype from the state, ctm/generic/env.py:78-83): north-star gate 1e-4 against the
+    reference's float64 result on the same (rounded) inputs; outputs come back in the input precision."""
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    low = torch.complex64 if next(iter(sites.values())).is_complex() else torch.float32
+    C, T = H.golden_env(z, 'mid_')
+    st = H.State({c: t.to(low).to(dev) for c, t in sites.items()}, v2s, lX, lY)
+    for d in orc.DIRECTIONS:
+        env = H.Env(chi, {k: v.to(low).to(dev) for k, v in C.items()}, {k: v.to(low).to(dev) for k, v in T.items()})
+        eng.move_generic(d, st, env)
+        assert all(v.dtype == low for v in list(env.C.values()) + list(env.T.values()))
+        Cg, Tg = H.golden_env(z, f'move_{d[0]}_{d[1]}_')
+        assert H.env_abs_diff({k: v.double() if low == torch.float32 else v.to(torch.complex128) for k, v in env.C.items()},
+                              {k: v.double() if low == torch.float32 else v.to(torch.complex128) for k, v in env.T.items()},
+                              Cg, Tg) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_single_precision_c4v_move_within_1e4(eng, dev, name):
+    z, meta = H.load_golden(name)
+    chi = meta['chi']
+    a64 = torch.from_numpy(z['site'])
+    low = torch.complex64 if a64.is_complex() else torch.float32
+    nC, nT, _ = eng.move_c4v(a64.to(low).to(dev), torch.from_numpy(z['mid_C']).to(low).to(dev),
+                             torch.from_numpy(z['mid_T']).to(low).to(dev), chi)
+    assert nC.dtype == low and nT.dtype == low
+    assert H.maxrel(nC.cpu().to(a64.dtype), torch.from_numpy(z['mid_nC'])) < 1e-4
+    assert H.maxrel(nT.abs().cpu().double(), torch.from_numpy(z['mid_nT']).abs()) < 1e-4
+
+
 @pytest.mark.parametrize('name', C4V)
 def test_c4v_against_reference_fixtures(eng, dev, name):
     z, meta = H.load_golden(name)
@@ -280,7 +314,12 @@ def test_errors_are_python_exceptions(eng, dev):
     with pytest.raises(TypeError):
         ctmrg.ctm_MOVE((0, -1), st, env, ctm_args=bad)
     with pytest.raises(TypeError):
-        eng.einsum2('ab,bc->ac', torch.zeros(2, 2, device=dev), torch.zeros(2, 2, device=dev))   # float32
+        eng.einsum2('ab,bc->ac', torch.zeros(2, 2, device=dev, dtype=torch.float16),
+                    torch.zeros(2, 2, device=dev, dtype=torch.float16))       # only float64/complex128 (+ widened float32/complex64)
+    # float32 operands are widened on entry and rounded on exit (north star: 1e-4 gate)
+    a32 = torch.rand(5, 7, device=dev); b32 = torch.rand(7, 3, device=dev)
+    c32 = eng.einsum2('ab,bc->ac', a32, b32)
+    assert c32.dtype == torch.float32 and float((c32 - a32 @ b32).abs().max()) < 1e-5
 
 
 def _graded(n, dt, decades, seed):
