@@ -529,8 +529,9 @@ def j1j2_hp(j1=1.0, j2=0.0, dtype=torch.float64):
     return 0.5 * j1 * nn + j2 * nnn
 
 
-def energy_j1j2(sites, v2s, C, T, j1=1.0, j2=0.0):
-    """models/j1j2.py:223-247 energy_per_site (= energy_2x2_4site / _2site)."""
+def energy_j1j2(sites, v2s, C, T, j1=1.0, j2=0.0, as_tensor=False):
+    """models/j1j2.py:223-247 energy_per_site (= energy_2x2_4site / _2site).  as_tensor: the 0-dim torch tensor (the
+    gradient tests differentiate through it)."""
     any_site = next(iter(sites.values()))
     hp = j1j2_hp(j1, j2, dtype=any_site.dtype)
     e = 0.
@@ -538,6 +539,8 @@ def energy_j1j2(sites, v2s, C, T, j1=1.0, j2=0.0):
         rho = rdm2x2(coord, sites, v2s, C, T)
         e = e + torch.einsum('ijklabcd,ijklabcd', rho, hp)
     e = e / len(sites)
+    if as_tensor:
+        return e.real if e.is_complex() else e
     return float(e.real if e.is_complex() else e)
 
 
@@ -605,7 +608,7 @@ def rdm2x2_c4v(a, C, T, open_sites=(0, 1, 2, 3), sym_pos_def=False):
     return rdm2x2((0, 0), OrderedDict({(0, 0): a}), v2s_1site, Cg, Tg, open_sites=open_sites, sym_pos_def=sym_pos_def)
 
 
-def energy_j1j2_c4v(a, C, T, j1=1.0, j2=0.0):
+def energy_j1j2_c4v(a, C, T, j1=1.0, j2=0.0, as_tensor=False):
     """models/j1j2.py:641-679 energy_1x1_lowmem (j3=hz_stag=h_uni=0): bipartite rotation
     on one sublattice, e = 2 j1 <SS_rot>_NN + 2 j2 <SS>_NNN with sym_pos_def RDMs."""
     from collections import OrderedDict
@@ -622,6 +625,8 @@ def energy_j1j2_c4v(a, C, T, j1=1.0, j2=0.0):
     if abs(j2) > 0:
         nnn = _sym_pos_def(torch.einsum('ijklajkd->ilad', rho), True)
         e = e + 2.0 * j2 * torch.einsum('ijab,ijab', nnn, SS)
+    if as_tensor:
+        return e.real if e.is_complex() else e
     return float(e.real if e.is_complex() else e)
 
 

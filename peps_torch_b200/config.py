@@ -23,6 +23,9 @@ class CTMARGS:
         self.verbosity_ctm_convergence = 0
         self.fpcm_init_iter = 1
         self.fpcm_freq = -1
+        # reverse-mode AD through the move (peps_torch_b200/ad.py; config.py:391,402-407 of the reference)
+        self.ad_decomp_reg = 1.0e-12
+        self.fwd_checkpoint_move = False
         # engine-specific (no counterpart in the reference)
         self.b200_rsvd_niter = None       # None: library default (ctmb_default_options, include/ctmb.h)
         self.b200_rsvd_rank_factor = None  # None: library default; sketch width k = ceil(rank_factor * chi)

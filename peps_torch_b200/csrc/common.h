@@ -143,13 +143,16 @@ void rdm_posdef_launch(void* out, const void* U, const double* D, int n, bool cp
 // amax of |x|
 void absmax_launch(const ScaleBatch& b, int nb, bool cplx, cudaStream_t stream);
 
-void resid_launch(const PtrBatch& MX, const PtrBatch& Y, const PtrBatch& S, int nb, int rows, int chi, double reltol,
+void resid_launch(const PtrBatch& MX, const PtrBatch& Y, const PtrBatch& S, int nb, int rows, int chi, int k, double reltol,
                   unsigned long long* out, bool cplx, cudaStream_t stream);
 void c4v_sym_launch(const void* tin, void* tout, int chi, int d, unsigned long long* amax, bool cplx,
                     cudaStream_t stream);
 void c4v_diag_launch(const double* D, void* cout, int chi, bool cplx, cudaStream_t stream);
 
 void fill_gaussian_launch(double* out, long long count, unsigned long long seed, cudaStream_t stream);
+void add_noise_launch(double* x, long long count, double amp, const unsigned long long* scale, unsigned long long seed,
+                      cudaStream_t stream);
+void axpby_launch(double* out, const double* x, double c1, const double* y, double c2, long long count, cudaStream_t stream);
 
 // fused double-layer absorption of the enlarged corner (dl_fused.cu)
 struct DlParams {

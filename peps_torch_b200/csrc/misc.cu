@@ -150,7 +150,7 @@ void proj_finalize_launch(const PtrBatch& U, const PtrBatch& V, const PtrBatch& 
 // |s_j| / |s_0| > reltol  (eigen mode: X = Y = U, s = lambda; SVD mode: X = V, Y = U, s = sigma)
 // ---------------------------------------------------------------------------------------------
 template <bool CPLX>
-__global__ void __launch_bounds__(256) resid_kernel(PtrBatch MXb, PtrBatch Yb, PtrBatch Sb, int rows, double reltol,
+__global__ void __launch_bounds__(256) resid_kernel(PtrBatch MXb, PtrBatch Yb, PtrBatch Sb, int rows, int k, double reltol,
                                                     unsigned long long* out) {
     using S = Sc<CPLX>;
     using T = typename S::T;
@@ -159,6 +159,8 @@ __global__ void __launch_bounds__(256) resid_kernel(PtrBatch MXb, PtrBatch Yb, P
     const T* y = reinterpret_cast<const T*>(Yb.p[b]) + (size_t)j * rows;
     const double* Sv = reinterpret_cast<const double*>(Sb.p[b]);
     const double s0 = fabs(Sv[0]), sj = Sv[j];
+    // out[2]: the smallest Ritz value of the k-dimensional block (edge of the Chebyshev filter of the Hermitian branch, move.cu)
+    if (j == 0 && threadIdx.x == 0) atomicMax(out + 2, (unsigned long long)__double_as_longlong(fabs(Sv[k - 1])));
     if (!(fabs(sj) > reltol * s0) || s0 == 0.0) return;
     // out[1]: dynamic range S_0 / S_j of the kept triplets (decides how many operator applications the range finder may
     // chain between two orthogonalisations, move.cu)
@@ -175,11 +177,11 @@ __global__ void __launch_bounds__(256) resid_kernel(PtrBatch MXb, PtrBatch Yb, P
     }
 }
 
-void resid_launch(const PtrBatch& MX, const PtrBatch& Y, const PtrBatch& S, int nb, int rows, int chi, double reltol,
+void resid_launch(const PtrBatch& MX, const PtrBatch& Y, const PtrBatch& S, int nb, int rows, int chi, int k, double reltol,
                   unsigned long long* out, bool cplx, cudaStream_t stream) {
     dim3 grid(chi, nb);
-    if (cplx) resid_kernel<true><<<grid, 256, 0, stream>>>(MX, Y, S, rows, reltol, out);
-    else resid_kernel<false><<<grid, 256, 0, stream>>>(MX, Y, S, rows, reltol, out);
+    if (cplx) resid_kernel<true><<<grid, 256, 0, stream>>>(MX, Y, S, rows, k, reltol, out);
+    else resid_kernel<false><<<grid, 256, 0, stream>>>(MX, Y, S, rows, k, reltol, out);
     CTMB_CUDA(cudaGetLastError());
 }
 
@@ -422,6 +424,37 @@ __global__ void gaussian_kernel(double* out, long long n, unsigned long long see
         double u2 = (b >> 11) * (1.0 / 9007199254740992.0);           // [0,1)
         out[i] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
     }
+}
+
+// x[i] += amp * (*scale) * N(0,1)  (tests: unstructured one-ulp noise on an intermediate, see ctmb_debug_set_m_noise)
+__global__ void add_noise_kernel(double* x, long long n, double amp, const unsigned long long* scale, unsigned long long seed) {
+    const double sc = amp * __longlong_as_double((long long)*scale);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long a = splitmix64(seed ^ (2ull * i));
+        unsigned long long b = splitmix64(seed ^ (2ull * i + 1ull));
+        double u1 = ((a >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+        double u2 = (b >> 11) * (1.0 / 9007199254740992.0);
+        x[i] += sc * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+}
+
+void add_noise_launch(double* x, long long count, double amp, const unsigned long long* scale, unsigned long long seed,
+                      cudaStream_t stream) {
+    int grid = (int)std::max(1ll, std::min((count + 255) / 256, 2368ll));
+    add_noise_kernel<<<grid, 256, 0, stream>>>(x, count, amp, scale, seed);
+    CTMB_CUDA(cudaGetLastError());
+}
+
+// out = c1 * x + c2 * y over `count` doubles (three-term recurrence of the Chebyshev filter, move.cu); out may alias x or y
+__global__ void axpby_kernel(double* out, const double* x, double c1, const double* y, double c2, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = c1 * x[i] + (y ? c2 * y[i] : 0.0);
+}
+
+void axpby_launch(double* out, const double* x, double c1, const double* y, double c2, long long count, cudaStream_t stream) {
+    int grid = (int)std::max(1ll, std::min((count + 255) / 256, 2368ll));
+    axpby_kernel<<<grid, 256, 0, stream>>>(out, x, c1, y, c2, count);
+    CTMB_CUDA(cudaGetLastError());
 }
 
 void fill_gaussian_launch(double* out, long long count, unsigned long long seed, cudaStream_t stream) {

@@ -370,6 +370,12 @@ struct FactoredM {
     }
 };
 
+static bool cheb_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* ev = getenv("CTMB_CHEB"); on = ev ? atoi(ev) : 1; }
+    return on != 0;
+}
+
 // M[b]: m x n row-major (or, with `fac`, given in factored form). eig_mode: M Hermitian (m == n), S receives signed eigenvalues.
 //
 // WARM START (`slots`: one tag per problem, or nullptr).  A CTM run decomposes, move after move, a slowly changing matrix
@@ -402,7 +408,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         if (created) { ProfScope ps(e, Engine::CAT_MISC); fill_gaussian_launch((double*)omega, (long long)n * k * (e.cplx ? 2 : 1), o.seed, e.stream); }
     }
     std::vector<Tn> Mt(nb);
-    PtrBatch pY{}, pZ{}, pQ{}, pR{}, pNull{}, pW{}, pSig{}, pS{}, pUh{}, pWs{}, pG{}, pX{}, pTau{}, pF1{}, pF2{};
+    PtrBatch pY{}, pZ{}, pQ{}, pR{}, pNull{}, pW{}, pSig{}, pS{}, pUh{}, pWs{}, pG{}, pX{}, pTau{}, pF1{}, pF2{}, pC1{}, pC2{};
     std::vector<void*> R2(nb), W(nb), sig(nb), Uh(nb), Ws(nb);
     const int mx = std::max(m, n);
     const bool wy = qr_wy_supported(m, k, e.cplx) && qr_wy_supported(n, k, e.cplx);
@@ -432,6 +438,9 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         }
         if (blocked) qr_blocked_alloc(e, qbw, b, mx, k, pw);
         if (fac) { pF1.p[b] = e.ws.alloc((size_t)k * n * es); pF2.p[b] = e.ws.alloc((size_t)k * n * es); }
+        if (eig_mode && k < n) {      // three-term recurrence of the Chebyshev filter (Hermitian branch)
+            pC1.p[b] = e.ws.alloc((size_t)k * mx * es); pC2.p[b] = e.ws.alloc((size_t)k * mx * es);
+        }
         R2[b] = e.ws.alloc((size_t)k * k * es);
         W[b] = e.ws.alloc((size_t)k * k * es);
         sig[b] = e.ws.alloc((size_t)k * 8);
@@ -570,7 +579,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     unsigned long long* dres = nullptr;
     unsigned long long* hres = nullptr;
     if (adaptive) {
-        dres = (unsigned long long*)e.persistent("resid", 32 * sizeof(unsigned long long));    // [0]: mine, [1..]: the group's
+        dres = (unsigned long long*)e.persistent("resid", 64 * sizeof(unsigned long long));    // [0..3]: mine, [4..]: the group's
         hres = e.pinned_words();                          // per-engine pinned read-back buffer (32 words)
     }
     int todo = complete ? 0 : o.rsvd_niter;               // full power iterations still to run
@@ -592,11 +601,13 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
     // lambda_0/lambda_chi = 25, so the iteration converges slowly AND needs few orthogonalisations) the measured range of
     // the previous decomposition of the same shape allows more: (m-1) log10(range) <= 12.
     int orth = 2;
+    double cheb_a = 0.0;         // Hermitian branch: estimate of |lambda_{k+1}|, the edge of the interval the filter damps
     if (adaptive && !o.rsvd_stateless) {
         auto it = e.iter_hint.find(hkey);
         if (it != e.iter_hint.end()) {
             if (it->second.known) todo = it->second.q;
             if (it->second.range > 1.0) orth = std::max(2, std::min(8, 1 + (int)(12.0 / std::log10(it->second.range * 1.5))));
+            if (eig_mode && it->second.known && it->second.tail > 0.0 && cheb_enabled()) cheb_a = it->second.tail;
         }
     }
     const int orth_iter = std::max(1, orth / 2);          // SVD branch: whole iterations (two applications each) per QR
@@ -632,6 +643,44 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             // Hermitian: subspace iteration with M itself (4 applications per "iteration": the spectrum of
             // the corner decays half as fast as that of M = R^T Rt), one QR per two applications, then
             // Rayleigh-Ritz; the eigenvectors are the normalised columns of the rotated (T + mu).
+            if (cheb_a > 0.0 && orth >= 2) {
+                // Chebyshev-filtered subspace iteration (the flat spectrum of the C4v corner, lambda_0 / lambda_chi = 25 at config 3,
+                // makes plain subspace iteration crawl: |lambda_{k+1} / lambda_chi| per application).  Between two QRs the block
+                // is multiplied by T_d(x), x = 2 M^2 / a^2 - 1, a = |lambda_{k+1}| (the k-th Ritz value of the previous
+                // decomposition of this shape): everything inside [-a, a] stays bounded by 1, |lambda| > a grows like
+                // (x + sqrt(x^2 - 1))^d.  Same number of operator applications (2 d per block, blocks as long as the measured
+                // range allows, see `orth`), T_{j+1} = (4 / a^2) M (M T_j) - 2 T_j - T_{j-1}.  The residual test below is the
+                // judge; a failed round falls back to plain iteration.
+                const long long cnt = (long long)n * k * (e.cplx ? 2 : 1);
+                const double ia2 = 1.0 / (cheb_a * cheb_a);
+                int napp = 4 * todo;
+                const int blk_max = std::max(2, orth & ~1);
+                while (napp > 0) {
+                    const int deg = std::min(napp, blk_max) / 2;
+                    PtrBatch cur = pY, prev{}, nxt = pC1, spare = pC2;
+                    for (int j = 0; j < deg; ++j) {
+                        for (int b = 0; b < nb; ++b)
+                            e.contract(Mt[b], false, make_tn(cur.p[b], "sj", {k, n}), false, make_tn(pZ.p[b], "si", {k, n}));   // Z = M T_j
+                        e.flush();
+                        for (int b = 0; b < nb; ++b) {
+                            ProfScope ps(e, Engine::CAT_MISC);
+                            axpby_launch((double*)nxt.p[b], (const double*)cur.p[b], j == 0 ? -1.0 : -2.0,
+                                         j == 0 ? nullptr : (const double*)prev.p[b], -1.0, cnt, e.stream);
+                        }
+                        for (int b = 0; b < nb; ++b)
+                            e.contract(Mt[b], false, make_tn(pZ.p[b], "sj", {k, n}), false, make_tn(nxt.p[b], "si", {k, n}), nullptr,
+                                       (j == 0 ? 2.0 : 4.0) * ia2, true);                                                          // += c M Z
+                        e.flush();
+                        // rotate: prev <- cur, cur <- nxt, nxt <- (old prev or the spare buffer)
+                        PtrBatch old_prev = prev;
+                        prev = cur; cur = nxt;
+                        nxt = (j == 0) ? spare : old_prev;
+                    }
+                    qr(cur, pNull, n);          // (swaps `cur` with its own scratch where it forms Q out of place)
+                    pY = cur; pC1 = prev; pC2 = nxt;       // T_{d-1} and the rotation's free buffer go back to the pool
+                    napp -= 2 * deg;
+                }
+            } else
             for (int it = 0; it < 4 * todo; ++it) {
                 for (int b = 0; b < nb; ++b) e.contract(Mt[b], false, tnY(b, "sj"), false, tnZ(b, "si"));
                 if ((it + 1) % orth == 0 || it + 1 == 4 * todo) qr(pZ, pNull, n);
@@ -658,37 +707,47 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             pYv.p[b] = r.U[b];
         }
         { PtrBatch pXin{}; for (int b = 0; b < nb; ++b) pXin.p[b] = eig_mode ? r.U[b] : r.V[b]; apply_op(pXin, pMX, chi, false); }
-        CTMB_CUDA(cudaMemsetAsync(dres, 0, 2 * sizeof(unsigned long long), e.stream));       // [0] residual, [1] range S_0 / S_chi
-        { ProfScope ps(e, Engine::CAT_MISC); resid_launch(pMX, pYv, pS, nb, m, chi, o.svd_reltol, dres, e.cplx, e.stream); }
-        int nwords = 2;
+        // [0] residual, [1] range S_0 / S_chi, [2] |S_{k-1}| (the smallest Ritz value of the block: edge of the Chebyshev filter)
+        CTMB_CUDA(cudaMemsetAsync(dres, 0, 4 * sizeof(unsigned long long), e.stream));
+        { ProfScope ps(e, Engine::CAT_MISC); resid_launch(pMX, pYv, pS, nb, m, chi, k, o.svd_reltol, dres, e.cplx, e.stream); }
+        int nwords = 4;
         if (e.coll_active()) {
             // every member of the group must take the same decisions below: exchange residual and range (rounding may
             // differ between devices through non-deterministic reduction orders, and a split decision would dead-lock)
-            CTMB_CHECK(e.coll_n <= 14, "group too large");
-            CTMB_CUDA(cudaMemcpyAsync(dres + 2 + 2 * e.coll_rank, dres, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e.stream));
-            e.allgather(dres + 2, 2 * sizeof(unsigned long long));
-            nwords = 2 * e.coll_n;
-            CTMB_CUDA(cudaMemcpyAsync(hres, dres + 2, nwords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
+            CTMB_CHECK(e.coll_n <= 7, "group too large");
+            CTMB_CUDA(cudaMemcpyAsync(dres + 4 + 4 * e.coll_rank, dres, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e.stream));
+            e.allgather(dres + 4, 4 * sizeof(unsigned long long));
+            nwords = 4 * e.coll_n;
+            CTMB_CUDA(cudaMemcpyAsync(hres, dres + 4, nwords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
         } else
-            CTMB_CUDA(cudaMemcpyAsync(hres, dres, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
+            CTMB_CUDA(cudaMemcpyAsync(hres, dres, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e.stream));
         CTMB_CUDA(cudaStreamSynchronize(e.stream));
-        double res = 0.0, range = 0.0;
-        for (int g = 0; g < nwords / 2; ++g) {
-            double rg, sg; memcpy(&rg, hres + 2 * g, sizeof rg); memcpy(&sg, hres + 2 * g + 1, sizeof sg);
-            res = std::max(res, rg); range = std::max(range, sg);
+        double res = 0.0, range = 0.0, tail = 0.0;
+        for (int g = 0; g < nwords / 4; ++g) {
+            double rg, sg, tg; memcpy(&rg, hres + 4 * g, sizeof rg); memcpy(&sg, hres + 4 * g + 1, sizeof sg); memcpy(&tg, hres + 4 * g + 2, sizeof tg);
+            res = std::max(res, rg); range = std::max(range, sg); tail = std::max(tail, tg);
         }
         static int dbg = -1;
         if (dbg < 0) { const char* ev = getenv("CTMB_DEBUG_RESID"); dbg = ev ? atoi(ev) : 0; }
-        if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d k=%d round %d iterations %d (QR every %d applications) residual %.3e (tol %.1e) range %.2e\n", m, n, k, round, used, orth, res, tol_eff, range);
+        if (dbg) fprintf(stderr, "[ctmb] rsvd %dx%d k=%d round %d iterations %d (QR every %d applications%s) residual %.3e (tol %.1e) range %.2e\n", m, n, k, round, used, orth, cheb_a > 0.0 ? ", Chebyshev filter" : "", res, tol_eff, range);
         Engine::IterHint& hint = e.iter_hint[hkey];
         hint.range = range;
+        // a filtered extra round that makes little progress: the edge estimate may sit above wanted eigenvalues -- plain
+        // iteration for the rest of this call and for the next calls of this shape
+        if (cheb_a > 0.0 && res > tol_eff && round >= 1 && prev_res > 0.0 && res > 0.1 * prev_res) { cheb_a = 0.0; hint.cheb_pause = 16; }
+        if (hint.cheb_pause > 0) { --hint.cheb_pause; hint.tail = 0.0; } else hint.tail = tail;
         ++e.rsvd_status.checks;
         if (res <= tol_eff) {
             if (round == 0) {
-                // passed first time: probe fewer iterations next time (two fewer with a margin of 64x, one with 8x) unless
-                // that count failed recently
+                // passed first time: probe fewer iterations next time -- two fewer with a margin of 64x, one with 8x.  The
+                // residual has a rounding floor (eps sqrt(n) kappa: 0.3 - 0.5 of the bound at configs 3 and 5), so a margin
+                // may never show although the count is far too high (a count doubled after a near miss stayed doubled: config
+                // 3 ran 18 iterations where 9 - 10 pass).  Hence, after three such passes in a row, bisect towards the largest
+                // count known to fail; a failed probe costs one short extra round (below) and is remembered in `lo`.
                 if (++hint.age > 64) { hint.lo = -1; hint.age = 0; }
                 int dec = res <= tol_eff / 64.0 ? 2 : (res <= 0.125 * tol_eff ? 1 : 0);
+                if (dec == 0 && ++hint.streak >= 3 && used - hint.lo >= 2) { dec = std::max(1, (used - hint.lo) / 2); hint.streak = 0; }
+                if (dec > 0) hint.streak = 0;
                 while (dec > 0 && !(used - dec >= q_min && used - dec > hint.lo)) --dec;
                 hint.q = used - dec;
             } else {
@@ -705,8 +764,9 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             hint.known = true;
             break;
         }
-        if (round == 0) { hint.lo = std::max(hint.lo, used); hint.age = 0; }
-        const bool floor_reached = prev_res > 0.0 && res > 0.5 * prev_res;    // rounding floor: more iterations do not help
+        if (round == 0) { hint.lo = std::max(hint.lo, used); hint.age = 0; hint.streak = 0; }
+        // rounding floor: more iterations do not help (less than 15 % gained per iteration of the last round)
+        const bool floor_reached = prev_res > 0.0 && todo > 0 && res > prev_res * std::pow(0.85, (double)todo);
         const bool out_of_rounds = round + 1 >= std::max(1, o.rsvd_max_rounds);
         if (floor_reached || out_of_rounds) {
             // the result is returned although it misses the bound: say so (ctmb_get_rsvd_status), and remember the count
@@ -719,8 +779,9 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
                              floor_reached ? "rounding floor" : "rsvd_max_rounds");
             break;
         }
-        // next round: from the second round on the measured decay rate predicts the missing iterations; until then double
-        int next = std::max(1, used);
+        // next round: from the second round on the measured decay rate predicts the missing iterations; until then double --
+        // or, after a near miss (within 32x of the bound), add a third
+        int next = res <= 32.0 * tol_eff ? std::max(1, (used + 2) / 3) : std::max(1, used);
         if (prev_res > res && res > 0.0 && todo > 0) {
             const double per_iter = std::log(prev_res / res) / todo;
             const int want = (int)std::ceil(std::log(res / (0.25 * tol_eff)) / per_iter);
@@ -754,6 +815,7 @@ struct MoveCtx {
     Engine& e; int dir, nsites, chi; const ctmb_site* sites; const ctmb_options& o;
 };
 
+static double g_m_noise = 0.0;                              // ctmb_debug_set_m_noise
 // R,Rt (n0 x n1 row-major) -> P, Pt (n0 x chi row-major)
 static void projectors_from_matrices(Engine& e, const std::vector<const void*>& R, const std::vector<const void*>& Rt,
                                      int n0, int n1, int chi, const ctmb_options& o,
@@ -773,6 +835,18 @@ static void projectors_from_matrices(Engine& e, const std::vector<const void*>& 
         e.contract(Rtn[b], false, Rttn[b], false, M);           // M = R^T Rt  (plain transpose)
     }
     e.flush();
+    if (g_m_noise > 0.0 && !e.ws.dry()) {
+        // tests only (ctmb_debug_set_m_noise): unstructured noise of `g_m_noise` x max|M| on every entry of the explicit M,
+        // i.e. what one more rounding of M would do -- measures how well the reference algorithm's own output is defined
+        unsigned long long* slot = (unsigned long long*)e.persistent("mnoise", TC_MAX_BATCH * sizeof(unsigned long long));
+        CTMB_CUDA(cudaMemsetAsync(slot, 0, TC_MAX_BATCH * sizeof(unsigned long long), e.stream));
+        ScaleBatch sb{};
+        for (int b = 0; b < nb; ++b) { sb.p[b] = const_cast<void*>(Mp[b]); sb.count[b] = (long long)n1 * n1; sb.amax[b] = slot + b; }
+        absmax_launch(sb, nb, e.cplx, e.stream);
+        for (int b = 0; b < nb; ++b)
+            add_noise_launch((double*)const_cast<void*>(Mp[b]), (long long)n1 * n1 * (e.cplx ? 2 : 1), g_m_noise, slot + b,
+                             0x1234567ull + b, e.stream);
+    }
     Rsvd r = rsvd_batch(e, Mp, n1, n1, chi, o, false, nullptr, slots);
     if (!e.ws.dry()) {
         PtrBatch pU{}, pV{}, pS{}, pSo{};
@@ -1173,6 +1247,8 @@ int ctmb_version(void) { return 100; }
 void ctmb_debug_jacobi_stats(unsigned long long* out) { ctmb::jacobi_stats(out); }
 // tests: force (2) / forbid (0) / auto (1) the matrix-free projector path regardless of the problem size
 void ctmb_debug_set_matrix_free(int mode) { ctmb::g_matrix_free_mode = mode; }
+// tests: relative amplitude of Gaussian noise added to the explicit M = R^T Rt before it is decomposed (0 = off)
+void ctmb_debug_set_m_noise(double amp) { ctmb::g_m_noise = amp; }
 // tests: 1 if square halves of extent n with environment dimension chi take the matrix-free projector path
 int ctmb_debug_uses_matrix_free(int n, int chi) { return ctmb::use_matrix_free(n, n, chi) ? 1 : 0; }
 const char* ctmb_last_error(void) { return get_error().c_str(); }

@@ -68,7 +68,13 @@ def ctm_MOVE(direction, state, env, ctm_args=cfg.ctm_args, global_args=cfg.globa
     eng = _engine()
     if direction not in ((0, -1), (-1, 0), (0, 1), (1, 0)):
         raise ValueError("Invalid direction: " + str(direction))
-    eng.move_generic(direction, state, env, **_options(ctm_args))
+    opts = _options(ctm_args)
+    from ... import ad
+    if ad.needs_grad(list(state.sites.values()) + list(env.C.values()) + list(env.T.values())):
+        # reverse-mode AD (optim_*.py): the same move from differentiable libctmb calls (peps_torch_b200/ad.py)
+        ad.ctm_move_generic(eng, direction, state, env, ctm_args)
+        return
+    eng.move_generic(direction, state, env, **opts)
 
 
 def _sync(dev):

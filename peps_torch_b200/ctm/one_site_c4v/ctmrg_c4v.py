@@ -21,6 +21,11 @@ def _sync(dev):
 
 def _move(a, env, ctm_args):
     eng = _engine()
+    from ... import ad
+    if ad.needs_grad((a, env.C[env.keyC], env.T[env.keyT])):
+        # reverse-mode AD (optim_j1j2_c4v.py): the same move from differentiable libctmb calls (peps_torch_b200/ad.py)
+        env.C[env.keyC], env.T[env.keyT] = ad.ctm_move_c4v(eng, a, env.C[env.keyC], env.T[env.keyT], env.chi, ctm_args)
+        return
     # ctmrg_c4v.py:182-197: C is always scaled by |C[0,0]|; T by the infinity norm ('inf') or the 2-norm (anything else)
     norm = 0 if getattr(ctm_args, 'ctm_absorb_normalization', 'inf') == 'inf' else 1
     nC, nT, _ = eng.move_c4v(a, env.C[env.keyC], env.T[env.keyT], env.chi, norm_type=norm,

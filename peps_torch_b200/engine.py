@@ -166,6 +166,12 @@ class CtmEngine:
         lib.ctmb_debug_set_matrix_free(int(mode))
         self._tables = {k: v for k, v in self._tables.items() if not (isinstance(k, tuple) and k and k[0] in ('ws', 'wsc4v'))}
 
+    def debug_set_m_noise(self, amp):
+        """tests: Gaussian noise of relative amplitude `amp` (x max|M|) on the explicit M = R^T Rt before its decomposition."""
+        lib.ctmb_debug_set_m_noise.argtypes = [C.c_double]
+        lib.ctmb_debug_set_m_noise.restype = None
+        lib.ctmb_debug_set_m_noise(float(amp))
+
     def group_reset(self):
         self._group_recs = []
 

@@ -56,14 +56,44 @@ def enable(engine_factory=None):
     ref_c4v.ctm_MOVE_dl = ctm_MOVE_dl
     # the plaquette density matrices behind the energies of the J1-J2 scripts (models/j1j2.py:223-247,641-679) run on
     # libctmb as well
+    # Under autograd (optim_*.py: the energy is differentiated with respect to the state, through the environment) the
+    # density matrices stay the reference's own torch code -- libctmb's RDM entry points are forward-only; AD is built for
+    # the move (peps_torch_b200/ad.py).  Everything evaluated under torch.no_grad() (convergence
+    # checks, observables) runs on libctmb.
+    from .ad import needs_grad
+
+    def _tensors(args):
+        for x in args:
+            for attr in ('sites', 'C', 'T'):
+                d = getattr(x, attr, None)
+                if isinstance(d, dict):
+                    yield from d.values()
+
+    def _dispatch(ours_fn, ref_fn):
+        def f(*args, **kw):
+            if needs_grad(list(_tensors(args)) + list(_tensors(kw.values()))):
+                return ref_fn(*args, **kw)
+            return ours_fn(*args, **kw)
+        f.__name__ = getattr(ours_fn, '__name__', 'rdm')
+        return f
+
     rdm = importlib.import_module('ctm.generic.rdm')
+    ref_legacy = rdm.rdm2x2_legacy
     for name in ('rdm2x2', 'rdm2x2_legacy', 'rdm1x1', 'rdm2x1', 'rdm1x2', 'rdm1x1_dl', 'rdm2x1_dl', 'rdm1x2_dl',
                  'rdm1x1_sl', 'rdm2x1_sl', 'rdm1x2_sl'):
-        setattr(rdm, name, getattr(ours_rdm, name))
+        ref_fn = getattr(rdm, name)
+        if name == 'rdm2x2':
+            # the reference's dispatching rdm2x2 needs opt_einsum (ctm/generic/rdm.py:1354-1362); its pure-torch
+            # rdm2x2_legacy takes (coord, state, env, sym_pos_def, ...) and is what runs under autograd
+            def ref_fn(coord, state, env, open_sites=[0, 1, 2, 3], sym_pos_def=False, **kw):
+                if list(open_sites) != [0, 1, 2, 3]:
+                    raise NotImplementedError("rdm2x2 with open_sites under autograd needs the reference's opt_einsum path")
+                return ref_legacy(coord, state, env, sym_pos_def=sym_pos_def)
+        setattr(rdm, name, _dispatch(getattr(ours_rdm, name), ref_fn))
     rdm_c4v = importlib.import_module('ctm.one_site_c4v.rdm_c4v')
     for name in ('rdm2x2_NN_lowmem_sl', 'rdm2x2_NNN_lowmem_sl', 'rdm2x2_NN_lowmem', 'rdm2x2_NNN_lowmem', 'rdm2x2',
                  'rdm1x1', 'rdm1x1_sl', 'rdm2x1', 'rdm2x1_sl'):
-        setattr(rdm_c4v, name, getattr(ours_rdm_c4v, name))
+        setattr(rdm_c4v, name, _dispatch(getattr(ours_rdm_c4v, name), getattr(rdm_c4v, name)))
     # (this also removes the reference's dependence on opt_einsum for these functions: without it its 'sl' one- and
     # two-site RDMs and the rdm2x2 dispatch do not run at all, ctm/generic/rdm.py:107-112,292,343-351,560,1354-1362)
     return ref, ref_c4v

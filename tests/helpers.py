@@ -151,6 +151,9 @@ class OracleEngine:
     def debug_set_matrix_free(self, mode):
         pass
 
+    def debug_set_m_noise(self, amp):
+        pass
+
     def halves(self, direction, coord, state, env):
         return orc.halves(direction, coord, state.sites, state.vertexToSite, env.C, env.T)
 
@@ -272,3 +275,70 @@ def check_c4v_variants(name, dev, tol_C=1e-10, tol_T=1e-8, tol_rdm=1e-12, tol_rd
             assert err < (tol_rdm_spd if spd else tol_rdm), (fname, spd, err)
             n_checked += 1
     return n_checked
+
+
+# ----------------------------------------------------------------------------------------------
+# tests/golden/grad_*.npz (oracle/gen_golden_grad.py): gradients of the J1-J2 energy written by the UNMODIFIED reference
+# (loss.backward() through its CTM moves).  The same checker runs on CPU with OracleEngine standing in for libctmb (this
+# validates peps_torch_b200/ad.py's adjoints and chains) and on the GPU box with libctmb.
+# ----------------------------------------------------------------------------------------------
+def c4v_symm(A):
+    if A.is_complex():
+        return orc.make_c4v_symm_A1(A.real) + 1j * orc.make_c4v_symm_A2(A.imag)
+    return orc.make_c4v_symm_A1(A)
+
+
+def check_grad_fixture(name, eng, dev, through_api=True):
+    """Returns (|energy - reference|, max |grad - reference grad|, max |reference grad|)."""
+    import json
+    from peps_torch_b200 import ad
+    from peps_torch_b200.config import CTMARGS
+    z = np.load(os.path.join(GOLD, name + '.npz'))
+    meta = json.loads(str(z['meta']))
+    args = CTMARGS()
+    args.ad_decomp_reg = meta['ad_decomp_reg']
+    args.fwd_checkpoint_move = name.endswith('_ckpt')
+    if meta['kind'] == 'c4v':
+        A = torch.from_numpy(z['site']).to(dev).requires_grad_(True)
+        a = c4v_symm(A)
+        C, T = torch.from_numpy(z['C0']).to(dev), torch.from_numpy(z['T0']).to(dev)
+        if through_api:      # the drop-in entry point: ctm_MOVE_sl dispatches to the AD path because `a` requires grad
+            from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v
+            from peps_torch_b200.env import ENV_C4V
+            from peps_torch_b200.ipeps import IPEPS_C4V
+            env = ENV_C4V(meta['chi'], IPEPS_C4V(a.detach()))
+            env.C[env.keyC], env.T[env.keyT] = C, T
+            for _ in range(meta['moves']):
+                ctmrg_c4v.ctm_MOVE_sl(a, env, None, ctm_args=args)
+            C, T = env.C[env.keyC], env.T[env.keyT]
+        else:
+            for _ in range(meta['moves']):
+                C, T = ad.ctm_move_c4v(eng, a, C, T, meta['chi'], args)
+        loss = orc.energy_j1j2_c4v(a.cpu(), C.cpu(), T.cpu(), 1.0, meta['j2'], as_tensor=True)
+        loss.backward()
+        g, g_ref = A.grad.cpu(), torch.from_numpy(z['grad'])
+        return abs(float(loss.detach()) - float(z['energy'][0])), float((g - g_ref).abs().max()), float(g_ref.abs().max())
+    coords = [(0, 0), (1, 0), (0, 1), (1, 1)]
+    sites = OrderedDict((c, torch.from_numpy(z[f'site_{c[0]}{c[1]}']).to(dev).requires_grad_(True)) for c in coords)
+    C, T = {}, {}
+    for key in z.files:
+        if key[:3] in ('C0_', 'T0_'):
+            c, vx, vy = key[3:].split('_', 1)[0], *key[3:].split('_')[1:]
+            k = ((int(c[0]), int(c[1])), (int(vx), int(vy)))
+            (C if key[0] == 'C' else T)[k] = torch.from_numpy(z[key]).to(dev)
+    st = State(sites, orc.v2s_4site, 2, 2)
+    env = Env(meta['chi'], C, T)
+    from peps_torch_b200.ctm.generic import ctmrg
+    for _ in range(meta['iters']):
+        for d in orc.DIRECTIONS:
+            for _r in range(2):
+                if through_api:
+                    ctmrg.ctm_MOVE(d, st, env, ctm_args=args)
+                else:
+                    ad.ctm_move_generic(eng, d, st, env, args)
+    loss = orc.energy_j1j2(OrderedDict((c, t.cpu()) for c, t in sites.items()), orc.v2s_4site,
+                           {k: v.cpu() for k, v in env.C.items()}, {k: v.cpu() for k, v in env.T.items()}, 1.0, meta['j2'], as_tensor=True)
+    loss.backward()
+    d_ = max(float((sites[c].grad.cpu() - torch.from_numpy(z[f'grad_{c[0]}{c[1]}'])).abs().max()) for c in coords)
+    s_ = max(float(np.abs(z[f'grad_{c[0]}{c[1]}']).max()) for c in coords)
+    return abs(float(loss.detach()) - float(z['energy'][0])), d_, s_
