@@ -154,6 +154,13 @@ int ctmb_truncated_eig_sym(ctmb_handle_t h, ctmb_dtype dt, const void* M, int n,
                            void* ws, size_t ws_bytes, void* stream);
 size_t ctmb_truncated_eig_sym_workspace(ctmb_handle_t h, ctmb_dtype dt, int n, int chi, const ctmb_options* opt);
 
+/* Thin Householder QR = torch.linalg.qr(M) as used by ctm_MOVE_QR_sl (ctm/one_site_c4v/ctmrg_c4v.py:513-516, the
+ * projector of the QR variant of the C4v move).  A: rows x k, COLUMN-major (= the transpose of a row-major torch matrix),
+ * rows >= k; on return A holds the explicit thin Q, R (k x k column-major) the upper-triangular factor.  Signs follow
+ * LAPACK's Householder convention (R_jj = -sign(alpha) ||x||), i.e. Q and R equal torch's up to rounding. */
+int ctmb_qr(ctmb_handle_t h, ctmb_dtype dt, void* A, int rows, int k, void* R, void* ws, size_t ws_bytes, void* stream);
+size_t ctmb_qr_workspace(ctmb_handle_t h, ctmb_dtype dt, int rows, int k);
+
 /* One directional move over all sites = ctm_MOVE (ctm/generic/ctmrg.py:179-319) including
  * projectors (4X4), absorb_truncate_CTM_MOVE_* (ctmrg.py:324-804) and move_normalize_c.
  *   sites[nsites]        the unit cell with its current environment

@@ -441,6 +441,21 @@ def ctm_move_c4v(a, C, T, chi, args=None, return_decomp=False):
     return nC, nT.contiguous()
 
 
+def ctm_move_qr_c4v(a, C, T, chi, args=None):
+    """ctm_MOVE_QR_sl (ctmrg_c4v.py:465-602): projector = thin Q of (C.T) reshaped to (chi d) x chi."""
+    args = args or OracleArgs()
+    C2X2 = c2x2_c4v(a, C, T)
+    C1x2 = torch.tensordot(C, T, ([1], [1])).permute(0, 2, 1).reshape(-1, chi)
+    P, _ = torch.linalg.qr(C1x2)
+    nC = P.t() @ C2X2 @ P
+    Pv = P.view(C.shape[0], T.shape[2], P.shape[1])
+    nT = sl_einsum('acl,aux,@uldr,cdy->xyr', (T, Pv, Pv.conj()), a)
+    nT = 0.5 * (nT + nT.conj().permute(1, 0, 2))
+    nC = nC / torch.abs(nC[0, 0])
+    nT = _normalize(nT, args.ctm_absorb_normalization)
+    return nC, nT.contiguous()
+
+
 def init_env_c4v(a, chi):
     """env_c4v.py:257-311 (_init_from_ipeps_pbc with a_bra = conj(a))."""
     d = a.shape

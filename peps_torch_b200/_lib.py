@@ -62,6 +62,8 @@ SIGNATURES = {
     'ctmb_truncated_svd_workspace': (_sz, [_vp, _i, _i, _i, _i, _PO]),
     'ctmb_truncated_eig_sym': (C.c_int, [_vp, _i, _vp, _i, _i, _PO, _vp, _vp, _vp, _sz, _vp]),
     'ctmb_truncated_eig_sym_workspace': (_sz, [_vp, _i, _i, _i, _PO]),
+    'ctmb_qr': (C.c_int, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    'ctmb_qr_workspace': (_sz, [_vp, _i, _i, _i]),
     'ctmb_move_generic': (C.c_int, [_vp, _i, _i, _i, _i, _PS, _PI, _PI, _PO, _PVP, _PVP, _PVP, _vp, _sz, _vp]),
     'ctmb_move_generic_workspace': (_sz, [_vp, _i, _i, _i, _i, _PS, _PI, _PI, _PO]),
     'ctmb_move_generic_projectors': (C.c_int, [_vp, _i, _i, _i, _i, _PS, _PI, _i, _PI, _PO, _PVP, _PVP, _vp, _sz, _vp]),

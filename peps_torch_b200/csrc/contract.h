@@ -64,7 +64,7 @@ public:
     cudaStream_t stream = nullptr;
     Workspace ws;
     long long launches = 0;        // kernels launched (our own), for bench accounting
-    struct IterHint { int q = 0; int lo = -1; int age = 0; double range = 0.0; bool known = false; double tail = 0.0; int cheb_pause = 0; int streak = 0; };   // range: S_0 / S_chi seen last time (0: unknown)   // q: start count; lo: largest count that failed recently
+    struct IterHint { int q = 0; int lo = -1; int age = 0; double range = 0.0; bool known = false; double tail = 0.0; int cheb_pause = 0; int streak = 0; bool cheb_seen = false; };   // range: S_0 / S_chi seen last time (0: unknown)   // q: start count; lo: largest count that failed recently
     std::map<std::string, IterHint> iter_hint;   // adaptive range finder, per problem shape: power iterations that satisfied
                                                  // the residual test last time, and how long not to probe below them
     double flops = 0;              // algorithmic real flops enqueued

@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(256) resid_kernel(PtrBatch MXb, PtrBatch Yb, P
     const T* y = reinterpret_cast<const T*>(Yb.p[b]) + (size_t)j * rows;
     const double* Sv = reinterpret_cast<const double*>(Sb.p[b]);
     const double s0 = fabs(Sv[0]), sj = Sv[j];
-    // out[2]: the smallest Ritz value of the k-dimensional block (edge of the Chebyshev filter of the Hermitian branch, move.cu)
-    if (j == 0 && threadIdx.x == 0) atomicMax(out + 2, (unsigned long long)__double_as_longlong(fabs(Sv[k - 1])));
+    // out[2]: the Ritz value of index k (edge of the Chebyshev filter of the Hermitian branch, move.cu: cheb_edge_index)
+    if (j == 0 && threadIdx.x == 0) atomicMax(out + 2, (unsigned long long)__double_as_longlong(fabs(Sv[k])));
     if (!(fabs(sj) > reltol * s0) || s0 == 0.0) return;
     // out[1]: dynamic range S_0 / S_j of the kept triplets (decides how many operator applications the range finder may
     // chain between two orthogonalisations, move.cu)

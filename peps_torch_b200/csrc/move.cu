@@ -370,6 +370,15 @@ struct FactoredM {
     }
 };
 
+// Which Ritz value stands for |lambda_{k+1}|, the edge of the interval the Chebyshev filter damps: the last ones of the block
+// are the least converged and far BELOW the eigenvalues they approximate (an edge set too low turns the filter into plain
+// power iteration); CTMB_CHEB_EDGE = fraction of the way from chi to k (default 0.75).
+static int cheb_edge_index(int chi, int k) {
+    static double f = -1.0;
+    if (f < 0.0) { const char* ev = getenv("CTMB_CHEB_EDGE"); f = ev ? atof(ev) : 0.75; }
+    return std::max(chi, std::min(k - 1, chi + (int)(f * (k - chi))));
+}
+
 static bool cheb_enabled() {
     static int on = -1;
     if (on < 0) { const char* ev = getenv("CTMB_CHEB"); on = ev ? atoi(ev) : 1; }
@@ -607,7 +616,11 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         if (it != e.iter_hint.end()) {
             if (it->second.known) todo = it->second.q;
             if (it->second.range > 1.0) orth = std::max(2, std::min(8, 1 + (int)(12.0 / std::log10(it->second.range * 1.5))));
-            if (eig_mode && it->second.known && it->second.tail > 0.0 && cheb_enabled()) cheb_a = it->second.tail;
+            if (eig_mode && it->second.known && it->second.tail > 0.0 && cheb_enabled()) {
+                cheb_a = it->second.tail;
+                // first filtered call of this shape: what is known about failing counts was learnt without the filter
+                if (!it->second.cheb_seen) { it->second.cheb_seen = true; it->second.lo = -1; it->second.streak = 2; }
+            }
         }
     }
     const int orth_iter = std::max(1, orth / 2);          // SVD branch: whole iterations (two applications each) per QR
@@ -709,7 +722,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         { PtrBatch pXin{}; for (int b = 0; b < nb; ++b) pXin.p[b] = eig_mode ? r.U[b] : r.V[b]; apply_op(pXin, pMX, chi, false); }
         // [0] residual, [1] range S_0 / S_chi, [2] |S_{k-1}| (the smallest Ritz value of the block: edge of the Chebyshev filter)
         CTMB_CUDA(cudaMemsetAsync(dres, 0, 4 * sizeof(unsigned long long), e.stream));
-        { ProfScope ps(e, Engine::CAT_MISC); resid_launch(pMX, pYv, pS, nb, m, chi, k, o.svd_reltol, dres, e.cplx, e.stream); }
+        { ProfScope ps(e, Engine::CAT_MISC); resid_launch(pMX, pYv, pS, nb, m, chi, cheb_edge_index(chi, k), o.svd_reltol, dres, e.cplx, e.stream); }
         int nwords = 4;
         if (e.coll_active()) {
             // every member of the group must take the same decisions below: exchange residual and range (rounding may
@@ -796,6 +809,56 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         for (int b = 0; b < nb; ++b)
             CTMB_CUDA(cudaMemcpyAsync(slot[b], eig_mode ? r.U[b] : r.V[b], (size_t)n * kw * es, cudaMemcpyDeviceToDevice, e.stream));
     return r;
+}
+
+// Thin Householder QR of one rows x k matrix (column-major, rows >= k) with its own scratch: A <- explicit Q, Rout <- R
+// (k x k column-major, upper triangular, LAPACK sign convention: diagonal = -sign(alpha) ||x||).  Same drivers as the
+// range finder above (register / cluster kernels, WY form, blocked factorisation), chosen by shape.
+static void qr_thin(Engine& e, void* A, void* Rout, int rows, int k) {
+    CTMB_CHECK(rows >= k && k >= 1, "qr: expects rows >= cols >= 1");
+    const size_t es = e.esize();
+    const size_t mark = e.ws.mark();
+    const bool wy = qr_wy_supported(rows, k, e.cplx);
+    int pw = std::min(qr_panel_width(rows, k, e.cplx), e.cplx ? 64 : 128);
+    const bool blocked = !wy && pw < k;
+    PtrBatch cur{}, pR{}, pQ{}, pG{}, pX{}, pTau{};
+    cur.p[0] = A; pR.p[0] = Rout;
+    QrBlockedWs qbw;
+    if (blocked) {
+        const int tw = qr_tall_panel_width(1, rows, k, e.cplx);
+        if (tw > pw || (tw > 0 && qr_tall_mode() == 2)) {
+            pw = tw;
+            if (!e.ws.dry()) qbw.tall = e.persistent("qrtall", qr_tall_scratch_bytes(TC_MAX_BATCH));
+        }
+        CTMB_CHECK(pw >= 4, "matrix too tall for the panel kernels");
+        qr_blocked_alloc(e, qbw, 0, rows, k, pw);
+    }
+    if (wy) {
+        pQ.p[0] = e.ws.alloc((size_t)k * rows * es);
+        pG.p[0] = e.ws.alloc((size_t)k * k * es);
+        pX.p[0] = e.ws.alloc((size_t)k * k * es);
+        pTau.p[0] = e.ws.alloc((size_t)k * es);
+    }
+    if (!e.ws.dry()) {
+        e.flush();
+        if (blocked) qr_blocked(e, cur, pR, 1, rows, k, qbw);
+        else if (!wy) { ProfScope ps(e, Engine::CAT_QR); qr_launch(cur, pR, 1, rows, k, rows, e.cplx, e.stream); }
+        else {
+            { ProfScope ps(e, Engine::CAT_QR); qr_wy_factor_launch(cur, pR, pTau, 1, rows, k, rows, e.cplx, e.stream); }
+            Tn V = make_tn(cur.p[0], "si", {k, rows});
+            e.contract(V, true, relabel(V, "ti"), false, make_tn(pG.p[0], "ts", {k, k}));
+            e.flush();
+            { ProfScope ps(e, Engine::CAT_QR); wy_tsolve_launch(pG, pTau, cur, pX, 1, k, rows, e.cplx, e.stream); }
+            e.contract(make_tn(cur.p[0], "si", {k, rows}), false, make_tn(pX.p[0], "cs", {k, k}), false,
+                       make_tn(pQ.p[0], "ci", {k, rows}), nullptr, -1.0);
+            e.flush();
+            { ProfScope ps(e, Engine::CAT_MISC); add_identity_launch(pQ, 1, k, rows, e.cplx, e.stream); }
+            std::swap(cur, pQ);
+        }
+        if (cur.p[0] != A)          // the drivers that form Q out of place leave it in their scratch
+            CTMB_CUDA(cudaMemcpyAsync(A, cur.p[0], (size_t)rows * k * es, cudaMemcpyDeviceToDevice, e.stream));
+    }
+    e.ws.release(mark);
 }
 
 static ProjFinalizeArgs finalize_args(const Rsvd& r, const ctmb_options& o, bool conj_u, bool scale) {
@@ -1457,6 +1520,21 @@ size_t ctmb_truncated_svd_workspace(ctmb_handle_t h, ctmb_dtype dt, int m, int n
     CTMB_TRY
     begin_dry(h, dt);
     svd_impl(h, nullptr, m, n, chi, opts_or_default(opt), nullptr, nullptr, nullptr);
+    return h->h.eng.ws.peak() + 256;
+    CTMB_CATCH(0)
+}
+
+int ctmb_qr(ctmb_handle_t h, ctmb_dtype dt, void* A, int rows, int k, void* R, void* ws, size_t ws_bytes, void* stream) {
+    CTMB_TRY
+    begin_call(h, dt, ws, ws_bytes, stream);
+    qr_thin(h->h.eng, A, R, rows, k);
+    return 0;
+    CTMB_CATCH(-1)
+}
+size_t ctmb_qr_workspace(ctmb_handle_t h, ctmb_dtype dt, int rows, int k) {
+    CTMB_TRY
+    begin_dry(h, dt);
+    qr_thin(h->h.eng, nullptr, nullptr, rows, k);
     return h->h.eng.ws.peak() + 256;
     CTMB_CATCH(0)
 }

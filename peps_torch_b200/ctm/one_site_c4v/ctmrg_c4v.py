@@ -6,7 +6,7 @@ from ... import config as cfg
 
 # all of these ask for the chi eigenpairs of largest magnitude of the Hermitian enlarged corner
 # (ctmrg_c4v.py:49-67,127-140); here every one of them runs libctmb's residual-checked subspace iteration
-_SUPPORTED_EIG = ('DEFAULT', 'SYMEIG', 'SYMARP', 'SYMLOBPCG')
+_SUPPORTED_EIG = ('DEFAULT', 'SYMEIG', 'SYMARP', 'SYMLOBPCG', 'QR')
 
 
 def _engine():
@@ -52,6 +52,37 @@ def ctm_MOVE_sl(a, env, f_c2x2_decomp=None, ctm_args=cfg.ctm_args, global_args=c
     _move(a, env, ctm_args)
 
 
+def ctm_MOVE_QR_sl(a, env, ctm_args=cfg.ctm_args, global_args=cfg.global_args, past_steps_data=None):
+    r"""
+    The QR variant of the C4v move (ctmrg_c4v.py:465-602, ``projector_svd_method='QR'``): the projector is the thin Q of the
+    (chi D^2) x chi matrix C.T instead of the leading eigenvectors of the enlarged corner; C' = P^T C2x2 P, T' as in
+    ctm_MOVE_sl.  Composed from libctmb calls: contraction chains, the Householder QR (ctmb_qr), element-wise
+    symmetrisation / normalisation on the device.  Forward only (no QR adjoint is built).
+    """
+    eng = _engine()
+    from ... import ad
+    C, T = env.C[env.keyC], env.T[env.keyT]
+    if a.dim() != 5:
+        raise ValueError("ctm_MOVE_QR_sl contracts the single-layer tensor a[s,u,l,d,r]")
+    if ad.needs_grad((a, C, T)):
+        raise NotImplementedError("ctm_MOVE_QR_sl: reverse-mode AD through the QR projector is not built")
+    with torch.no_grad():
+        t = ad.sl_chain(eng, 'ab,xbu,ael,@uldr->edxr', (C, T, T), a)
+        C2X2 = t.reshape(t.shape[0] * t.shape[1], t.shape[2] * t.shape[3])
+        C1x2 = eng.einsum2('ab,cbd->adc', C, T).reshape(-1, env.chi)
+        P, _ = eng.qr(C1x2)
+        P = P.contiguous()
+        nC = eng.einsum2('ki,kj->ij', P, eng.einsum2('ik,kj->ij', C2X2, P))          # P^T C2X2 P (plain transpose)
+        Pv = P.reshape(C.shape[0], T.shape[2], P.shape[1])
+        nT = ad.sl_chain(eng, 'acl,aux,@uldr,cdy->xyr', (T, Pv, Pv), a, conj_last=True)
+        nT = 0.5 * (nT + nT.conj().permute(1, 0, 2))
+        nC = nC / torch.abs(nC[0, 0])
+        norm = getattr(ctm_args, 'ctm_absorb_normalization', 'inf')
+        nT = nT / torch.linalg.vector_norm(nT, ord=float('inf') if norm == 'inf' else 2)
+    env.C[env.keyC] = nC
+    env.T[env.keyT] = nT.contiguous()
+
+
 def ctm_MOVE_dl(a, env, f_c2x2_decomp=None, ctm_args=cfg.ctm_args, global_args=cfg.global_args):
     r"""
     :param a: on-site C4v symmetric tensor a[s,u,l,d,r], or the double-layer tensor A[D^2,D^2,D^2,D^2]
@@ -79,7 +110,11 @@ def _run(state, env, conv_check, ctm_args, global_args, move):
     for i in range(ctm_args.ctm_max_iter):
         _sync(eng.device)
         t0_ctm = time.perf_counter()
-        move(a, env, None, ctm_args=ctm_args, global_args=global_args)
+        if ctm_args.projector_svd_method == 'QR' and i > getattr(ctm_args, 'fpcm_init_iter', 1) and move is ctm_MOVE_sl:
+            # ctmrg_c4v.py:87-89: the first moves use the eigenvalue projector, then the QR projector takes over
+            ctm_MOVE_QR_sl(a, env, ctm_args=ctm_args, global_args=global_args)
+        else:
+            move(a, env, None, ctm_args=ctm_args, global_args=global_args)
         _sync(eng.device)
         t1_ctm = time.perf_counter()
         t0_obs = time.perf_counter()

@@ -335,6 +335,19 @@ class CtmEngine:
                                      _ptr(ws), ws.numel(), self._stream()))
         return U.t(), S, V.t()
 
+    def qr(self, M):
+        """Thin QR of a rows x k matrix, rows >= k (torch.linalg.qr(M), LAPACK sign convention) -> (Q, R)."""
+        M = self._prep(M, self.device)
+        rows, k = M.shape
+        A = M.t().contiguous()                      # row-major k x rows = column-major rows x k
+        R = torch.empty((k, k), dtype=M.dtype, device=self.device)
+        nb = lib.ctmb_qr_workspace(self._h, _dt(M), rows, k)
+        if nb == 0:
+            raise _lib.CtmbError(lib.ctmb_last_error().decode())
+        ws = self._workspace(nb)
+        check(lib.ctmb_qr(self._h, _dt(M), _ptr(A), rows, k, _ptr(R), _ptr(ws), ws.numel(), self._stream()))
+        return A.t(), R.t()
+
     def truncated_eig_sym(self, M, chi, **opt):
         M = self._prep(M, self.device)
         n = M.shape[0]

@@ -26,12 +26,14 @@ class ENV:
         self.C, self.T = dict(), dict()
         if state is not None:
             self.dtype, self.device = state.dtype, state.device
+            # single-layer sites a[s,u,l,d,r]: the environment legs are (ket, bra) pairs; double-layer A[u,l,d,r]: the legs themselves
+            numl = 2 if next(iter(state.sites.values())).dim() > 4 else 1
             for coord, site in state.sites.items():
-                D = site.shape[1:]
-                self.T[(coord, (0, -1))] = torch.empty((chi, D[0] ** 2, chi), dtype=self.dtype, device=self.device)
-                self.T[(coord, (-1, 0))] = torch.empty((chi, chi, D[1] ** 2), dtype=self.dtype, device=self.device)
-                self.T[(coord, (0, 1))] = torch.empty((D[2] ** 2, chi, chi), dtype=self.dtype, device=self.device)
-                self.T[(coord, (1, 0))] = torch.empty((chi, D[3] ** 2, chi), dtype=self.dtype, device=self.device)
+                D = site.shape[-4:]
+                self.T[(coord, (0, -1))] = torch.empty((chi, D[0] ** numl, chi), dtype=self.dtype, device=self.device)
+                self.T[(coord, (-1, 0))] = torch.empty((chi, chi, D[1] ** numl), dtype=self.dtype, device=self.device)
+                self.T[(coord, (0, 1))] = torch.empty((D[2] ** numl, chi, chi), dtype=self.dtype, device=self.device)
+                self.T[(coord, (1, 0))] = torch.empty((chi, D[3] ** numl, chi), dtype=self.dtype, device=self.device)
                 for vec in [(-1, -1), (-1, 1), (1, -1), (1, 1)]:
                     self.C[(coord, vec)] = torch.empty((chi, chi), dtype=self.dtype, device=self.device)
 
@@ -115,17 +117,82 @@ def init_random(env, verbosity=0):
 
 def init_env(state, env, ctm_args=None):
     """Initialise ``env`` as CTMARGS.ctm_env_init_type says (env.py:235-265): 'CTMRG' (default) or 'RANDOM'; the
-    product-state and open-boundary variants ('PROD', 'CTMRG_OBC') are not built here."""
+    product-state and open-boundary variants 'PROD' (env.py:274-365) and 'CTMRG_OBC' (:538-715) as well."""
     kind = getattr(ctm_args if ctm_args is not None else cfg.ctm_args, 'ctm_env_init_type', 'CTMRG')
     if next(iter(state.sites.values())).dim() == 4 and kind not in ('PROD', 'CTMRG_OBC', 'RANDOM'):
         raise RuntimeError("Incompatible ENV initialization")
     if kind == 'RANDOM':
         return init_random(env)
-    if kind in ('PROD', 'CTMRG_OBC'):
-        raise NotImplementedError(f"ctm_env_init_type='{kind}' is not built in peps_torch_b200; use the reference's init_env")
+    if kind == 'PROD':
+        return init_prod(state, env)
+    if kind == 'CTMRG_OBC':
+        return init_from_ipeps_obc(state, env)
     if kind != 'CTMRG':
         raise ValueError("Invalid environment initialization: " + str(kind))
     init_from_ipeps_pbc(state, env)
+
+
+# open-boundary / product initialisations: (vec, leg kept of a double-layer A[u,l,d,r], single-layer einsum over (A, .), kept legs)
+_OBC_C = {(-1, -1): ('ijef->ef', 'mijef,mklab->eafb', (3, 4)), (1, -1): ('iefj->ef', 'miefj,mkabl->eafb', (2, 3)),
+          (1, 1): ('efij->ef', 'mefij,mabkl->eafb', (1, 2)), (-1, 1): ('eijf->ef', 'meijf,maklb->eafb', (1, 4))}
+_OBC_T = {(0, -1): ('iefg->efg', 'miefg,mkabc->eafbgc', (2, 3, 4), (True, False, True)),
+          (-1, 0): ('eifg->efg', 'meifg,makbc->eafbgc', (1, 3, 4), (True, True, False)),
+          (0, 1): ('efig->efg', 'mefig,mabkc->eafbgc', (1, 2, 4), (False, True, True)),
+          (1, 0): ('efgi->efg', 'mefgi,mabck->eafbgc', (1, 2, 3), (True, False, True))}
+# 'PROD': (vec, double-layer einsum, single-layer einsum, where the vector sits, normalised?)  -- the (0,-1) vector is NOT
+# divided by its largest magnitude in the reference (env.py:282-292 vs :303, :322, :341); kept as it is
+_PROD_T = {(0, -1): ('uldr->d', 'miefg,miebg->fb', (0, slice(None), 0), False),
+           (-1, 0): ('uldr->r', 'meifg,meifc->gc', (0, 0, slice(None)), True),
+           (0, 1): ('uldr->u', 'mefig,mafig->ea', (slice(None), 0, 0), True),
+           (1, 0): ('uldr->l', 'mefgi,mebgi->fb', (0, slice(None), 0), True)}
+
+
+def init_prod(state, env, verbosity=0):
+    """'PROD' (env.py:274-365): C = e_0 e_0^T, T = the on-site double-layer tensor traced over the three legs that do not
+    face the site, placed in the (0, 0) slot of the environment legs."""
+    chi = env.chi
+    any_site = next(iter(state.sites.values()))
+    for coord in state.sites.keys():
+        for vec in _INIT_C:
+            c = torch.zeros(chi, chi, dtype=any_site.dtype, device=any_site.device)
+            c[0, 0] = 1.0
+            env.C[(coord, vec)] = c
+        for vec, (dl, sl, where, normalise) in _PROD_T.items():
+            A = state.site((coord[0] + vec[0], coord[1] + vec[1]))
+            if A.dim() == 4:
+                a = torch.einsum(dl, A).contiguous()
+            else:
+                a = torch.einsum(sl, A, A.conj()).contiguous()
+                a = a.view(a.size(0) ** 2)
+            if normalise:
+                a = a / a.abs().max()
+            shape = [a.size(0) if isinstance(w, slice) else chi for w in where]
+            t = torch.zeros(shape, dtype=A.dtype, device=A.device)
+            t[where] = a
+            env.T[(coord, vec)] = t
+
+
+def init_from_ipeps_obc(state, env, verbosity=0):
+    """'CTMRG_OBC' (env.py:538-715): as 'CTMRG', but the legs that point away from the site are summed over separately in
+    the two layers (open boundary) instead of being traced; the reference contracts (A, A) here, not (A, conj A)."""
+    chi = env.chi
+    for coord in state.sites.keys():
+        for table, store in ((_OBC_C, env.C), (_OBC_T, env.T)):
+            for vec, spec in table.items():
+                dl, sl, legs = spec[0], spec[1], spec[2]
+                is_chi = spec[3] if len(spec) > 3 else (True, True)
+                A = state.site((coord[0] + vec[0], coord[1] + vec[1]))
+                d = A.shape
+                if A.dim() == 4:
+                    t = torch.einsum(dl, A)
+                else:
+                    t = torch.einsum(sl, A, A).contiguous().view(*[d[l] ** 2 for l in legs])
+                t = t / t.abs().max()
+                shape = [chi if f else t.shape[i] for i, f in enumerate(is_chi)]
+                out = torch.zeros(shape, dtype=A.dtype, device=A.device)
+                sl_ = tuple(slice(0, min(chi, t.shape[i])) if f else slice(None) for i, f in enumerate(is_chi))
+                out[sl_] = t[sl_]
+                store[(coord, vec)] = out
 
 
 def init_from_ipeps_pbc(state, env, verbosity=0):
@@ -302,3 +369,48 @@ def init_env_c4v(state, env, C_and_T=None, ctm_args=None):
     T = torch.zeros(chi, chi, dk[3], dtype=a.dtype, device=a.device)
     T[:r, :r, :] = t[:r, :r, :]
     env.C[env.keyC], env.T[env.keyT] = C, T
+
+
+@torch.no_grad()
+def ctmrg_conv_rdm2x1(state, env, history, ctm_args=None, min_history=1, lag=0):
+    """Convergence criterion of the C4v scripts (examples/j1j2/ctmrg_j1j2_c4v.py:101-129; optim_j1j2_c4v.py:72-86 with
+    min_history=0): 2-norm distance between the nearest-neighbour density matrices (rdm2x1_sl, on libctmb) of consecutive
+    iterations; history = {'log': [dist...], 'rdm': last rdm}; converged when dist < ctm_conv_tol, stops at ctm_max_iter.
+
+    lag=0 reproduces the reference decision for decision, with ONE host synchronisation per call (the .item() of the
+    reference).  lag=1 never stalls the stream: the distance is reduced on the device, copied to pinned memory asynchronously
+    and the decision of THIS call is taken on the distance of the PREVIOUS one, which has long arrived while the next move
+    was being enqueued; the run then makes one move more than the reference."""
+    from .ctm.one_site_c4v.rdm_c4v import rdm2x1_sl
+    ctm_args = ctm_args if ctm_args is not None else cfg.ctm_args
+    if not history:
+        history = {'log': [], 'pending': []}
+    rdm = rdm2x1_sl(state, env)
+    n = len(history['log']) + len(history.get('pending', []))
+    dist = float('inf')
+    if lag == 0:
+        if n > min_history:
+            dist = torch.dist(rdm, history['rdm'], p=2).item()           # the one synchronisation
+        history['log'].append(dist)
+    else:
+        pend = history.setdefault('pending', [])
+        if n > min_history:
+            host = torch.empty((), dtype=torch.float64, pin_memory=rdm.is_cuda)
+            host.copy_(torch.dist(rdm, history['rdm'], p=2).to(torch.float64), non_blocking=True)
+            ev = torch.cuda.Event() if rdm.is_cuda else None
+            if ev is not None:
+                ev.record()
+            pend.append((host, ev))
+        else:
+            pend.append((None, None))
+        while len(pend) > lag:                                               # distances old enough to have arrived
+            host, ev = pend.pop(0)
+            if ev is not None:
+                ev.synchronize()                                             # completed long ago: returns at once
+            history['log'].append(float(host) if host is not None else float('inf'))
+        dist = history['log'][-1] if history['log'] else float('inf')
+    history['rdm'] = rdm
+    converged = dist < ctm_args.ctm_conv_tol
+    if converged or n + 1 >= ctm_args.ctm_max_iter:
+        return bool(converged), history
+    return False, history

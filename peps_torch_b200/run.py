@@ -52,8 +52,12 @@ def enable(engine_factory=None):
     # the reference's own run / run_overlap / run_dl loops stay: they look these names up at call time, build the
     # double-layer tensors themselves under ctm_force_dl and hand rank-4 sites to ctm_MOVE, which libctmb accepts
     ref.ctm_MOVE = ctm_MOVE
+    def ctm_MOVE_QR_sl(a, env, ctm_args=ref_c4v.cfg.ctm_args, global_args=ref_c4v.cfg.global_args, past_steps_data=None):
+        return ours_c4v.ctm_MOVE_QR_sl(a, env, ctm_args=ctm_args, global_args=global_args, past_steps_data=past_steps_data)
+
     ref_c4v.ctm_MOVE_sl = ctm_MOVE_sl
     ref_c4v.ctm_MOVE_dl = ctm_MOVE_dl
+    ref_c4v.ctm_MOVE_QR_sl = ctm_MOVE_QR_sl
     # the plaquette density matrices behind the energies of the J1-J2 scripts (models/j1j2.py:223-247,641-679) run on
     # libctmb as well
     # Under autograd (optim_*.py: the energy is differentiated with respect to the state, through the environment) the
@@ -94,6 +98,14 @@ def enable(engine_factory=None):
     for name in ('rdm2x2_NN_lowmem_sl', 'rdm2x2_NNN_lowmem_sl', 'rdm2x2_NN_lowmem', 'rdm2x2_NNN_lowmem', 'rdm2x2',
                  'rdm1x1', 'rdm1x1_sl', 'rdm2x1', 'rdm2x1_sl'):
         setattr(rdm_c4v, name, _dispatch(getattr(ours_rdm_c4v, name), getattr(rdm_c4v, name)))
+    # the transfer-operator spectra at the tail of the scripts (ctm/generic/transferops.py:38-205): mat-vecs on libctmb
+    from .ctm.generic import transferops as ours_top
+    top = importlib.import_module('ctm.generic.transferops')
+    if engine_factory is not None:
+        from .ctm.generic import corrf as ours_corrf
+        ours_corrf._engine = engine_factory
+    top.get_Top_spec = ours_top.get_Top_spec
+    top.get_Top_w0_spec = ours_top.get_Top_w0_spec
     # (this also removes the reference's dependence on opt_einsum for these functions: without it its 'sl' one- and
     # two-site RDMs and the rdm2x2 dispatch do not run at all, ctm/generic/rdm.py:107-112,292,343-351,560,1354-1362)
     return ref, ref_c4v

@@ -193,6 +193,9 @@ class OracleEngine:
     def sym_pos_def(self, rdm, sym_pos_def=False):
         return orc._sym_pos_def(rdm, sym_pos_def)
 
+    def qr(self, M):
+        return torch.linalg.qr(M)
+
 
 # ----------------------------------------------------------------------------------------------
 # tests/golden/variants_*.npz (oracle/gen_golden_variants.py): outputs of the UNMODIFIED reference for the variants of

@@ -794,3 +794,85 @@ def test_config2_script_known_answer_on_gpu(eng, dev):
     hp = orc.j1j2_hp(1.0, 0.3)
     e = sum(torch.einsum('ijklabcd,ijklabcd', rdm.rdm2x2(c, st, env).cpu(), hp) for c in sites) / len(sites)
     assert abs(float(e) - 0.6424192641900255) < 1e-10 * 0.64
+
+
+@pytest.mark.parametrize('lag', [0, 1])
+def test_conv_rdm2x1_criterion_on_gpu(eng, dev, lag):
+    """ctmrg_conv_rdm2x1 (examples/j1j2/ctmrg_j1j2_c4v.py:101-129) with libctmb moves and density matrices on the config-1
+    state: the distances the unmodified script prints on CPU; lag=1 is the variant without a stream stall."""
+    import test_conv_rdm_cpu as T
+    T.check(T.run_config1(dev, lag), lag)
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.complex128])
+def test_householder_qr_entry_point(eng, dev, dt):
+    """ctmb_qr against torch.linalg.qr (same LAPACK sign convention: element-wise), through all drivers: register kernel
+    (432 x 84), WY form (1024 x 128), blocked factorisation (1536 x 96, the C.T matrix of config 3; 4096 x 200)."""
+    for rows, k in ((64, 16), (432, 84), (1024, 128), (1536, 96), (4096, 200)):
+        g = torch.Generator().manual_seed(rows + k)
+        M = torch.randn(rows, k, dtype=dt, generator=g)
+        Q, R = eng.qr(M.to(dev))
+        Q, R = Q.cpu(), R.cpu()
+        Qr, Rr = torch.linalg.qr(M)
+        eye = torch.eye(k, dtype=dt)
+        assert float((Q.conj().t() @ Q - eye).abs().max()) < 1e-13, (rows, k)
+        assert H.maxrel(Q @ R, M) < 1e-13, (rows, k)
+        assert float(R.tril(-1).abs().max()) == 0.0
+        # unique up to the phase of each column / row of R: LAPACK makes the diagonal of R real; compare after aligning
+        ph = (R.diagonal() / Rr.diagonal())
+        ph = ph / ph.abs()
+        assert H.maxrel(Q * ph.conj()[None, :], Qr) < 1e-11, (rows, k)
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_c4v_qr_move_against_oracle(eng, dev, name):
+    """ctm_MOVE_QR_sl (ctmrg_c4v.py:465-602) composed from libctmb calls against the oracle (pinned element-wise against the
+    reference by tests/test_oracle_vs_reference_cpu.py); also at the size of config 3 (D = 4, chi = 96, complex)."""
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v
+    from peps_torch_b200.env import ENV_C4V
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    z, meta = H.load_golden(name)
+    a = torch.from_numpy(z['site'])
+    cases = [(a, meta['chi'])]
+    if a.is_complex():
+        cases.append((orc.random_state_c4v(4, family='B', dtype=torch.complex128), 96))
+    for a, chi in cases:
+        C, T = orc.init_env_c4v(a, chi)
+        for _ in range(2):
+            C, T = orc.ctm_move_c4v(a, C, T, chi)
+        env = ENV_C4V(chi, IPEPS_C4V(a.to(dev)))
+        env.C[env.keyC], env.T[env.keyT] = C.to(dev), T.to(dev)
+        for _ in range(2):
+            C, T = orc.ctm_move_qr_c4v(a, C, T, chi)
+            ctmrg_c4v.ctm_MOVE_QR_sl(a.to(dev), env)
+            assert H.maxrel(env.C[env.keyC].abs().cpu(), C.abs()) < 1e-11
+            assert H.maxrel(env.T[env.keyT].abs().cpu(), T.abs()) < 1e-11
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'])
+def test_transfer_operator_matvecs_and_spectra(eng, dev, name, monkeypatch):
+    """apply_TM_1sO / apply_TM_0sO and get_Top_spec / get_Top_w0_spec (ctm/generic/corrf.py, transferops.py) on libctmb against
+    the same functions with the oracle as engine (which tests/test_transferops_cpu.py pins against the unmodified reference)."""
+    from peps_torch_b200.ctm.generic import transferops as ot, corrf as oc
+    from test_transferops_cpu import edge_shapes, DIRS
+    z, meta = H.load_golden(name)
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'final_' if any(k.startswith('final_') for k in z.files) else 'mid_')
+    dt = next(iter(sites.values())).dtype
+    st_c, env_c = H.State(sites, v2s, lX, lY), H.Env(meta['chi'], dict(C), dict(T))
+    st_g, env_g = H.State(H.to_dev(sites, dev), v2s, lX, lY), H.Env(meta['chi'], H.to_dev(C, dev), H.to_dev(T, dev))
+    oracle = H.OracleEngine()
+    for d in DIRS:
+        g = torch.Generator().manual_seed(1)
+        chi1, d2, chi2 = edge_shapes(st_c, env_c, d)
+        V = torch.randn(chi1, d2, chi2, dtype=dt, generator=g)
+        V0 = torch.randn(chi1, chi2, dtype=dt, generator=g)
+        monkeypatch.setattr(oc, '_engine', lambda: oracle)
+        want1, want0 = oc.apply_TM_1sO((0, 0), d, st_c, env_c, V), oc.apply_TM_0sO((0, 0), d, st_c, env_c, V0)
+        Lw, Ww = ot.get_Top_spec(3, (0, 0), d, st_c, env_c), ot.get_Top_w0_spec(3, (0, 0), d, st_c, env_c)
+        monkeypatch.setattr(oc, '_engine', lambda: eng)
+        assert H.maxrel(oc.apply_TM_1sO((0, 0), d, st_g, env_g, V.to(dev)).cpu(), want1) < 1e-13
+        assert H.maxrel(oc.apply_TM_0sO((0, 0), d, st_g, env_g, V0.to(dev)).cpu(), want0) < 1e-13
+        assert float((ot.get_Top_spec(3, (0, 0), d, st_g, env_g).cpu() - Lw).abs().max()) < 1e-10
+        assert float((ot.get_Top_w0_spec(3, (0, 0), d, st_g, env_g).cpu().abs() - Ww.abs()).abs().max()) < 1e-10

@@ -147,3 +147,36 @@ def test_env_c4v_methods_match_reference(ref, name):
     init_env_c4v(st, e3, C_and_T=(Cf, Tf))
     ref_init(rs, r3, C_and_T=(Cf, Tf))
     assert torch.equal(e3.get_C(), r3.get_C()) and torch.equal(e3.get_T(), r3.get_T())
+
+
+@pytest.mark.parametrize('kind', ['PROD', 'CTMRG_OBC', 'RANDOM'])
+@pytest.mark.parametrize('dl', [False, True])
+def test_env_initialisations_match_reference(ref, kind, dl):
+    """ctm_env_init_type 'PROD' (env.py:274-365) and 'CTMRG_OBC' (:538-715) element for element, on single-layer and on
+    double-layer (rank-4) sites; 'RANDOM' through shapes and dtype (the draws differ)."""
+    from ipeps.ipeps import IPEPS as RefIPEPS
+    from ctm.generic.env import ENV as RefENV, init_env as ref_init_env
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    from peps_torch_b200.config import CTMARGS
+    for name in ('generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128'):
+        sites, v2s, lX, lY, chi, z = _generic(name)
+        if dl:
+            sites = type(sites)((c, orc.double_layer(a)) for c, a in sites.items())
+        ref.global_args.dtype = 'complex128' if next(iter(sites.values())).is_complex() else 'float64'
+        ref.global_args.torch_dtype = next(iter(sites.values())).dtype
+        for chi_ in (chi, 3):                       # 3 < D^2: the truncating branch of the OBC copy
+            rs = RefIPEPS(sites={c: t.clone() for c, t in sites.items()}, vertexToSite=v2s, lX=lX, lY=lY)
+            renv = RefENV(chi_, rs)
+            ref.ctm_args.ctm_env_init_type = kind
+            ref_init_env(rs, renv, ctm_args=ref.ctm_args)
+            st = IPEPS(sites, v2s, lX, lY)
+            env = ENV(chi_, st)
+            args = CTMARGS(); args.ctm_env_init_type = kind
+            init_env(st, env, args)
+            assert set(env.C) == set(renv.C) and set(env.T) == set(renv.T)
+            for a, b in [(env.C[k], renv.C[k]) for k in renv.C] + [(env.T[k], renv.T[k]) for k in renv.T]:
+                assert a.shape == b.shape and a.dtype == b.dtype
+                if kind != 'RANDOM':
+                    assert float((a - b).abs().max()) < 1e-15, (kind, dl, name, chi_)
+    ref.global_args.dtype, ref.global_args.torch_dtype = 'float64', torch.float64

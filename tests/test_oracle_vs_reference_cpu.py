@@ -272,3 +272,41 @@ def test_oracle_c4v_small_rdms_match_reference_elementwise(ref, name):
             r_orc = orc.rdm_small_c4v(kind, a, C, T, spd)
             assert r_ref.shape == r_orc.shape
             assert float((r_ref - r_orc).abs().max()) < 1e-12, (kind, spd, f_ref.__name__)
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_oracle_c4v_qr_move_matches_reference(ref, name, monkeypatch):
+    """ctm_MOVE_QR_sl (ctmrg_c4v.py:465-602): the oracle's restatement element-wise (the same LAPACK QR on both sides), and
+    the drop-in composed from engine calls (peps_torch_b200/ctm/one_site_c4v/ctmrg_c4v.py, oracle as engine) through |.|."""
+    import helpers as H
+    import ctm_oracle as orc
+    from ctm.one_site_c4v import ctmrg_c4v
+    from ctm.one_site_c4v.env_c4v import ENV_C4V
+    from ipeps.ipeps_c4v import IPEPS_C4V
+    from peps_torch_b200.ctm.one_site_c4v import ctmrg_c4v as ours
+    from peps_torch_b200.env import ENV_C4V as OurEnv
+    from peps_torch_b200.ipeps import IPEPS_C4V as OurState
+    from peps_torch_b200.config import CTMARGS
+    z, meta = H.load_golden(name)
+    a = torch.from_numpy(z['site'])
+    chi = meta['chi']
+    if a.is_complex():
+        ref.global_args.dtype = 'complex128'
+    C, T = orc.init_env_c4v(a, chi)
+    for _ in range(2):
+        C, T = orc.ctm_move_c4v(a, C, T, chi)
+    state = IPEPS_C4V(a.clone())
+    env = ENV_C4V(chi, state)
+    env.C[env.keyC], env.T[env.keyT] = C.clone(), T.clone()
+    eng = H.OracleEngine()
+    monkeypatch.setattr(ours, '_engine', lambda: eng)
+    env2 = OurEnv(chi, OurState(a.clone()))
+    env2.C[env2.keyC], env2.T[env2.keyT] = C.clone(), T.clone()
+    for _ in range(3):
+        ctmrg_c4v.ctm_MOVE_QR_sl(a, env, ctm_args=ref.ctm_args, global_args=ref.global_args)
+        C, T = orc.ctm_move_qr_c4v(a, C, T, chi)
+        ours.ctm_MOVE_QR_sl(a, env2, ctm_args=CTMARGS())
+        assert float((env.C[env.keyC] - C).abs().max()) < 1e-12
+        assert float((env.T[env.keyT] - T).abs().max()) < 1e-12
+        assert float((env2.C[env2.keyC].abs() - C.abs()).abs().max()) < 1e-12
+        assert float((env2.T[env2.keyT].abs() - T.abs()).abs().max()) < 1e-12

@@ -1,0 +1,68 @@
+"""Transfer-operator mat-vecs and leading spectra: peps_torch_b200/ctm/generic/{corrf,transferops}.py against
+the unmodified reference (ctm/generic/corrf.py:278-650, transferops.py:14-205) with the oracle standing in for libctmb.
+Needs the reference tree (build container only); the GPU suite compares libctmb with the oracle-engine result."""
+import copy
+import os
+import sys
+import pytest
+import torch
+import helpers as H
+
+REF = os.environ.get('PEPS_TORCH_REF', '/root/reference')
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'ctm', 'generic')), reason='reference tree not present')
+DIRS = [(0, -1), (-1, 0), (0, 1), (1, 0)]
+
+
+@pytest.fixture()
+def ref(tmp_path):
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    sys.path.insert(0, REF)
+    sys.dont_write_bytecode = True
+    import config as cfg
+    saved = copy.deepcopy(cfg.global_args.__dict__)
+    try:
+        yield cfg
+    finally:
+        cfg.global_args.__dict__.clear()
+        cfg.global_args.__dict__.update(saved)
+        os.chdir(cwd)
+        sys.path.remove(REF)
+
+
+def edge_shapes(st, env, d):
+    from peps_torch_b200.ctm.generic import transferops as ot
+    chi1, chi2 = ot._get_chis(st, env, (0, 0), d, 0)
+    leg = {(0, -1): 1, (-1, 0): 2, (0, 1): 3, (1, 0): 4}[(-d[0], -d[1])]
+    return chi1, st.sites[(0, 0)].shape[leg] ** 2, chi2
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'])
+def test_transfer_operators_match_reference(ref, name, monkeypatch):
+    from ipeps.ipeps import IPEPS as RI
+    from ctm.generic.env import ENV as RE
+    from ctm.generic import transferops as rt, corrf as rc
+    from peps_torch_b200.ctm.generic import transferops as ot, corrf as oc
+    eng = H.OracleEngine()
+    monkeypatch.setattr(oc, '_engine', lambda: eng)
+    z, meta = H.load_golden(name)
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'final_' if any(k.startswith('final_') for k in z.files) else 'mid_')
+    dt = next(iter(sites.values())).dtype
+    ref.global_args.dtype, ref.global_args.torch_dtype, ref.global_args.device = ('complex128' if dt.is_complex else 'float64'), dt, 'cpu'
+    rs = RI(sites={c: t.clone() for c, t in sites.items()}, vertexToSite=v2s, lX=lX, lY=lY)
+    re = RE(meta['chi'], rs)
+    re.C, re.T = dict(C), dict(T)
+    st, env = H.State(sites, v2s, lX, lY), H.Env(meta['chi'], dict(C), dict(T))
+    for d in DIRS:
+        g = torch.Generator().manual_seed(1)
+        chi1, d2, chi2 = edge_shapes(st, env, d)
+        V = torch.randn(chi1, d2, chi2, dtype=dt, generator=g)
+        assert H.maxrel(oc.apply_TM_1sO((0, 0), d, st, env, V), rc.apply_TM_1sO((0, 0), d, rs, re, V)) < 1e-13
+        V0 = torch.randn(chi1, chi2, dtype=dt, generator=g)
+        assert H.maxrel(oc.apply_TM_0sO((0, 0), d, st, env, V0), rc.apply_TM_0sO((0, 0), d, rs, re, V0)) < 1e-13
+        La, Lb = ot.get_Top_spec(3, (0, 0), d, st, env), rt.get_Top_spec(3, (0, 0), d, rs, re)
+        assert float((La - Lb).abs().max()) < 1e-10, (d, La, Lb)
+        Wa, Wb = ot.get_Top_w0_spec(3, (0, 0), d, st, env), rt.get_Top_w0_spec(3, (0, 0), d, rs, re)
+        assert float((Wa.abs() - Wb.abs()).abs().max()) < 1e-10, (d, Wa, Wb)
