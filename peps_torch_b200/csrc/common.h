@@ -34,6 +34,10 @@ struct TcTables {
     const int* a_m; const int* a_k;
     const int* b_k; const int* b_n;
     const int* c_m; const int* c_n;
+    // lin != 0: A and B are plain strided matrices, a_m[m] = m * a_sm, a_k[k] = k * a_sk, b_k[k] = k * b_sk, b_n[n] = n * b_sn
+    // (element strides) -- what the TMA-fed kernel needs to describe them by tensor maps (tc_gemm_tma.cu)
+    int lin, a_sm, a_sk, b_sk, b_sn;
+    int c_lin, c_sm, c_sn;      // c_lin != 0: C is a plain strided matrix as well, c_m[m] = m * c_sm, c_n[n] = n * c_sn
 };
 
 struct TcBatchEntry {
@@ -67,6 +71,8 @@ void tc_tile_shape(const TcParams& p, bool cplx, int& bm, int& bn);
 // C[c_m[m] + c_n[n]] (+)= alpha * sum_s partial[z][s][m][n], optional max|.|
 void tc_splitk_reduce_launch(const TcParams& p, bool cplx, cudaStream_t stream);
 void tc_init_attributes();
+// TMA-fed variant of the 128 x 128 x 16 warp-specialised kernel; false (nothing launched) if the batch does not qualify
+bool tc_run_tma(const TcParams& p, bool a_kfast, bool b_kfast, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------
 // dense helpers (qr.cu, jacobi.cu, misc.cu) -- all batched over `nb` problems

@@ -221,6 +221,14 @@ const Plan& Engine::get_plan(const Tn& A, bool conjA, const Tn& B, bool conjB, c
     p.tab.a_m = p.dev + offs[0]; p.tab.a_k = p.dev + offs[1];
     p.tab.b_k = p.dev + offs[2]; p.tab.b_n = p.dev + offs[3];
     p.tab.c_m = p.dev + offs[4]; p.tab.c_n = p.dev + offs[5];
+    // plain strided operands (every table an arithmetic progression): eligible for the TMA-fed kernel
+    auto linear = [](const std::vector<int>& v, int& stride) {
+        stride = v.size() > 1 ? v[1] : 0;
+        for (size_t i = 0; i < v.size(); ++i) if ((long long)v[i] != (long long)i * stride) return false;
+        return true;
+    };
+    p.tab.lin = (linear(t[0], p.tab.a_sm) && linear(t[1], p.tab.a_sk) && linear(t[2], p.tab.b_sk) && linear(t[3], p.tab.b_sn)) ? 1 : 0;
+    p.tab.c_lin = (linear(t[4], p.tab.c_sm) && linear(t[5], p.tab.c_sn)) ? 1 : 0;
     auto res = plans_.emplace(key, p);
     return res.first->second;
 }

@@ -1129,6 +1129,7 @@ static void move_absorb(MoveCtx& mc, const int* nb_site, const std::vector<int>&
 // reduced density matrix of a 2x2 plaquette (ctm/generic/rdm.py:1306-1592, strategy of rdm2x2_legacy):
 // four enlarged corners -- with open physical legs at the sites kept open -- upper = LU.RU, lower = LD.RD, rho = upper.lower
 // ------------------------------------------------------------------------------------------
+static int g_rdm_block_rows = 0;                            // ctmb_debug_set_rdm_block_rows (tests: force the blocked trace)
 static void rdm2x2_impl(Engine& e, int chi, const ctmb_site* const s4[4], int open_mask, void* rho) {
     static const int kinds[4] = {CTMB_LU, CTMB_RU, CTMB_LD, CTMB_RD};       // s0 s1 / s2 s3
     CTMB_CHECK(chi > 0 && s4 && open_mask > 0 && open_mask < 16, "bad arguments (at least one site must stay open)");
@@ -1165,17 +1166,47 @@ static void rdm2x2_impl(Engine& e, int chi, const ctmb_site* const s4[4], int op
         for (const Tn* t : {&X, &Y}) for (int q = 2; q < t->nd; ++q) { lab.push_back(t->idx[q]); d.push_back(t->dim[q]); }
         return e.temp(lab, d);
     };
-    Tn upper = half(LU, RU, 'a', 'c'), lower = half(LD, RD, 'a', 'c');
-    e.contract(LU, false, RU, false, upper);
-    e.contract(LD, false, RD, false, lower);
-    e.flush();
     // rho[kets..., bras...] in the site order s0 s1 s2 s3
     std::string lab; std::vector<int64_t> d;
     for (int pass = 0; pass < 2; ++pass)
         for (int q = 0; q < 4; ++q)
             if ((open_mask >> q) & 1) { lab.push_back(pass ? "IJKL"[q] : "ijkl"[q]); d.push_back(pd[q]); }
-    e.contract(upper, false, lower, false, make_tn(rho, lab, d));
-    e.flush();
+    // The halves carry the open physical legs: rows x cols x p^4 elements each.  At config-5 size (n = 16384, p = 2: 4.3e9)
+    // that exceeds the 32-bit offset tables of the contraction kernel, so the row index `a` is processed in blocks:
+    // upper_blk = LU[a_blk] . RU, lower_blk = LD[a_blk] . RD, rho += upper_blk . lower_blk  (round 1 refused this size).
+    const int64_t per_row = std::max(cols[1] * pd[0] * pd[0] * pd[1] * pd[1], cols[3] == 0 ? 0 : rows[3] * pd[2] * pd[2] * pd[3] * pd[3]);
+    int64_t blk = rows[0];
+    if (g_rdm_block_rows > 0) blk = std::min<int64_t>(blk, g_rdm_block_rows);
+    while (blk > 1 && blk * per_row >= ((int64_t)1 << 31) / 2) blk = (blk + 1) / 2;
+    if (blk >= rows[0]) {
+        Tn upper = half(LU, RU, 'a', 'c'), lower = half(LD, RD, 'a', 'c');
+        e.contract(LU, false, RU, false, upper);
+        e.contract(LD, false, RD, false, lower);
+        e.flush();
+        e.contract(upper, false, lower, false, make_tn(rho, lab, d));
+        e.flush();
+    } else {
+        const size_t es = e.esize();
+        const size_t bmark = e.ws.mark();
+        for (int64_t a0 = 0; a0 < rows[0]; a0 += blk) {
+            const int64_t ab = std::min(blk, rows[0] - a0);
+            auto rows_of = [&](const Tn& t, int q) {          // rows a0 .. a0+ab of the corner matrix q (row-major, phys legs minor)
+                Tn v = t;
+                v.ptr = e.ws.dry() ? nullptr : (void*)((char*)t.ptr + (size_t)a0 * cols[q] * pd[q] * pd[q] * es);
+                v.dim[0] = ab;
+                return v;
+            };
+            e.ws.release(bmark);
+            const Tn LUb = rows_of(LU, 0), LDb = rows_of(LD, 2);
+            Tn upper = half(LUb, RU, 'a', 'c'), lower = half(LDb, RD, 'a', 'c');
+            e.contract(LUb, false, RU, false, upper);
+            e.contract(LDb, false, RD, false, lower);
+            e.flush();
+            e.contract(upper, false, lower, false, make_tn(rho, lab, d), nullptr, 1.0, a0 > 0);
+            e.flush();
+        }
+        e.ws.release(bmark);
+    }
     e.ws.release(mark);
 }
 
@@ -1310,6 +1341,8 @@ int ctmb_version(void) { return 100; }
 void ctmb_debug_jacobi_stats(unsigned long long* out) { ctmb::jacobi_stats(out); }
 // tests: force (2) / forbid (0) / auto (1) the matrix-free projector path regardless of the problem size
 void ctmb_debug_set_matrix_free(int mode) { ctmb::g_matrix_free_mode = mode; }
+// tests: process the rows of the plaquette's halves in blocks of this many rows (0 = only where the offsets demand it)
+void ctmb_debug_set_rdm_block_rows(int rows) { ctmb::g_rdm_block_rows = rows; }
 // tests: relative amplitude of Gaussian noise added to the explicit M = R^T Rt before it is decomposed (0 = off)
 void ctmb_debug_set_m_noise(double amp) { ctmb::g_m_noise = amp; }
 // tests: 1 if square halves of extent n with environment dimension chi take the matrix-free projector path

@@ -432,6 +432,7 @@ static bool tc_run_ws(const TcParams& p, cudaStream_t stream) {
             if (((f & TC_A_KFAST) != 0) == ak && ((f & TC_B_KFAST) != 0) == bk) q.batch[q.nbatch++] = p.batch[i];
         }
         if (q.nbatch == 0) continue;
+        if (tc_run_tma(q, ak, bk, stream)) continue;          // plain strided operands: fed by the TMA unit
         if (ak && bk) tc_run_ws_t<true, true>(q, stream);
         else if (ak) tc_run_ws_t<true, false>(q, stream);
         else if (bk) tc_run_ws_t<false, true>(q, stream);

@@ -166,6 +166,13 @@ class CtmEngine:
         lib.ctmb_debug_set_matrix_free(int(mode))
         self._tables = {k: v for k, v in self._tables.items() if not (isinstance(k, tuple) and k and k[0] in ('ws', 'wsc4v'))}
 
+    def debug_set_rdm_block_rows(self, rows):
+        """tests: rdm2x2 processes the rows of its halves in blocks of `rows` (0: only where 32-bit offsets demand it)."""
+        lib.ctmb_debug_set_rdm_block_rows.argtypes = [C.c_int]
+        lib.ctmb_debug_set_rdm_block_rows.restype = None
+        lib.ctmb_debug_set_rdm_block_rows(int(rows))
+        self._tables = {k: v for k, v in self._tables.items() if not (isinstance(k, tuple) and k and k[0] in ('ws', 'wsc4v'))}
+
     def debug_set_m_noise(self, amp):
         """tests: Gaussian noise of relative amplitude `amp` (x max|M|) on the explicit M = R^T Rt before its decomposition."""
         lib.ctmb_debug_set_m_noise.argtypes = [C.c_double]

@@ -876,3 +876,26 @@ def test_transfer_operator_matvecs_and_spectra(eng, dev, name, monkeypatch):
         assert H.maxrel(oc.apply_TM_0sO((0, 0), d, st_g, env_g, V0.to(dev)).cpu(), want0) < 1e-13
         assert float((ot.get_Top_spec(3, (0, 0), d, st_g, env_g).cpu() - Lw).abs().max()) < 1e-10
         assert float((ot.get_Top_w0_spec(3, (0, 0), d, st_g, env_g).cpu().abs() - Ww.abs()).abs().max()) < 1e-10
+
+
+def test_tma_fed_gemm_layouts_and_edges(eng, dev):
+    """tc_kernel_tma (tc_gemm_tma.cu): plain strided operands of large real contractions are fed by cp.async.bulk.tensor.
+    All four fast-direction pairs (2-D swizzled map for k-fast, 3-D map for m-fast operands), extents that are not multiples
+    of the 128 x 128 tile (out-of-bounds rows are zero-filled by the TMA unit), transposed output, strided views."""
+    g = torch.Generator().manual_seed(11)
+    for (M, N, K) in ((2048, 2000, 512), (1992, 2048, 1024), (4096, 4096, 256)):
+        A = torch.randn(M, K, dtype=torch.float64, generator=g).to(dev)
+        B = torch.randn(K, N, dtype=torch.float64, generator=g).to(dev)
+        At, Bt = A.t().contiguous(), B.t().contiguous()
+        want = A @ B
+        scale = float(want.abs().max())
+        for spec, X, Y in (('ik,kj->ij', A, B), ('ki,kj->ij', At, B), ('ik,jk->ij', A, Bt), ('ki,jk->ij', At, Bt),
+                           ('ik,kj->ji', A, B), ('ki,jk->ji', At, Bt)):
+            out = eng.einsum2(spec, X, Y)
+            ref = want if spec.endswith('ij') else want.t()
+            assert float((out - ref).abs().max()) < 1e-12 * scale, (spec, M, N, K)
+    # operands that are views with a leading dimension larger than their extent (the blocks of the blocked QR, slabs)
+    big = torch.randn(2304, 2304, dtype=torch.float64, generator=g).to(dev)
+    A, B = big[:2048, 128:128 + 512], big[256:256 + 512, :2048]
+    out = eng.einsum2('ik,kj->ij', A.contiguous(), B.contiguous())
+    assert float((out - A @ B).abs().max()) < 1e-12 * float((A @ B).abs().max())

@@ -368,3 +368,51 @@ def test_warm_started_range_finder_keeps_parity_and_saves_iterations(dev):
         assert abs(e_gpu - e_cpu) <= 1e-10 * abs(e_cpu), (stateless, e_gpu, e_cpu)
     print('power iterations per decomposition: warm', used[0], 'stateless', used[1])
     assert used[0] < used[1], used
+
+
+def test_rdm2x2_blocked_trace_matches_unblocked(eng, dev):
+    """rdm2x2 processes the rows of the plaquette's halves in blocks where their rows x cols x p^4 elements exceed the 32-bit
+    offset tables (config-5 size); forced here on a fixture: identical to the one-shot evaluation up to summation order."""
+    z, meta = H.load_golden('generic_4site_D3_chi12_B')
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'final_')
+    st = H.State(H.to_dev(sites, dev), v2s, lX, lY)
+    env = H.Env(meta['chi'], H.to_dev(C, dev), H.to_dev(T, dev))
+    for open_sites in ((0, 1, 2, 3), (0, 3), (1,)):
+        want = eng.rdm2x2((0, 0), st, env, open_sites=open_sites, raw=True)
+        try:
+            eng.debug_set_rdm_block_rows(17)                  # 108 rows -> seven blocks, the last one ragged
+            got = eng.rdm2x2((0, 0), st, env, open_sites=open_sites, raw=True)
+        finally:
+            eng.debug_set_rdm_block_rows(0)
+        assert H.maxrel(got.cpu(), want.cpu()) < 1e-13, open_sites
+        ref = orc.rdm2x2((0, 0), sites, v2s, C, T, raw=True, open_sites=open_sites)
+        assert H.maxrel(got.cpu(), ref) < 1e-12, open_sites
+
+
+def test_rdm2x2_at_config5_size(eng, dev):
+    """The plaquette density matrix at D=8, chi=256 (n = 16384): halves with open legs hold 4.3e9 elements, beyond the
+    32-bit offset tables (round 1 refused this size; DESIGN section 8).  No CPU reference affords it (1.4e14 FLOP per half);
+    checked through identities that hold for ANY environment: tracing sites out of the four-site matrix must give the
+    matrices computed with those sites closed -- the one-site case is evaluated unblocked, by different code."""
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    D, chi = 8, 256
+    a = orc.random_state_4site(D, family='B')[(0, 0)]
+    st = IPEPS(OrderedDict({(0, 0): a.to(dev)}), orc.v2s_1site, 1, 1)
+    env = ENV(chi, st)
+    init_env(st, env)
+    for d in (orc.UP, orc.LEFT):
+        eng.move_generic(d, st, env)
+    full = eng.rdm2x2((0, 0), st, env, open_sites=(0, 1, 2, 3), raw=True)      # [i j k l  I J K L]
+    nn = eng.rdm2x2((0, 0), st, env, open_sites=(0, 1), raw=True)
+    one = eng.rdm2x2((0, 0), st, env, open_sites=(0,), raw=True)
+    scale = float(full.abs().max())
+    assert H.maxrel(torch.einsum('ijklIJkl->ijIJ', full).cpu(), nn.cpu()) < 1e-10
+    assert H.maxrel(torch.einsum('ijklIjkl->iI', full).cpu(), one.cpu()) < 1e-10
+    rho = eng.sym_pos_def(full)
+    m = rho.reshape(16, 16).cpu()
+    assert abs(float(m.diagonal().sum()) - 1.0) < 1e-12 and float((m - m.t()).abs().max()) < 1e-14
+    # hermiticity of the raw matrix measures the quality of the environment, not of the kernel; recorded for the log
+    print('rdm2x2 at config-5 size: raw asymmetry', float((full.reshape(16, 16) - full.reshape(16, 16).t()).abs().max()) / scale)
