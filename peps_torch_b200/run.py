@@ -106,6 +106,16 @@ def enable(engine_factory=None):
         ours_corrf._engine = engine_factory
     top.get_Top_spec = ours_top.get_Top_spec
     top.get_Top_w0_spec = ours_top.get_Top_w0_spec
+    # the kagome density matrices behind energy_triangle_dn / _up and eval_obs of models/spin_half_kagome.py (config 4)
+    from .ctm.pess_kagome import rdm_kagome as ours_kag
+    if engine_factory is not None:
+        ours_kag._engine = engine_factory
+    try:
+        kag = importlib.import_module('ctm.pess_kagome.rdm_kagome')
+        for name in ('trace1x1_dn_kagome', 'rdm2x2_dn_triangle_with_operator', 'rdm2x2_up_triangle_open'):
+            setattr(kag, name, _dispatch(getattr(ours_kag, name), getattr(kag, name)))
+    except ImportError:
+        pass
     # (this also removes the reference's dependence on opt_einsum for these functions: without it its 'sl' one- and
     # two-site RDMs and the rdm2x2 dispatch do not run at all, ctm/generic/rdm.py:107-112,292,343-351,560,1354-1362)
     return ref, ref_c4v

@@ -3,6 +3,7 @@ oracle and the committed reference fixtures.  Tolerances: deterministic contract
 quantities behind the truncated SVD/EVD are compared through gauge invariants at
 max(1e-10, measured reference-vs-reference noise floor) (SURVEY 8c, BASELINE.md section 3);
 energy 1e-10 relative (north star)."""
+from collections import OrderedDict
 import numpy as np
 import pytest
 import torch
@@ -899,3 +900,36 @@ def test_tma_fed_gemm_layouts_and_edges(eng, dev):
     A, B = big[:2048, 128:128 + 512], big[256:256 + 512, :2048]
     out = eng.einsum2('ik,kj->ij', A.contiguous(), B.contiguous())
     assert float((out - A @ B).abs().max()) < 1e-12 * float((A @ B).abs().max())
+
+
+def test_kagome_density_matrices_on_gpu(eng, dev, monkeypatch):
+    """trace1x1_dn_kagome / rdm2x2_dn_triangle_with_operator / rdm2x2_up_triangle_open (ctm/pess_kagome/rdm_kagome.py) on
+    libctmb against the same functions with the oracle as engine (pinned against the unmodified reference and the energies of
+    models/spin_half_kagome.py by tests/test_kagome_rdm_cpu.py); also at the size of config 4 (D = 3, chi = 64, p = 8)."""
+    from peps_torch_b200.ctm.pess_kagome import rdm_kagome as ok
+    from test_kagome_rdm_cpu import kagome_fixture
+    sites, v2s, lX, lY, C, T, chi = kagome_fixture()
+    cases = [(sites, v2s, lX, lY, C, T, chi)]
+    a = orc.random_state_kagome(3, family='B')
+    s4 = OrderedDict({(0, 0): a})
+    C4, T4 = orc.init_env(s4, orc.v2s_1site, 64)
+    for d in orc.DIRECTIONS:
+        orc.ctm_move(d, s4, orc.v2s_1site, C4, T4, 64)
+    cases.append((s4, orc.v2s_1site, 1, 1, C4, T4, 64))
+    oracle = H.OracleEngine()
+    g = torch.Generator().manual_seed(3)
+    op = torch.randn(8, 8, dtype=torch.float64, generator=g)
+    for sites, v2s, lX, lY, C, T, chi in cases:
+        st_c, env_c = H.State(sites, v2s, lX, lY), H.Env(chi, dict(C), dict(T))
+        st_g, env_g = H.State(H.to_dev(sites, dev), v2s, lX, lY), H.Env(chi, H.to_dev(C, dev), H.to_dev(T, dev))
+        monkeypatch.setattr(ok, '_engine', lambda: oracle)
+        w1 = ok.trace1x1_dn_kagome((0, 0), st_c, env_c, op)
+        w2, wn = ok.rdm2x2_dn_triangle_with_operator((0, 0), st_c, env_c, op)
+        w3 = ok.rdm2x2_up_triangle_open((0, 0), st_c, env_c)
+        monkeypatch.setattr(ok, '_engine', lambda: eng)
+        g1 = ok.trace1x1_dn_kagome((0, 0), st_g, env_g, op.to(dev))
+        g2, gn = ok.rdm2x2_dn_triangle_with_operator((0, 0), st_g, env_g, op.to(dev))
+        g3 = ok.rdm2x2_up_triangle_open((0, 0), st_g, env_g)
+        assert abs(float(g1) - float(w1)) < 1e-11 * abs(float(w1))
+        assert abs(float(g2) - float(w2)) < 1e-11 and abs(float(gn) - float(wn)) < 1e-11 * abs(float(wn))
+        assert float((g3.cpu() - w3).abs().max()) < 1e-12
