@@ -16,6 +16,9 @@
 //       element (k, m) at ((m>>3)*16 + k)*64 B + (m&7)*8 B  -- consecutive k are 64 B apart, so the four k of a fragment
 //       alternate between the two halves of the 128-byte bank window (two wavefronts for 256 B: the minimum).
 // In global memory the 3-D box is still one contiguous kilobyte per k (m_hi has stride 64 B).
+//
+// Scheduling: one CTA per output tile, or -- where the tile count leaves the last wave of CTAs under-filled -- stream-K:
+// the k-tiles of all tiles are dealt evenly to one persistent CTA per SM (see the kernel and tc_run_tma).
 #include "common.h"
 #include <cuda.h>
 #include <cstring>
@@ -84,14 +87,26 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tc_kernel_tma(const __grid_cons
     unsigned long long* empty = full + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TcBatchEntry be = p.batch[blockIdx.z];
-    const TcTables tb = p.tab[be.tab];
     const int ntn = (p.N + BN - 1) / BN;
-    const int m0 = (blockIdx.x / ntn) * BM, n0 = (blockIdx.x % ntn) * BN;
     const int M = p.M, N = p.N;
-    // gridDim.y = 2: the two halves of the reduction run as separate CTAs and meet in C through atomic adds (see tc_run_tma)
-    const int ktiles = p.K / BK / (int)gridDim.y;             // the launcher only takes K % (16 gridDim.y) == 0
-    const int kt0 = (int)blockIdx.y * ktiles;
+    // Work = units of one k-tile, ordered (batch entry, output tile, k-tile).  A CTA owns the contiguous range [u0, u1) and
+    // walks it in SEGMENTS (the part of its range inside one output tile):
+    //   standard launch  grid (tiles, 1, nbatch): one segment = one whole tile;
+    //   stream-K launch  grid (G, 1, 1), p.pad = 1: the units are dealt evenly to G = #SM CTAs, so no wave is left
+    //   under-filled; a tile cut between two CTAs is completed in C by red.global.add.f64 (C zeroed by the launcher).  The
+    //   launcher only chooses it when a CTA's share is at least one tile long, so a tile has at most TWO contributors and the
+    //   sum does not depend on their order (0 + a + b == 0 + b + a): deterministic.
+    const long long KT = p.K / BK;                            // the launcher only takes K % 16 == 0
+    const long long per_entry = (long long)ntn * ((M + BM - 1) / BM) * KT;
+    long long u0, u1;
+    if (p.pad) {
+        const long long total = per_entry * p.nbatch;
+        u0 = total * blockIdx.x / gridDim.x;
+        u1 = total * (blockIdx.x + 1) / gridDim.x;
+    } else {
+        u0 = ((long long)blockIdx.z * (per_entry / KT) + blockIdx.x) * KT;
+        u1 = u0 + KT;
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], TM_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -101,17 +116,26 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tc_kernel_tma(const __grid_cons
     if (warp == TM_CONSUMERS / 32) {
         // ------------------------------ producer: one elected lane drives the TMA unit ------------------------------
         if (lane == 0) {
-            const CUtensorMap* ma = &maps.a[blockIdx.z];
-            const CUtensorMap* mb = &maps.b[blockIdx.z];
-            for (int kt = 0; kt < ktiles; ++kt) {
-                const int s = kt % STAGES;
-                mb_wait(&empty[s], ((kt / STAGES) & 1) ^ 1);
-                mb_expect_tx(&full[s], TM_STAGE_BYTES);
-                const int k0 = (kt0 + kt) * BK;
-                if (A_KF) tma_load_2d(As + s * TM_TILE, ma, k0, m0, &full[s]);
-                else tma_load_3d(As + s * TM_TILE, ma, 0, k0, m0 >> 3, &full[s]);
-                if (B_KF) tma_load_2d(Bs + s * TM_TILE, mb, k0, n0, &full[s]);
-                else tma_load_3d(Bs + s * TM_TILE, mb, 0, k0, n0 >> 3, &full[s]);
+            int it = 0;                                       // k-tiles issued so far: stage = it % STAGES
+            for (long long u = u0; u < u1;) {
+                const int b = (int)(u / per_entry);
+                const long long rem = u - (long long)b * per_entry;
+                const int tile = (int)(rem / KT), kbeg = (int)(rem % KT);
+                const int kend = (int)((u1 - u < KT - kbeg) ? kbeg + (u1 - u) : KT);
+                const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+                const CUtensorMap* ma = &maps.a[b];
+                const CUtensorMap* mb = &maps.b[b];
+                for (int kt = kbeg; kt < kend; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    mb_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    mb_expect_tx(&full[s], TM_STAGE_BYTES);
+                    const int k0 = kt * BK;
+                    if (A_KF) tma_load_2d(As + s * TM_TILE, ma, k0, m0, &full[s]);
+                    else tma_load_3d(As + s * TM_TILE, ma, 0, k0, m0 >> 3, &full[s]);
+                    if (B_KF) tma_load_2d(Bs + s * TM_TILE, mb, k0, n0, &full[s]);
+                    else tma_load_3d(Bs + s * TM_TILE, mb, 0, k0, n0 >> 3, &full[s]);
+                }
+                u += kend - kbeg;
             }
         }
         return;
@@ -134,60 +158,81 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tc_kernel_tma(const __grid_cons
     const int b_base = B_KF ? (wn0 + fr) * BK : (wn0 >> 3) * (BK * 8) + fr;
     constexpr int a_si = A_KF ? 8 * BK : BK * 8;              // eight rows further: 8 x 128 B resp. one m_hi block (16 x 64 B)
     constexpr int b_si = B_KF ? 8 * BK : BK * 8;
-    double acc[TM][TN][2];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int kt = 0; kt < ktiles; ++kt) {
-        const int s = kt % STAGES;
-        mb_wait(&full[s], (kt / STAGES) & 1);
-        const double* as = As + s * TM_TILE + a_base;
-        const double* bs = Bs + s * TM_TILE + b_base;
-#pragma unroll
-        for (int q = 0; q < BK / 4; ++q) {
-            double af[TM], bf[TN];
-#pragma unroll
-            for (int i = 0; i < TM; ++i) af[i] = as[i * a_si + a_koff[q]];
-#pragma unroll
-            for (int j = 0; j < TN; ++j) bf[j] = bs[j * b_si + b_koff[q]];
-#pragma unroll
-            for (int i = 0; i < TM; ++i)
-#pragma unroll
-                for (int j = 0; j < TN; ++j) dmma8(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-        __syncwarp();
-        if (lane == 0) mb_arrive(&empty[s]);
-    }
-    double* __restrict__ C = reinterpret_cast<double*>(be.C);
     const double alpha = p.alpha;
-    const bool accum = (be.flags & TC_ACCUM) != 0;
-    const bool split = gridDim.y > 1;
-    double lmax = 0.0;
+    int it = 0;
+    for (long long u = u0; u < u1;) {
+        const int b = (int)(u / per_entry);
+        const long long rem = u - (long long)b * per_entry;
+        const int tile = (int)(rem / KT), kbeg = (int)(rem % KT);
+        const int kend = (int)((u1 - u < KT - kbeg) ? kbeg + (u1 - u) : KT);
+        const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+        double acc[TM][TN][2];
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int r = m0 + wm0 + i * 8 + (lane >> 2);
-        if (r >= M) continue;
-        const int ro = tb.c_m[r];
+        for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
+            for (int j = 0; j < TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kt = kbeg; kt < kend; ++kt, ++it) {
+            const int s = it % STAGES;
+            mb_wait(&full[s], (it / STAGES) & 1);
+            const double* as = As + s * TM_TILE + a_base;
+            const double* bs = Bs + s * TM_TILE + b_base;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = n0 + wn0 + j * 8 + (lane & 3) * 2 + h;
-                if (c >= N) continue;
-                double v = alpha * acc[i][j][h];
-                if (split) { atomicAdd(&C[ro + tb.c_n[c]], v); continue; }     // C was zeroed: 0 + a + b == 0 + b + a
-                if (accum) v += C[ro + tb.c_n[c]];
-                C[ro + tb.c_n[c]] = v;
-                lmax = fmax(lmax, fabs(v));
+            for (int q = 0; q < BK / 4; ++q) {
+                double af[TM], bf[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) af[i] = as[i * a_si + a_koff[q]];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bf[j] = bs[j * b_si + b_koff[q]];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) dmma8(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mb_arrive(&empty[s]);
+        }
+        u += kend - kbeg;
+        // ---- epilogue of the segment ----
+        const TcBatchEntry be = p.batch[b];
+        const TcTables tb = p.tab[be.tab];
+        double* __restrict__ C = reinterpret_cast<double*>(be.C);
+        const bool accum = (be.flags & TC_ACCUM) != 0;
+        const bool partial = !(kbeg == 0 && kend == (int)KT);
+        double lmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int r = m0 + wm0 + i * 8 + (lane >> 2);
+            if (r >= M) continue;
+            const int ro = tb.c_m[r];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = n0 + wn0 + j * 8 + (lane & 3) * 2 + h;
+                    if (c >= N) continue;
+                    double v = alpha * acc[i][j][h];
+                    if (partial) { atomicAdd(&C[ro + tb.c_n[c]], v); continue; }
+                    if (accum) v += C[ro + tb.c_n[c]];
+                    C[ro + tb.c_n[c]] = v;
+                    lmax = fmax(lmax, fabs(v));
+                }
             }
         }
-    }
-    if (be.amax != nullptr) {
+        if (be.amax != nullptr) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-        if (lane == 0) atomicMax(be.amax, (unsigned long long)__double_as_longlong(lmax));
+            for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            if (lane == 0) atomicMax(be.amax, (unsigned long long)__double_as_longlong(lmax));
+        }
     }
+}
+
+int tma_sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0; cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -233,7 +278,7 @@ bool encode_operand(CUtensorMap* map, const void* base, int rows, int K, long lo
 }
 
 template <bool A_KF, bool B_KF>
-void run_tma_t(const TcParams& p, const TmaMaps& maps, int ksplit, cudaStream_t stream) {
+void run_tma_t(const TcParams& p0, const TmaMaps& maps, bool streamk, cudaStream_t stream) {
     auto kern = tc_kernel_tma<A_KF, B_KF>;
     static bool attr_set = false;
     const size_t smem = (size_t)TM_STAGES * TM_STAGE_BYTES + 2 * TM_STAGES * 8 + 1024;
@@ -241,9 +286,11 @@ void run_tma_t(const TcParams& p, const TmaMaps& maps, int ksplit, cudaStream_t 
         CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    const long long tiles = (long long)((p.N + TM_BN - 1) / TM_BN) * ((p.M + TM_BM - 1) / TM_BM);
+    const long long tiles = (long long)((p0.N + TM_BN - 1) / TM_BN) * ((p0.M + TM_BM - 1) / TM_BM);
     CTMB_CHECK(tiles < (1ll << 31), "too many tiles for one launch");
-    dim3 grid((unsigned)tiles, (unsigned)ksplit, p.nbatch);
+    TcParams p = p0;
+    p.pad = streamk ? 1 : 0;
+    dim3 grid = streamk ? dim3((unsigned)tma_sm_count(), 1, 1) : dim3((unsigned)tiles, 1, p.nbatch);
     kern<<<grid, TM_THREADS, smem, stream>>>(p, maps);
     CTMB_CUDA(cudaGetLastError());
 }
@@ -265,17 +312,18 @@ bool tc_run_tma(const TcParams& p, bool a_kfast, bool b_kfast, cudaStream_t stre
         if (!encode_operand(&maps.b[i], be.B, p.N, p.K, tb.b_sn, tb.b_sk, b_kfast)) return false;
     }
     // Wave quantisation: one CTA per SM, so 512 tiles (a 16384 x 512 block of the range finder) take four waves of 148 of
-    // which the last is 46 % full -- 13 % of the tensor pipe idle.  Where that is the case, the reduction is cut in two halves
-    // that run as separate CTAs (1024 units: 6.9 waves) and add into a zeroed C with red.global.add.f64: with exactly two
-    // addends per element the result does not depend on their order (0 + a + b == 0 + b + a), so it stays deterministic.
-    int ksplit = 1;
+    // which the last is 46 % full -- 13 % of the tensor pipe idle; 256 tiles (the half block of a group member) 1.73 waves.
+    // Where that costs more than 7 %, the launch is scheduled stream-K (see the kernel): the k-tiles of all output tiles are
+    // dealt evenly to one CTA per SM and tiles cut between two CTAs are completed with red.global.add.f64 into a zeroed C.
+    // Chosen only when a CTA's share is at least one tile long (tiles >= #SM), so every element has at most two addends.
+    bool streamk = false;
     {
         static int mode2 = -1;
         if (mode2 < 0) { const char* ev = getenv("CTMB_GEMM_TMA_SPLIT"); mode2 = ev ? atoi(ev) : 1; }
         const long long units = (long long)((p.N + TM_BN - 1) / TM_BN) * ((p.M + TM_BM - 1) / TM_BM) * p.nbatch;
-        int sms = 148;
-        auto eff = [&](long long u) { const double w = (double)u / sms; return w / std::ceil(w); };
-        bool ok = mode2 && (p.K % (2 * TM_BK)) == 0 && p.K >= 1024 && eff(units) < 0.93 && eff(2 * units) > eff(units) + 0.04;
+        const int sms = tma_sm_count();
+        const double w = (double)units / sms;
+        bool ok = mode2 && units >= sms && p.K >= 1024 && w / std::ceil(w) < 0.93;
         for (int i = 0; ok && i < p.nbatch; ++i) {
             const TcBatchEntry& be = p.batch[i];
             const TcTables& tb = p.tab[be.tab];
@@ -283,15 +331,15 @@ bool tc_run_tma(const TcParams& p, bool a_kfast, bool b_kfast, cudaStream_t stre
             if (!dense || (be.flags & TC_ACCUM) || be.amax != nullptr) ok = false;
         }
         if (ok) {
-            ksplit = 2;
+            streamk = true;
             for (int i = 0; i < p.nbatch; ++i)
                 CTMB_CUDA(cudaMemsetAsync(p.batch[i].C, 0, (size_t)p.M * p.N * 8, stream));
         }
     }
-    if (a_kfast && b_kfast) run_tma_t<true, true>(p, maps, ksplit, stream);
-    else if (a_kfast) run_tma_t<true, false>(p, maps, ksplit, stream);
-    else if (b_kfast) run_tma_t<false, true>(p, maps, ksplit, stream);
-    else run_tma_t<false, false>(p, maps, ksplit, stream);
+    if (a_kfast && b_kfast) run_tma_t<true, true>(p, maps, streamk, stream);
+    else if (a_kfast) run_tma_t<true, false>(p, maps, streamk, stream);
+    else if (b_kfast) run_tma_t<false, true>(p, maps, streamk, stream);
+    else run_tma_t<false, false>(p, maps, streamk, stream);
     return true;
 }
 

@@ -7,7 +7,7 @@ from peps_torch_b200.engine import default_engine
 eng = default_engine()
 dev = torch.device('cuda:0')
 out = {}
-for (M, N, K) in ((8192, 8192, 8192), (16384, 512, 16384), (4096, 4096, 4096)):
+for (M, N, K) in ((8192, 8192, 8192), (16384, 512, 16384), (16384, 256, 16384), (4096, 4096, 4096)):
     A = torch.randn(M, K, dtype=torch.float64, device=dev); B = torch.randn(K, N, dtype=torch.float64, device=dev)
     At, Bt = A.t().contiguous(), B.t().contiguous()
     for spec, X, Y in (('ik,kj->ij', A, B), ('ki,kj->ij', At, B), ('ik,jk->ij', A, Bt), ('ki,jk->ij', At, Bt)):
