@@ -49,8 +49,10 @@ typedef struct {
     int jacobi_max_sweeps;     /* default 40 */
     int norm_type;             /* ctm_absorb_normalization (ctmrg.py:210-230): 0 = 'inf' (max |x|, default), 1 = any other value of
                                   the reference = vector 2-norm (the C4v move scales C by |C[0,0]| either way, ctmrg_c4v.py:182-197) */
-    int rsvd_max_rounds;       /* adaptive mode: at most this many rounds q, +q, +2q, +4q ... (default 5); a round that does not
-                                  halve the residual ends the iteration (rounding floor) */
+    int rsvd_max_rounds;       /* adaptive mode: at most this many rounds (default 5): a round that misses the bound adds a third of
+                                  the count (near miss), the count again, or what the measured decay rate predicts; a round that
+                                  gains less than 15 % per iteration ends the iteration (rounding floor).  A result that still
+                                  misses the bound is returned AND counted: ctmb_get_rsvd_status */
     unsigned long long seed;   /* seed of the Gaussian sketch (deterministic) */
     double rsvd_tol;           /* > 0 (default 2e-15): residual-checked range finder.  After the power iterations
                                   max_j ||M v_j - s_j u_j|| / s_0 <= rsvd_tol * sqrt(n) is checked on the kept triplets (one host
@@ -60,8 +62,12 @@ typedef struct {
     int projector_method;      /* CTMARGS.projector_method: 0 = '4X4' (halves of the 4x4 network, ctm_projectors.py:14-64; default),
                                   1 = '4X2' (R, Rt = the two enlarged corners next to the bond, ctm_projectors.py:66-136) */
     int rsvd_stateless;        /* 0 (default): the handle remembers, per problem shape, the iteration count that passed the residual
-                                  test last time and starts there (a CTM run decomposes a slowly changing matrix once per move);
-                                  1: every call starts from rsvd_niter, so its result does not depend on the handle's history */
+                                  test last time (bisecting towards the largest count known to fail) and, per (direction, site)
+                                  slot of the moves, the ordered Ritz vectors of the previous decomposition, which replace most of
+                                  the Gaussian sketch (warm start: n x k elements per slot; a CTM run decomposes a slowly changing
+                                  matrix once per move) -- only the NUMBER of iterations depends on it, every result passes the same
+                                  residual test;  1: every call starts from a Gaussian sketch and rsvd_niter, so its result does not
+                                  depend on the handle's history */
 } ctmb_options;
 
 /* One unit-cell site: on-site tensor and its eight environment tensors. */

@@ -158,6 +158,7 @@ void c4v_diag_launch(const double* D, void* cout, int chi, bool cplx, cudaStream
 void fill_gaussian_launch(double* out, long long count, unsigned long long seed, cudaStream_t stream);
 void add_noise_launch(double* x, long long count, double amp, const unsigned long long* scale, unsigned long long seed,
                       cudaStream_t stream);
+void shift_axpy_launch(double* y, const double* x, const unsigned long long* sumsq, double sign, long long count, cudaStream_t stream);
 void axpby_launch(double* out, const double* x, double c1, const double* y, double c2, long long count, cudaStream_t stream);
 
 // fused double-layer absorption of the enlarged corner (dl_fused.cu)

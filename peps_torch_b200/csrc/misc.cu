@@ -445,6 +445,20 @@ void add_noise_launch(double* x, long long count, double amp, const unsigned lon
     CTMB_CUDA(cudaGetLastError());
 }
 
+// y[i] += sign * sqrt(*sumsq) * (x ? x[i] : 1): the spectral shift mu = ||A||_F of the preconditioned Hermitian Jacobi (move.cu),
+// with mu living on the device (the slot holds sum |a|^2 from sumsq_launch)
+__global__ void shift_axpy_kernel(double* y, const double* x, const unsigned long long* sumsq, double sign, long long n) {
+    const double mu = sign * sqrt(__longlong_as_double((long long)*sumsq));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] += x ? mu * x[i] : mu;
+}
+
+void shift_axpy_launch(double* y, const double* x, const unsigned long long* sumsq, double sign, long long count, cudaStream_t stream) {
+    int grid = (int)std::max(1ll, std::min((count + 255) / 256, 2368ll));
+    shift_axpy_kernel<<<grid, 256, 0, stream>>>(y, x, sumsq, sign, count);
+    CTMB_CUDA(cudaGetLastError());
+}
+
 // out = c1 * x + c2 * y over `count` doubles (three-term recurrence of the Chebyshev filter, move.cu); out may alias x or y
 __global__ void axpby_kernel(double* out, const double* x, double c1, const double* y, double c2, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

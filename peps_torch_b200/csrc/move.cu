@@ -557,9 +557,48 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
         // no sketch at all, the shifted one-sided Jacobi runs on M itself.  Row-major M read as column-major is M^T =
         // conj(M): same eigenvalues, conjugated eigenvectors -- undone at the end in the complex case.
         e.flush();
-        for (int b = 0; b < nb; ++b)
-            CTMB_CUDA(cudaMemcpyAsync(R2[b], M[b], (size_t)k * k * es, cudaMemcpyDeviceToDevice, e.stream));
-        { ProfScope ps(e, Engine::CAT_JACOBI, 0, 2.0 * es * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
+        // PRECONDITIONED START (slots given, i.e. the C4v move of a CTM run: the same slowly changing matrix every call).  With
+        // A the matrix as the kernel reads it and U the eigenvectors of the previous call, the Jacobi runs on G0 = (A + mu) U
+        // instead of A + mu: G0 = V S W^H gives A + mu = V S (U W)^H, so V are the eigenvectors whatever U was; if A has hardly
+        // changed the columns of G0 are nearly orthogonal already and the sweep count drops from ~11 to 2-3 (config 1 spends
+        // 87 % of its move in this 64 x 64 problem).  The orthogonality of V comes from the sweeps, not from U: nothing drifts.
+        std::vector<void*> prev(nb, nullptr);
+        bool precond = slots != nullptr && !o.rsvd_stateless;
+        if (precond)
+            for (int b = 0; b < nb; ++b) {
+                char sk[160];
+                snprintf(sk, sizeof sk, "eigprev:%s:%d:%d", (*slots)[b].c_str(), n, (int)e.cplx);
+                bool created = false;
+                prev[b] = e.persistent(sk, (size_t)k * k * es, &created);
+                if (created) precond = false;               // first call of the slot (the buffers are filled below)
+            }
+        if (precond) {
+            unsigned long long* ssq = (unsigned long long*)e.persistent("eigmu", TC_MAX_BATCH * sizeof(unsigned long long));
+            CTMB_CUDA(cudaMemsetAsync(ssq, 0, TC_MAX_BATCH * sizeof(unsigned long long), e.stream));
+            ScaleBatch sb{};
+            for (int b = 0; b < nb; ++b) { sb.p[b] = const_cast<void*>(M[b]); sb.count[b] = (long long)k * k; sb.amax[b] = ssq + b; }
+            { ProfScope ps(e, Engine::CAT_MISC); sumsq_launch(sb, nb, e.cplx, e.stream); }
+            for (int b = 0; b < nb; ++b)        // G0[c][i] = sum_j A[i,j] U[j,c] with A[i,j] = M[j,i] (row-major M read column-major)
+                e.contract(make_tn(const_cast<void*>(M[b]), "ji", {k, k}), false, make_tn(prev[b], "cj", {k, k}), false,
+                           make_tn(R2[b], "ci", {k, k}));
+            e.flush();
+            for (int b = 0; b < nb; ++b) {
+                ProfScope ps(e, Engine::CAT_MISC);
+                shift_axpy_launch((double*)R2[b], (const double*)prev[b], ssq + b, 1.0, (long long)k * k * (e.cplx ? 2 : 1), e.stream);
+            }
+            { ProfScope ps(e, Engine::CAT_JACOBI, 0, 2.0 * es * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 0, 0, e.stream); }
+            for (int b = 0; b < nb; ++b) {
+                ProfScope ps(e, Engine::CAT_MISC);
+                shift_axpy_launch((double*)sig[b], nullptr, ssq + b, -1.0, k, e.stream);
+            }
+        } else {
+            for (int b = 0; b < nb; ++b)
+                CTMB_CUDA(cudaMemcpyAsync(R2[b], M[b], (size_t)k * k * es, cudaMemcpyDeviceToDevice, e.stream));
+            { ProfScope ps(e, Engine::CAT_JACOBI, 0, 2.0 * es * nb * (double)k * k); jacobi_launch(pR, pNull, pSig, nb, k, e.cplx, o.jacobi_max_sweeps, 1, 0, e.stream); }
+        }
+        if (slots != nullptr && !o.rsvd_stateless)
+            for (int b = 0; b < nb; ++b)
+                if (prev[b]) CTMB_CUDA(cudaMemcpyAsync(prev[b], R2[b], (size_t)k * k * es, cudaMemcpyDeviceToDevice, e.stream));
         { ProfScope ps(e, Engine::CAT_MISC); sortcols_launch(pR, pNull, pSig, pS, pUh, pNull, nb, k, chi, e.cplx, 1, e.stream); }
         for (int b = 0; b < nb; ++b) {
             CTMB_CUDA(cudaMemcpyAsync(r.U[b], Uh[b], (size_t)k * chi * es, cudaMemcpyDeviceToDevice, e.stream));
@@ -1174,7 +1213,7 @@ static void rdm2x2_impl(Engine& e, int chi, const ctmb_site* const s4[4], int op
     // The halves carry the open physical legs: rows x cols x p^4 elements each.  At config-5 size (n = 16384, p = 2: 4.3e9)
     // that exceeds the 32-bit offset tables of the contraction kernel, so the row index `a` is processed in blocks:
     // upper_blk = LU[a_blk] . RU, lower_blk = LD[a_blk] . RD, rho += upper_blk . lower_blk  (round 1 refused this size).
-    const int64_t per_row = std::max(cols[1] * pd[0] * pd[0] * pd[1] * pd[1], cols[3] == 0 ? 0 : rows[3] * pd[2] * pd[2] * pd[3] * pd[3]);
+    const int64_t per_row = std::max(cols[1] * pd[0] * pd[0] * pd[1] * pd[1], rows[3] * pd[2] * pd[2] * pd[3] * pd[3]);   // elements of one row of upper / lower
     int64_t blk = rows[0];
     if (g_rdm_block_rows > 0) blk = std::min<int64_t>(blk, g_rdm_block_rows);
     while (blk > 1 && blk * per_row >= ((int64_t)1 << 31) / 2) blk = (blk + 1) / 2;
