@@ -276,8 +276,13 @@ void Engine::flush() {
         const long long tiles = (long long)((pend_.M + bm - 1) / bm) * ((pend_.N + bn - 1) / bn) * pend_.nbatch;
         static int sk_mode = -1;
         if (sk_mode < 0) { const char* ev = getenv("CTMB_SPLITK"); sk_mode = ev ? atoi(ev) : 1; }
-        if (sk_mode && pend_.K >= 1024 && tiles <= 148) {
-            int S = (int)std::min<long long>(std::min<long long>(296 / tiles, pend_.K / 256), 32);
+        // two regimes: long reductions on at most one wave of tiles (K >= 1024: 296 CTAs, chunks of >= 256), and the small
+        // latency-bound products of configs 2 / 4 (128 <= K < 1024, a few hundred 32 x 32 tiles: the serial k loop of a CTA
+        // is the latency of the launch; 1184 CTAs, chunks of >= 64: +2 % moves/s at config 2, +5 % at config 4)
+        const bool long_k = pend_.K >= 1024 && tiles <= 148;
+        const bool small_k = pend_.K >= 128 && pend_.K < 1024 && tiles <= 592;
+        if (sk_mode && (long_k || small_k)) {
+            int S = (int)std::min<long long>(std::min<long long>((long_k ? 296 : 1184) / tiles, pend_.K / (long_k ? 256 : 64)), 32);
             if (S >= 2) {
                 int kchunk = ((pend_.K + S - 1) / S + 31) & ~31;
                 S = (pend_.K + kchunk - 1) / kchunk;

@@ -416,3 +416,36 @@ def test_rdm2x2_at_config5_size(eng, dev):
     assert abs(float(m.diagonal().sum()) - 1.0) < 1e-12 and float((m - m.t()).abs().max()) < 1e-14
     # hermiticity of the raw matrix measures the quality of the environment, not of the kernel; recorded for the log
     print('rdm2x2 at config-5 size: raw asymmetry', float((full.reshape(16, 16) - full.reshape(16, 16).t()).abs().max()) / scale)
+
+
+def test_stateless_moves_are_bitwise_reproducible(dev):
+    """ctmb_options.rsvd_stateless = 1: no iteration-count memory, no warm start -- the result of a move must not depend on
+    the history of the handle, bit for bit.  At config-5 size this also covers the stream-K schedule of
+    the TMA GEMM, whose split tiles meet through red.global.add.f64 with exactly two addends (order-independent)."""
+    from peps_torch_b200.engine import CtmEngine
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    if not torch.cuda.is_available():
+        pytest.skip('GPU tests need a CUDA device')
+    for D, chi in ((3, 48), (8, 256)):
+        a = orc.random_state_4site(D, family='B')[(0, 0)]
+        st = IPEPS(OrderedDict({(0, 0): a.to(dev)}), orc.v2s_1site, 1, 1)
+        env0 = ENV(chi, st)
+        init_env(st, env0)
+        outs = []
+        for history in (0, 2):
+            eng = CtmEngine()
+            eng.options.rsvd_stateless = 1
+            scratch = H.Env(chi, dict(env0.C), dict(env0.T))
+            for _ in range(history):                     # a different call history on the second handle
+                eng.move_generic(orc.LEFT, st, scratch)
+            env = H.Env(chi, dict(env0.C), dict(env0.T))
+            eng.move_generic(orc.UP, st, env)
+            eng.move_generic(orc.UP, st, env)
+            outs.append(env)
+            del eng, scratch
+            torch.cuda.empty_cache()
+        for k in outs[0].C:
+            assert torch.equal(outs[0].C[k], outs[1].C[k]), (D, chi, k)
+        for k in outs[0].T:
+            assert torch.equal(outs[0].T[k], outs[1].T[k]), (D, chi, k)
