@@ -12,6 +12,7 @@
 // independent: each is rotated by a group of GS lanes using warp shuffles for the three dot
 // products; rounds are separated by one __syncthreads().
 #include "common.h"
+#include <cooperative_groups.h>
 #include "cx.h"
 
 namespace ctmb {
@@ -464,6 +465,179 @@ __global__ void __launch_bounds__(JC_THREADS) jacobi_coop_kernel(PtrBatch Gb, Pt
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster-resident variant for the sizes in between (one matrix does not fit the shared memory of one SM, but fits the
+// DISTRIBUTED shared memory of a thread-block cluster: k = 192 complex, the Rayleigh-Ritz problem of config 3; the full
+// decompositions of the AD path): column c lives in the shared memory of CTA c % CL, every warp reads and writes the two
+// columns of its pair through DSMEM, rounds are separated by the hardware cluster barrier (~0.25 us) instead of the
+// atomic-and-spin barrier in global memory of the cooperative kernel (~2 us per round at 191 rounds x 9 sweeps).
+// MEASURED [B200, config 3, k = 192 complex]: correct (same tests pass) but SLOWER than the cooperative kernel -- Jacobi
+// 7.9 ms against 5.2 ms per move (24.7 against 21.8 ms per move): a warp's 16 dependent remote loads / stores per lane
+// cost more through DSMEM than the in-flight ld.global.cg of the L2-resident version saves on the barrier.  Kept behind
+// CTMB_JACOBI_CLUSTER=1 as a recorded experiment (profiles/r2_experiments.md); the cooperative kernel stays the default.
+// ---------------------------------------------------------------------------------------------
+constexpr int JCL_THREADS = 384;
+template <bool CPLX, int NR>
+__global__ void __launch_bounds__(JCL_THREADS) jacobi_cluster_kernel(PtrBatch Gb, PtrBatch Wb, PtrBatch Sb, int k, int CL,
+                                                                      int max_sweeps) {
+    using S = Sc<CPLX>;
+    using T = typename S::T;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int mat = blockIdx.x / CL;
+    T* G = reinterpret_cast<T*>(Gb.p[mat]);
+    T* W = reinterpret_cast<T*>(Wb.p[mat]);
+    double* sig = reinterpret_cast<double*>(Sb.p[mat]);
+    const bool accw = W != nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = JCL_THREADS / 32;
+    const int gw = rank * NWARP + warp, nw = CL * NWARP;
+    const int cpc = (k + CL - 1) / CL;                    // column slots per CTA
+    extern __shared__ __align__(16) unsigned char jcl_smem[];
+    T* Gs = reinterpret_cast<T*>(jcl_smem);                // [cpc][k]
+    T* Ws = Gs + (size_t)cpc * k;                          // [cpc][k] (only with accw)
+    __shared__ int flags[3][2];                            // (the copy of CTA 0 is the one in use)
+    // own columns: global -> shared
+    for (int slot = 0; slot < cpc; ++slot) {
+        const int c = slot * CL + rank;
+        if (c >= k) break;
+        for (int r = tid; r < k; r += JCL_THREADS) {
+            Gs[(size_t)slot * k + r] = G[(size_t)c * k + r];
+            if (accw) Ws[(size_t)slot * k + r] = W[(size_t)c * k + r];
+        }
+    }
+    if (tid < 6) flags[tid / 2][tid % 2] = 0;
+    cluster.sync();
+    auto colG = [&](int c) { return cluster.map_shared_rank(Gs, c % CL) + (size_t)(c / CL) * k; };
+    auto colW = [&](int c) { return cluster.map_shared_rank(Ws, c % CL) + (size_t)(c / CL) * k; };
+    int (*flag0)[2] = reinterpret_cast<int (*)[2]>(cluster.map_shared_rank(&flags[0][0], 0));
+    const int kk = (k + 1) & ~1, npairs = kk / 2;
+    const double tol = 2.2e-16 * sqrt((double)k);
+    const double tol2 = tol * tol;
+    int sweeps_done = max_sweeps;
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        if (rank == 0 && tid == 0) { flags[(sweep + 1) % 3][0] = 0; flags[(sweep + 1) % 3][1] = 0; }
+        int rot = 0, big = 0;
+        for (int round = 0; round < kk - 1; ++round) {
+            for (int pi = gw; pi < npairs; pi += nw) {
+                int p, q;
+                if (pi == 0) { p = kk - 1; q = round; }
+                else { p = (round + pi) % (kk - 1); q = (round - pi + (kk - 1)) % (kk - 1); }
+                if (p >= k || q >= k) continue;
+                if (p > q) { int t = p; p = q; q = t; }
+                T* gp = colG(p);
+                T* gq = colG(q);
+                double a = 0.0, b = 0.0;
+                T g = S::zero();
+                T xr[NR], yr[NR];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    const int r = lane + 32 * i;
+                    xr[i] = r < k ? gp[r] : S::zero();
+                    yr[i] = r < k ? gq[r] : S::zero();
+                }
+#pragma unroll
+                for (int i = 0; i < NR; ++i) {
+                    a += S::abs2(xr[i]); b += S::abs2(yr[i]);
+                    g = S::fma(S::conj(xr[i]), yr[i], g);
+                }
+                a = warp_sum(a); b = warp_sum(b); g = warp_sum_t<CPLX>(g);
+                const double ag2 = S::abs2(g);
+                if (ag2 > tol2 * a * b && ag2 > 0.0) {
+                    const double d = b - a;
+                    const double r = rsqrt(d * d + 4.0 * ag2);
+                    const double c2 = 0.5 + 0.5 * fabs(d) * r;
+                    const double rc = rsqrt(c2);
+                    rot = 1;
+                    if (ag2 * r * r * rc * rc > 1.0e-16 && ag2 > 4.0 * tol2 * a * b) big = 1;
+                    const double c = c2 * rc;
+                    const T al = S::scale(S::conj(g), copysign(r * rc, d));
+                    const T cal = S::conj(al);
+#pragma unroll
+                    for (int i = 0; i < NR; ++i) {
+                        const int rr = lane + 32 * i;
+                        if (rr < k) {
+                            gp[rr] = S::sub(S::scale(xr[i], c), S::mul(al, yr[i]));
+                            gq[rr] = S::add(S::mul(cal, xr[i]), S::scale(yr[i], c));
+                        }
+                    }
+                    if (accw) {
+                        T* wp = colW(p);
+                        T* wq = colW(q);
+#pragma unroll
+                        for (int i = 0; i < NR; ++i) {
+                            const int rr = lane + 32 * i;
+                            if (rr < k) {
+                                const T u = wp[rr], v = wq[rr];
+                                wp[rr] = S::sub(S::scale(u, c), S::mul(al, v));
+                                wq[rr] = S::add(S::mul(cal, u), S::scale(v, c));
+                            }
+                        }
+                    }
+                }
+            }
+            cluster.sync();
+        }
+        if (lane == 0 && rot) { atomicOr(&flag0[sweep % 3][0], 1); if (big) atomicOr(&flag0[sweep % 3][1], 1); }
+        cluster.sync();
+        const int any = *(volatile int*)&flag0[sweep % 3][0], anybig = *(volatile int*)&flag0[sweep % 3][1];
+        cluster.sync();                                   // everybody has read the flags before CTA 0 may reuse the slot
+        if (!any || !anybig) { sweeps_done = sweep + 1; break; }
+    }
+    if (rank == 0 && tid == 0) { atomicAdd(&g_jac_stats[0], (unsigned long long)sweeps_done); atomicAdd(&g_jac_stats[1], 1ull); }
+    // column norms; own columns are written back NORMALISED
+    const double mu = g_jc_mu[mat];
+    for (int slot = warp; slot < cpc; slot += NWARP) {
+        const int c = slot * CL + rank;
+        if (c >= k) continue;
+        const T* gc = Gs + (size_t)slot * k;
+        double a = 0.0;
+        for (int r = lane; r < k; r += 32) a += S::abs2(gc[r]);
+        a = warp_sum(a);
+        const double nrm = sqrt(a);
+        if (lane == 0) sig[c] = nrm - mu;
+        const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+        for (int r = lane; r < k; r += 32) G[(size_t)c * k + r] = S::scale(gc[r], inv);
+        if (accw) {
+            const T* wc = Ws + (size_t)slot * k;
+            double w2 = 0.0;
+            for (int r = lane; r < k; r += 32) w2 += S::abs2(wc[r]);
+            w2 = warp_sum(w2);
+            const double winv = w2 > 0.0 ? rsqrt(w2) : 0.0;
+            for (int r = lane; r < k; r += 32) W[(size_t)c * k + r] = S::scale(wc[r], winv);
+        }
+    }
+    cluster.sync();                                       // no CTA may exit while peers can still read its shared memory
+}
+
+template <bool CPLX, int NR>
+static bool jacobi_cluster_run(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, int nb, int k, int max_sweeps,
+                               cudaStream_t stream) {
+    const bool accw = W.p[0] != nullptr;
+    const int CL = 8;
+    const size_t es = CPLX ? 16 : 8;
+    const size_t smem = (size_t)(accw ? 2 : 1) * ((k + CL - 1) / CL) * k * es;
+    if (smem > 200 * 1024) return false;
+    auto kern = jacobi_cluster_kernel<CPLX, NR>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nb * CL);
+    cfg.blockDim = dim3(JCL_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CTMB_CUDA(cudaLaunchKernelEx(&cfg, kern, G, W, sig, k, CL, max_sweeps));
+    return true;
+}
+
 void jacobi_stats(unsigned long long out[2]) {
     cudaMemcpyFromSymbol(out, g_jac_stats, sizeof(unsigned long long) * 2);
     unsigned long long z[2] = {0, 0};
@@ -490,6 +664,21 @@ void jacobi_launch(const PtrBatch& G, const PtrBatch& W, const PtrBatch& sig, in
     const size_t smem = use_smem ? need : 0;
     static int coop_mode = -1;
     if (coop_mode < 0) { const char* ev = getenv("CTMB_JACOBI_COOP"); coop_mode = ev ? atoi(ev) : 1; }
+    static int cl_mode = -1;
+    if (cl_mode < 0) { const char* ev = getenv("CTMB_JACOBI_CLUSTER"); cl_mode = ev ? atoi(ev) : 0; }   // off: measured slower
+    if (!use_smem && cl_mode && k <= 256 && nb * 8 <= 128) {
+        // in between: the matrix fits the distributed shared memory of a cluster of eight CTAs
+        const size_t need8 = (accw ? 2 : 1) * (size_t)((k + 7) / 8) * k * (cplx ? 16 : 8);
+        if (need8 <= 200 * 1024) {
+            if (cplx) jacobi_prep_kernel<true><<<nb, 1024, 0, stream>>>(G, W, k, shift, transpose_in);
+            else jacobi_prep_kernel<false><<<nb, 1024, 0, stream>>>(G, W, k, shift, transpose_in);
+            CTMB_CUDA(cudaGetLastError());
+            bool ok;
+            if (k <= 128) ok = cplx ? jacobi_cluster_run<true, 4>(G, W, sig, nb, k, max_sweeps, stream) : jacobi_cluster_run<false, 4>(G, W, sig, nb, k, max_sweeps, stream);
+            else ok = cplx ? jacobi_cluster_run<true, 8>(G, W, sig, nb, k, max_sweeps, stream) : jacobi_cluster_run<false, 8>(G, W, sig, nb, k, max_sweeps, stream);
+            if (ok) return;
+        }
+    }
     if (!use_smem && coop_mode) {
         int dev = 0, nsm = 0;
         CTMB_CUDA(cudaGetDevice(&dev));
