@@ -6,7 +6,8 @@ import os
 import runpy
 import sys
 
-plain = sys.argv[1] == '--plain'
+plain = sys.argv[1] in ('--plain', '--plain-legacy-rdm')
+legacy = sys.argv[1] == '--plain-legacy-rdm'      # untouched moves; only rdm2x2 -> rdm2x2_legacy (opt_einsum is absent)
 script = sys.argv[2] if plain else sys.argv[1]
 rest = sys.argv[3:] if plain else sys.argv[2:]
 repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -18,6 +19,12 @@ root = launcher.find_reference_root(script)
 for p in (os.path.dirname(os.path.abspath(script)), root):
     sys.path.insert(0, p)
 sys.dont_write_bytecode = True
+if legacy:
+    import importlib   # noqa: E402
+    _rdm = importlib.import_module('ctm.generic.rdm')
+    _legacy = _rdm.rdm2x2_legacy
+    _rdm.rdm2x2 = lambda coord, state, env, open_sites=[0, 1, 2, 3], sym_pos_def=False, **kw: _legacy(coord, state, env, sym_pos_def=sym_pos_def)
+    _rdm.rdm1x1, _rdm.rdm2x1, _rdm.rdm1x2 = _rdm.rdm1x1_dl, _rdm.rdm2x1_dl, _rdm.rdm1x2_dl      # the patch of SURVEY 8c, caveat 1
 if not plain:
     import helpers as H   # noqa: E402
     from peps_torch_b200 import ad   # noqa: E402

@@ -61,3 +61,32 @@ def test_optim_script_through_the_launcher(tmp_path):
     assert len(e_l) == len(e_p) >= 4
     assert max(abs(a - b) for a, b in zip(e_l, e_p)) < 1e-10, (e_l, e_p)
     assert e_l[-1] < e_l[0] - 1e-4     # the optimiser moved downhill
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'examples', 'j1j2')), reason='reference tree not present (GPU box)')
+def test_generic_optim_script_through_the_launcher(tmp_path):
+    """examples/j1j2/optim_j1j2.py (4SITE), unmodified, two L-BFGS steps: through the launcher every differentiated move goes
+    through ad.ctm_move_generic and the energies equal those of the untouched script (whose density matrices are switched to
+    the reference's own opt_einsum-free variants, SURVEY 8c caveat 1 -- opt_einsum is not installed here)."""
+    args = ['--tiling', '4SITE', '--bond_dim', '2', '--chi', '4', '--seed', '123', '--j2', '0.3', '--opt_max_iter', '2',
+            '--CTMARGS_ctm_max_iter', '2', '--out_prefix', 'adg']
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', OMP_NUM_THREADS='2')
+    script = os.path.join(REF, 'examples', 'j1j2', 'optim_j1j2.py')
+    outs = []
+    for pre in ([], ['--plain-legacy-rdm']):
+        d = tmp_path / ('plain' if pre else 'launcher')
+        d.mkdir()
+        out = subprocess.run([sys.executable, os.path.join(HERE, 'launcher_probe_ad.py')] + pre + [script] + args,
+                             cwd=d, env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(out.stdout)
+    calls = [ln for ln in outs[0].splitlines() if ln.startswith('AD_CALLS')][-1].split()
+    assert int(calls[2]) >= 16         # 8 moves per CTM iteration, every differentiated iteration through ad.ctm_move_generic
+
+    def energies(text):
+        rows = [ln.split(', ') for ln in text.splitlines() if ln[:1].isdigit() or ln[:2] == '-1']
+        return [float(r[1]) for r in rows if len(r) > 3]
+    e_l, e_p = energies(outs[0]), energies(outs[1])
+    assert len(e_l) == len(e_p) >= 3
+    assert max(abs(a - b) for a, b in zip(e_l, e_p)) < 1e-10, (e_l, e_p)
+    assert e_l[-1] < e_l[0] - 1e-3

@@ -80,3 +80,23 @@ def test_optim_script_unmodified_on_gpu(tmp_path):
 # python tests/launcher_probe_ad.py --plain /root/reference/examples/j1j2/optim_j1j2_c4v.py --instate tests/golden/config1_instate.json
 #   --chi 8 --j2 0.3 --opt_max_iter 3 --CTMARGS_ctm_max_iter 6   (CPU, unmodified reference): epochs -1, 1, 2, 3 and the final line
 EXPECTED_OPTIM_ENERGIES = [-0.350032580493549, -0.350032580493549, -0.35011155529283033, -0.35046260896724446, -0.3504626089672445]
+
+
+def test_generic_optim_script_unmodified_on_gpu(tmp_path):
+    """examples/j1j2/optim_j1j2.py --tiling 4SITE, unmodified, through the launcher on cuda:0 from the CPU seed-123 state of
+    config 2 (tests/golden/config2_instate.json, D = 3, chi 6: n = 54 per projector): two L-BFGS steps; the energies are those
+    of the untouched script on CPU from the same file (tests/launcher_probe_ad.py --plain-legacy-rdm)."""
+    script = os.path.join(REF, 'examples', 'j1j2', 'optim_j1j2.py')
+    if not os.path.isfile(script):
+        pytest.skip('baseline/_ref (staged copy of the reference) not present')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    out = subprocess.run([sys.executable, '-m', 'peps_torch_b200.run', script, '--tiling', '4SITE', '--instate',
+                          os.path.join(ROOT, 'tests', 'golden', 'config2_instate.json'), '--chi', '6', '--j2', '0.3',
+                          '--opt_max_iter', '2', '--CTMARGS_ctm_max_iter', '2', '--out_prefix', 'adg',
+                          '--GLOBALARGS_device', 'cuda:0'], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    rows = [ln.split(', ') for ln in out.stdout.splitlines() if ln[:1].isdigit() or ln[:2] == '-1']
+    e = [float(r[1]) for r in rows if len(r) > 3]
+    want = [0.6424192637819899, 0.6424192637819899, 0.6416966780618278, 0.6416966780618278]
+    assert len(e) == len(want), out.stdout[-2000:]
+    assert max(abs(a - b) for a, b in zip(e, want)) < 1e-8, (e, want)
