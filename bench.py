@@ -441,8 +441,11 @@ def run_ours(args):
             else:
                 ctmrg.run(state, e, ctm_args=ctm_args)
         moves_per_step = 1 if per_move else 2 * (lX + lY)
-    # a few moves so that the timed environment is not the zero-padded initial one
-    for _ in range(1 if per_move else max(args.warmup, 3)):
+    # a few moves so that the timed environment is not the zero-padded initial one; for the per-move workloads one full
+    # iteration (2(lX+lY) moves: every direction once per row / column), during which the residual-checked range finder also
+    # settles its iteration count -- a failed downward probe costs an extra round, and with 10-20 timed moves on a rank that
+    # holds ONE site job two of those are a 10 % swing of the reported value (measured: 739 vs 812 ms at N = 4)
+    for _ in range(2 * (lX + lY) if per_move else max(args.warmup, 3)):
         one_step(st, env)
     torch.cuda.synchronize(dev)
 

@@ -104,6 +104,13 @@ void* Engine::persistent(const std::string& key, size_t bytes, bool* created) {
     return p;
 }
 
+void Engine::drop_persistent(const std::string& prefix, const std::string& keep) {
+    for (auto it = persist_.begin(); it != persist_.end();) {
+        if (it->first != keep && it->first.compare(0, prefix.size(), prefix) == 0) { cudaFree(it->second.first); it = persist_.erase(it); }
+        else ++it;
+    }
+}
+
 Tn Engine::temp(const std::string& idx, const std::vector<int64_t>& dims, bool back) {
     int64_t n = 1; for (auto d : dims) n *= d;
     void* p = ws.alloc((size_t)n * esize(), back);

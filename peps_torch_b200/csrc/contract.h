@@ -118,6 +118,9 @@ public:
 
     // persistent device scratch owned by the engine (random sketch matrices, amax slots ...)
     void* persistent(const std::string& key, size_t bytes, bool* created = nullptr);
+    // frees every persistent buffer whose key starts with `prefix` except `keep` (a warm-start slot whose shape changed,
+    // e.g. after env.extend(): the old basis is of no use and must not pile up)
+    void drop_persistent(const std::string& prefix, const std::string& keep);
 
 private:
     const Plan& get_plan(const Tn& A, bool conjA, const Tn& B, bool conjB, const Tn& C);

@@ -615,6 +615,7 @@ static Rsvd rsvd_batch(Engine& e, const std::vector<const void*>& M, int m, int 
             snprintf(sk, sizeof sk, "warm:%s:%d:%d:%d:%d:%d", (*slots)[b].c_str(), m, n, k, (int)eig_mode, (int)e.cplx);
             bool created = false;
             slot[b] = e.persistent(sk, (size_t)n * k * es, &created);
+            if (created) e.drop_persistent("warm:" + (*slots)[b] + ":", sk);     // the slot's basis for another shape, if any
             if (created) {      // first decomposition of this slot: plain Gaussian sketch
                 CTMB_CUDA(cudaMemcpyAsync(slot[b], omega, (size_t)n * k * es, cudaMemcpyDeviceToDevice, e.stream));
                 all_warm = false;
