@@ -151,7 +151,9 @@ def _safe_inverse_2(x, epsilon):
 
 
 class _SvdFull(torch.autograd.Function):
-    """M = U S V^H, complete (k = min(m, n) triplets), U's columns phase-fixed as linalg/svd_gesdd.py:18-26."""
+    """M = U S V^H, complete (k = min(m, n) triplets), U's columns phase-fixed as linalg/svd_gesdd.py:18-26.  The move only
+    decomposes square matrices (M = R^T Rt); the m > k / n > k terms of the reference's backward are carried along for
+    completeness and are not exercised by the tests."""
 
     @staticmethod
     def forward(ctx, eng, M, reg):

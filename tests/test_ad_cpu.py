@@ -90,3 +90,55 @@ def test_generic_optim_script_through_the_launcher(tmp_path):
     assert len(e_l) == len(e_p) >= 3
     assert max(abs(a - b) for a, b in zip(e_l, e_p)) < 1e-10, (e_l, e_p)
     assert e_l[-1] < e_l[0] - 1e-3
+
+
+@pytest.mark.parametrize('dt', ['float64', 'complex128'])
+@pytest.mark.parametrize('shape', [(12, 12), (21, 21)])
+def test_full_svd_adjoint_against_torch_autograd(dt, shape):
+    """_SvdFull (the reference's regularised SVDGESDD.backward, linalg/svd_gesdd.py:209-328) against torch's own SVD autograd on
+    a gauge-invariant function of (U, S, V); the regularisation 1e-12 is invisible on a well-separated spectrum.  Square
+    matrices: the projector matrix M = R^T Rt of the move always is."""
+    import torch
+    from peps_torch_b200 import ad
+    dtype = getattr(torch, dt)
+    g = torch.Generator().manual_seed(7)
+    A0 = torch.randn(shape, dtype=dtype, generator=g)
+    Wm = torch.randn(shape, dtype=dtype, generator=g)
+    k = min(shape)
+
+    def f(U, S, V):
+        # gauge invariant: depends on U S^2 V^H, U diag(w) U^H and S only
+        w = torch.linspace(1.0, 2.0, k, dtype=S.dtype)
+        P = (U * w.to(U.dtype)) @ U.conj().t()
+        return ((U * (S ** 2).to(U.dtype)) @ V.conj().t() * Wm.conj()).sum().real + P.abs().pow(2).sum() + (S ** 3).sum()
+    A1 = A0.clone().requires_grad_(True)
+    U, S, V = ad._SvdFull.apply(H.OracleEngine(), A1, 1.0e-12)
+    f(U[:, :k], S, V[:, :k]).backward()
+    A2 = A0.clone().requires_grad_(True)
+    U2, S2, Vh2 = torch.linalg.svd(A2, full_matrices=False)
+    f(U2, S2, Vh2.conj().t()).backward()
+    assert float((A1.grad - A2.grad).abs().max()) < 1e-9 * float(A2.grad.abs().max())
+
+
+@pytest.mark.parametrize('dt', ['float64', 'complex128'])
+def test_full_eig_adjoint_against_torch_autograd(dt):
+    """_EigSymFull (SYMEIG.backward, linalg/eig_sym.py:56-78) against torch.linalg.eigh's autograd."""
+    import torch
+    from peps_torch_b200 import ad
+    dtype = getattr(torch, dt)
+    g = torch.Generator().manual_seed(9)
+    X = torch.randn(14, 14, dtype=dtype, generator=g)
+    A0 = 0.5 * (X + X.conj().t())
+    w = torch.linspace(1.0, 2.0, 14, dtype=torch.float64)
+
+    def f(D, U):
+        # eigenvalues come sorted by magnitude from ours, ascending from torch: use a permutation-invariant, gauge-invariant function
+        return (D ** 3).sum() + ((U * torch.tanh(D).to(U.dtype)) @ U.conj().t()).abs().pow(2).sum() + ((U * D.to(U.dtype)) @ U.conj().t() * A0.conj()).sum().real
+    A1 = A0.clone().requires_grad_(True)
+    D, U = ad._EigSymFull.apply(H.OracleEngine(), 0.5 * (A1 + A1.conj().t()), 1.0e-12)
+    f(D, U).backward()
+    A2 = A0.clone().requires_grad_(True)
+    D2, U2 = torch.linalg.eigh(0.5 * (A2 + A2.conj().t()))
+    f(D2, U2).backward()
+    assert float((A1.grad - A2.grad).abs().max()) < 1e-9 * float(A2.grad.abs().max())
+    del w
