@@ -53,3 +53,23 @@ def test_config2_script_unmodified_on_gpu(tmp_path):
     vals, _ = _final('examples/j1j2/ctmrg_j1j2.py', ['--instate', os.path.join(GOLD, 'config2_instate.json'), '--tiling', '4SITE',
                                                    '--chi', '48', '--j2', '0.3'], tmp_path)
     assert abs(vals[0] - 0.6424192641900255) < 1e-10 * 0.64, vals[0]
+
+
+def test_kagome_rvb_known_answer_unmodified_on_gpu(tmp_path):
+    """The reference's own golden vector for the kagome family (BASELINE config 4's script; TestCtmrg_IPESS_D3_RVB,
+    ctmrg_spin_half_kagome.py:360-417: IPESS D=3 chi=18 complex128 on test-input/IPESS_KAGOME_D3_RVB.in, 21 numbers at 1e-6):
+    the unmodified script through the launcher on cuda:0 -- moves, kagome density matrices and transfer-operator mat-vecs on
+    libctmb."""
+    from test_launcher_cpu import check_kagome_rvb_final
+    script = os.path.join(REF, 'examples', 'kagome', 'ctmrg_spin_half_kagome.py')
+    instate = os.path.join(REF, 'test-input', 'IPESS_KAGOME_D3_RVB.in')
+    if not (os.path.isfile(script) and os.path.isfile(instate)):
+        pytest.skip('baseline/_ref (staged copy of the reference) not present')
+    if not torch.cuda.is_available():
+        pytest.skip('GPU tests need a CUDA device')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    out = subprocess.run([sys.executable, '-m', 'peps_torch_b200.run', script, '--ansatz', 'IPESS', '--instate', instate,
+                          '--bond_dim', '3', '--chi', '18', '--j1', '1.0', '--GLOBALARGS_dtype', 'complex128', '--out_prefix', 'kg',
+                          '--GLOBALARGS_device', 'cuda:0'], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    check_kagome_rvb_final(out.stdout)

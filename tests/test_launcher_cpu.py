@@ -42,3 +42,39 @@ def test_kagome_script_calls_the_rebound_move(tmp_path):
                                                                       '--GLOBALARGS_dtype', 'complex128'], tmp_path)
     assert g == 8 and c == 0           # 2 iterations x 2(lX+lY) moves of the 1x1 cell
     assert 'spectrum(T)' in out        # the script ran to its end (observables, transfer-matrix spectra)
+
+
+KAGOME_RVB_REF = """-0.3931221584692804, (-0.5896832690555696+0j), (-0.5896832063522717+0j), (7.59716523160245e-32+0j),
+    (-4.331814810151939e-31+0j), (8.592175414886632e-32+0j), (3.07218410812194e-16+0j),
+    (-3.674157727896386e-17+0j), (5.011080358949883e-16+0j), (-3.953569086037768e-16+0j),
+    (6.82165674627862e-16+0j), (-8.641428147458597e-16+0j), (-1.0617693286257969e-16+0j),
+    (-9.980184244909592e-16+0j), (-7.479642784634561e-17+0j), (-0.19656089027856907+0j),
+    (-0.19656149813919332+0j), (-0.1965608806378064+0j), (-0.19656141466722352+0j),
+    (-0.19656089010487604+0j), (-0.19656090158017214+0j)"""
+
+
+def check_kagome_rvb_final(stdout):
+    """The reference's own golden vector for the kagome RVB state (examples/kagome/ctmrg_spin_half_kagome.py:405-417,
+    TestCtmrg_IPESS_D3_RVB: 21 numbers at 1e-6): energy per site, down / up triangle energies, magnetisations, bond SS."""
+    from cmath import isclose
+    final = [ln for ln in stdout.splitlines() if ln.startswith('FINAL')]
+    assert final, stdout[-2000:]
+    got = [complex(x) for x in final[-1][len('FINAL'):].split(',')]
+    want = [complex(x) for x in KAGOME_RVB_REF.split(',')]
+    assert len(got) >= len(want)
+    for g, w in zip(got, want):
+        assert isclose(g, w, rel_tol=1e-6, abs_tol=1e-6), (g, w)
+
+
+def test_kagome_rvb_known_answer_through_the_launcher(tmp_path):
+    """Unmodified kagome script on the reference's RVB test state (IPESS D=3, chi=18, complex128) with the moves, the kagome
+    density matrices (peps_torch_b200/ctm/pess_kagome/rdm_kagome.py) and the transfer-operator spectra rebound -- the oracle
+    standing in for libctmb -- must reproduce the reference's golden vector.  (The GPU suite runs the same with libctmb.)"""
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', OMP_NUM_THREADS='4')
+    out = subprocess.run([sys.executable, os.path.join(HERE, 'launcher_probe_ad.py'),
+                          os.path.join(REF, 'examples', 'kagome', 'ctmrg_spin_half_kagome.py'), '--ansatz', 'IPESS', '--instate',
+                          os.path.join(REF, 'test-input', 'IPESS_KAGOME_D3_RVB.in'), '--bond_dim', '3', '--chi', '18', '--j1', '1.0',
+                          '--GLOBALARGS_dtype', 'complex128', '--out_prefix', 'kg'],
+                         cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    check_kagome_rvb_final(out.stdout)
