@@ -100,3 +100,25 @@ def test_generic_optim_script_unmodified_on_gpu(tmp_path):
     want = [0.6424192637819899, 0.6424192637819899, 0.6416966780618278, 0.6416966780618278]
     assert len(e) == len(want), out.stdout[-2000:]
     assert max(abs(a - b) for a, b in zip(e, want)) < 1e-8, (e, want)
+
+
+@pytest.mark.parametrize('extra', [['--GLOBALARGS_dtype', 'complex128'],
+                                   ['--CTMARGS_projector_svd_method', 'SYMEIG', '--OPTARGS_line_search', 'backtracking'],
+                                   ['--CTMARGS_projector_svd_method', 'SYMEIG', '--OPTARGS_line_search', 'backtracking',
+                                    '--OPTARGS_line_search_svd_method', 'SYMARP'],
+                                   ['--CTMARGS_fwd_checkpoint_move', 'True']])
+def test_reference_optimisation_smoke_cases_on_gpu(tmp_path, extra):
+    """The reference's own optimisation smoke tests (examples/j1j2/optim_j1j2_c4v.py:179-236 TestOpt: complex128, SYMEIG,
+    back-tracking line search, a different decomposition during the line search; plus activation checkpointing of the move)
+    through the launcher on cuda:0: the script runs to its end and the energy goes down."""
+    script = os.path.join(REF, 'examples', 'j1j2', 'optim_j1j2_c4v.py')
+    if not os.path.isfile(script):
+        pytest.skip('baseline/_ref (staged copy of the reference) not present')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    out = subprocess.run([sys.executable, '-m', 'peps_torch_b200.run', script, '--bond_dim', '2', '--chi', '16', '--j2', '0.0',
+                          '--seed', '123', '--opt_max_iter', '3', '--out_prefix', 'smoke', '--GLOBALARGS_device', 'cuda:0'] + extra,
+                         cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    rows = [ln.split(', ') for ln in out.stdout.splitlines() if ln[:1].isdigit() or ln[:2] == '-1']
+    e = [complex(r[1]).real for r in rows if len(r) > 3]
+    assert len(e) >= 3 and e[-1] < e[0], e
