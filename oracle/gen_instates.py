@@ -46,3 +46,8 @@ a = final('examples/j1j2/ctmrg_j1j2_c4v.py', ['--bond_dim', '2', '--chi', '16', 
 b = final('examples/j1j2/ctmrg_j1j2_c4v.py', ['--instate', f1, '--chi', '16', '--j2', '0.3'])
 print(a); print(b)
 assert a == b, 'the instate file does not reproduce the seed-123 run'
+
+# the state of the reference's optimisation test TestOpt4SITE (examples/j1j2/optim_j1j2.py:371-440: 4SITE, D = 2, seed 123)
+f3 = os.path.abspath(os.path.join(GOLD, 'opt4site_instate.json'))
+IPEPS(orc.random_state_4site(2, family='A'), vertexToSite=orc.v2s_4site, lX=2, lY=2).write_to_file(f3)
+print('written', f3)

@@ -122,3 +122,33 @@ def test_reference_optimisation_smoke_cases_on_gpu(tmp_path, extra):
     rows = [ln.split(', ') for ln in out.stdout.splitlines() if ln[:1].isdigit() or ln[:2] == '-1']
     e = [complex(r[1]).real for r in rows if len(r) > 3]
     assert len(e) >= 3 and e[-1] < e[0], e
+
+
+# python tests/launcher_probe_ad.py --plain-legacy-rdm /root/reference/examples/j1j2/optim_j1j2.py --tiling 4SITE --instate
+#   tests/golden/opt4site_instate.json --chi 8 --j2 0.3 --opt_max_iter 12 --CTMARGS_ctm_conv_tol 1.0e-6   (CPU, untouched reference)
+OPT4SITE_ENERGIES = [0.5865136452682431, 0.5865136452682431, 0.5668468740270627, 0.5257390704000275, 0.46916646325588474,
+                     0.39656116571952127, 0.3114193581367074, 0.22158132552887572, -0.045070082696970354, -0.14431043188626064,
+                     -0.194611087332481, -0.3044738386772121, -0.34371690083316675, -0.3437169008331657]
+
+
+def test_opt4site_trajectory_on_gpu(tmp_path):
+    """The case of the reference's optimisation test TestOpt4SITE (examples/j1j2/optim_j1j2.py:371-440: 4SITE, D = 2, chi = 8,
+    seed 123, j2 = 0.3, CTM converged to 1e-6 inside every loss evaluation), first twelve L-BFGS epochs, unmodified script on
+    cuda:0: the energy of EVERY epoch must follow the untouched reference's trajectory.  (All 40 epochs through the launcher
+    with the oracle as engine end at -0.5430338624891 against -0.5430338624888 for the untouched script in this container;
+    the number printed in the reference's source, -0.5430086212529559, is what its authors' environment gave.)"""
+    script = os.path.join(REF, 'examples', 'j1j2', 'optim_j1j2.py')
+    if not os.path.isfile(script):
+        pytest.skip('baseline/_ref (staged copy of the reference) not present')
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    out = subprocess.run([sys.executable, '-m', 'peps_torch_b200.run', script, '--tiling', '4SITE', '--instate',
+                          os.path.join(ROOT, 'tests', 'golden', 'opt4site_instate.json'), '--chi', '8', '--j2', '0.3',
+                          '--opt_max_iter', '12', '--CTMARGS_ctm_conv_tol', '1.0e-6', '--out_prefix', 'T4',
+                          '--GLOBALARGS_device', 'cuda:0'], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
+    rows = [ln.split(', ') for ln in out.stdout.splitlines() if ln[:1].isdigit() or ln[:2] == '-1']
+    e = [float(r[1]) for r in rows if len(r) > 3]
+    assert len(e) == len(OPT4SITE_ENERGIES), out.stdout[-2000:]
+    worst = max(abs(a - b) for a, b in zip(e, OPT4SITE_ENERGIES))
+    print('opt4site: worst deviation from the reference trajectory over 12 epochs', worst)
+    assert worst < 1e-8, (e, OPT4SITE_ENERGIES)          # measured on B200: 5.4e-12
