@@ -73,3 +73,36 @@ def test_kagome_rvb_known_answer_unmodified_on_gpu(tmp_path):
                           '--GLOBALARGS_device', 'cuda:0'], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-3000:])
     check_kagome_rvb_final(out.stdout)
+
+
+# the reference's own golden vectors for the generic J1-J2 script (TestCtmrg_States, examples/j1j2/ctmrg_j1j2.py:244-308, 1e-6)
+J1J2_STATES = [
+    (['--tiling', 'BIPARTITE', '--j3', '0.125', '--h_uni', '3.9', '0', '0'],
+     'BIPARTITE_j2_0_j3_1250_h_39000_D_3_chi_32_seed_100_state.json',
+     """-1.3896897615463615, 0.4884474386344192, 0.48844697363007333, 0.4884479036387651,
+        -0.46200561021924863, 0.1585284270227813, 0.1585284270227813, -0.4620060817268178,
+        -0.15852991836412875, -0.15852991836412875, 0.1751621217404098, 0.17516618332251627,
+        0.17516347390256323, 0.17516132836311246"""),
+    (['--tiling', '2SITE', '--j2', '0.55'],
+     'gesdd-D2-chi50-j20.55-run0-iRND2x1_state.json',
+     """-0.4434603770143078, 0.3184895704619597, 0.31842030538406385, 0.31855883553985553,
+        -0.26397659399034457, 0.17806697814624955, 0.1780669781462514, 0.26446699770693394,
+        -0.17758642635176156, -0.1775864263517598"""),
+]
+
+
+@pytest.mark.parametrize('case', [0, 1])
+def test_j1j2_states_known_answers_unmodified_on_gpu(tmp_path, case):
+    """TestCtmrg_States of the reference: BIPARTITE D=3 chi=32 with j3 and a field (14 numbers) and 2SITE D=2 chi=32 at
+    j2 = 0.55 (10 numbers: energy, magnetisations, bond correlators), unmodified script through the launcher on cuda:0."""
+    from cmath import isclose
+    args, instate, ref = J1J2_STATES[case]
+    script = os.path.join(REF, 'examples', 'j1j2', 'ctmrg_j1j2.py')
+    f = os.path.join(REF, 'test-input', instate)
+    if not (os.path.isfile(script) and os.path.isfile(f)):
+        pytest.skip('baseline/_ref (staged copy of the reference) not present')
+    vals, _ = _final('examples/j1j2/ctmrg_j1j2.py', args + ['--instate', f, '--chi', '32', '--CTMARGS_ctm_max_iter', '100'], tmp_path)
+    want = [float(x) for x in ref.split(',')]
+    assert len(vals) >= len(want)
+    for g, w in zip(vals, want):
+        assert isclose(g, w, rel_tol=1e-6, abs_tol=1e-6), (vals, want)
