@@ -93,10 +93,11 @@ def _chain(eng, subs, ops, conj, out):
     return cur
 
 
-def sl_chain(eng, spec, ops, a, conj_last=False):
+def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None):
     """The double-layer einsum `spec` ('@' = the on-site double-layer tensor) evaluated layer by layer without forming
     a (x) a*: every fused label of '@' is split into (ket, bra) on the operands that carry it (SURVEY Appendix A;
-    ctm_components.py:372-434).  A rank-4 `a` is the double-layer tensor itself and enters as one operand."""
+    ctm_components.py:372-434).  A rank-4 `a` is the double-layer tensor itself and enters as one operand.  `a_ket`
+    replaces the ket layer (an operator applied to the physical leg, corrf.py:415-419); the bra layer stays conj(a)."""
     lhs, out = spec.split('->')
     terms = lhs.split(',')
     a_pos = [i for i, t in enumerate(terms) if t.startswith('@')][0]
@@ -115,7 +116,7 @@ def sl_chain(eng, spec, ops, a, conj_last=False):
     for i, t in enumerate(terms):
         if i == a_pos:
             subs += ['s' + a_idx, 's' + a_idx.upper()]
-            xs += [a, a]
+            xs += [a if a_ket is None else a_ket, a]
             cj += [False, True]
             continue
         x = ops[k]; k += 1

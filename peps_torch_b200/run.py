@@ -106,6 +106,26 @@ def enable(engine_factory=None):
         ours_corrf._engine = engine_factory
     top.get_Top_spec = ours_top.get_Top_spec
     top.get_Top_w0_spec = ours_top.get_Top_w0_spec
+    # the two-point functions behind eval_corrf_* of the models (ctm/generic/corrf.py:10-104,234-277,364-650,980-1067);
+    # MPO-carrying edges / operators and anything under autograd stay the reference's torch code
+    from .ctm.generic import corrf as ours_cf
+    cf = importlib.import_module('ctm.generic.corrf')
+    ref_tm1, ref_apply_edge = cf.apply_TM_1sO, cf.apply_edge
+
+    def apply_TM_1sO(coord, direction, state, env, edge, op=None, verbosity=0):
+        plain = edge.dim() == 3 and (op is None or op.dim() == 2) and all(t.dim() == 5 for t in state.sites.values())
+        if not plain or needs_grad(list(_tensors((state, env))) + [edge]):
+            return ref_tm1(coord, direction, state, env, edge, op=op, verbosity=verbosity)
+        return ours_cf.apply_TM_1sO(coord, direction, state, env, edge, op=op, verbosity=verbosity)
+
+    def apply_edge(coord, direction, state, env, vec, verbosity=0):
+        if vec.dim() != 3 or needs_grad(list(_tensors((state, env))) + [vec]):
+            return ref_apply_edge(coord, direction, state, env, vec, verbosity=verbosity)
+        return ours_cf.apply_edge(coord, direction, state, env, vec, verbosity=verbosity)
+
+    cf.apply_TM_1sO, cf.apply_edge = apply_TM_1sO, apply_edge
+    cf.get_edge = _dispatch(ours_cf.get_edge, cf.get_edge)
+    cf.corrf_1sO1sO = _dispatch(ours_cf.corrf_1sO1sO, cf.corrf_1sO1sO)
     # the kagome density matrices behind energy_triangle_dn / _up and eval_obs of models/spin_half_kagome.py (config 4)
     from .ctm.pess_kagome import rdm_kagome as ours_kag
     if engine_factory is not None:

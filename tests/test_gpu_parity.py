@@ -879,6 +879,42 @@ def test_transfer_operator_matvecs_and_spectra(eng, dev, name, monkeypatch):
         assert float((ot.get_Top_w0_spec(3, (0, 0), d, st_g, env_g).cpu().abs() - Ww.abs()).abs().max()) < 1e-10
 
 
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'])
+def test_edges_operator_insertions_and_corrf(eng, dev, name, monkeypatch):
+    """get_edge / apply_edge / apply_TM_1sO with a one-site operator / corrf_1sO1sO (ctm/generic/corrf.py:10-104, 234-277,
+    415-419, 980-1067) on libctmb against the same functions with the oracle as engine (pinned against the unmodified
+    reference by tests/test_transferops_cpu.py)."""
+    from peps_torch_b200.ctm.generic import corrf as oc
+    from test_transferops_cpu import edge_shapes, DIRS
+    z, meta = H.load_golden(name)
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'final_' if any(k.startswith('final_') for k in z.files) else 'mid_')
+    dt = next(iter(sites.values())).dtype
+    st_c, env_c = H.State(sites, v2s, lX, lY), H.Env(meta['chi'], dict(C), dict(T))
+    st_g, env_g = H.State(H.to_dev(sites, dev), v2s, lX, lY), H.Env(meta['chi'], H.to_dev(C, dev), H.to_dev(T, dev))
+    oracle = H.OracleEngine()
+    p = next(iter(sites.values())).shape[0]
+    g = torch.Generator().manual_seed(5)
+    op1 = torch.randn(p, p, dtype=dt, generator=g)
+    ops2 = [torch.randn(p, p, dtype=dt, generator=g) for _ in range(5)]
+    for d in DIRS:
+        chi1, d2, chi2 = edge_shapes(st_c, env_c, d)
+        V = torch.randn(chi1, d2, chi2, dtype=dt, generator=g)
+        monkeypatch.setattr(oc, '_engine', lambda: oracle)
+        w_edge = oc.get_edge((0, 0), d, st_c, env_c)
+        w_tm = oc.apply_TM_1sO((0, 0), d, st_c, env_c, V, op=op1)
+        Ve = torch.randn(*w_edge.shape, dtype=dt, generator=g)
+        w_s = oc.apply_edge((0, 0), d, st_c, env_c, Ve)
+        w_c = oc.corrf_1sO1sO((0, 0), d, st_c, env_c, op1, lambda r: ops2[r], 4)
+        monkeypatch.setattr(oc, '_engine', lambda: eng)
+        assert H.maxrel(oc.get_edge((0, 0), d, st_g, env_g).cpu(), w_edge) < 1e-13
+        assert H.maxrel(oc.apply_TM_1sO((0, 0), d, st_g, env_g, V.to(dev), op=op1.to(dev)).cpu(), w_tm) < 1e-13
+        assert abs(complex(oc.apply_edge((0, 0), d, st_g, env_g, Ve.to(dev)).cpu()) - complex(w_s)) < 1e-13 * abs(complex(w_s)) + 1e-15 * float(Ve.abs().max() * w_edge.abs().max()) * Ve.numel()
+        got = oc.corrf_1sO1sO((0, 0), d, st_g, env_g, op1.to(dev), lambda r: ops2[r].to(dev), 4)
+        assert got.device.type == 'cuda' and H.maxrel(got.cpu(), w_c) < 1e-11, (d, got, w_c)
+
+
 def test_tma_fed_gemm_layouts_and_edges(eng, dev):
     """tc_kernel_tma (tc_gemm_tma.cu): plain strided operands of large real contractions are fed by cp.async.bulk.tensor.
     All four fast-direction pairs (2-D swizzled map for k-fast, 3-D map for m-fast operands), extents that are not multiples

@@ -78,3 +78,42 @@ def test_kagome_rvb_known_answer_through_the_launcher(tmp_path):
                          cwd=tmp_path, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     check_kagome_rvb_final(out.stdout)
+
+
+def _ss_lines(stdout):
+    rows, take = [], False
+    for ln in stdout.splitlines():
+        if ln.startswith('SS[('):
+            take = True
+            continue
+        if take:
+            f = ln.split()
+            if len(f) >= 2 and f[0].isdigit():
+                rows.append([complex(x) for x in f[1:]])
+            elif ln.strip():
+                take = False
+    return rows
+
+
+def test_correlation_functions_of_the_script_through_the_launcher(tmp_path):
+    """The SS correlation functions printed at the tail of ctmrg_j1j2.py (models/j1j2.py:476-508 -> corrf_1sO1sO) through the
+    launcher (get_edge / apply_TM_1sO with operators / apply_edge rebound, oracle standing in for libctmb) against the script
+    run untouched."""
+    args = ['--tiling', '4SITE', '--bond_dim', '2', '--chi', '8', '--seed', '123', '--j2', '0.3', '--CTMARGS_ctm_max_iter', '4',
+            '--corrf_r', '5']
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', OMP_NUM_THREADS='2')
+    script = os.path.join(REF, 'examples', 'j1j2', 'ctmrg_j1j2.py')
+    outs = []
+    for mode in (['--plain-legacy-rdm'], []):
+        for sub in ('a', 'b'):
+            os.makedirs(tmp_path / sub, exist_ok=True)
+        out = subprocess.run([sys.executable, os.path.join(HERE, 'launcher_probe_ad.py')] + mode + [script] + args,
+                             cwd=tmp_path / ('a' if mode else 'b'), env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(_ss_lines(out.stdout))
+    want, got = outs
+    assert len(want) == 10 and len(got) == 10      # 5 distances x 2 directions
+    for a, b in zip(got, want):
+        assert len(a) == len(b) == 4
+        for x, y in zip(a, b):
+            assert abs(x - y) < 1e-9 * max(1.0, abs(y)), (got, want)

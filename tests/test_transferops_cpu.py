@@ -66,3 +66,49 @@ def test_transfer_operators_match_reference(ref, name, monkeypatch):
         assert float((La - Lb).abs().max()) < 1e-10, (d, La, Lb)
         Wa, Wb = ot.get_Top_w0_spec(3, (0, 0), d, st, env), rt.get_Top_w0_spec(3, (0, 0), d, rs, re)
         assert float((Wa.abs() - Wb.abs()).abs().max()) < 1e-10, (d, Wa, Wb)
+
+
+@pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'])
+def test_edges_operator_insertions_and_corrf_match_reference(ref, name, monkeypatch):
+    """get_edge, apply_edge, apply_TM_1sO with a one-site operator and corrf_1sO1sO (corrf.py:10-104, 234-277, 415-419,
+    980-1067), with and without the rl_0 eigenvector edges, in all four directions."""
+    from ipeps.ipeps import IPEPS as RI
+    from ctm.generic.env import ENV as RE
+    from ctm.generic import corrf as rc
+    from peps_torch_b200.ctm.generic import corrf as oc
+    eng = H.OracleEngine()
+    monkeypatch.setattr(oc, '_engine', lambda: eng)
+    z, meta = H.load_golden(name)
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'final_' if any(k.startswith('final_') for k in z.files) else 'mid_')
+    dt = next(iter(sites.values())).dtype
+    ref.global_args.dtype, ref.global_args.torch_dtype, ref.global_args.device = ('complex128' if dt.is_complex else 'float64'), dt, 'cpu'
+    rs = RI(sites={c: t.clone() for c, t in sites.items()}, vertexToSite=v2s, lX=lX, lY=lY)
+    re = RE(meta['chi'], rs)
+    re.C, re.T = dict(C), dict(T)
+    st, env = H.State(sites, v2s, lX, lY), H.Env(meta['chi'], dict(C), dict(T))
+    p = next(iter(sites.values())).shape[0]
+    g = torch.Generator().manual_seed(5)
+    op1 = torch.randn(p, p, dtype=dt, generator=g)
+    ops2 = [torch.randn(p, p, dtype=dt, generator=g) for _ in range(4)]
+    for d in DIRS:
+        rev = (-d[0], -d[1])
+        assert H.maxrel(oc.get_edge((0, 0), d, st, env), rc.get_edge((0, 0), d, rs, re)) < 1e-13
+        chi1, d2, chi2 = edge_shapes(st, env, d)
+        V = torch.randn(chi1, d2, chi2, dtype=dt, generator=g)
+        assert H.maxrel(oc.apply_TM_1sO((0, 0), d, st, env, V, op=op1), rc.apply_TM_1sO((0, 0), d, rs, re, V, op=op1)) < 1e-13
+        Ve = torch.randn(*rc.get_edge((1, 0), d, rs, re).shape, dtype=dt, generator=g)
+        a, b = oc.apply_edge((1, 0), d, st, env, Ve), rc.apply_edge((1, 0), d, rs, re, Ve)
+        assert abs(complex(a) - complex(b)) < 1e-13 * abs(complex(b))
+        ca = oc.corrf_1sO1sO((0, 0), d, st, env, op1, lambda r: ops2[r], 3)
+        cb = rc.corrf_1sO1sO((0, 0), d, rs, re, op1, lambda r: ops2[r], 3)
+        assert ca.shape == cb.shape and H.maxrel(ca, cb) < 1e-11, (d, ca, cb)
+        # eigenvector edges in place of the environment's (the rl_0 argument)
+        L = {c: torch.randn(*rc.get_edge(c, rev, rs, re).shape, dtype=dt, generator=g) for c in sites}
+        R = {c: torch.randn(*rc.get_edge(c, d, rs, re).shape, dtype=dt, generator=g) for c in sites}
+        rl_a = (lambda c: L[st.vertexToSite(c)], lambda c: R[st.vertexToSite(c)])
+        rl_b = (lambda c: L[rs.vertexToSite(c)], lambda c: R[rs.vertexToSite(c)])
+        ca = oc.corrf_1sO1sO((0, 0), d, st, env, op1, lambda r: ops2[r], 2, rl_0=rl_a)
+        cb = rc.corrf_1sO1sO((0, 0), d, rs, re, op1, lambda r: ops2[r], 2, rl_0=rl_b)
+        assert H.maxrel(ca, cb) < 1e-11, (d, ca, cb)
