@@ -93,11 +93,13 @@ def _chain(eng, subs, ops, conj, out):
     return cur
 
 
-def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None):
+def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None, ket_extra=''):
     """The double-layer einsum `spec` ('@' = the on-site double-layer tensor) evaluated layer by layer without forming
     a (x) a*: every fused label of '@' is split into (ket, bra) on the operands that carry it (SURVEY Appendix A;
     ctm_components.py:372-434).  A rank-4 `a` is the double-layer tensor itself and enters as one operand.  `a_ket`
-    replaces the ket layer (an operator applied to the physical leg, corrf.py:415-419); the bra layer stays conj(a)."""
+    replaces the ket layer (an operator applied to the physical leg, corrf.py:415-419); the bra layer stays conj(a).
+    `ket_extra` labels trailing indices of `a_ket` beyond [s,u,l,d,r] (the bond of a two-site operator split over two
+    sites, corrf_c4v.py:501-503)."""
     lhs, out = spec.split('->')
     terms = lhs.split(',')
     a_pos = [i for i, t in enumerate(terms) if t.startswith('@')][0]
@@ -115,7 +117,7 @@ def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None):
     k = 0
     for i, t in enumerate(terms):
         if i == a_pos:
-            subs += ['s' + a_idx, 's' + a_idx.upper()]
+            subs += ['s' + a_idx + ket_extra, 's' + a_idx.upper()]
             xs += [a if a_ket is None else a_ket, a]
             cj += [False, True]
             continue

@@ -22,7 +22,7 @@ def _get_chis(state, env, coord, direction, width):
     return env.T[(coord, (0, -1))].size(0), env.T[(cs, (0, 1))].size(1)
 
 
-def _leading(n, dim, mv, cplx, device, eigenvectors=False):
+def _leading(n, dim, mv, cplx, device, eigenvectors=False, normalize=True):
     T = LinearOperator((dim, dim), matvec=mv, dtype="complex128" if cplx else "float64")
     if eigenvectors:
         vals, vecs = eigs(T, k=n, v0=None, return_eigenvectors=True)
@@ -30,7 +30,8 @@ def _leading(n, dim, mv, cplx, device, eigenvectors=False):
         vals = eigs(T, k=n, v0=None, return_eigenvectors=False)
     ind = np.argsort(np.abs(vals))[::-1]
     vals = vals[ind]
-    vals = (1.0 / np.abs(vals[0])) * vals
+    if normalize:
+        vals = (1.0 / np.abs(vals[0])) * vals
     L = torch.zeros((n, 2), dtype=torch.float64, device=device)
     L[:, 0] = torch.as_tensor(np.real(vals))
     L[:, 1] = torch.as_tensor(np.imag(vals))

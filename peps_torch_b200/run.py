@@ -9,6 +9,7 @@ The reference's move modules look ``ctm_MOVE`` up as a module global at call tim
 Everything else of the reference (states, models, RDMs, config, argparse) is used as it is.
 """
 import importlib
+import torch
 import os
 import runpy
 import sys
@@ -126,6 +127,23 @@ def enable(engine_factory=None):
     cf.apply_TM_1sO, cf.apply_edge = apply_TM_1sO, apply_edge
     cf.get_edge = _dispatch(ours_cf.get_edge, cf.get_edge)
     cf.corrf_1sO1sO = _dispatch(ours_cf.corrf_1sO1sO, cf.corrf_1sO1sO)
+    # the same for the C4v ansatz (ctm/one_site_c4v/corrf_c4v.py, transferops_c4v.py:10-68): eval_corrf_SS / eval_corrf_DD_H
+    # and the transfer-operator spectrum at the tail of ctmrg_j1j2_c4v.py
+    from .ctm.one_site_c4v import corrf_c4v as ours_cf4, transferops_c4v as ours_top4
+    if engine_factory is not None:
+        ours_cf4._engine = engine_factory
+    cf4 = importlib.import_module('ctm.one_site_c4v.corrf_c4v')
+    for name in ('get_edge', 'apply_edge', 'apply_TM_1sO', 'apply_TM_2sO', 'corrf_1sO1sO', 'corrf_2sOH2sOH_E1'):
+        ref_fn = getattr(cf4, name)
+
+        def f(state, env, *args, _ours=getattr(ours_cf4, name), _ref=ref_fn, **kw):
+            extra = [x for x in args if isinstance(x, torch.Tensor)]
+            if needs_grad(list(_tensors((state, env))) + extra):
+                return _ref(state, env, *args, **kw)
+            return _ours(state, env, *args, **kw)
+        setattr(cf4, name, f)
+    top4 = importlib.import_module('ctm.one_site_c4v.transferops_c4v')
+    top4.get_Top_spec_c4v = ours_top4.get_Top_spec_c4v
     # the kagome density matrices behind energy_triangle_dn / _up and eval_obs of models/spin_half_kagome.py (config 4)
     from .ctm.pess_kagome import rdm_kagome as ours_kag
     if engine_factory is not None:

@@ -915,6 +915,44 @@ def test_edges_operator_insertions_and_corrf(eng, dev, name, monkeypatch):
         assert got.device.type == 'cuda' and H.maxrel(got.cpu(), w_c) < 1e-11, (d, got, w_c)
 
 
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_c4v_correlation_functions(eng, dev, name, monkeypatch):
+    """ctm/one_site_c4v/corrf_c4v.py (edges, one- and two-site transfer matrices with operators, corrf_1sO1sO,
+    corrf_2sOH2sOH_E1) and get_Top_spec_c4v on libctmb against the same functions with the oracle as engine (pinned against
+    the unmodified reference by tests/test_transferops_cpu.py)."""
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    from peps_torch_b200.ctm.one_site_c4v import corrf_c4v as oc, transferops_c4v as ot
+    from test_transferops_cpu import c4v_case
+    a, chi, C, T = c4v_case(name)
+    dt = a.dtype
+    st_c, st_g = IPEPS_C4V(a), IPEPS_C4V(a.to(dev))
+    env_c, env_g = ENV_C4V(chi, st_c), ENV_C4V(chi, st_g)
+    env_c.C[env_c.keyC], env_c.T[env_c.keyT] = C.clone(), T.clone()
+    env_g.C[env_g.keyC], env_g.T[env_g.keyT] = C.to(dev), T.to(dev)
+    oracle = H.OracleEngine()
+    p = a.shape[0]
+    g = torch.Generator().manual_seed(9)
+    op1 = torch.randn(p, p, dtype=dt, generator=g)
+    ops1 = [torch.randn(p, p, dtype=dt, generator=g) for _ in range(5)]
+    op2 = torch.randn(p, p, p, p, dtype=torch.float64, generator=g).to(dt)
+    ops2 = [torch.randn(p, p, p, p, dtype=torch.float64, generator=g).to(dt) for _ in range(4)]
+    V = torch.randn(chi, a.shape[1] ** 2, chi, dtype=dt, generator=g)
+    monkeypatch.setattr(oc, '_engine', lambda: oracle)
+    want = [oc.get_edge(st_c, env_c), oc.apply_TM_1sO(st_c, env_c, V, op=op1), oc.apply_TM_2sO(st_c, env_c, V, op=op2),
+            oc.apply_edge(st_c, env_c, V).reshape(1), oc.corrf_1sO1sO(st_c, env_c, op1, lambda r: ops1[r], 4),
+            oc.corrf_2sOH2sOH_E1(st_c, env_c, op2, lambda r: ops2[r], 3)]
+    Lw = ot.get_Top_spec_c4v(3, st_c, env_c)
+    monkeypatch.setattr(oc, '_engine', lambda: eng)
+    Vg = V.to(dev)
+    got = [oc.get_edge(st_g, env_g), oc.apply_TM_1sO(st_g, env_g, Vg, op=op1.to(dev)), oc.apply_TM_2sO(st_g, env_g, Vg, op=op2.to(dev)),
+           oc.apply_edge(st_g, env_g, Vg).reshape(1), oc.corrf_1sO1sO(st_g, env_g, op1.to(dev), lambda r: ops1[r].to(dev), 4),
+           oc.corrf_2sOH2sOH_E1(st_g, env_g, op2.to(dev), lambda r: ops2[r].to(dev), 3)]
+    for i, (x, y) in enumerate(zip(got, want)):
+        assert x.device.type == 'cuda' and H.maxrel(x.cpu(), y) < 1e-10, (i, x, y)
+    assert float((ot.get_Top_spec_c4v(3, st_g, env_g).cpu() - Lw).abs().max()) < 1e-10
+
+
 def test_tma_fed_gemm_layouts_and_edges(eng, dev):
     """tc_kernel_tma (tc_gemm_tma.cu): plain strided operands of large real contractions are fed by cp.async.bulk.tensor.
     All four fast-direction pairs (2-D swizzled map for k-fast, 3-D map for m-fast operands), extents that are not multiples

@@ -83,7 +83,7 @@ def test_kagome_rvb_known_answer_through_the_launcher(tmp_path):
 def _ss_lines(stdout):
     rows, take = [], False
     for ln in stdout.splitlines():
-        if ln.startswith('SS[('):
+        if ln.startswith(('SS[(', 'SS r', 'DD r', 'spectrum(T)')):
             take = True
             continue
         if take:
@@ -93,6 +93,30 @@ def _ss_lines(stdout):
             elif ln.strip():
                 take = False
     return rows
+
+
+def test_c4v_correlation_functions_of_the_script_through_the_launcher(tmp_path):
+    """SS and dimer-dimer correlation functions and the transfer-operator spectrum at the tail of ctmrg_j1j2_c4v.py
+    (models/j1j2.py:826-893 -> corrf_c4v.corrf_1sO1sO / corrf_2sOH2sOH_E1, transferops_c4v.get_Top_spec_c4v) through the
+    launcher with the oracle as engine against the script run untouched."""
+    args = ['--bond_dim', '2', '--chi', '8', '--seed', '123', '--j2', '0.3', '--CTMARGS_ctm_max_iter', '6', '--corrf_r', '4',
+            '--top_n', '3']
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', OMP_NUM_THREADS='2')
+    script = os.path.join(REF, 'examples', 'j1j2', 'ctmrg_j1j2_c4v.py')
+    outs = []
+    for mode in (['--plain'], []):
+        wd = tmp_path / ('a' if mode else 'b')
+        os.makedirs(wd, exist_ok=True)
+        out = subprocess.run([sys.executable, os.path.join(HERE, 'launcher_probe_ad.py')] + mode + [script] + args,
+                             cwd=wd, env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append(_ss_lines(out.stdout))
+    want, got = outs
+    assert len(want) == 4 + 4 + 3 and len(got) == len(want)     # SS rows, DD rows, spectrum rows
+    for a, b in zip(got, want):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert abs(x - y) < 1e-8 * max(1.0, abs(y)), (got, want)
 
 
 def test_correlation_functions_of_the_script_through_the_launcher(tmp_path):
@@ -112,8 +136,8 @@ def test_correlation_functions_of_the_script_through_the_launcher(tmp_path):
         assert out.returncode == 0, out.stderr[-2000:]
         outs.append(_ss_lines(out.stdout))
     want, got = outs
-    assert len(want) == 10 and len(got) == 10      # 5 distances x 2 directions
+    assert len(want) >= 10 and len(got) == len(want)      # 5 distances x 2 directions, then the spectrum(T) rows
     for a, b in zip(got, want):
-        assert len(a) == len(b) == 4
+        assert len(a) == len(b)
         for x, y in zip(a, b):
             assert abs(x - y) < 1e-9 * max(1.0, abs(y)), (got, want)

@@ -112,3 +112,57 @@ def test_edges_operator_insertions_and_corrf_match_reference(ref, name, monkeypa
         ca = oc.corrf_1sO1sO((0, 0), d, st, env, op1, lambda r: ops2[r], 2, rl_0=rl_a)
         cb = rc.corrf_1sO1sO((0, 0), d, rs, re, op1, lambda r: ops2[r], 2, rl_0=rl_b)
         assert H.maxrel(ca, cb) < 1e-11, (d, ca, cb)
+
+
+def c4v_case(name):
+    """(site tensor, chi, C, T) of a C4v golden fixture (tests/golden/c4v_*.npz)."""
+    z, meta = H.load_golden(name)
+    return torch.from_numpy(z['site']), meta['chi'], torch.from_numpy(z['final_C']), torch.from_numpy(z['final_T'])
+
+
+@pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
+def test_c4v_correlation_functions_match_reference(ref, name, monkeypatch):
+    """ctm/one_site_c4v/corrf_c4v.py (get_edge, apply_edge, apply_TM_1sO, apply_TM_2sO, corrf_1sO1sO with and without rl_0,
+    corrf_2sOH2sOH_E1) and transferops_c4v.get_Top_spec_c4v against the unmodified reference."""
+    from ipeps.ipeps_c4v import IPEPS_C4V as RS
+    from ctm.one_site_c4v.env_c4v import ENV_C4V as RE
+    from ctm.one_site_c4v import corrf_c4v as rc, transferops_c4v as rt
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    from peps_torch_b200.ctm.one_site_c4v import corrf_c4v as oc, transferops_c4v as ot
+    eng = H.OracleEngine()
+    monkeypatch.setattr(oc, '_engine', lambda: eng)
+    a, chi, C, T = c4v_case(name)
+    dt = a.dtype
+    ref.global_args.dtype, ref.global_args.torch_dtype, ref.global_args.device = ('complex128' if dt.is_complex else 'float64'), dt, 'cpu'
+    rs, st = RS(a.clone()), IPEPS_C4V(a)
+    re, env = RE(chi, rs), ENV_C4V(chi, st)
+    for e in (re, env):
+        e.C[e.keyC], e.T[e.keyT] = C.clone(), T.clone()
+    p = a.shape[0]
+    g = torch.Generator().manual_seed(9)
+    op1 = torch.randn(p, p, dtype=dt, generator=g)
+    ops1 = [torch.randn(p, p, dtype=dt, generator=g) for _ in range(4)]
+    # two-site operators: real-valued (cast to the state's dtype), as the models' S.S is -- the reference's split of a complex
+    # operator transposes V without conjugating it (corrf_c4v.py:470), which is reproduced but is not a decomposition of op
+    op2 = torch.randn(p, p, p, p, dtype=torch.float64, generator=g).to(dt)
+    ops2 = [torch.randn(p, p, p, p, dtype=torch.float64, generator=g).to(dt) for _ in range(3)]
+    assert H.maxrel(oc.get_edge(st, env), rc.get_edge(rs, re)) < 1e-13
+    V = torch.randn(chi, a.shape[1] ** 2, chi, dtype=dt, generator=g)
+    assert abs(complex(oc.apply_edge(st, env, V)) - complex(rc.apply_edge(rs, re, V))) < 1e-13 * abs(complex(rc.apply_edge(rs, re, V)))
+    for op in (None, op1):
+        assert H.maxrel(oc.apply_TM_1sO(st, env, V, op=op), rc.apply_TM_1sO(rs, re, V, op=op)) < 1e-13
+    for op in (None, op2):
+        assert H.maxrel(oc.apply_TM_2sO(st, env, V, op=op), rc.apply_TM_2sO(rs, re, V, op=op)) < 1e-12
+    ca, cb = oc.corrf_1sO1sO(st, env, op1, lambda r: ops1[r], 3), rc.corrf_1sO1sO(rs, re, op1, lambda r: ops1[r], 3)
+    assert H.maxrel(ca, cb) < 1e-11, (ca, cb)
+    L, R = torch.randn(*V.shape, dtype=dt, generator=g), torch.randn(*V.shape, dtype=dt, generator=g)
+    ca = oc.corrf_1sO1sO(st, env, op1, lambda r: ops1[r], 2, rl_0=(L, R))
+    cb = rc.corrf_1sO1sO(rs, re, op1, lambda r: ops1[r], 2, rl_0=(L, R))
+    assert H.maxrel(ca, cb) < 1e-11, (ca, cb)
+    ca, cb = oc.corrf_2sOH2sOH_E1(st, env, op2, lambda r: ops2[r], 2), rc.corrf_2sOH2sOH_E1(rs, re, op2, lambda r: ops2[r], 2)
+    assert H.maxrel(ca, cb) < 1e-10, (ca, cb)
+    La, Lb = ot.get_Top_spec_c4v(3, st, env), rt.get_Top_spec_c4v(3, rs, re)
+    assert float((La - Lb).abs().max()) < 1e-10, (La, Lb)
+    Ua, Ub = ot.get_Top_spec_c4v(2, st, env, normalize=False), rt.get_Top_spec_c4v(2, rs, re, normalize=False)
+    assert float((Ua - Ub).abs().max()) < 1e-10 * float(Ub.abs().max()), (Ua, Ub)
