@@ -104,6 +104,7 @@ def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None, ket_extra=''):
     terms = lhs.split(',')
     a_pos = [i for i, t in enumerate(terms) if t.startswith('@')][0]
     a_idx = terms[a_pos][1:]
+    assert 's' not in lhs.replace(',', '') + out, "sl_chain: 's' is the physical index"
     nops = len(ops)
     if a.dim() == 4:
         xs = list(ops[:a_pos]) + [a] + list(ops[a_pos:])

@@ -133,7 +133,8 @@ def enable(engine_factory=None):
     if engine_factory is not None:
         ours_cf4._engine = engine_factory
     cf4 = importlib.import_module('ctm.one_site_c4v.corrf_c4v')
-    for name in ('get_edge', 'apply_edge', 'apply_TM_1sO', 'apply_TM_2sO', 'corrf_1sO1sO', 'corrf_2sOH2sOH_E1'):
+    for name in ('get_edge', 'apply_edge', 'get_edge_L', 'apply_edge_L', 'apply_TM_1sO', 'apply_TM_1sO_2', 'apply_TM_2sO',
+                 'corrf_1sO1sO', 'corrf_2sOH2sOH_E1', 'corrf_2sOV2sOV_E2'):
         ref_fn = getattr(cf4, name)
 
         def f(state, env, *args, _ours=getattr(ours_cf4, name), _ref=ref_fn, **kw):
@@ -144,6 +145,7 @@ def enable(engine_factory=None):
         setattr(cf4, name, f)
     top4 = importlib.import_module('ctm.one_site_c4v.transferops_c4v')
     top4.get_Top_spec_c4v = ours_top4.get_Top_spec_c4v
+    top4.get_Top2_spec_c4v = ours_top4.get_Top2_spec_c4v
     # the kagome density matrices behind energy_triangle_dn / _up and eval_obs of models/spin_half_kagome.py (config 4)
     from .ctm.pess_kagome import rdm_kagome as ours_kag
     if engine_factory is not None:

@@ -938,19 +938,26 @@ def test_c4v_correlation_functions(eng, dev, name, monkeypatch):
     op2 = torch.randn(p, p, p, p, dtype=torch.float64, generator=g).to(dt)
     ops2 = [torch.randn(p, p, p, p, dtype=torch.float64, generator=g).to(dt) for _ in range(4)]
     V = torch.randn(chi, a.shape[1] ** 2, chi, dtype=dt, generator=g)
+    W = torch.randn(chi, a.shape[1] ** 2, a.shape[1] ** 2, chi, dtype=dt, generator=g)
     monkeypatch.setattr(oc, '_engine', lambda: oracle)
     want = [oc.get_edge(st_c, env_c), oc.apply_TM_1sO(st_c, env_c, V, op=op1), oc.apply_TM_2sO(st_c, env_c, V, op=op2),
             oc.apply_edge(st_c, env_c, V).reshape(1), oc.corrf_1sO1sO(st_c, env_c, op1, lambda r: ops1[r], 4),
-            oc.corrf_2sOH2sOH_E1(st_c, env_c, op2, lambda r: ops2[r], 3)]
-    Lw = ot.get_Top_spec_c4v(3, st_c, env_c)
+            oc.corrf_2sOH2sOH_E1(st_c, env_c, op2, lambda r: ops2[r], 3),
+            oc.get_edge_L(st_c, env_c, l=2), oc.apply_TM_1sO_2(st_c, env_c, W, op=op2), oc.apply_edge_L(st_c, env_c, W).reshape(1),
+            oc.corrf_2sOV2sOV_E2(st_c, env_c, op2, lambda r: ops2[r], 3)]
+    Lw, L2w = ot.get_Top_spec_c4v(3, st_c, env_c), ot.get_Top2_spec_c4v(2, st_c, env_c)
     monkeypatch.setattr(oc, '_engine', lambda: eng)
     Vg = V.to(dev)
     got = [oc.get_edge(st_g, env_g), oc.apply_TM_1sO(st_g, env_g, Vg, op=op1.to(dev)), oc.apply_TM_2sO(st_g, env_g, Vg, op=op2.to(dev)),
            oc.apply_edge(st_g, env_g, Vg).reshape(1), oc.corrf_1sO1sO(st_g, env_g, op1.to(dev), lambda r: ops1[r].to(dev), 4),
-           oc.corrf_2sOH2sOH_E1(st_g, env_g, op2.to(dev), lambda r: ops2[r].to(dev), 3)]
+           oc.corrf_2sOH2sOH_E1(st_g, env_g, op2.to(dev), lambda r: ops2[r].to(dev), 3),
+           oc.get_edge_L(st_g, env_g, l=2), oc.apply_TM_1sO_2(st_g, env_g, W.to(dev), op=op2.to(dev)),
+           oc.apply_edge_L(st_g, env_g, W.to(dev)).reshape(1),
+           oc.corrf_2sOV2sOV_E2(st_g, env_g, op2.to(dev), lambda r: ops2[r].to(dev), 3)]
     for i, (x, y) in enumerate(zip(got, want)):
         assert x.device.type == 'cuda' and H.maxrel(x.cpu(), y) < 1e-10, (i, x, y)
     assert float((ot.get_Top_spec_c4v(3, st_g, env_g).cpu() - Lw).abs().max()) < 1e-10
+    assert float((ot.get_Top2_spec_c4v(2, st_g, env_g).cpu().abs().sort(0)[0] - L2w.abs().sort(0)[0]).abs().max()) < 1e-9
 
 
 def test_tma_fed_gemm_layouts_and_edges(eng, dev):

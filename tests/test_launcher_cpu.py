@@ -83,7 +83,7 @@ def test_kagome_rvb_known_answer_through_the_launcher(tmp_path):
 def _ss_lines(stdout):
     rows, take = [], False
     for ln in stdout.splitlines():
-        if ln.startswith(('SS[(', 'SS r', 'DD r', 'spectrum(T)')):
+        if ln.startswith(('SS[(', 'SS r', 'DD r', 'DD_v r', 'spectrum(T)', 'spectrum(T2)')):
             take = True
             continue
         if take:
@@ -97,10 +97,11 @@ def _ss_lines(stdout):
 
 def test_c4v_correlation_functions_of_the_script_through_the_launcher(tmp_path):
     """SS and dimer-dimer correlation functions and the transfer-operator spectrum at the tail of ctmrg_j1j2_c4v.py
-    (models/j1j2.py:826-893 -> corrf_c4v.corrf_1sO1sO / corrf_2sOH2sOH_E1, transferops_c4v.get_Top_spec_c4v) through the
+    (models/j1j2.py:826-925 -> corrf_c4v.corrf_1sO1sO / corrf_2sOH2sOH_E1 / corrf_2sOV2sOV_E2, transferops_c4v.get_Top_spec_c4v /
+    get_Top2_spec_c4v) through the
     launcher with the oracle as engine against the script run untouched."""
     args = ['--bond_dim', '2', '--chi', '8', '--seed', '123', '--j2', '0.3', '--CTMARGS_ctm_max_iter', '6', '--corrf_r', '4',
-            '--top_n', '3']
+            '--top_n', '3', '--corrf_dd_v', '--top2']
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', OMP_NUM_THREADS='2')
     script = os.path.join(REF, 'examples', 'j1j2', 'ctmrg_j1j2_c4v.py')
     outs = []
@@ -112,7 +113,7 @@ def test_c4v_correlation_functions_of_the_script_through_the_launcher(tmp_path):
         assert out.returncode == 0, out.stderr[-2000:]
         outs.append(_ss_lines(out.stdout))
     want, got = outs
-    assert len(want) == 4 + 4 + 3 and len(got) == len(want)     # SS rows, DD rows, spectrum rows
+    assert len(want) == 4 + 4 + 4 + 3 + 3 and len(got) == len(want)     # SS, DD, DD_v rows, spectrum(T), spectrum(T2) rows
     for a, b in zip(got, want):
         assert len(a) == len(b)
         for x, y in zip(a, b):

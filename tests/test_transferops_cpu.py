@@ -166,3 +166,16 @@ def test_c4v_correlation_functions_match_reference(ref, name, monkeypatch):
     assert float((La - Lb).abs().max()) < 1e-10, (La, Lb)
     Ua, Ub = ot.get_Top_spec_c4v(2, st, env, normalize=False), rt.get_Top_spec_c4v(2, rs, re, normalize=False)
     assert float((Ua - Ub).abs().max()) < 1e-10 * float(Ub.abs().max()), (Ua, Ub)
+    # width-2 edges and transfer matrix (vertical dimers, get_Top2_spec_c4v)
+    for l in (1, 2, 3):
+        assert H.maxrel(oc.get_edge_L(st, env, l=l), rc.get_edge_L(rs, re, l=l)) < 1e-13
+    d2 = a.shape[1] ** 2
+    W = torch.randn(chi, d2, d2, chi, dtype=dt, generator=g)
+    sa, sb = oc.apply_edge_L(st, env, W), rc.apply_edge_L(rs, re, W)
+    assert abs(complex(sa) - complex(sb)) < 1e-13 * abs(complex(sb))
+    for op in (None, op2):
+        assert H.maxrel(oc.apply_TM_1sO_2(st, env, W, op=op), rc.apply_TM_1sO_2(rs, re, W, op=op)) < 1e-12
+    ca, cb = oc.corrf_2sOV2sOV_E2(st, env, op2, lambda r: ops2[r], 2), rc.corrf_2sOV2sOV_E2(rs, re, op2, lambda r: ops2[r], 2)
+    assert H.maxrel(ca, cb) < 1e-10, (ca, cb)
+    La, Lb = ot.get_Top2_spec_c4v(2, st, env), rt.get_Top2_spec_c4v(2, rs, re)
+    assert float((La.abs().sort(0)[0] - Lb.abs().sort(0)[0]).abs().max()) < 1e-9, (La, Lb)
