@@ -108,25 +108,19 @@ def enable(engine_factory=None):
     top.get_Top_spec = ours_top.get_Top_spec
     top.get_Top_w0_spec = ours_top.get_Top_w0_spec
     # the two-point functions behind eval_corrf_* of the models (ctm/generic/corrf.py:10-104,234-277,364-650,980-1067);
-    # MPO-carrying edges / operators and anything under autograd stay the reference's torch code
+    # double-layer (rank-4) sites and anything under autograd stay the reference's torch code
     from .ctm.generic import corrf as ours_cf
     cf = importlib.import_module('ctm.generic.corrf')
-    ref_tm1, ref_apply_edge = cf.apply_TM_1sO, cf.apply_edge
-
-    def apply_TM_1sO(coord, direction, state, env, edge, op=None, verbosity=0):
-        plain = edge.dim() == 3 and (op is None or op.dim() == 2) and all(t.dim() == 5 for t in state.sites.values())
-        if not plain or needs_grad(list(_tensors((state, env))) + [edge]):
-            return ref_tm1(coord, direction, state, env, edge, op=op, verbosity=verbosity)
-        return ours_cf.apply_TM_1sO(coord, direction, state, env, edge, op=op, verbosity=verbosity)
-
-    def apply_edge(coord, direction, state, env, vec, verbosity=0):
-        if vec.dim() != 3 or needs_grad(list(_tensors((state, env))) + [vec]):
-            return ref_apply_edge(coord, direction, state, env, vec, verbosity=verbosity)
-        return ours_cf.apply_edge(coord, direction, state, env, vec, verbosity=verbosity)
-
-    cf.apply_TM_1sO, cf.apply_edge = apply_TM_1sO, apply_edge
-    cf.get_edge = _dispatch(ours_cf.get_edge, cf.get_edge)
-    cf.corrf_1sO1sO = _dispatch(ours_cf.corrf_1sO1sO, cf.corrf_1sO1sO)
+    for name in ('get_edge', 'get_edge_2', 'apply_edge', 'apply_TM_1sO', 'apply_TM_2sO_1sChannel', 'apply_TM_2sO_2sChannel',
+                 'corrf_1sO1sO', 'corrf_2sOH2sOH_E1', 'corrf_2sOV2sOV_E2'):
+        def f(coord, direction, state, env, *args, _ours=getattr(ours_cf, name), _ref=getattr(cf, name), **kw):
+            extra = [x for x in list(args) + list(kw.values()) if isinstance(x, torch.Tensor)]
+            single_layer = all(t.dim() == 5 for t in state.sites.values())
+            if not single_layer or needs_grad(list(_tensors((state, env))) + extra):
+                return _ref(coord, direction, state, env, *args, **kw)
+            return _ours(coord, direction, state, env, *args, **kw)
+        f.__name__ = name
+        setattr(cf, name, f)
     # the same for the C4v ansatz (ctm/one_site_c4v/corrf_c4v.py, transferops_c4v.py:10-68): eval_corrf_SS / eval_corrf_DD_H
     # and the transfer-operator spectrum at the tail of ctmrg_j1j2_c4v.py
     from .ctm.one_site_c4v import corrf_c4v as ours_cf4, transferops_c4v as ours_top4

@@ -898,6 +898,8 @@ def test_edges_operator_insertions_and_corrf(eng, dev, name, monkeypatch):
     g = torch.Generator().manual_seed(5)
     op1 = torch.randn(p, p, dtype=dt, generator=g)
     ops2 = [torch.randn(p, p, dtype=dt, generator=g) for _ in range(5)]
+    t2 = torch.randn(p, p, p, p, dtype=dt, generator=g)
+    t2s = [torch.randn(p, p, p, p, dtype=dt, generator=g) for _ in range(3)]
     for d in DIRS:
         chi1, d2, chi2 = edge_shapes(st_c, env_c, d)
         V = torch.randn(chi1, d2, chi2, dtype=dt, generator=g)
@@ -913,6 +915,25 @@ def test_edges_operator_insertions_and_corrf(eng, dev, name, monkeypatch):
         assert abs(complex(oc.apply_edge((0, 0), d, st_g, env_g, Ve.to(dev)).cpu()) - complex(w_s)) < 1e-13 * abs(complex(w_s)) + 1e-15 * float(Ve.abs().max() * w_edge.abs().max()) * Ve.numel()
         got = oc.corrf_1sO1sO((0, 0), d, st_g, env_g, op1.to(dev), lambda r: ops2[r].to(dev), 4)
         assert got.device.type == 'cuda' and H.maxrel(got.cpu(), w_c) < 1e-11, (d, got, w_c)
+        # two-site operators along (MPO bond on the edge) and across (width-2 transfer matrix; down / right) the direction
+        rev = (-d[0], -d[1])
+        monkeypatch.setattr(oc, '_engine', lambda: oracle)
+        W = torch.randn(*oc.get_edge_2((0, 0), rev, st_c, env_c).shape, dtype=dt, generator=g)
+        want = [oc.apply_TM_2sO_1sChannel((0, 0), d, st_c, env_c, V, op=t2), oc.corrf_2sOH2sOH_E1((0, 0), d, st_c, env_c, t2, lambda r: t2s[r], 2),
+                oc.get_edge_2((0, 0), d, st_c, env_c), oc.apply_edge((1, 0), d, st_c, env_c, W).reshape(1)]
+        if d in ((0, 1), (1, 0)):
+            want += [oc.apply_TM_2sO_2sChannel((0, 0), d, st_c, env_c, W, op=t2),
+                     oc.corrf_2sOV2sOV_E2((0, 0), d, st_c, env_c, t2, lambda r: t2s[r], 2)]
+        monkeypatch.setattr(oc, '_engine', lambda: eng)
+        t2g, Wg = t2.to(dev), W.to(dev)
+        have = [oc.apply_TM_2sO_1sChannel((0, 0), d, st_g, env_g, V.to(dev), op=t2g),
+                oc.corrf_2sOH2sOH_E1((0, 0), d, st_g, env_g, t2g, lambda r: t2s[r].to(dev), 2),
+                oc.get_edge_2((0, 0), d, st_g, env_g), oc.apply_edge((1, 0), d, st_g, env_g, Wg).reshape(1)]
+        if d in ((0, 1), (1, 0)):
+            have += [oc.apply_TM_2sO_2sChannel((0, 0), d, st_g, env_g, Wg, op=t2g),
+                     oc.corrf_2sOV2sOV_E2((0, 0), d, st_g, env_g, t2g, lambda r: t2s[r].to(dev), 2)]
+        for i, (x, y) in enumerate(zip(have, want)):
+            assert x.device.type == 'cuda' and H.maxrel(x.cpu(), y) < 1e-10, (d, i, x, y)
 
 
 @pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])

@@ -104,6 +104,44 @@ def test_edges_operator_insertions_and_corrf_match_reference(ref, name, monkeypa
         ca = oc.corrf_1sO1sO((0, 0), d, st, env, op1, lambda r: ops2[r], 3)
         cb = rc.corrf_1sO1sO((0, 0), d, rs, re, op1, lambda r: ops2[r], 3)
         assert ca.shape == cb.shape and H.maxrel(ca, cb) < 1e-11, (d, ca, cb)
+        # MPO pieces: rank-3 operator opens an MPO index, rank-4 passes it on, rank-3 closes it (corrf.py:423-450)
+        o3, o4 = torch.randn(p, p, 3, dtype=dt, generator=g), torch.randn(p, p, 3, 2, dtype=dt, generator=g)
+        o3b = torch.randn(p, p, 2, dtype=dt, generator=g)
+        Ea, Eb = oc.apply_TM_1sO((0, 0), d, st, env, V, op=o3), rc.apply_TM_1sO((0, 0), d, rs, re, V, op=o3)
+        assert Ea.shape == Eb.shape and H.maxrel(Ea, Eb) < 1e-13
+        c1 = (d[0], d[1])
+        Ea, Eb = oc.apply_TM_1sO(c1, d, st, env, Ea, op=o4), rc.apply_TM_1sO(c1, d, rs, re, Eb, op=o4)
+        assert Ea.shape == Eb.shape and Ea.shape[-1] == 2 and H.maxrel(Ea, Eb) < 1e-12
+        c2 = (2 * d[0], 2 * d[1])
+        Ea, Eb = oc.apply_TM_1sO(c2, d, st, env, Ea, op=o3b), rc.apply_TM_1sO(c2, d, rs, re, Eb, op=o3b)
+        assert Ea.dim() == 3 and Ea.shape == Eb.shape and H.maxrel(Ea, Eb) < 1e-12
+        with pytest.raises(ValueError):
+            oc.apply_TM_1sO((0, 0), d, st, env, V, op=o4)           # a rank-4 piece needs an incoming MPO index
+        # two-site operators along the direction of growth
+        t2 = torch.randn(p, p, p, p, dtype=dt, generator=g)
+        t2s = [torch.randn(p, p, p, p, dtype=dt, generator=g) for _ in range(3)]
+        for op in (None, t2):
+            assert H.maxrel(oc.apply_TM_2sO_1sChannel((0, 0), d, st, env, V, op=op),
+                            rc.apply_TM_2sO_1sChannel((0, 0), d, rs, re, V, op=op)) < 1e-12
+        ca = oc.corrf_2sOH2sOH_E1((0, 0), d, st, env, t2, lambda r: t2s[r], 2)
+        cb = rc.corrf_2sOH2sOH_E1((0, 0), d, rs, re, t2, lambda r: t2s[r], 2)
+        assert H.maxrel(ca, cb) < 1e-10, (d, ca, cb)
+        # width-2 edges, and (down / right only, as in the reference) the width-2 transfer matrix and its correlator
+        assert H.maxrel(oc.get_edge_2((0, 0), d, st, env), rc.get_edge_2((0, 0), d, rs, re)) < 1e-13
+        W = torch.randn(*rc.get_edge_2((0, 0), rev, rs, re).shape, dtype=dt, generator=g)
+        We = torch.randn(*rc.get_edge_2((1, 1), d, rs, re).shape, dtype=dt, generator=g)
+        sa, sb = oc.apply_edge((1, 1), d, st, env, We), rc.apply_edge((1, 1), d, rs, re, We)
+        assert abs(complex(sa) - complex(sb)) < 1e-13 * abs(complex(sb))
+        if d in ((0, 1), (1, 0)):
+            for op in (None, t2):
+                assert H.maxrel(oc.apply_TM_2sO_2sChannel((0, 0), d, st, env, W, op=op),
+                                rc.apply_TM_2sO_2sChannel((0, 0), d, rs, re, W, op=op)) < 1e-12
+            ca = oc.corrf_2sOV2sOV_E2((0, 0), d, st, env, t2, lambda r: t2s[r], 2)
+            cb = rc.corrf_2sOV2sOV_E2((0, 0), d, rs, re, t2, lambda r: t2s[r], 2)
+            assert H.maxrel(ca, cb) < 1e-10, (d, ca, cb)
+        else:
+            with pytest.raises(ValueError):
+                oc.apply_TM_2sO_2sChannel((0, 0), d, st, env, W)
         # eigenvector edges in place of the environment's (the rl_0 argument)
         L = {c: torch.randn(*rc.get_edge(c, rev, rs, re).shape, dtype=dt, generator=g) for c in sites}
         R = {c: torch.randn(*rc.get_edge(c, d, rs, re).shape, dtype=dt, generator=g) for c in sites}
