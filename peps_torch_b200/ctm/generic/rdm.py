@@ -27,16 +27,19 @@ def rdm2x2_legacy(coord, state, env, sym_pos_def=False, verbosity=0):
     return _engine().rdm2x2(coord, state, env, sym_pos_def=sym_pos_def)
 
 
-def _no_operator(operator):
-    if operator is not None:
-        raise NotImplementedError("libctmb returns the density matrix; contract it with the operator on the caller's side")
+def _rdm1x1(coord, state, env, operator, sym_pos_def):
+    """With ``operator`` the reference returns the scalar sum_{s s'} rho[s;s'] operator[s';s] of the UNNORMALISED network
+    (rdm.py:89-90,175-181,275-299): the raw 1-site network comes from libctmb, the p x p trace against the operator is taken here."""
+    if operator is None:
+        return _engine().rdm_small('1x1', coord, state, env, sym_pos_def=sym_pos_def)
+    raw = _engine().rdm_small('1x1', coord, state, env, raw=True)
+    return (raw * operator.to(dtype=raw.dtype, device=raw.device).t()).sum()
 
 
 def rdm1x1(coord, state, env, mode='sl', operator=None, sym_pos_def=False, force_cpu=False, verbosity=0):
     r""":return: 1-site reduced density matrix with indices :math:`s;s'` (ctm/generic/rdm.py:71-112); ``mode`` selects
     between equivalent contraction orders in the reference and is ignored"""
-    _no_operator(operator)
-    return _engine().rdm_small('1x1', coord, state, env, sym_pos_def=sym_pos_def)
+    return _rdm1x1(coord, state, env, operator, sym_pos_def)
 
 
 def rdm2x1(coord, state, env, mode='sl', sym_pos_def=False, force_cpu=False, unroll=False, checkpoint_unrolled=False,
@@ -52,8 +55,7 @@ def rdm1x2(coord, state, env, mode='sl', sym_pos_def=False, force_cpu=False, unr
 
 
 def rdm1x1_dl(coord, state, env, operator=None, sym_pos_def=False, force_cpu=False, verbosity=0):
-    _no_operator(operator)
-    return _engine().rdm_small('1x1', coord, state, env, sym_pos_def=sym_pos_def)
+    return _rdm1x1(coord, state, env, operator, sym_pos_def)
 
 
 def rdm2x1_dl(coord, state, env, sym_pos_def=False, force_cpu=False, verbosity=0):

@@ -250,6 +250,17 @@ def test_oracle_small_rdms_match_reference_elementwise(ref):
                     r_orc = f_orc(coord, sites, v2s, C, T, sym_pos_def=spd)
                     assert r_ref.shape == r_orc.shape
                     assert float((r_ref - r_orc).abs().max()) < 1e-13, (name, coord, spd, f_orc.__name__)
+            # operator= : the unnormalised expectation value (rdm.py:89-90,175-181) through the host wrapper over the raw network
+            from peps_torch_b200.ctm.generic import rdm as ours
+            p = sites[coord].shape[0]
+            op = torch.randn(p, p, dtype=sites[coord].dtype, generator=torch.Generator().manual_seed(3))
+            saved, ours._engine = ours._engine, (lambda: H.OracleEngine())
+            try:
+                got = ours.rdm1x1(coord, H.State(sites, v2s, lX, lY), H.Env(meta['chi'], dict(C), dict(T)), operator=op)
+            finally:
+                ours._engine = saved
+            want = rdm.rdm1x1_dl(coord, st, env, operator=op)
+            assert abs(complex(got) - complex(want)) < 1e-13 * abs(complex(want)), (name, coord, got, want)
 
 
 @pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
