@@ -720,6 +720,12 @@ def test_small_rdms_against_oracle(eng, dev, name):
                 # exit since round 2: no fixture-specific bound)
                 tol = 1e-10 if spd else 1e-12
                 assert r.shape == r_ref.shape and float((r.cpu() - r_ref).abs().max()) < tol, (f.__name__, coord, spd)
+        # operator= : the unnormalised expectation value over the raw one-site network (rdm.py:89-90,175-181)
+        p = sites[coord].shape[0]
+        op = torch.randn(p, p, dtype=sites[coord].dtype, generator=torch.Generator().manual_seed(3))
+        want = (orc.rdm1x1(coord, sites, v2s, C, T, raw=True) * op.t()).sum()
+        got = rdm.rdm1x1(coord, st, env, operator=op.to(dev))
+        assert abs(complex(got.cpu()) - complex(want)) < 1e-12 * abs(complex(want)), (coord, got, want)
 
 
 @pytest.mark.parametrize('name', C4V)
