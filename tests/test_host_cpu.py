@@ -246,8 +246,10 @@ def test_host_rdm_modules_map_sites_and_env_correctly(monkeypatch):
     assert H.maxrel(rdm_c4v.rdm2x1_sl(stc, envc, sym_pos_def=True), orc.rdm_small_c4v('2x1', a, Cc, Tc, True)) < 1e-13
     for f, g in ((rdm.rdm1x1, orc.rdm1x1), (rdm.rdm2x1, orc.rdm2x1), (rdm.rdm1x2, orc.rdm1x2)):
         assert torch.equal(f((0, 1), st, env), g((0, 1), sites, orc.v2s_4site, C, T))
-    with pytest.raises(NotImplementedError):
-        rdm.rdm1x1((0, 0), st, env, operator=torch.eye(2))
+    # operator=: the unnormalised expectation value; with the identity, the trace of the raw network (rdm.py:89-90)
+    raw = orc.rdm1x1((0, 0), sites, orc.v2s_4site, C, T, raw=True)
+    val = rdm.rdm1x1((0, 0), st, env, operator=torch.eye(2, dtype=raw.dtype))
+    assert val.dim() == 0 and abs(float(val) - float(raw.diagonal().sum())) < 1e-13 * abs(float(val))
 
 
 def test_anisotropic_and_ragged_unit_cells_plan_or_fail_loudly():
