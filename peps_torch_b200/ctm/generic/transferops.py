@@ -90,3 +90,63 @@ def get_Top_spec(n, coord, direction, state, env, eigenvectors=False, verbosity=
         return V.reshape(chi1 * d2 * chi2).cpu().numpy()
     with torch.no_grad():
         return _leading(n, chi1 * d2 * chi2, _mv, dtype.is_complex, device, eigenvectors)
+
+
+def _ring_mv(Ts, V):
+    """The ring MPO of the tensors ``Ts[i][chi_i, chi_{i+1}, o_i, v_i]`` (chi_L = chi_0: periodic) applied to ``V[v_0 .. v_{L-1}]``
+    -- the mat-vec of transferops.py:304-318 as L pairwise contractions through libctmb."""
+    from ... import ad
+    eng = corrf._engine()
+    L = len(Ts)
+    v = [chr(ord('a') + i) for i in range(L)]
+    o = [chr(ord('A') + i) for i in range(L)]
+    run = 'y'
+    idx = ''.join(v[1:]) + 'x' + run + o[0]
+    cur = ad.contract(eng, f'x{run}{o[0]}{v[0]},{"".join(v)}->{idx}', Ts[0], V)
+    for i in range(1, L - 1):
+        nxt = 'z' if run == 'y' else 'y'
+        new = ''.join(ch for ch in idx if ch not in (run, v[i])) + nxt + o[i]
+        cur = ad.contract(eng, f'{run}{nxt}{o[i]}{v[i]},{idx}->{new}', Ts[i], cur)
+        idx, run = new, nxt
+    return ad.contract(eng, f'{run}x{o[L - 1]}{v[L - 1]},{idx}->{"".join(o)}', Ts[L - 1], cur)
+
+
+def _ttensor(state, env, c, d):
+    """T of site ``c`` on side ``d`` as [chi, chi, D, D] (ket, bra), the two chi legs in the order transferops.py:285-298 fixes."""
+    leg = {(0, -1): 1, (-1, 0): 2, (0, 1): 3, (1, 0): 4}[d]
+    perm = {(0, -1): (0, 2, 1), (-1, 0): (0, 1, 2), (0, 1): (1, 2, 0), (1, 0): (0, 2, 1)}[d]
+    D = state.site(c).size(leg)
+    return env.T[(c, d)].permute(*perm).contiguous().view(env.chi, env.chi, D, D)
+
+
+def get_EH_spec_Ttensor(n, L, coord, direction, state, env, verbosity=0):
+    r"""Leading ``n`` eigenvalues of the approximate :math:`\exp(-H_{ent})` of an L-leg cylinder: the product of the two ring MPOs
+    built from the T tensors on side ``direction`` and on the opposite side (transferops.py:207-370; one-site unit cells)."""
+    import warnings
+    assert L > 1, "L must be larger than 1"
+    assert state.lX == state.lY == 1, "only single-site unit cell is supported"
+    dir_to_ind = {(0, -1): 1, (-1, 0): 2, (0, 1): 3, (1, 0): 4}
+    d_grow = {(0, -1): (1, 0), (-1, 0): (0, -1), (0, 1): (-1, 0), (1, 0): (0, 1)}[direction]
+    d_opp = (-direction[0], -direction[1])
+    cs = [state.vertexToSite((coord[0] + i * d_grow[0], coord[1] + i * d_grow[1])) for i in range(L)]
+    ads = [state.site(c).size(dir_to_ind[direction]) for c in cs]
+    dim = int(np.prod(ads))
+    if dim <= n:
+        warnings.warn("Total dimension of H_ent operator is <= n.", RuntimeWarning)
+        return None
+    device, dtype = _dev_dtype(state, env)
+    rings = [[_ttensor(state, env, c, d) for c in cs] for d in (direction, d_opp)]
+
+    def _mv(v0):
+        V = torch.as_tensor(v0).to(dtype=dtype, device=device).view(ads)
+        for Ts in rings:
+            V = _ring_mv(Ts, V.contiguous())
+        return V.reshape(dim).cpu().numpy()
+    with torch.no_grad():
+        op = LinearOperator((dim, dim), matvec=_mv, dtype="complex128" if dtype.is_complex else "float64")
+        vals = np.copy(eigs(op, k=n, v0=None, return_eigenvectors=False)[::-1])
+    vals = (1.0 / np.abs(vals[0])) * vals
+    S = torch.zeros((n, 2), dtype=torch.float64, device=next(iter(state.sites.values())).device)
+    S[:, 0] = torch.as_tensor(np.real(vals))
+    S[:, 1] = torch.as_tensor(np.imag(vals))
+    return S

@@ -43,3 +43,27 @@ def get_Top2_spec_c4v(n, state, env_c4v, verbosity=0):
     L[:, 0] = torch.as_tensor(np.real(vals))
     L[:, 1] = torch.as_tensor(np.imag(vals))
     return L
+
+
+def get_EH_spec_Ttensor(n, L, state, env_c4v, verbosity=0):
+    r"""Leading ``n`` eigenvalues of the approximate :math:`\exp(-H_{ent})` of an L-leg cylinder, the ring MPO of L copies of
+    the C4v T tensor (transferops_c4v.py:119-181)."""
+    from ..generic.transferops import _ring_mv
+    assert L > 1, "L must be larger than 1"
+    a = next(iter(state.sites.values()))
+    T0 = env_c4v.T[env_c4v.keyT]
+    chi, D = T0.size(0), a.size(4)
+    T = T0.contiguous().view(chi, chi, D, D)
+    dim = D ** L
+
+    def _mv(v0):
+        V = torch.as_tensor(v0).to(dtype=T.dtype, device=T.device).view([D] * L)
+        return _ring_mv([T] * L, V.contiguous()).reshape(dim).cpu().numpy()
+    with torch.no_grad():
+        op = LinearOperator((dim, dim), matvec=_mv, dtype="complex128" if T.dtype.is_complex else "float64")
+        vals = np.copy(eigs(op, k=n, v0=None, return_eigenvectors=False)[::-1])
+    vals = (1.0 / np.abs(vals[0])) * vals
+    S = torch.zeros((n, 2), dtype=torch.float64, device=a.device)
+    S[:, 0] = torch.as_tensor(np.real(vals))
+    S[:, 1] = torch.as_tensor(np.imag(vals))
+    return S

@@ -107,6 +107,7 @@ def enable(engine_factory=None):
         ours_corrf._engine = engine_factory
     top.get_Top_spec = ours_top.get_Top_spec
     top.get_Top_w0_spec = ours_top.get_Top_w0_spec
+    top.get_EH_spec_Ttensor = ours_top.get_EH_spec_Ttensor
     # the two-point functions behind eval_corrf_* of the models (ctm/generic/corrf.py:10-104,234-277,364-650,980-1067);
     # double-layer (rank-4) sites and anything under autograd stay the reference's torch code
     from .ctm.generic import corrf as ours_cf
@@ -140,6 +141,7 @@ def enable(engine_factory=None):
     top4 = importlib.import_module('ctm.one_site_c4v.transferops_c4v')
     top4.get_Top_spec_c4v = ours_top4.get_Top_spec_c4v
     top4.get_Top2_spec_c4v = ours_top4.get_Top2_spec_c4v
+    top4.get_EH_spec_Ttensor = ours_top4.get_EH_spec_Ttensor
     # the kagome density matrices behind energy_triangle_dn / _up and eval_obs of models/spin_half_kagome.py (config 4)
     from .ctm.pess_kagome import rdm_kagome as ours_kag
     if engine_factory is not None:

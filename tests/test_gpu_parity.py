@@ -883,6 +883,12 @@ def test_transfer_operator_matvecs_and_spectra(eng, dev, name, monkeypatch):
         assert H.maxrel(oc.apply_TM_0sO((0, 0), d, st_g, env_g, V0.to(dev)).cpu(), want0) < 1e-13
         assert float((ot.get_Top_spec(3, (0, 0), d, st_g, env_g).cpu() - Lw).abs().max()) < 1e-10
         assert float((ot.get_Top_w0_spec(3, (0, 0), d, st_g, env_g).cpu().abs() - Ww.abs()).abs().max()) < 1e-10
+        if lX == lY == 1:           # entanglement spectrum of the L-leg cylinder (transferops.py:207-370; one-site cells)
+            from test_transferops_cpu import _spec
+            monkeypatch.setattr(oc, '_engine', lambda: oracle)
+            Sw = ot.get_EH_spec_Ttensor(2, 3, (0, 0), d, st_c, env_c)
+            monkeypatch.setattr(oc, '_engine', lambda: eng)
+            assert float((_spec(ot.get_EH_spec_Ttensor(2, 3, (0, 0), d, st_g, env_g).cpu()) - _spec(Sw)).abs().max()) < 1e-9
 
 
 @pytest.mark.parametrize('name', ['generic_4site_D2_chi8_B', 'generic_4site_D2_chi8_B_c128', 'kagome_1site_D2_chi8_A'])
@@ -985,6 +991,14 @@ def test_c4v_correlation_functions(eng, dev, name, monkeypatch):
         assert x.device.type == 'cuda' and H.maxrel(x.cpu(), y) < 1e-10, (i, x, y)
     assert float((ot.get_Top_spec_c4v(3, st_g, env_g).cpu() - Lw).abs().max()) < 1e-10
     assert float((ot.get_Top2_spec_c4v(2, st_g, env_g).cpu().abs().sort(0)[0] - L2w.abs().sort(0)[0]).abs().max()) < 1e-9
+    # entanglement spectrum of the L-leg cylinder (ring MPO of T tensors, transferops_c4v.py:119-181)
+    from test_transferops_cpu import _spec
+    monkeypatch.setattr(oc, '_engine', lambda: oracle)
+    from peps_torch_b200.ctm.generic import corrf as gc
+    monkeypatch.setattr(gc, '_engine', lambda: oracle)
+    Sw = ot.get_EH_spec_Ttensor(2, 4, st_c, env_c)
+    monkeypatch.setattr(gc, '_engine', lambda: eng)
+    assert float((_spec(ot.get_EH_spec_Ttensor(2, 4, st_g, env_g).cpu()) - _spec(Sw)).abs().max()) < 1e-9
 
 
 def test_tma_fed_gemm_layouts_and_edges(eng, dev):

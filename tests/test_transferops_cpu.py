@@ -217,3 +217,53 @@ def test_c4v_correlation_functions_match_reference(ref, name, monkeypatch):
     assert H.maxrel(ca, cb) < 1e-10, (ca, cb)
     La, Lb = ot.get_Top2_spec_c4v(2, st, env), rt.get_Top2_spec_c4v(2, rs, re)
     assert float((La.abs().sort(0)[0] - Lb.abs().sort(0)[0]).abs().max()) < 1e-9, (La, Lb)
+
+
+def _spec(S):
+    """Magnitudes of an (n x 2) [re, im] list of eigenvalues, relative to the largest, ascending: the functions divide by the
+    FIRST value in ARPACK's (reversed) order, which is not always the largest, and ARPACK's order depends on rounding."""
+    m = (S[:, 0] ** 2 + S[:, 1] ** 2).sqrt()
+    return (m / m.max()).sort()[0]
+
+
+def test_entanglement_spectra_match_reference(ref, monkeypatch):
+    """get_EH_spec_Ttensor of ctm/generic/transferops.py:207-370 (one-site cell: the kagome fixture, four directions) and of
+    ctm/one_site_c4v/transferops_c4v.py:119-181: ring MPO of T tensors under ARPACK."""
+    from ipeps.ipeps import IPEPS as RI
+    from ctm.generic.env import ENV as RE
+    from ctm.generic import transferops as rt
+    from ipeps.ipeps_c4v import IPEPS_C4V as RS4
+    from ctm.one_site_c4v.env_c4v import ENV_C4V as RE4
+    from ctm.one_site_c4v import transferops_c4v as rt4
+    from peps_torch_b200.ipeps import IPEPS_C4V
+    from peps_torch_b200.env import ENV_C4V
+    from peps_torch_b200.ctm.generic import transferops as ot, corrf as oc
+    from peps_torch_b200.ctm.one_site_c4v import transferops_c4v as ot4
+    eng = H.OracleEngine()
+    monkeypatch.setattr(oc, '_engine', lambda: eng)
+    z, meta = H.load_golden('kagome_1site_D2_chi8_A')
+    sites = H.golden_sites(z)
+    v2s, lX, lY = H.v2s_for(sites)
+    C, T = H.golden_env(z, 'final_' if any(k.startswith('final_') for k in z.files) else 'mid_')
+    dt = next(iter(sites.values())).dtype
+    ref.global_args.dtype, ref.global_args.torch_dtype, ref.global_args.device = ('complex128' if dt.is_complex else 'float64'), dt, 'cpu'
+    rs = RI(sites={c: t.clone() for c, t in sites.items()}, vertexToSite=v2s, lX=lX, lY=lY)
+    re = RE(meta['chi'], rs)
+    re.C, re.T = dict(C), dict(T)
+    st, env = H.State(sites, v2s, lX, lY), H.Env(meta['chi'], dict(C), dict(T))
+    for d in DIRS:
+        for L in (3, 4):
+            Sa, Sb = ot.get_EH_spec_Ttensor(2, L, (0, 0), d, st, env), rt.get_EH_spec_Ttensor(2, L, (0, 0), d, rs, re)
+            assert float((_spec(Sa) - _spec(Sb)).abs().max()) < 1e-9, (d, L, Sa, Sb)
+    with pytest.warns(RuntimeWarning):
+        assert ot.get_EH_spec_Ttensor(4, 2, (0, 0), (0, -1), st, env) is None         # D^L <= n
+    for name in ('c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'):
+        a, chi, C4, T4 = c4v_case(name)
+        ref.global_args.dtype, ref.global_args.torch_dtype = ('complex128' if a.is_complex() else 'float64'), a.dtype
+        rs4, st4 = RS4(a.clone()), IPEPS_C4V(a)
+        re4, env4 = RE4(chi, rs4), ENV_C4V(chi, st4)
+        for e in (re4, env4):
+            e.C[e.keyC], e.T[e.keyT] = C4.clone(), T4.clone()
+        for L in (3, 5):
+            Sa, Sb = ot4.get_EH_spec_Ttensor(2, L, st4, env4), rt4.get_EH_spec_Ttensor(2, L, rs4, re4)
+            assert float((_spec(Sa) - _spec(Sb)).abs().max()) < 1e-9, (name, L, Sa, Sb)
