@@ -19,7 +19,7 @@ DRY = ['test_pieces_against_reference_fixtures', 'test_run_energy_and_spectra_ag
        'test_c4v_rdms_and_energy_against_reference_fixture', 'test_small_rdms_against_oracle',
        'test_c4v_small_rdms_against_oracle', 'test_variants_against_reference_fixtures_generic',
        'test_variants_against_reference_fixtures_c4v', 'test_config1_script_known_answer_on_gpu',
-       'test_config2_script_known_answer_on_gpu',
+       'test_config2_script_known_answer_on_gpu', 'test_rectangular_cell_with_direction_dependent_bonds',
        # tests/test_gpu_parity_sizes.py
        'test_config3_size_c4v_complex_against_live_oracle', 'test_config4_size_kagome_against_live_oracle',
        'test_shard_entry_points_on_one_gpu', 'test_halves_against_reference_fixtures', 'test_clustered_spectrum_orthogonality']

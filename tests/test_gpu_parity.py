@@ -235,6 +235,40 @@ def test_config2_size_against_live_oracle(eng, dev, family):
     assert abs(e_gpu - e_cpu) <= 1e-10 * abs(e_cpu)
 
 
+@pytest.mark.parametrize('dt', [torch.float64, torch.complex128])
+def test_rectangular_cell_with_direction_dependent_bonds(eng, dev, dt):
+    """A 3 x 2 unit cell of six different sites whose vertical bonds (D = 2) differ from the horizontal ones (D = 3): the
+    number of moves per direction follows lX / lY (ctmrg.py:88-96), the enlarged corners are rectangular in the bond
+    dimensions, and up/down projectors have a different shape from left/right ones.  Two iterations against the live oracle."""
+    from peps_torch_b200.ipeps import IPEPS
+    from peps_torch_b200.env import ENV, init_env
+    from peps_torch_b200.ctm.generic import ctmrg
+    lX, lY, chi, Dv, Dh = 3, 2, 12, 2, 3
+    g = torch.Generator().manual_seed(77)
+    sites = OrderedDict()
+    for y in range(lY):
+        for x in range(lX):
+            a = torch.randn(2, Dv, Dh, Dv, Dh, dtype=dt, generator=g)
+            sites[(x, y)] = a / a.abs().max()
+
+    def v2s(c):
+        return (c[0] % lX, c[1] % lY)
+    C, T = orc.init_env(sites, v2s, chi)
+    orc.run(sites, v2s, lX, lY, C, T, chi, 2)
+    st = IPEPS(H.to_dev(sites, dev), v2s, lX, lY)
+    env = ENV(chi, st)
+    init_env(st, env)
+    for _ in range(2):
+        for d in orc.DIRECTIONS:
+            for _r in range(lX if d in (orc.LEFT, orc.RIGHT) else lY):
+                ctmrg.ctm_MOVE(d, st, env)
+    assert set(env.C) == set(C) and set(env.T) == set(T)
+    for k in T:
+        assert tuple(env.T[k].shape) == tuple(T[k].shape), k
+    assert H.spectra_diff(env.C, C) < 1e-9
+    assert H.env_abs_diff(env.C, env.T, C, T) < 1.2e-8
+
+
 def _decaying(n, dt, dev, rate, seed):
     """n x n matrix with singular values rate^j (the CTM matrices M = R^T Rt decay geometrically)."""
     g = torch.Generator().manual_seed(seed)

@@ -321,3 +321,38 @@ def test_oracle_c4v_qr_move_matches_reference(ref, name, monkeypatch):
         assert float((env.T[env.keyT] - T).abs().max()) < 1e-12
         assert float((env2.C[env2.keyC].abs() - C.abs()).abs().max()) < 1e-12
         assert float((env2.T[env2.keyT].abs() - T.abs()).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.complex128])
+def test_oracle_rectangular_cell_direction_dependent_bonds_matches_reference_run(ref, dt):
+    """3 x 2 unit cell, six different sites, vertical bonds D = 2 and horizontal bonds D = 3: the reference's own run
+    (ctm/generic/ctmrg.py:18-110, init_env 'CTMRG') for two iterations against the oracle's -- pins the oracle for the
+    GPU test test_rectangular_cell_with_direction_dependent_bonds."""
+    import helpers as H
+    import ctm_oracle as orc
+    from ipeps.ipeps import IPEPS
+    from ctm.generic.env import ENV, init_env
+    from ctm.generic import ctmrg
+    lX, lY, chi, Dv, Dh = 3, 2, 12, 2, 3
+    g = torch.Generator().manual_seed(77)
+    sites = OrderedDict()
+    for y in range(lY):
+        for x in range(lX):
+            a = torch.randn(2, Dv, Dh, Dv, Dh, dtype=dt, generator=g)
+            sites[(x, y)] = a / a.abs().max()
+
+    def v2s(c):
+        return (c[0] % lX, c[1] % lY)
+    C, T = orc.init_env(sites, v2s, chi)
+    orc.run(sites, v2s, lX, lY, C, T, chi, 2)
+    ref.global_args.dtype, ref.global_args.torch_dtype = ('complex128' if dt.is_complex else 'float64'), dt
+    ref.ctm_args.ctm_max_iter, ref.ctm_args.projector_svd_method = 2, 'GESDD'
+    try:
+        state = IPEPS(sites={c: t.clone() for c, t in sites.items()}, vertexToSite=v2s, lX=lX, lY=lY)
+        env = ENV(chi, state)
+        init_env(state, env)
+        env, *_ = ctmrg.run(state, env, conv_check=None, ctm_args=ref.ctm_args)
+    finally:
+        ref.global_args.torch_dtype = torch.float64
+    assert H.spectra_diff(env.C, C) < 1e-10
+    assert _abs_worst(env.C, env.T, C, T) < 4e-9       # the reference-vs-reference floor of SURVEY 8c
