@@ -751,11 +751,21 @@ static bool qr_reg_try(const PtrBatch& A, const PtrBatch& Rout, const PtrBatch& 
     return true;
 }
 
+// dynamic shared memory of wy_tsolve_kernel: X (k x k) and either all of G or the 16 columns of G one block step needs
+constexpr size_t WY_TSOLVE_SMEM_MAX = 200 * 1024;
+static size_t wy_tsolve_smem(int k, bool cplx, int* g_in_smem) {
+    const size_t es = cplx ? 16 : 8;
+    const int both = 2 * (size_t)k * k * es <= WY_TSOLVE_SMEM_MAX;
+    if (g_in_smem) *g_in_smem = both;
+    return both ? 2 * (size_t)k * k * es : ((size_t)k * k + 16 * (size_t)k) * es;
+}
+
 bool qr_wy_supported(int rows, int cols, bool cplx) {
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("CTMB_QR_WY"); mode = e ? atoi(e) : 1; }
     int rpl, cl;
-    if ((size_t)cols * cols * (cplx ? 16 : 8) > 200 * 1024) return false;   // wy_tsolve keeps X in shared memory
+    // wy_tsolve keeps X and a block of G in shared memory (complex: k <= 105; wider sketches take the plain / blocked QR)
+    if (cols > 128 || wy_tsolve_smem(cols, cplx, nullptr) > WY_TSOLVE_SMEM_MAX) return false;
     return mode && qr_reg_shape(rows, cols, cplx, rpl, cl);
 }
 
@@ -875,19 +885,18 @@ __global__ void __launch_bounds__(TS_THREADS) wy_tsolve_kernel(PtrBatch Gb, PtrB
 
 void wy_tsolve_launch(const PtrBatch& G, const PtrBatch& Tau, const PtrBatch& V, const PtrBatch& X, int nb, int k,
                       int ldv, bool cplx, cudaStream_t stream) {
-    CTMB_CHECK(k <= 128 && (size_t)k * k * (cplx ? 16 : 8) <= 200 * 1024, "wy_tsolve: k too large");
-    const size_t es = cplx ? 16 : 8;
-    const int g_in_smem = 2 * (size_t)k * k * es <= 200 * 1024;
-    const size_t smem = g_in_smem ? 2 * (size_t)k * k * es : ((size_t)k * k + 16 * (size_t)k) * es;
+    int g_in_smem = 0;
+    const size_t smem = wy_tsolve_smem(k, cplx, &g_in_smem);
+    CTMB_CHECK(k <= 128 && smem <= WY_TSOLVE_SMEM_MAX, "wy_tsolve: k too large");
     if (cplx) {
         auto kern = wy_tsolve_kernel<true>;
         static bool set = false;
-        if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
+        if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WY_TSOLVE_SMEM_MAX)); set = true; }
         kern<<<nb, TS_THREADS, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
     } else {
         auto kern = wy_tsolve_kernel<false>;
         static bool set = false;
-        if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = true; }
+        if (!set) { CTMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WY_TSOLVE_SMEM_MAX)); set = true; }
         kern<<<nb, TS_THREADS, smem, stream>>>(G, Tau, V, X, k, ldv, g_in_smem);
     }
     CTMB_CUDA(cudaGetLastError());

@@ -848,8 +848,11 @@ def test_conv_rdm2x1_criterion_on_gpu(eng, dev, lag):
 @pytest.mark.parametrize('dt', [torch.float64, torch.complex128])
 def test_householder_qr_entry_point(eng, dev, dt):
     """ctmb_qr against torch.linalg.qr (same LAPACK sign convention: element-wise), through all drivers: register kernel
-    (432 x 84), WY form (1024 x 128), blocked factorisation (1536 x 96, the C.T matrix of config 3; 4096 x 200)."""
-    for rows, k in ((64, 16), (432, 84), (1024, 128), (1536, 96), (4096, 200)):
+    (432 x 84), WY form (1024 x 128), blocked factorisation (1536 x 96, the C.T matrix of config 3; 4096 x 200); square
+    matrices; widths around the shared-memory bound of the WY solve (complex: k = 105 is the last WY width, 106-113 used to
+    pass the support test and then fail at launch)."""
+    for rows, k in ((64, 16), (432, 84), (1024, 128), (1536, 96), (4096, 200), (108, 108), (420, 105), (420, 106), (339, 113),
+                    (128, 128)):
         g = torch.Generator().manual_seed(rows + k)
         M = torch.randn(rows, k, dtype=dt, generator=g)
         Q, R = eng.qr(M.to(dev))
