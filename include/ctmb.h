@@ -163,7 +163,10 @@ size_t ctmb_truncated_eig_sym_workspace(ctmb_handle_t h, ctmb_dtype dt, int n, i
 /* Thin Householder QR = torch.linalg.qr(M) as used by ctm_MOVE_QR_sl (ctm/one_site_c4v/ctmrg_c4v.py:513-516, the
  * projector of the QR variant of the C4v move).  A: rows x k, COLUMN-major (= the transpose of a row-major torch matrix),
  * rows >= k; on return A holds the explicit thin Q, R (k x k column-major) the upper-triangular factor.  Signs follow
- * LAPACK's Householder convention (R_jj = -sign(alpha) ||x||), i.e. Q and R equal torch's up to rounding. */
+ * LAPACK's Householder convention (R_jj = -sign(alpha) ||x||), i.e. Q and R equal torch's up to rounding.  One difference:
+ * for a SQUARE complex matrix LAPACK also rotates the last diagonal entry of R to the real axis; here that entry keeps its
+ * phase (the last column has nothing below the diagonal and gets no reflector).  Tall matrices -- every use on the path -- are
+ * not affected. */
 int ctmb_qr(ctmb_handle_t h, ctmb_dtype dt, void* A, int rows, int k, void* R, void* ws, size_t ws_bytes, void* stream);
 size_t ctmb_qr_workspace(ctmb_handle_t h, ctmb_dtype dt, int rows, int k);
 

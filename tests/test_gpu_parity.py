@@ -862,10 +862,14 @@ def test_householder_qr_entry_point(eng, dev, dt):
         assert float((Q.conj().t() @ Q - eye).abs().max()) < 1e-13, (rows, k)
         assert H.maxrel(Q @ R, M) < 1e-13, (rows, k)
         assert float(R.tril(-1).abs().max()) == 0.0
-        # unique up to the phase of each column / row of R: LAPACK makes the diagonal of R real; compare after aligning
+        # unique up to the phase of each column of Q / row of R.  LAPACK makes the diagonal of R real; so does libctmb, except
+        # for the last column of a SQUARE complex matrix (no entries below the diagonal: no reflector is generated and
+        # R[k-1,k-1] keeps its phase).  Compare after aligning the phases: Q_ours diag(ph) = Q_lapack.
         ph = (R.diagonal() / Rr.diagonal())
         ph = ph / ph.abs()
-        assert H.maxrel(Q * ph.conj()[None, :], Qr) < 1e-11, (rows, k)
+        if dt.is_complex and rows != k:
+            assert float(ph.imag.abs().max()) < 1e-12, (rows, k)          # real diagonal, as LAPACK's
+        assert H.maxrel(Q * ph[None, :], Qr) < 1e-11, (rows, k)
 
 
 @pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
