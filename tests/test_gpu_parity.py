@@ -278,7 +278,8 @@ def _decaying(n, dt, dev, rate, seed):
     return ((Q1 * s.to(dt)) @ Q2.conj().t()).to(dev)
 
 
-@pytest.mark.parametrize('shape', [(3, 48, torch.float64, 0.9), (4, 32, torch.complex128, 0.93), (8, 24, torch.float64, 0.97)])
+@pytest.mark.parametrize('shape', [(3, 48, torch.float64, 0.9), (4, 32, torch.complex128, 0.93), (8, 24, torch.float64, 0.97),
+                                   (2, 64, torch.complex128, 0.9), (2, 61, torch.complex128, 0.9)])   # complex sketches 112 / 106 wide
 def test_projector_biorthogonality_property(eng, dev, shape):
     """Size-independent property: Pt^T P = diag(1 on kept, 0 on cut) (ctm_projectors.py:279-293:
     P = R conj(U) S^-1/2, Pt = Rt V S^-1/2 with M = R^T Rt = U S V^H), at the full n of configs 2-4."""
