@@ -614,6 +614,24 @@ def rdm_small_c4v(kind, a, C, T, sym_pos_def=False):
     return f((0, 0), OrderedDict({(0, 0): a}), v2s_1site, Cg, Tg, sym_pos_def=sym_pos_def)
 
 
+def rdm3x1_c4v(a, C, T, sym_pos_def=False):
+    """rdm3x1 / rdm3x1_sl of ctm/one_site_c4v/rdm_c4v.py:667-1011: the two END sites of a row of three (centre traced), indices
+    s0 s1 ; s0' s1' (ket ; bra).  Restated column by column with plain einsums: left boundary C-T-C, three columns T-(a a*)-T
+    (the first and the last with open physical indices), right boundary."""
+    D = a.shape[1]
+    chi = C.shape[0]
+    Tk = T.reshape(chi, chi, D, D)                                    # [chi, chi, ket, bra]
+    E = torch.einsum('ab,acd,ce->bde', C, T, C).reshape(chi, D, D, chi)
+    col_open = 'axuU,xyYz,puydr,qUYDR,zedD->arRepq'
+    col = 'axuU,xyYz...,suydr,sUYDR,zedD->arRe...'
+    E = torch.einsum(col_open, Tk, E, a, a.conj(), Tk)
+    E = torch.einsum(col, Tk, E, a, a.conj(), Tk)
+    E = torch.einsum('axuU,xyYzij,puydr,qUYDR,zedD->arReijpq', Tk, E, a, a.conj(), Tk)
+    R = torch.einsum('xc,tcy,tz->xyz', C, T, C).reshape(chi, D, D, chi)
+    rho = torch.einsum('arReijpq,arRe->ipjq', E, R)
+    return _sym_pos_def(rho, sym_pos_def)
+
+
 def rdm2x2_c4v(a, C, T, open_sites=(0, 1, 2, 3), sym_pos_def=False):
     """The 2x2 plaquette of the one-site C4v state through the generic construction: open_sites=(0,1) is
     rdm2x2_NN_lowmem_sl, (0,3) rdm2x2_NNN_lowmem_sl, all four rdm2x2 (ctm/one_site_c4v/rdm_c4v.py:1160-1202,

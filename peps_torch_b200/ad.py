@@ -93,18 +93,19 @@ def _chain(eng, subs, ops, conj, out):
     return cur
 
 
-def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None, ket_extra=''):
+def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None, ket_extra='', phys='ss'):
     """The double-layer einsum `spec` ('@' = the on-site double-layer tensor) evaluated layer by layer without forming
     a (x) a*: every fused label of '@' is split into (ket, bra) on the operands that carry it (SURVEY Appendix A;
     ctm_components.py:372-434).  A rank-4 `a` is the double-layer tensor itself and enters as one operand.  `a_ket`
     replaces the ket layer (an operator applied to the physical leg, corrf.py:415-419); the bra layer stays conj(a).
     `ket_extra` labels trailing indices of `a_ket` beyond [s,u,l,d,r] (the bond of a two-site operator split over two
-    sites, corrf_c4v.py:501-503)."""
+    sites, corrf_c4v.py:501-503).  `phys` = the labels of the physical index on the ket and on the bra layer: equal (default)
+    contracts it, two different labels that also appear in the output keep both open (density matrices)."""
     lhs, out = spec.split('->')
     terms = lhs.split(',')
     a_pos = [i for i, t in enumerate(terms) if t.startswith('@')][0]
     a_idx = terms[a_pos][1:]
-    assert 's' not in lhs.replace(',', '') + out, "sl_chain: 's' is the physical index"
+    assert phys != 'ss' or 's' not in lhs.replace(',', '') + out, "sl_chain: 's' is the physical index"
     nops = len(ops)
     if a.dim() == 4:
         xs = list(ops[:a_pos]) + [a] + list(ops[a_pos:])
@@ -118,7 +119,7 @@ def sl_chain(eng, spec, ops, a, conj_last=False, a_ket=None, ket_extra=''):
     k = 0
     for i, t in enumerate(terms):
         if i == a_pos:
-            subs += ['s' + a_idx + ket_extra, 's' + a_idx.upper()]
+            subs += [phys[0] + a_idx + ket_extra, phys[1] + a_idx.upper()]
             xs += [a if a_ket is None else a_ket, a]
             cj += [False, True]
             continue

@@ -1,6 +1,6 @@
 """Drop-in for the density matrices of ctm/one_site_c4v/rdm_c4v.py used by the C4v J1-J2 energy and observables
 (models/j1j2.py:641-679, eval_obs): rdm2x2_NN_lowmem(_sl) :1117-1202, rdm2x2_NNN_lowmem(_sl) :1286-1371, rdm2x2 :1446-1546,
-rdm1x1(_sl) :168-392, rdm2x1(_sl) :394-665.
+rdm1x1(_sl) :168-392, rdm2x1(_sl) :394-665, rdm3x1(_sl) :667-1011 (the J3 term of energy_1x1_lowmem, models/j1j2.py:671-677).
 The reference rotates ONE enlarged corner; here the single (C, T) pair is rotated into the eight tensors of a generic
 1x1-cell environment (env_c4v.py:25-45 vs env.py:57-77) and libctmb contracts the generic 2x2 network, tracing the
 sites that are not kept (closed corners)."""
@@ -59,3 +59,24 @@ def rdm2x1_sl(state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
 
 rdm1x1 = rdm1x1_sl
 rdm2x1 = rdm2x1_sl
+
+
+def rdm3x1_sl(state, env, sym_pos_def=False, force_cpu=False, verbosity=0):
+    r""":return: 2-site density matrix :math:`s_0s_1;s'_0s'_1` of the two END sites of a row of three, the centre site traced
+    (rdm_c4v.py:829-1011).  Built like the correlation functions (corrf_c4v.py): the left boundary C--T--C takes three
+    transfer matrices -- the first and the third with the physical indices of both layers left open -- and is closed with
+    the right boundary; every step is one libctmb chain and no double-layer tensor is formed."""
+    from ... import ad
+    eng = _engine()
+    a = next(iter(state.sites.values()))
+    C_, T = env.C[env.keyC], env.T[env.keyT]
+    E = ad.contract(eng, 'bcd,ce->bde', ad.contract(eng, 'ab,acd->bcd', C_, T), C_)                  # left boundary
+    E = ad.sl_chain(eng, 'axu,xyz,@uydr,zed->arepq', (T, E, T), a, phys='pq')                          # site 0, open
+    E = ad.sl_chain(eng, 'axu,xyzpq,@uydr,zed->arepq', (T, E.contiguous(), T), a)                     # centre, traced
+    E = ad.sl_chain(eng, 'axu,xyzpq,@uydr,zed->arepqvw', (T, E.contiguous(), T), a, phys='vw')         # site 1, open
+    R = ad.contract(eng, 'xty,tz->xyz', ad.contract(eng, 'xc,tcy->xty', C_, T), C_)                   # right boundary
+    rho = ad.contract(eng, 'arepqvw,are->pvqw', E.contiguous(), R)
+    return eng.sym_pos_def(rho, sym_pos_def)
+
+
+rdm3x1 = rdm3x1_sl

@@ -97,7 +97,7 @@ def enable(engine_factory=None):
         setattr(rdm, name, _dispatch(getattr(ours_rdm, name), ref_fn))
     rdm_c4v = importlib.import_module('ctm.one_site_c4v.rdm_c4v')
     for name in ('rdm2x2_NN_lowmem_sl', 'rdm2x2_NNN_lowmem_sl', 'rdm2x2_NN_lowmem', 'rdm2x2_NNN_lowmem', 'rdm2x2',
-                 'rdm1x1', 'rdm1x1_sl', 'rdm2x1', 'rdm2x1_sl'):
+                 'rdm1x1', 'rdm1x1_sl', 'rdm2x1', 'rdm2x1_sl', 'rdm3x1', 'rdm3x1_sl'):
         setattr(rdm_c4v, name, _dispatch(getattr(ours_rdm_c4v, name), getattr(rdm_c4v, name)))
     # the transfer-operator spectra at the tail of the scripts (ctm/generic/transferops.py:38-205): mat-vecs on libctmb
     from .ctm.generic import transferops as ours_top

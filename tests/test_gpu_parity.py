@@ -777,6 +777,7 @@ def test_c4v_small_rdms_against_oracle(eng, dev, name):
     for spd in (False, True):
         assert float((rdm_c4v.rdm1x1_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm_small_c4v('1x1', a, Cc, Tc, spd)).abs().max()) < 1e-12
         assert float((rdm_c4v.rdm2x1_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm_small_c4v('2x1', a, Cc, Tc, spd)).abs().max()) < 1e-12
+        assert float((rdm_c4v.rdm3x1_sl(stc, envc, sym_pos_def=spd).cpu() - orc.rdm3x1_c4v(a, Cc, Tc, spd)).abs().max()) < 1e-12
 
 
 # ------------------------------------------------------------------------------------------

@@ -244,6 +244,8 @@ def test_host_rdm_modules_map_sites_and_env_correctly(monkeypatch):
     assert H.maxrel(rdm_c4v.rdm2x2(stc, envc), orc.rdm2x2_c4v(a, Cc, Tc)) < 1e-13
     assert H.maxrel(rdm_c4v.rdm1x1_sl(stc, envc), orc.rdm_small_c4v('1x1', a, Cc, Tc)) < 1e-13
     assert H.maxrel(rdm_c4v.rdm2x1_sl(stc, envc, sym_pos_def=True), orc.rdm_small_c4v('2x1', a, Cc, Tc, True)) < 1e-13
+    assert H.maxrel(rdm_c4v.rdm3x1_sl(stc, envc, sym_pos_def=True), orc.rdm3x1_c4v(a, Cc, Tc, True)) < 1e-13
+    assert H.maxrel(rdm_c4v.rdm3x1(stc, envc), orc.rdm3x1_c4v(a, Cc, Tc)) < 1e-13
     for f, g in ((rdm.rdm1x1, orc.rdm1x1), (rdm.rdm2x1, orc.rdm2x1), (rdm.rdm1x2, orc.rdm1x2)):
         assert torch.equal(f((0, 1), st, env), g((0, 1), sites, orc.v2s_4site, C, T))
     # operator=: the unnormalised expectation value; with the identity, the trace of the raw network (rdm.py:89-90)

@@ -100,11 +100,11 @@ def test_c4v_correlation_functions_of_the_script_through_the_launcher(tmp_path):
     (models/j1j2.py:826-925 -> corrf_c4v.corrf_1sO1sO / corrf_2sOH2sOH_E1 / corrf_2sOV2sOV_E2, transferops_c4v.get_Top_spec_c4v /
     get_Top2_spec_c4v) through the
     launcher with the oracle as engine against the script run untouched."""
-    args = ['--bond_dim', '2', '--chi', '8', '--seed', '123', '--j2', '0.3', '--CTMARGS_ctm_max_iter', '6', '--corrf_r', '4',
-            '--top_n', '3', '--corrf_dd_v', '--top2']
+    args = ['--bond_dim', '2', '--chi', '8', '--seed', '123', '--j2', '0.3', '--j3', '0.1', '--CTMARGS_ctm_max_iter', '6',
+            '--corrf_r', '4', '--top_n', '3', '--corrf_dd_v', '--top2']
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', OMP_NUM_THREADS='2')
     script = os.path.join(REF, 'examples', 'j1j2', 'ctmrg_j1j2_c4v.py')
-    outs = []
+    outs, finals = [], []
     for mode in (['--plain'], []):
         wd = tmp_path / ('a' if mode else 'b')
         os.makedirs(wd, exist_ok=True)
@@ -112,6 +112,9 @@ def test_c4v_correlation_functions_of_the_script_through_the_launcher(tmp_path):
                              cwd=wd, env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
         outs.append(_ss_lines(out.stdout))
+        finals.append([complex(x) for x in [ln for ln in out.stdout.splitlines() if ln.startswith('FINAL')][-1][6:].split(',')])
+    # j3 != 0: the energy goes through rdm3x1_sl as well (models/j1j2.py:671-677)
+    assert len(finals[0]) == len(finals[1]) and all(abs(x - y) < 1e-9 for x, y in zip(*finals)), finals
     want, got = outs
     assert len(want) == 4 + 4 + 4 + 3 + 3 and len(got) == len(want)     # SS, DD, DD_v rows, spectrum(T), spectrum(T2) rows
     for a, b in zip(got, want):

@@ -283,6 +283,10 @@ def test_oracle_c4v_small_rdms_match_reference_elementwise(ref, name):
             r_orc = orc.rdm_small_c4v(kind, a, C, T, spd)
             assert r_ref.shape == r_orc.shape
             assert float((r_ref - r_orc).abs().max()) < 1e-12, (kind, spd, f_ref.__name__)
+        # rdm3x1(_sl) (rdm_c4v.py:667-1011): the J3 term of energy_1x1_lowmem (models/j1j2.py:671-677)
+        for f_ref in (rdm_c4v.rdm3x1_sl, rdm_c4v.rdm3x1):
+            r_ref, r_orc = f_ref(st, env, sym_pos_def=spd), orc.rdm3x1_c4v(a, C, T, spd)
+            assert r_ref.shape == r_orc.shape and float((r_ref - r_orc).abs().max()) < 1e-13, (spd, f_ref.__name__)
 
 
 @pytest.mark.parametrize('name', ['c4v_D2_chi8_B', 'c4v_D2_chi8_B_c128'])
