@@ -27,6 +27,12 @@ def rdm2x2_legacy(coord, state, env, sym_pos_def=False, verbosity=0):
     return _engine().rdm2x2(coord, state, env, sym_pos_def=sym_pos_def)
 
 
+def rdm2x2_oe(coord, state, env, open_sites=[0, 1, 2, 3], unroll=False, checkpoint_unrolled=False, checkpoint_on_device=False,
+              sym_pos_def=False, force_cpu=False, verbosity=0, global_args=cfg.global_args):
+    r"""The opt_einsum variant the reference's ``rdm2x2`` dispatches to (rdm.py:1594-1675): the same density matrix."""
+    return _engine().rdm2x2(coord, state, env, open_sites=open_sites, sym_pos_def=sym_pos_def)
+
+
 def _rdm1x1(coord, state, env, operator, sym_pos_def):
     """With ``operator`` the reference returns the scalar sum_{s s'} rho[s;s'] operator[s';s] of the UNNORMALISED network
     (rdm.py:89-90,175-181,275-299): the raw 1-site network comes from libctmb, the p x p trace against the operator is taken here."""

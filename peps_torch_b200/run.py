@@ -84,7 +84,7 @@ def enable(engine_factory=None):
 
     rdm = importlib.import_module('ctm.generic.rdm')
     ref_legacy = rdm.rdm2x2_legacy
-    for name in ('rdm2x2', 'rdm2x2_legacy', 'rdm1x1', 'rdm2x1', 'rdm1x2', 'rdm1x1_dl', 'rdm2x1_dl', 'rdm1x2_dl',
+    for name in ('rdm2x2', 'rdm2x2_legacy', 'rdm2x2_oe', 'rdm1x1', 'rdm2x1', 'rdm1x2', 'rdm1x1_dl', 'rdm2x1_dl', 'rdm1x2_dl',
                  'rdm1x1_sl', 'rdm2x1_sl', 'rdm1x2_sl'):
         ref_fn = getattr(rdm, name)
         if name == 'rdm2x2':
